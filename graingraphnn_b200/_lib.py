@@ -1,0 +1,93 @@
+"""ctypes binding of libgraingnn_b200.so (the C ABI declared in include/graingnn_b200.h).
+
+There is no CPU fallback: if the library is missing, `lib()` raises; if a kernel rejects its arguments or the
+launch fails, `check()` raises RuntimeError with the library's message.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+from . import build as _build
+
+_LIB = None
+
+GG_GATE_RAW, GG_GATE_RELU, GG_GATE_LSTM, GG_GATE_LSTM0 = 0, 1, 2, 3
+
+
+class AggInput(Structure):
+    _fields_ = [('agg', c_void_p), ('ld_agg', c_int32), ('ea', c_void_p), ('rowptr', c_void_p),
+                ('W2', c_void_p), ('We', c_void_p), ('b2', c_void_p), ('weighted', c_int32)]
+
+
+_P, _I, _L, _F, _S = c_void_p, c_int32, c_int64, c_float, c_size_t
+_PROTOS = {
+    'gg_error_string': (c_char_p, [_I]),
+    'gg_version': (_I, []),
+    'gg_device_is_sm100': (_I, []),
+    'gg_csr_workspace_bytes': (_S, [_L, _I]),
+    'gg_csr_build': (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _S, _P]),
+    'gg_permute_f32': (_I, [_P, _P, _P, _L, _P]),
+    'gg_edge_length': (_I, [_P, _I, _P, _I, _P, _L, _P, _P, _P, _P]),
+    'gg_node_proj': (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _I, _I, _I, _P]),
+    'gg_pgat_gather': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P]),
+    'gg_gate_update': (_I, [POINTER(AggInput), _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'gg_node_head': (_I, [_P, _I, _I, _P, _P, _I, POINTER(c_int32), _P, _I, _P, _I, _F, _P, _I, _P]),
+    'gg_edge_head': (_I, [_P, _I, _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'gg_feature_update': (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _F, _F, _P, _P]),
+    'gg_gather_rows': (_I, [_P, _I, _P, _I, _I, _P, _I, _P]),
+    'gg_scatter_rows': (_I, [_P, _I, _P, _I, _I, _P, _I, _P]),
+}
+# entry points of the tcgen05 path (gemm_tc.cu); bound when present
+_OPTIONAL = {
+    'gg_tc_supported': (_I, []),
+    'gg_node_proj_tc': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P]),
+    'gg_split_tf32': (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _P, _I, _I, _P]),
+}
+
+
+def lib_path():
+    return _build.lib_path()
+
+
+def lib():
+    """Load (once) and return the ctypes handle. Raises if the shared library has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f'{path} not found: build it with `python -m graingraphnn_b200.build` '
+                '(or __graft_entry__.build()); graingraphnn_b200 has no CPU fallback')
+        h = ctypes.CDLL(path)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        for name, (res, args) in _OPTIONAL.items():
+            if hasattr(h, name):
+                fn = getattr(h, name)
+                fn.restype, fn.argtypes = res, args
+        _LIB = h
+    return _LIB
+
+
+def exported_symbols():
+    return list(_PROTOS)
+
+
+# kernels launched by one successful call of each entry point (for bench.py's gpu_launches accounting)
+KERNELS_PER_CALL = {'gg_csr_build': 6, 'gg_permute_f32': 1, 'gg_edge_length': 2, 'gg_node_proj': 1, 'gg_pgat_gather': 1,
+                    'gg_gate_update': 1, 'gg_node_head': 1, 'gg_edge_head': 1, 'gg_feature_update': 3,
+                    'gg_gather_rows': 1, 'gg_scatter_rows': 1, 'gg_node_proj_tc': 1, 'gg_split_tf32': 1}
+LAUNCHES = [0]
+
+
+def check(rc, what=''):
+    LAUNCHES[0] += KERNELS_PER_CALL.get(what, 0)
+    if rc != 0:
+        msg = lib().gg_error_string(int(rc)).decode()
+        raise RuntimeError(f'{what or "graingnn_b200"} failed ({rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())

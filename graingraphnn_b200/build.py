@@ -1,0 +1,52 @@
+"""Build libgraingnn_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIBDIR = os.path.join(HERE, 'lib')
+LIBNAME = 'libgraingnn_b200.so'
+SOURCES = ['api.cu', 'csr.cu', 'edge.cu', 'gather.cu', 'gemm_simt.cu', 'gemm_tc.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall']
+
+
+def lib_path():
+    return os.path.join(LIBDIR, LIBNAME)
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ into one shared library. Returns its path."""
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+    hdrs.append(os.path.join(HERE, '..', 'include', 'graingnn_b200.h'))
+    objs = []
+    for s in srcs:
+        o = os.path.join(LIBDIR, os.path.basename(s)[:-3] + '.o')
+        if force or _stale(o, [s] + hdrs):
+            cmd = [nvcc] + NVCC_FLAGS + ['-c', '-o', o, s]
+            if verbose:
+                print(' '.join(cmd))
+            subprocess.run(cmd, check=True)
+        objs.append(o)
+    out = lib_path()
+    if force or _stale(out, objs):
+        cmd = [nvcc, '-shared', '-o', out] + objs + ['-lcuda']
+        if verbose:
+            print(' '.join(cmd))
+        subprocess.run(cmd, check=True)
+    return out
+
+
+if __name__ == '__main__':
+    print(build(force=True, verbose=True))

@@ -1,0 +1,111 @@
+"""Execution of one packed cell (all gates of a HeteroConv{PeriodConv} stack) on the CUDA kernels.
+
+Three kernel families per call, in this order:
+  (c)  gg_node_proj   per node type   : P_t = [X_t | h_t] Wcat_t^T + bcat_t
+  (b)  gg_pgat_gather per edge type   : agg_e, ea_e  (periodic wrap + scores + segment softmax + aggregation)
+  (c') gg_gate_update per node type   : lin_l2 / lin_edge / lin_skip + biases + gate non-linearities / LSTM update
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import AggInput, check, ptr
+from .graph import _stream
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f'graingraphnn_b200: {what} must live on a CUDA device; this package has no CPU path')
+
+
+def pad_features(x, k1p):
+    """[N, K1] -> contiguous fp32 [N, K1p] (zero columns appended) — rows become 16-byte aligned."""
+    x = x.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.shape[1] == k1p:
+        return x.contiguous()
+    return F.pad(x, (0, k1p - x.shape[1])).contiguous()
+
+
+def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=None):
+    """xpad[t]: [N_t, K1p] fp32 (x,y,z in columns 0..2); h[t]: [N_t, K2] or None; c[t]: [N_t, C] or None;
+    csr[e]: EdgeCSR; ea_csr[e]: [E] edge attribute in CSR order.  Returns (out_h, out_c) dicts."""
+    L = _lib.lib()
+    C, G = pk.C, pk.G
+    GC = G * C
+    st = _stream()
+    work = {} if work is None else work
+    dev = next(iter(xpad.values())).device
+
+    def buf(name, shape):
+        """flat grow-only workspace per name, viewed at the requested shape (encoder/decoder share storage)"""
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        b = work.get(name)
+        if b is None or b.numel() < numel or b.device != dev:
+            b = torch.empty(max(numel, 1), dtype=torch.float32, device=dev)
+            work[name] = b
+        return b[:numel].view(shape)
+
+    with torch.cuda.device(dev):
+        # (c) node projections
+        P = {}
+        for t in pk.node_types:
+            x = xpad[t]
+            n = x.shape[0]
+            ht = None if h is None else h[t]
+            P[t] = buf(('P', t), (n, pk.ncols[t]))
+            check(L.gg_node_proj(ptr(x), x.stride(0), pk.k1p[t],
+                                 ptr(ht), 0 if ht is None else ht.stride(0), 0 if ht is None else ht.shape[1],
+                                 ptr(pk.Wcat[t]), pk.kin[t], ptr(pk.bcat[t]),
+                                 ptr(P[t]), pk.ncols[t], n, pk.ncols[t], st), 'gg_node_proj')
+        # (b) fused gather per edge type
+        agg, ea = {}, {}
+        for e in pk.edge_types:
+            s, _, d = e
+            nd = xpad[d].shape[0]
+            agg[e] = buf(('agg', e), (nd, GC))
+            ea[e] = buf(('ea', e), (nd, G))
+            g = csr[e]
+            check(L.gg_pgat_gather(ptr(P[s]), pk.ncols[s], pk.koff[e], pk.voff[e],
+                                   ptr(P[d]), pk.ncols[d], pk.qoff[e], pk.qxoff[e],
+                                   ptr(xpad[s]), xpad[s].stride(0), ptr(xpad[d]), xpad[d].stride(0),
+                                   ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(pk.Wv3[e]),
+                                   nd, G, C, 1 if pk.weighted else 0, ptr(agg[e]), GC, ptr(ea[e]), st), 'gg_pgat_gather')
+        # (c') gate GEMM + LSTM update per node type
+        out_h = {} if out_h is None else out_h
+        out_c = {} if out_c is None else out_c
+        lstm = mode in (_lib.GG_GATE_LSTM, _lib.GG_GATE_LSTM0)
+        for t in pk.node_types:
+            x = xpad[t]
+            n = x.shape[0]
+            ins = pk.into[t]
+            if not ins:          # PyG HeteroConv emits nothing for a node type no edge type ends in
+                continue
+            arr = (AggInput * len(ins))()
+            for i, e in enumerate(ins):
+                arr[i] = AggInput(agg[e].data_ptr(), GC, ea[e].data_ptr(), csr[e].rowptr.data_ptr(),
+                                  pk.W2[e].data_ptr(), pk.We[e].data_ptr(), pk.b2[e].data_ptr(), 1 if pk.weighted else 0)
+            ht = None if h is None else h[t]
+            ct = None if c is None else c[t]
+            if t not in out_h:
+                out_h[t] = torch.empty((n, C if lstm else GC), dtype=torch.float32, device=dev)
+            if lstm and t not in out_c:
+                out_c[t] = torch.empty((n, C), dtype=torch.float32, device=dev)
+            check(L.gg_gate_update(arr, len(ins), ptr(x), x.stride(0), pk.k1p[t],
+                                   ptr(ht), 0 if ht is None else ht.stride(0),
+                                   ptr(pk.Wskip[t]), pk.kin[t], ptr(pk.btot[t]),
+                                   ptr(ct), ptr(out_h[t]), ptr(out_c[t]) if lstm else None,
+                                   n, G, C, mode, st), 'gg_gate_update')
+    return out_h, out_c
+
+
+def _as_f32c(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

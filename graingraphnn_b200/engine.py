@@ -1,0 +1,215 @@
+"""RolloutEngine — the resident-on-GPU rollout step (the "nn-step" of SURVEY.md §8d).
+
+One step = regressor forward + classifier forward (encoder + decoder cell each) + heads + in-place feature update +
+edge-length rebuild, i.e. test.py:382-383, :400-407, :562-575 for a fixed topology.  Node features, CSR indices, edge
+attributes, hidden states and all workspaces stay in HBM between steps; a step launches ~40 kernels and can be replayed
+from a CUDA graph.  The host topology update of the reference (`Cmodel.update`, models.py:614-845) plugs in between steps
+through `x`, `pred` and `set_topology()`.
+"""
+import torch
+
+from . import _lib
+from .cell import run_cell
+from .graph import build_csr, edge_length
+from .heads import edge_head, feature_update, node_head
+from .models import GrainNN_classifier, GrainNN_regressor
+from .packing import pad4
+
+ET_GJ, ET_JG, ET_JJ = ('grain', 'push', 'joint'), ('joint', 'pull', 'grain'), ('joint', 'connect', 'joint')
+DEFAULT_EDGE_TYPES = (ET_GJ, ET_JG, ET_JJ)
+
+
+class _Hyper:
+    def __init__(self, features, targets, layer_size, metadata, device):
+        self.features, self.targets, self.layer_size, self.layers = features, targets, layer_size, 1
+        self.metadata, self.device, self.out_win, self.window = metadata, device, 1, 1
+
+
+class RolloutEngine:
+    def __init__(self, regressor, classifier, device='cuda'):
+        self.device = torch.device(device)
+        self.R, self.Cm = regressor.to(self.device).eval(), classifier.to(self.device).eval()
+        self.C = regressor.out_channels
+        self.edge_types = tuple(regressor.metadata[1])
+        self.node_types = tuple(regressor.in_channels_dict)
+        self.train_frames = 120
+        self._graph = None
+        self._work = {}
+        self.x, self.xbuf, self.edge_index, self.edge_attr, self.ea_csr, self.csr = {}, {}, {}, {}, {}, {}
+        self.pred = {}
+        self._scratch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._packs = None
+        self.launches_per_step = 0
+
+    # ---------------------------------------------------------------------------------------------------- setup
+    @classmethod
+    def from_state_dicts(cls, sd_regressor, sd_classifier, device='cuda', n_grain_feat=11, n_joint_feat=8,
+                         edge_types=DEFAULT_EDGE_TYPES):
+        C = sd_regressor['linear.grain.weight'].shape[1]
+        hp = _Hyper({'grain': list(range(n_grain_feat)), 'joint': list(range(n_joint_feat))},
+                    {'grain': [0, 1], 'joint': [0, 1]}, C, (['grain', 'joint'], list(edge_types)), 'cuda')
+        R = GrainNN_regressor(hp)
+        R.load_state_dict(sd_regressor)
+        Cm = GrainNN_classifier(hp, R)
+        Cm.load_state_dict(sd_classifier)
+        return cls(R, Cm, device)
+
+    def _pack(self):
+        if self._packs is None:
+            self._packs = {}
+            for name, m in (('R', self.R), ('C', self.Cm)):
+                enc, dec = m.gclstm_encoder.cell_list[0], m.gclstm_decoder.cell_list[0]
+                self._packs[name] = (enc.packed(('i', 'c', 'o'), False, self.device, self.edge_types),
+                                     dec.packed(('i', 'f', 'c', 'o'), True, self.device, self.edge_types))
+        return self._packs
+
+    def set_graph(self, x_dict, edge_index_dict, edge_attr_dict=None):
+        """Copy features into padded resident buffers, build the CSR of every edge type, take (or compute) edge lengths."""
+        self._graph = None
+        for t in self.node_types:
+            xt = x_dict[t].to(self.device, torch.float32)
+            buf = torch.zeros(xt.shape[0], pad4(xt.shape[1]), dtype=torch.float32, device=self.device)
+            buf[:, :xt.shape[1]] = xt
+            self.xbuf[t] = buf
+            self.x[t] = buf[:, :xt.shape[1]]          # user-visible view; in-place edits land in the resident buffer
+        self.set_topology(edge_index_dict, edge_attr_dict)
+
+    def set_topology(self, edge_index_dict, edge_attr_dict=None):
+        self._graph = None
+        for e in self.edge_types:
+            ei = edge_index_dict[e].to(self.device).contiguous()
+            self.edge_index[e] = ei
+            self.csr[e] = build_csr(ei, self.xbuf[e[0]].shape[0], self.xbuf[e[2]].shape[0])
+            self.edge_attr[e] = torch.empty(ei.shape[1], 1, dtype=torch.float32, device=self.device)
+            self.ea_csr[e] = torch.empty(ei.shape[1], dtype=torch.float32, device=self.device)
+        if edge_attr_dict is None:
+            self.rebuild_edge_attr()
+        else:
+            L = _lib.lib()
+            for e in self.edge_types:
+                self.edge_attr[e].copy_(edge_attr_dict[e].to(self.device, torch.float32).reshape(-1, 1))
+                _lib.check(L.gg_permute_f32(_lib.ptr(self.edge_attr[e]), _lib.ptr(self.csr[e].perm), _lib.ptr(self.ea_csr[e]),
+                                            self.ea_csr[e].numel(), torch.cuda.current_stream().cuda_stream), 'gg_permute_f32')
+
+    def rebuild_edge_attr(self):
+        """test.py:562-575 for every edge type, written in original and CSR order."""
+        L = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        for e in self.edge_types:
+            xs, xd = self.xbuf[e[0]], self.xbuf[e[2]]
+            ei = self.edge_index[e]
+            _lib.check(L.gg_edge_length(_lib.ptr(xs), xs.stride(0), _lib.ptr(xd), xd.stride(0), _lib.ptr(ei), ei.shape[1],
+                                        _lib.ptr(self.csr[e].perm), _lib.ptr(self.edge_attr[e]), _lib.ptr(self.ea_csr[e]), st),
+                       'gg_edge_length')
+
+    # ---------------------------------------------------------------------------------------------------- step
+    def _model_forward(self, name):
+        pk_enc, pk_dec = self._pack()[name]
+        w = self._work
+        st = self._state.setdefault(name, {'he': {}, 'ce': {}, 'hd': {}, 'cd': {}})
+        self.exchange_x_hook()
+        run_cell(pk_enc, self.xbuf, None, None, self.csr, self.ea_csr, _lib.GG_GATE_LSTM0, st['he'], st['ce'], w)
+        self.exchange_h_hook(st['he'])
+        run_cell(pk_dec, self.xbuf, st['he'], st['ce'], self.csr, self.ea_csr, _lib.GG_GATE_LSTM, st['hd'], st['cd'], w)
+        return st['hd'], st['cd']
+
+    _state = None
+
+    def exchange_x_hook(self):      # overridden by the slab-partitioned engine (halo exchange of X rows)
+        pass
+
+    def exchange_h_hook(self, h):   # overridden by the slab-partitioned engine (halo exchange of encoder h rows)
+        pass
+
+    def _step_impl(self, span):
+        if self._state is None:
+            self._state = {}
+        R, Cm = self.R, self.Cm
+        hd, _ = self._model_forward('R')
+        yj, _ = node_head(hd['joint'], R.linear['joint'].weight, R.linear['joint'].bias, [1, 1])
+        yg, area = node_head(hd['grain'], R.linear['grain'].weight, R.linear['grain'].bias, [1, 2],
+                             area_in=self.xbuf['grain'][:, 3], area_scale=20.0)
+        hc, _ = self._model_forward('C')
+        ev, ed = edge_head(hc['joint'], self.edge_index[ET_JJ], self.edge_attr[ET_JJ],
+                           Cm.lin1.weight, Cm.lin1.bias, Cm.lin2.weight, Cm.lin2.bias)
+        feature_update(self.x['joint'], self.x['grain'], yj, yg, span / (self.train_frames + 1),
+                       self.train_frames / (self.train_frames + 1), self._scratch)
+        self.post_update_hook()
+        self.rebuild_edge_attr()
+        return {'joint': yj, 'grain': yg, 'grain_area': area, 'edge_event': ev, 'edge': ed}
+
+    def post_update_hook(self):
+        pass
+
+    @torch.no_grad()
+    def step(self, span=6):
+        """One rollout step on the resident graph. Returns the prediction dict (device tensors)."""
+        if self._graph is not None and self._graph[0] == span:
+            self._graph[1].replay()
+            return self.pred
+        with torch.cuda.device(self.device):
+            out = self._step_impl(span)
+        self.pred = out
+        return out
+
+    @torch.no_grad()
+    def capture(self, span=6, warmup=2):
+        """Capture the step into a CUDA graph (fixed topology): later step(span) calls replay it.
+        NOTE: capturing advances the rollout state by `warmup` + 1 steps."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                l0 = _lib.LAUNCHES[0]
+                self._step_impl(span)
+                self.launches_per_step = _lib.LAUNCHES[0] - l0
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.pred = self._step_impl(span)
+        self._graph = (span, g)
+        return g
+
+    # ---------------------------------------------------------------------------------------------------- host I/O
+    def host_features(self):
+        """CPU copies of the (unpadded) node features."""
+        return {t: self.x[t].detach().cpu().contiguous() for t in self.node_types}
+
+    def load_features(self, host_x):
+        """H2D: overwrite the resident node features from (ideally pinned) host tensors."""
+        for t in self.node_types:
+            self.x[t].copy_(host_x[t], non_blocking=True)
+
+    def fetch_predictions(self, pred, out=None, keys=('joint', 'grain', 'grain_area', 'edge_event')):
+        """D2H of the step outputs the host topology update consumes (models.py:626-628, test.py:418) into pinned buffers."""
+        if out is None:
+            out = {k: torch.empty(pred[k].shape, dtype=pred[k].dtype, pin_memory=True) for k in keys}
+        for k in keys:
+            out[k].copy_(pred[k], non_blocking=True)
+        return out
+
+    # ---------------------------------------------------------------------------------------------------- accounting
+    def algorithmic_work(self):
+        """Algorithmic bytes (gather) and flops (GEMMs) of ONE step on this engine's graph — DESIGN.md §roofline.
+        gather: per edge type and cell  4*G*C*(2 N_src + 2 N_dst) + 12 (N_src + N_dst) + 4 (N_dst + 1) + 8 E  bytes
+        node_proj: 2 * N_t * K_t * ncols_t flop per node type and cell (K = F (+C with hidden state), unpadded)
+        gate_update: 2 * N_t * G*C * (C * n_in_types + K_t) flop per node type and cell"""
+        n = {t: self.xbuf[t].shape[0] for t in self.node_types}
+        F = {t: self.x[t].shape[1] for t in self.node_types}
+        C = self.C
+        out = {'gg_pgat_gather': 0.0, 'gg_node_proj': 0.0, 'gg_gate_update': 0.0}
+        for name in ('R', 'C'):
+            for pk, with_h in zip(self._pack()[name], (False, True)):
+                G = pk.G
+                for e in self.edge_types:
+                    ns, nd, E = n[e[0]], n[e[2]], int(self.edge_index[e].shape[1])
+                    out['gg_pgat_gather'] += 4.0 * G * C * (2 * ns + 2 * nd) + 12.0 * (ns + nd) + 4.0 * (nd + 1) + 8.0 * E
+                for t in self.node_types:
+                    K = F[t] + (C if with_h else 0)
+                    out['gg_node_proj'] += 2.0 * n[t] * K * pk.ncols[t]
+                    out['gg_gate_update'] += 2.0 * n[t] * G * C * (C * len(pk.into[t]) + K)
+        return out
+
+    def counts(self):
+        ng, nj = self.xbuf['grain'].shape[0], self.xbuf['joint'].shape[0]
+        return {'n_grain': ng, 'n_joint': nj, 'edges': sum(int(self.edge_index[e].shape[1]) for e in self.edge_types)}

@@ -1,0 +1,151 @@
+"""Weight packing: reference `state_dict` layout -> the fused buffers the kernels read.
+
+All re-associations are linear and exact in real arithmetic (SURVEY.md §7 "Algebra"):
+  * lin_key / lin_value / lin_query act per NODE on cat([X, h]); the periodic displacement of the source's x,y,z
+    (periodGATconv.py:209-211) becomes a rank-3 correction with the first three weight columns (Wv3; for the key it
+    collapses into the 4 scalars QX = [Wk[:, :3]^T q, We . q] per target and gate).
+  * lin_l2, lin_edge and lin_skip move behind the aggregation (sum_e alpha_e = 1).
+  * all gates of a cell share one projection GEMM; lin_skip of the edge types that end in the same node type are summed.
+Packing runs once per weight version (on whatever device the parameters live on) in float64, then rounds to fp32.
+"""
+import torch
+
+
+def pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class ConvWeights:
+    """The tensors of one PeriodConv (periodGATconv.py:119-143), PyG [out, in] layout."""
+
+    __slots__ = ('wk', 'bk', 'wq', 'bq', 'wv', 'bv', 'w2', 'b2', 'we', 'ws', 'bs')
+
+    def __init__(self, conv):
+        g = lambda lin, name: getattr(lin, name, None)  # noqa: E731
+        self.wk, self.bk = conv.lin_key.weight, g(conv.lin_key, 'bias')
+        self.wq, self.bq = conv.lin_query.weight, g(conv.lin_query, 'bias')
+        self.wv, self.bv = conv.lin_value.weight, g(conv.lin_value, 'bias')
+        self.w2, self.b2 = conv.lin_l2.weight, g(conv.lin_l2, 'bias')
+        self.we = conv.lin_edge.weight
+        self.ws, self.bs = conv.lin_skip.weight, g(conv.lin_skip, 'bias')
+
+    def tensors(self):
+        return [getattr(self, n) for n in self.__slots__ if getattr(self, n) is not None]
+
+
+def _cols(w, k1, k1p, k2):
+    """[out, k1+k2] -> [out, k1p+k2] with zero columns inserted after the first k1."""
+    w = w.detach().double()
+    assert w.shape[1] == k1 + k2, (tuple(w.shape), k1, k2)
+    out = torch.zeros(w.shape[0], k1p + k2, dtype=torch.float64, device=w.device)
+    out[:, :k1] = w[:, :k1]
+    out[:, k1p:] = w[:, k1:]
+    return out
+
+
+def _vec(b, n, dev):
+    return torch.zeros(n, dtype=torch.float64, device=dev) if b is None else b.detach().double().reshape(n)
+
+
+class PackedCell:
+    """Packed weights of `len(gates)` HeteroConv{edge_type: PeriodConv} layers that read the same input.
+
+    conv_of(gate, edge_type) -> ConvWeights ; gate_bias(gate, node_type) -> tensor [1,C] or None
+    in_dims[node_type] = (K1, K2): widths of the two input pieces (X and h); K2 may be 0.
+    """
+
+    def __init__(self, edge_types, gates, in_dims, C, conv_of, gate_bias=None, weighted=True, device=None):
+        self.edge_types, self.gates, self.C, self.G = list(edge_types), list(gates), C, len(gates)
+        self.weighted = bool(weighted)
+        self.in_dims = dict(in_dims)
+        self.node_types = list(self.in_dims)
+        G = self.G
+        GC = G * C
+        self.k1p = {t: pad4(k[0]) for t, k in self.in_dims.items()}
+        self.kin = {t: self.k1p[t] + self.in_dims[t][1] for t in self.in_dims}
+        self.koff, self.voff, self.qoff, self.qxoff, self.ncols = {}, {}, {}, {}, {}
+        self.Wcat, self.bcat, self.Wskip, self.btot = {}, {}, {}, {}
+        self.Wv3, self.W2, self.We, self.b2 = {}, {}, {}, {}
+        self.into = {t: [e for e in self.edge_types if e[2] == t] for t in self.node_types}
+
+        for t in self.node_types:
+            k1, k2 = self.in_dims[t]
+            k1p = self.k1p[t]
+            rows_w, rows_b, off = [], [], 0
+            for e in self.edge_types:              # source roles: K and V gate blocks
+                if e[0] != t:
+                    continue
+                for role, store in (('k', self.koff), ('v', self.voff)):
+                    store[e] = off
+                    for g in self.gates:
+                        cw = conv_of(g, e)
+                        w, b = (cw.wk, cw.bk) if role == 'k' else (cw.wv, cw.bv)
+                        rows_w.append(_cols(w, k1, k1p, k2)); rows_b.append(_vec(b, C, w.device))
+                    off += GC
+            for e in self.edge_types:              # target roles: Q gate block
+                if e[2] != t:
+                    continue
+                self.qoff[e] = off
+                for g in self.gates:
+                    cw = conv_of(g, e)
+                    rows_w.append(_cols(cw.wq, k1, k1p, k2)); rows_b.append(_vec(cw.bq, C, cw.wq.device))
+                off += GC
+            for e in self.edge_types:              # target roles: QX block = [Wk[:, :3]^T q (3), We . q (1)] per gate
+                if e[2] != t:
+                    continue
+                self.qxoff[e] = off
+                for g in self.gates:
+                    cw = conv_of(g, e)
+                    wq, bq = _cols(cw.wq, k1, k1p, k2), _vec(cw.bq, C, cw.wq.device)
+                    m = torch.cat([cw.wk.detach().double()[:, :3], cw.we.detach().double().reshape(C, 1)], dim=1)  # [C,4]
+                    rows_w.append(m.t() @ wq); rows_b.append(m.t() @ bq)
+                off += 4 * G
+            if off == 0:                            # a node type that is neither source nor target of anything
+                rows_w.append(torch.zeros(4, k1p + k2, dtype=torch.float64)); rows_b.append(torch.zeros(4, dtype=torch.float64))
+                off = 4
+            self.ncols[t] = off
+            self.Wcat[t] = torch.cat(rows_w, 0)
+            self.bcat[t] = torch.cat(rows_b, 0)
+            assert self.Wcat[t].shape == (off, k1p + k2)
+
+            ws = torch.zeros(GC, k1p + k2, dtype=torch.float64, device=self.Wcat[t].device)
+            bt = torch.zeros(GC, dtype=torch.float64, device=self.Wcat[t].device)
+            for gi, g in enumerate(self.gates):
+                for e in self.into[t]:
+                    cw = conv_of(g, e)
+                    ws[gi * C:(gi + 1) * C] += _cols(cw.ws, k1, k1p, k2)
+                    bt[gi * C:(gi + 1) * C] += _vec(cw.bs, C, ws.device)
+                if gate_bias is not None:
+                    gb = gate_bias(g, t)
+                    if gb is not None:
+                        bt[gi * C:(gi + 1) * C] += gb.detach().double().reshape(C)
+            self.Wskip[t], self.btot[t] = ws, bt
+
+        for e in self.edge_types:
+            wv3 = torch.zeros(GC, 4, dtype=torch.float64)
+            w2, we, b2 = [], [], []
+            for gi, g in enumerate(self.gates):
+                cw = conv_of(g, e)
+                wv3 = wv3.to(cw.wv.device)
+                wv3[gi * C:(gi + 1) * C, :3] = cw.wv.detach().double()[:, :3]
+                w2.append(cw.w2.detach().double()); we.append(cw.we.detach().double().reshape(C))
+                b2.append(_vec(cw.b2, C, cw.w2.device))
+            self.Wv3[e], self.W2[e] = wv3, torch.stack(w2, 0)
+            self.We[e], self.b2[e] = torch.stack(we, 0), torch.stack(b2, 0)
+
+        for d in (self.Wcat, self.bcat, self.Wskip, self.btot, self.Wv3, self.W2, self.We, self.b2):
+            for k in d:
+                d[k] = d[k].to(torch.float32).contiguous()
+                if device is not None:
+                    d[k] = d[k].to(device)
+
+    def to(self, device):
+        for d in (self.Wcat, self.bcat, self.Wskip, self.btot, self.Wv3, self.W2, self.We, self.b2):
+            for k in d:
+                d[k] = d[k].to(device)
+        return self
+
+
+def version_key(tensors):
+    """Changes whenever any of the tensors is rebound, moved or modified in place (load_state_dict, .to(), optimizer)."""
+    return tuple((t.data_ptr(), t._version, t.device.type, t.device.index) for t in tensors)

@@ -1,0 +1,169 @@
+/* graingnn_b200.h — C ABI of libgraingnn_b200.so (hand-written CUDA for sm_100a).
+ *
+ * Drop-in boundary for the GrainGNN rollout message-passing path.  Every entry point
+ * replaces a piece of the reference's Python hot path; the citation on each prototype is the reference
+ * file:line whose arithmetic it takes over (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in `_host`.  No entry point allocates, frees or
+ *    retains memory; scratch is passed in by the caller (sizes from the *_workspace_bytes helpers).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Launches are asynchronous.
+ *  - Return value: 0 on success, a negative GG_E* code for a rejected argument, or a positive cudaError_t.
+ *    gg_error_string() renders either.  Nothing falls back to the CPU.
+ *  - Row-major everywhere; `ld*` are row strides in elements.  Node features are fp32, the reference's edge
+ *    index is int64 [2,E] (row 0 = source, row 1 = target), CSR arrays are int32.
+ *  - Hidden width C must be a multiple of 32 with C <= 128 (the reference uses 96, parameters.py:18-21).
+ *  - "Gate block": G*C contiguous columns, gate-major (gate g occupies columns [g*C,(g+1)*C)).
+ */
+#ifndef GRAINGNN_B200_H
+#define GRAINGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_EINVAL   (-1)  /* bad argument (null pointer, negative size, unsupported width)              */
+#define GG_ERANGE   (-2)  /* an edge endpoint outside [0, N) was found (reported by gg_csr_build)      */
+#define GG_EALIGN   (-3)  /* a pointer / leading dimension violates a documented 16-byte alignment     */
+#define GG_ENOSPC   (-4)  /* workspace too small                                                       */
+#define GG_EARCH    (-5)  /* device is not sm_100 (tcgen05 paths only)                                 */
+
+const char* gg_error_string(int code);
+int gg_version(void);                 /* 100 * major + minor                                        */
+int gg_device_is_sm100(void);         /* 1 when the current device has compute capability 10.x      */
+
+/* ------------------------------------------------------------------------------------------------
+ * (a) dst-sorted CSR builder.  Replaces the per-call COO handling of PyG `MessagePassing.propagate`
+ *     (called at periodGATconv.py:174) and torch-scatter's atomics: edges are stably sorted by target,
+ *     so row i of the CSR lists the in-edges of node i in ORIGINAL edge order (bit-exact vs
+ *     numpy.argsort(kind="stable")).
+ *       rowptr[n_dst+1], col[E] = source of the e-th sorted edge, perm[E] = its original edge id.
+ *     status (device int32[1]) receives 0, or GG_ERANGE if any endpoint is out of range.
+ * ---------------------------------------------------------------------------------------------- */
+size_t gg_csr_workspace_bytes(int64_t n_edges, int32_t n_dst);
+int gg_csr_build(const int64_t* edge_index, int64_t n_edges, int32_t n_src, int32_t n_dst,
+                 int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* status,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i] = src[perm[i]] (fp32) — puts a per-edge attribute into CSR order. */
+int gg_permute_f32(const float* src, const int32_t* perm, float* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a11) wrapped 2-D edge length, test.py:562-575:  d = x_src[s,:2] - x_dst[t,:2];  d += (d<-.5) - (d>.5);
+ *       out = sqrt(dx^2+dy^2).  `out` is in original edge order; if out_csr != NULL it also receives the
+ *       same values in CSR order (out_csr[i] = out[perm[i]]), so kernel (b) needs no indirection.
+ * ---------------------------------------------------------------------------------------------- */
+int gg_edge_length(const float* x_src, int32_t ld_src, const float* x_dst, int32_t ld_dst,
+                   const int64_t* edge_index, int64_t n_edges,
+                   const int32_t* perm /* nullable */, float* out, float* out_csr /* nullable */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (c) node projections.  out[m, n] = sum_k [A1|A2][m,k] * W[n,k] + bias[n]
+ *     Takes over the per-EDGE lin_key / lin_value / lin_query GEMMs of periodGATconv.py:216-218 by
+ *     re-associating them per NODE: W is the row-concatenation of the PyG [out,in] weights
+ *     of every role x gate a node type plays, A = cat([X, h]) (heteropgclstm.py:112) given as two pieces so
+ *     the concat is never materialised (A2 == NULL means h == 0, the encoder case of models.py:237-238).
+ *     mode 0: fp32 SIMT FMA.   mode 1: tcgen05 3xTF32 tensor-core path (needs gg_tc_* packing, see below).
+ * ---------------------------------------------------------------------------------------------- */
+int gg_node_proj(const float* A1, int32_t lda1, int32_t K1,
+                 const float* A2, int32_t lda2, int32_t K2,
+                 const float* W, int32_t ldw, const float* bias /* nullable */,
+                 float* out, int32_t ldo, int32_t M, int32_t N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (b) fused periodic-attention gather.  One launch = one edge type, all G gates of one cell.
+ *     Per target node i and gate g (PeriodConv.message, periodGATconv.py:204-236, applied to per-node
+ *     projections):
+ *        w_e   = (r<-.5) - (r>.5),  r = p_j - p_i                       (:209-210, periodic wrap)
+ *        s_e   = (Q_i . K_j + QX_i[0:3] . w_e + QX_i[3] * a_e) / sqrt(C) (:216-226; the p_i term and every
+ *                 per-target constant cancel in the softmax)
+ *        al_e  = exp(s_e - max_i) / (sum_i + 1e-16)                      (:227, PyG utils.softmax)
+ *        agg_i = sum_e al_e * relu(V_j + Wv3 (w_e - p_i))                (:211,:218 — lin_l2 is applied after
+ *                 aggregation by gg_gate_update)          ea_i = sum_e al_e * a_e     (:222,:233)
+ *     With weighted == 0 (periodconv.py:235) al_e = 1.
+ *     Layout: P_src row = [... K block @k_off (G*C) ... V block @v_off (G*C) ...];
+ *             P_dst row = [... Q block @q_off (G*C) ... QX block @qx_off (G*4: Wk3^T q (3), We . q (1)) ...];
+ *             Wv3 is [G*C][4] (x,y,z weights of lin_value, 4th = 0); pos_* point at column 0 (x,y,z) of the node
+ *             features; eattr_csr is a_e in CSR order.  Outputs: agg [n_dst, ld_agg] gate block, ea [n_dst, G].
+ *     One warp per target node (8 lanes x C/8 channels per gate, 128-bit loads), no atomics; edges of a row
+ *     are accumulated in CSR (= original) order, matching the sequential index_add_ of the CPU reference.
+ *     All row pointers / leading dimensions / offsets must be multiples of 4 floats (GG_EALIGN otherwise).
+ * ---------------------------------------------------------------------------------------------- */
+int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off, int32_t v_off,
+                   const float* P_dst, int32_t ld_dst, int32_t q_off, int32_t qx_off,
+                   const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
+                   const int32_t* rowptr, const int32_t* col, const float* eattr_csr,
+                   const float* Wv3, int32_t n_dst, int32_t G, int32_t C, int32_t weighted,
+                   float* agg, int32_t ld_agg, float* ea, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (c) post-aggregation gate GEMM fused with the LSTM update.  Per node m of one node type, gate g:
+ *        pre_g = sum_t [ W2_{t,g} agg_t[m,g] + We_{t,g} ea_t[m,g] + b2_{t,g} * cnt_t(m) ]      (lin_l2, lin_edge;
+ *                 periodGATconv.py:218,:222,:231-235 moved after the sum; cnt = [deg>0] weighted, deg unweighted)
+ *              + Wskip_g [X|h][m] + btot_g                     (lin_skip :186,192 summed over edge types
+ *                 + HeteroConv sum + gate bias b_g, heteropgclstm.py:113-116)
+ *     mode GG_GATE_RAW : out_h = pre (G*C wide)                      — a bare PeriodConv.forward
+ *     mode GG_GATE_RELU: out_h = relu(pre), G == 1                   — HeteroPGC, heteropgclstm.py:243-251
+ *     mode GG_GATE_LSTM: gates (i,f,c,o): c' = s(f) c + s(i) tanh(c~); h' = s(o) tanh(c')   (:133,:145)
+ *     mode GG_GATE_LSTM0: gates (i,c,o) with c == 0 (encoder, models.py:237-238): c' = s(i) tanh(c~)
+ * ---------------------------------------------------------------------------------------------- */
+enum { GG_GATE_RAW = 0, GG_GATE_RELU = 1, GG_GATE_LSTM = 2, GG_GATE_LSTM0 = 3 };
+
+typedef struct gg_agg_input {
+    const float*   agg;      /* [M, ld_agg] gate block written by gg_pgat_gather                 */
+    int32_t        ld_agg;
+    const float*   ea;       /* [M, G]                                                            */
+    const int32_t* rowptr;   /* CSR rowptr of that edge type (for cnt)                            */
+    const float*   W2;       /* [G][C][C]  lin_l2.weight per gate, PyG [out,in]                   */
+    const float*   We;       /* [G][C]     lin_edge.weight[:,0]                                   */
+    const float*   b2;       /* [G][C]     lin_l2.bias                                            */
+    int32_t        weighted; /* 1: attention (cnt = deg>0), 0: periodconv sum variant (cnt = deg) */
+} gg_agg_input;
+
+int gg_gate_update(const gg_agg_input* inputs_host, int32_t n_inputs,
+                   const float* X, int32_t ldx, int32_t K1, const float* H /* nullable */, int32_t ldh,
+                   const float* Wskip, int32_t ldw, const float* btot,
+                   const float* c_in /* nullable */, float* out_h, float* out_c /* nullable */,
+                   int32_t M, int32_t G, int32_t C, int32_t mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (d) heads.
+ *  gg_node_head: y = W h + b with n_out <= 4 rows (models.py:433), act[j]: 0 none, 1 tanh, 2 relu (:443,:450-452);
+ *      if area_out: area_out[m] = tanh(raw y[m,0]) / area_scale + area_in[m*ld_area]   (:445)
+ *  gg_edge_head: pair = [h[src], h[dst], a]  (:602) -> edge_event = lin2(pair) (:607), edge = tanh(lin1(pair)) (:609)
+ *      fused with the joint-pair gather; outputs in ORIGINAL edge order (Cmodel.update indexes them by edge id,
+ *      models.py:626-628).  W1 [2, 2C+1], W2 [1, 2C+1] are the PyG/torch [out,in] weights.
+ * ---------------------------------------------------------------------------------------------- */
+int gg_node_head(const float* h, int32_t ldh, int32_t C, const float* W, const float* b, int32_t n_out,
+                 const int32_t* act_host, float* y, int32_t ldy,
+                 const float* area_in, int32_t ld_area, float area_scale, float* area_out,
+                 int32_t M, void* stream);
+int gg_edge_head(const float* h, int32_t ldh, int32_t C, const int64_t* edge_index, int64_t n_edges,
+                 const float* eattr, const float* W1, const float* b1, const float* W2, const float* b2,
+                 float* edge_event, float* edge /* [E,2] nullable */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a12) in-place feature update, models.py:503-516 + test.py:401-407.
+ *   x_j[:, :2] += y_j/5; x_j[:,6:8] = y_j; x_g[:,3] += y_g0/20; x_g[:,4] = y_g1; x_g[:,last] = y_g0;
+ *   z += dz on both, then if x_g[0,2] > z_max: z = z_max everywhere.   scratch: device int32[1].
+ * ---------------------------------------------------------------------------------------------- */
+int gg_feature_update(float* x_joint, int32_t ld_j, int32_t n_joint, const float* y_joint,
+                      float* x_grain, int32_t ld_g, int32_t n_grain, const float* y_grain,
+                      float dz, float z_max, int32_t* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (e) halo pack / unpack for the slab-partitioned domain: out[i, :] = src[idx[i], :] and the inverse.
+ *     width must be a multiple of 4 floats and rows 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+int gg_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int32_t n, int32_t width,
+                   float* out, int32_t ld_out, void* stream);
+int gg_scatter_rows(const float* src, int32_t ld_src, const int32_t* idx, int32_t n, int32_t width,
+                    float* out, int32_t ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAINGNN_B200_H */

@@ -1,0 +1,260 @@
+"""GPU (-m gpu): the CUDA path, called through the boundary modules / C ABI, against the CPU oracle and the committed
+golden vectors.  Bars: indices bit-exact; floating point within 1e-4 relative (max |a-b| / max |ref|) per step."""
+import numpy as np
+import pytest
+import torch
+
+import grain_oracle as orc
+from util import ET, SHORT, load_golden, load_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def to_dev(d):
+    return {k: v.to(dev()) for k, v in d.items()}
+
+
+def hyper():
+    from graingraphnn_b200.engine import _Hyper
+    return _Hyper({'grain': list(range(11)), 'joint': list(range(8))}, {'grain': [0, 1], 'joint': [0, 1]}, 96,
+                  (['grain', 'joint', 'mask'], list(ET)), 'cuda')
+
+
+def models(seed_r=1, seed_c=2):
+    from graingraphnn_b200.models import GrainNN_classifier, GrainNN_regressor
+    R = GrainNN_regressor(hyper())
+    R.load_state_dict(orc.synth_state_dict('regressor', seed_r))
+    C = GrainNN_classifier(hyper(), R)
+    C.load_state_dict(orc.synth_state_dict('classifier', seed_c))
+    return R.to(dev()).eval(), C.to(dev()).eval()
+
+
+def random_graph(n_src, n_dst, E, seed, hub=None):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n_src, (E,), generator=g)
+    dst = torch.randint(0, n_dst, (E,), generator=g)
+    if hub is not None:
+        dst[: E // 3] = hub          # one long row (exercises the > 32 in-edge path)
+    return torch.stack([src, dst])
+
+
+# ------------------------------------------------------------------------------------------------ (a) CSR, bit-exact
+@pytest.mark.parametrize('case', ['c1', 'c2', 'random', 'hub', 'empty', 'big'])
+def test_csr_build_bit_exact(case):
+    from graingraphnn_b200.graph import build_csr
+    if case in ('c1', 'c2'):
+        x, ei, _ = load_graph(case)
+        todo = [(ei[e], x[e[0]].shape[0], x[e[2]].shape[0]) for e in ET]
+    elif case == 'random':
+        todo = [(random_graph(50, 70, 400, 0), 50, 70), (random_graph(7, 5000, 3000, 1), 7, 5000)]
+    elif case == 'hub':
+        todo = [(random_graph(100, 40, 900, 2, hub=11), 100, 40)]
+    elif case == 'empty':
+        todo = [(torch.zeros(2, 0, dtype=torch.int64), 10, 10)]
+    else:
+        todo = [(random_graph(200000, 300000, 1500000, 3), 200000, 300000)]
+    for ei, ns, nd in todo:
+        g = build_csr(ei.to(dev()), ns, nd)
+        rp, col, perm = orc.csr_by_dst(ei, nd)
+        assert np.array_equal(g.rowptr.cpu().numpy(), rp)
+        assert np.array_equal(g.perm.cpu().numpy(), perm)
+        assert np.array_equal(g.col.cpu().numpy(), col)
+
+
+def test_csr_rejects_out_of_range_endpoints():
+    from graingraphnn_b200.graph import build_csr
+    ei = torch.tensor([[0, 1, 2], [0, 9, 1]])
+    with pytest.raises(IndexError):
+        build_csr(ei.to(dev()), 3, 3)
+
+
+# ------------------------------------------------------------------------------------------------ (a11) edge length
+@pytest.mark.parametrize('name', ['c1', 'c2'])
+def test_edge_length_bit_exact(name):
+    from graingraphnn_b200.graph import build_csr, edge_length
+    x, ei, ea = load_graph(name)
+    ref = orc.edge_attr_rebuild(x, ei)
+    xd = to_dev(x)
+    for e in ET:
+        g = build_csr(ei[e].to(dev()), x[e[0]].shape[0], x[e[2]].shape[0])
+        out, out_csr = edge_length(xd[e[0]], xd[e[2]], ei[e].to(dev()), g)
+        assert torch.equal(out.cpu(), ref[e])                       # IEEE sub / mul / add / sqrt: bit-exact
+        assert torch.equal(out_csr.cpu(), ref[e].reshape(-1)[g.perm.cpu().long()])
+
+
+# ------------------------------------------------------------------------------------------------ (b)+(c) single conv
+@pytest.mark.parametrize('tag', ['gat', 'sum'])
+@pytest.mark.parametrize('et', [ET[0], ET[2]])
+def test_period_conv_matches_golden_and_oracle(tag, et):
+    from graingraphnn_b200.periodconv import PeriodConv as SumConv
+    from graingraphnn_b200.periodGATconv import PeriodConv
+    x, ei, ea = load_graph('c1')
+    g = load_golden('c1')
+    h, _ = orc.encode_decode(orc.synth_state_dict('regressor', 1), x, ei, ea)
+    xin = {t: torch.cat([x[t], h[t]], 1) for t in x}
+    sd = orc.synth_state_dict('regressor', 3)
+    pre = f'gclstm_decoder.cell_list.0.conv_i.convs.{"__".join(et)}.'
+    conv = (PeriodConv if tag == 'gat' else SumConv)(in_channels=(-1, -1), out_channels=96)
+    conv.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    conv = conv.to(dev())
+    xx = xin[et[0]].to(dev()) if et[0] == et[2] else (xin[et[0]].to(dev()), xin[et[2]].to(dev()))
+    out = conv(xx, ei[et].to(dev()), ea[et].to(dev()))
+    assert rel_err(out, g[f'conv_{tag}_{SHORT[et]}']) < TOL
+
+
+@pytest.mark.parametrize('C', [32, 64, 128])
+def test_period_conv_other_widths_and_ragged_graph(C):
+    """Widths of the reference's hyper-parameter grid (parameters.py:18-21), a ragged random graph with empty rows and one
+    row of > 32 in-edges (recompute path)."""
+    from graingraphnn_b200.periodGATconv import PeriodConv
+    torch.manual_seed(C)
+    ns, nd, E = 300, 200, 1500
+    ei = random_graph(ns, nd, E, C, hub=5)
+    ei = ei[:, ei[1] != 17]                                # node 17 has no in-edges
+    xs, xd = torch.rand(ns, 10), torch.rand(nd, 7)
+    ea = torch.rand(ei.shape[1], 1) * 0.1
+    conv = PeriodConv(in_channels=(10, 7), out_channels=C)
+    sd = {k: v.clone() for k, v in conv.state_dict().items()}
+    ref = orc.period_conv({'c.' + k: v for k, v in sd.items()}, 'c', xs, xd, ei, ea)
+    out = conv.to(dev())((xs.to(dev()), xd.to(dev())), ei.to(dev()), ea.to(dev()))
+    assert rel_err(out, ref) < TOL
+    skip = xd @ sd['lin_skip.weight'].t() + sd['lin_skip.bias']
+    assert rel_err(out[17].cpu(), skip[17]) < 1e-5 and torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------------------------------------ cells
+def test_pgclstm_cell_encoder_and_decoder_states():
+    x, ei, ea = load_graph('c1')
+    g = load_golden('c1')
+    R, _ = models()
+    xd, eid, ead = to_dev(x), to_dev(ei), to_dev(ea)
+    enc = R.gclstm_encoder(xd, eid, ead, None)
+    dec = R.gclstm_decoder(xd, eid, ead, enc)
+    assert rel_err(enc[0][0]['joint'], g['r_enc_h_joint']) < TOL and rel_err(enc[0][1]['grain'], g['r_enc_c_grain']) < TOL
+    for k, v in (('r_dec_h_joint', dec[0][0]['joint']), ('r_dec_h_grain', dec[0][0]['grain']),
+                 ('r_dec_c_joint', dec[0][1]['joint']), ('r_dec_c_grain', dec[0][1]['grain'])):
+        assert rel_err(v, g[k]) < TOL, k
+
+
+def test_pgclstm_cell_with_h_but_without_c():
+    from graingraphnn_b200.heteropgclstm import HeteroPGCLSTM
+    x, ei, ea = load_graph('c1')
+    sd = orc.synth_state_dict('regressor', 1)
+    pre = 'gclstm_decoder.cell_list.0.'
+    cell = HeteroPGCLSTM({'grain': 11, 'joint': 8}, 96, (['grain', 'joint'], list(ET)))
+    cell.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    h0 = {t: torch.rand(v.shape[0], 96) - 0.5 for t, v in x.items()}
+    href, cref = orc.pgclstm_cell(sd, pre[:-1], x, ei, ea, h0, None)
+    hh, cc = cell.to(dev())(to_dev(x), to_dev(ei), to_dev(ea), to_dev(h0), None)
+    assert all(rel_err(hh[t], href[t]) < TOL and rel_err(cc[t], cref[t]) < TOL for t in x)
+
+
+def test_pgc_cell_matches_golden():
+    from graingraphnn_b200.heteropgclstm import HeteroPGC
+    x, ei, ea = load_graph('c1')
+    g = load_golden('c1')
+    h, c = orc.encode_decode(orc.synth_state_dict('regressor', 1), x, ei, ea)
+    sd = orc.synth_state_dict('regressor', 4)
+    pre = 'gclstm_decoder.cell_list.0.'
+    cell = HeteroPGC({'grain': 11, 'joint': 8}, 96, (['grain', 'joint'], list(ET)))
+    cell.load_state_dict({k[len(pre):]: v for k, v in sd.items()
+                          if k.startswith(pre + 'conv_i.') or k.startswith(pre + 'b_i.')})
+    hh, cc = cell.to(dev())(to_dev(x), to_dev(ei), to_dev(ea), to_dev(h), to_dev(c))
+    assert rel_err(hh['joint'], g['pgc_h_joint']) < TOL and rel_err(hh['grain'], g['pgc_h_grain']) < TOL
+    assert torch.equal(cc['grain'].cpu(), c['grain'])
+
+
+# ------------------------------------------------------------------------------------------------ models
+@pytest.mark.parametrize('name', ['c1', 'c2'])
+def test_regressor_and_classifier_forward_match_reference_golden(name):
+    x, ei, ea = load_graph(name)
+    g = load_golden(name)
+    R, C = models()
+    xd, eid, ead = to_dev(x), to_dev(ei), to_dev(ea)
+    y = R(xd, eid, ead)
+    yc = C(xd, eid, ead)
+    for k, v in (('r_joint', y['joint']), ('r_grain', y['grain']), ('r_grain_area', y['grain_area']),
+                 ('c_edge_event', yc['edge_event']), ('c_edge', yc['edge'])):
+        assert rel_err(v, g[k]) < TOL, (k, rel_err(v, g[k]))
+    # event decisions (models.py:626-628: sigmoid(edge_event) > 0.6; test.py:418: area < 1e-4) are identical
+    assert torch.equal(torch.sigmoid(yc['edge_event']).cpu() > 0.6, torch.sigmoid(g['c_edge_event']) > 0.6)
+    assert torch.equal(y['grain_area'].cpu() < 1e-4, g['r_grain_area'] < 1e-4)
+
+
+def test_engine_three_rollout_steps_match_reference_golden():
+    """RolloutEngine (resident state + fused step) over 3 steps vs reference Rmodel.update + edge-attr rebuild."""
+    from graingraphnn_b200.engine import RolloutEngine
+    x, ei, ea = load_graph('c1')
+    g = load_golden('c1')
+    eng = RolloutEngine.from_state_dicts(orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2), dev())
+    eng.set_graph(to_dev(x), to_dev(ei), to_dev(ea))
+    for step in range(3):
+        pred = eng.step(span=6)
+        assert rel_err(pred['edge_event'], g[f'step{step}_edge_event']) < TOL
+        assert rel_err(pred['grain_area'], g[f'step{step}_grain_area']) < TOL
+        assert rel_err(eng.x['joint'], g[f'step{step}_x_joint']) < TOL
+        assert rel_err(eng.x['grain'], g[f'step{step}_x_grain']) < TOL
+        assert rel_err(eng.edge_attr[ET[2]], g[f'step{step}_ea_jj']) < TOL
+        assert torch.equal(torch.sigmoid(pred['edge_event']).cpu() > 0.6, torch.sigmoid(g[f'step{step}_edge_event']) > 0.6)
+
+
+def test_engine_cuda_graph_replay_equals_eager():
+    from graingraphnn_b200.engine import RolloutEngine
+    x, ei, ea = load_graph('c1')
+    sd_r, sd_c = orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
+    outs = []
+    for use_graph in (False, True):
+        eng = RolloutEngine.from_state_dicts(sd_r, sd_c, dev())
+        eng.set_graph(to_dev(x), to_dev(ei), to_dev(ea))
+        if use_graph:
+            eng.capture(span=6, warmup=1)      # advances 2 steps
+            pred = eng.step(6)
+        else:
+            for _ in range(3):
+                pred = eng.step(6)
+        torch.cuda.synchronize()
+        outs.append((pred['edge_event'].clone(), eng.x['joint'].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_feature_update_exact_including_z_clamp():
+    from graingraphnn_b200.heads import feature_update
+    x, _, _ = load_graph('c1')
+    for z0 in (0.0, 118.0 / 121.0):
+        xo = {k: v.clone() for k, v in x.items()}
+        xo['grain'][:, 2] = z0; xo['joint'][:, 2] = z0
+        y = {'joint': torch.rand(236, 2) - 0.5, 'grain': torch.rand(118, 2) - 0.5}
+        xd = to_dev(xo)
+        feature_update(xd['joint'], xd['grain'], y['joint'].to(dev()), y['grain'].to(dev()), 6 / 121, 120 / 121)
+        orc.regressor_update(xo, y, span=6)
+        assert torch.equal(xd['joint'].cpu(), xo['joint']) and torch.equal(xd['grain'].cpu(), xo['grain'])
+
+
+def test_full_size_properties_100k_grains():
+    """At a BASELINE-size domain (C3, ~10^5 grains) the oracle is too slow; check size-independent properties instead:
+    permutation invariance of the edge order, zero attention leakage across rows, finite outputs."""
+    from graingraphnn_b200.synth import honeycomb_graph
+    from graingraphnn_b200.engine import RolloutEngine
+    x, ei = honeycomb_graph(320, 320, seed=0)            # 102,400 grains
+    sd_r, sd_c = orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
+    eng = RolloutEngine.from_state_dicts(sd_r, sd_c, dev())
+    eng.set_graph(to_dev(x), to_dev(ei))
+    p1 = {k: v.clone() for k, v in eng.step(6).items()}
+    gen = torch.Generator().manual_seed(1)
+    ei2, perms = {}, {}
+    for e in ET:
+        perms[e] = torch.randperm(ei[e].shape[1], generator=gen)
+        ei2[e] = ei[e][:, perms[e]]
+    eng2 = RolloutEngine.from_state_dicts(sd_r, sd_c, dev())
+    eng2.set_graph(to_dev(x), to_dev(ei2))
+    p2 = eng2.step(6)
+    assert all(torch.isfinite(v).all() for v in p1.values())
+    # node outputs: same up to summation order inside a row; edge outputs: permuted the same way
+    assert rel_err(p2['joint'], p1['joint']) < 1e-5 and rel_err(p2['grain_area'], p1['grain_area']) < 1e-5
+    assert rel_err(p2['edge_event'], p1['edge_event'][perms[ET[2]].to(dev())]) < 1e-5

@@ -1,0 +1,145 @@
+"""CPU: host-side logic of the product — module API, state_dict layout, lazy materialisation, deepcopy, weight packing
+(checked by running a torch emulation of the kernels on the packed buffers against the oracle), and the no-CPU-fallback rule."""
+import copy
+
+import pytest
+import torch
+
+import grain_oracle as orc
+from emulate import emu_cell
+from util import ET, load_graph, rel_err
+
+from graingraphnn_b200 import _lib
+from graingraphnn_b200.cell import pad_features
+from graingraphnn_b200.engine import _Hyper
+from graingraphnn_b200.heteropgclstm import HeteroPGC, HeteroPGCLSTM
+from graingraphnn_b200.models import GrainNN_classifier, GrainNN_regressor
+from graingraphnn_b200.periodconv import PeriodConv as SumConv
+from graingraphnn_b200.periodGATconv import PeriodConv
+
+
+def hyper():
+    return _Hyper({'grain': list(range(11)), 'joint': list(range(8))}, {'grain': [0, 1], 'joint': [0, 1]}, 96,
+                  (['grain', 'joint', 'mask'], list(ET)), 'cpu')
+
+
+def test_state_dict_layout_equals_reference():
+    R = GrainNN_regressor(hyper())
+    C = GrainNN_classifier(hyper(), R)
+    for m, kind, n in ((R, 'regressor', 1204612), (C, 'classifier', 1204806)):
+        shapes = orc.param_shapes(kind)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+        assert sum(p.numel() for p in m.parameters()) == n
+        res = m.load_state_dict(orc.synth_state_dict(kind, 7))
+        assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_classifier_deepcopies_regressor_cells():
+    R = GrainNN_regressor(hyper())
+    R.load_state_dict(orc.synth_state_dict('regressor', 1))
+    C = GrainNN_classifier(hyper(), R)
+    a = R.gclstm_encoder.cell_list[0].conv_i.conv(ET[0]).lin_key.weight
+    b = C.gclstm_encoder.cell_list[0].conv_i.conv(ET[0]).lin_key.weight
+    assert torch.equal(a, b) and a.data_ptr() != b.data_ptr()
+
+
+def test_lazy_periodconv_materialises_on_load_and_survives_deepcopy():
+    conv = PeriodConv(in_channels=(-1, -1), out_channels=96)
+    assert not conv.lin_key.materialized
+    conv2 = copy.deepcopy(conv)
+    sd = {k[len('gclstm_decoder.cell_list.0.conv_i.convs.grain__push__joint.'):]: v
+          for k, v in orc.synth_state_dict('regressor', 3).items()
+          if k.startswith('gclstm_decoder.cell_list.0.conv_i.convs.grain__push__joint.')}
+    conv2.load_state_dict(sd)
+    assert conv2.lin_key.weight.shape == (96, 107) and conv2.lin_query.weight.shape == (96, 104)
+    assert conv2.lin_edge.weight.shape == (96, 1) and conv2.lin_beta is None
+
+
+def test_constructor_rejects_unsupported_variants():
+    with pytest.raises(NotImplementedError):
+        PeriodConv(8, 96, heads=2)
+    with pytest.raises(NotImplementedError):
+        PeriodConv(8, 96, beta=True)
+    assert SumConv(8, 96).weighted is False and PeriodConv(8, 96).weighted is True
+
+
+def test_no_cpu_fallback():
+    x, ei, ea = load_graph('c1')
+    R = GrainNN_regressor(hyper())
+    with pytest.raises(RuntimeError, match='no CPU'):
+        R(x, ei, ea)
+    conv = PeriodConv(8, 96)
+    with pytest.raises(RuntimeError, match='no CPU'):
+        conv(x['joint'], ei[ET[2]], ea[ET[2]])
+
+
+def _csr(ei, x):
+    csr = {}
+    for e in ET:
+        rp, col, perm = orc.csr_by_dst(ei[e], x[e[2]].shape[0])
+        csr[e] = (torch.from_numpy(rp), torch.from_numpy(col), torch.from_numpy(perm).long())
+    return csr
+
+
+@pytest.mark.parametrize('cls,gates,mode', [(HeteroPGCLSTM, ('i', 'f', 'c', 'o'), _lib.GG_GATE_LSTM),
+                                            (HeteroPGC, ('i',), _lib.GG_GATE_RELU)])
+def test_packed_cell_algebra_matches_oracle(cls, gates, mode):
+    """fp64 emulation of the three kernels on the packed (fp32-rounded) weights == oracle cell to ~1e-7."""
+    x, ei, ea = load_graph('c1', torch.float64)
+    sd = orc.synth_state_dict('regressor', 1)
+    cell = cls({'grain': 11, 'joint': 8}, 96, (['grain', 'joint'], list(ET)))
+    pre = 'gclstm_decoder.cell_list.0.'
+    cell.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)
+                          and any(f'.conv_{g}.' in '.' + k[len(pre):] or k[len(pre):].startswith(f'b_{g}.') or
+                                  k[len(pre):].startswith(f'conv_{g}.') for g in gates)})
+    sd64 = {k: v.double() for k, v in sd.items()}
+    h0, c0 = orc.pgclstm_cell(sd64, 'gclstm_encoder.cell_list.0', x, ei, ea)
+    csr = _csr(ei, x)
+    eac = {e: ea[e].reshape(-1)[csr[e][2]] for e in ET}
+    pk = cell.packed(gates, True, 'cpu')
+    xpad = {t: pad_features(x[t].float(), pk.k1p[t]).double() for t in x}
+    hh, cc = emu_cell(pk, xpad, h0, c0, {e: csr[e][:2] for e in ET}, eac, mode)
+    if cls is HeteroPGCLSTM:
+        href, cref = orc.pgclstm_cell(sd64, 'gclstm_decoder.cell_list.0', x, ei, ea, h0, c0)
+        assert all(rel_err(cc[t], cref[t]) < 1e-6 for t in x)
+    else:
+        href, _ = orc.pgc_cell(sd64, 'gclstm_decoder.cell_list.0', x, ei, ea, h0, c0)
+    assert all(rel_err(hh[t], href[t]) < 1e-6 for t in x)
+
+
+def test_packed_encoder_drops_forget_gate_and_hidden_columns():
+    x, ei, ea = load_graph('c1', torch.float64)
+    sd = orc.synth_state_dict('classifier', 2)
+    C = GrainNN_classifier(hyper())
+    C.load_state_dict(sd)
+    cell = C.gclstm_encoder.cell_list[0]
+    pk = cell.packed(('i', 'c', 'o'), False, 'cpu')
+    assert pk.G == 3 and pk.Wcat['grain'].shape[1] == 12 and pk.Wcat['joint'].shape[1] == 8
+    assert pk.ncols['joint'] == 6 * 3 * 96 + 2 * 3 * 4 and pk.ncols['grain'] == 3 * 3 * 96 + 3 * 4
+    csr = _csr(ei, x)
+    eac = {e: ea[e].reshape(-1)[csr[e][2]] for e in ET}
+    xpad = {t: pad_features(x[t].float(), pk.k1p[t]).double() for t in x}
+    hh, cc = emu_cell(pk, xpad, None, None, {e: csr[e][:2] for e in ET}, eac, _lib.GG_GATE_LSTM0)
+    href, cref = orc.pgclstm_cell({k: v.double() for k, v in sd.items()}, 'gclstm_encoder.cell_list.0', x, ei, ea)
+    assert all(rel_err(hh[t], href[t]) < 1e-6 and rel_err(cc[t], cref[t]) < 1e-6 for t in x)
+
+
+@pytest.mark.parametrize('weighted', [True, False])
+def test_packed_single_conv_matches_oracle(weighted):
+    x, ei, ea = load_graph('c1', torch.float64)
+    sd = orc.synth_state_dict('regressor', 3)
+    pre = 'gclstm_decoder.cell_list.0.conv_i.convs.grain__push__joint.'
+    conv = (PeriodConv if weighted else SumConv)(in_channels=(-1, -1), out_channels=96)
+    conv.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    xs = torch.cat([x['grain'], torch.randn(118, 96, dtype=torch.float64)], 1)
+    xd = torch.cat([x['joint'], torch.randn(236, 96, dtype=torch.float64)], 1)
+    ref = orc.period_conv({k: v.double() for k, v in sd.items()}, pre[:-1], xs, xd, ei[ET[0]], ea[ET[0]], weighted)
+    pk = conv._pack(107, 104, False, 'cpu')
+    rp, col, perm = orc.csr_by_dst(ei[ET[0]], 236)
+    et = pk.edge_types[0]
+    xpad = {'s': pad_features(xs.float(), pk.k1p['s']).double(), 'd': pad_features(xd.float(), pk.k1p['d']).double()}
+    out, _ = emu_cell(pk, xpad, None, None, {et: (torch.from_numpy(rp), torch.from_numpy(col))},
+                      {et: ea[ET[0]].reshape(-1)[torch.from_numpy(perm).long()]}, _lib.GG_GATE_RAW)
+    assert rel_err(out['d'], ref) < 1e-6
