@@ -150,7 +150,8 @@ def kernel_breakdown(eng, peak):
         eng._graph = saved
     finally:
         _lib._LIB = real
-    return {k: {'calls': len(v), 'ms_total': sum(a.elapsed_time(b) for a, b in v)} for k, v in times.items()}
+    return {k: {'calls': len(v), 'ms_total': sum(a.elapsed_time(b) for a, b in v), 'ms_each': [round(a.elapsed_time(b), 4) for a, b in v]}
+            for k, v in times.items()}
 
 
 def main():
@@ -291,6 +292,8 @@ def main():
     else:
         roof = {'kernel': top, 'bound': 'hbm', 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None, 'traffic': None}
     roof['breakdown_ms'] = {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}
+    if os.environ.get('GG_BENCH_VERBOSE'):
+        roof['per_call_ms'] = {k: v['ms_each'] for k, v in bd.items()}
 
     cpu = None if args.no_cpu_baseline else cpu_reference_run(5, 1)
     steps_per_s = args.steps / (ms / 1e3)

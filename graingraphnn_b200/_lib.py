@@ -33,7 +33,7 @@ _PROTOS = {
     'gg_gate_update': (_I, [POINTER(AggInput), _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'gg_node_head': (_I, [_P, _I, _I, _P, _P, _I, POINTER(c_int32), _P, _I, _P, _I, _F, _P, _I, _P]),
     'gg_edge_head': (_I, [_P, _I, _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
-    'gg_feature_update': (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _F, _F, _P, _P]),
+    'gg_feature_update': (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P]),
     'gg_gather_rows': (_I, [_P, _I, _P, _I, _I, _P, _I, _P]),
     'gg_scatter_rows': (_I, [_P, _I, _P, _I, _I, _P, _I, _P]),
 }

@@ -6,6 +6,7 @@ Three kernel families per call, in this order:
   (c') gg_gate_update per node type   : lin_l2 / lin_edge / lin_skip + biases + gate non-linearities / LSTM update
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -28,6 +29,21 @@ def pad_features(x, k1p):
     if x.shape[1] == k1p:
         return x.contiguous()
     return F.pad(x, (0, k1p - x.shape[1])).contiguous()
+
+
+def gemm_mode():
+    """'tc' (tcgen05 3xTF32 projections) or 'simt' (fp32 CUDA cores); GG_GEMM overrides, default = tc when supported."""
+    m = os.environ.get('GG_GEMM', 'auto').lower()
+    if m in ('tc', 'simt'):
+        return m
+    global _AUTO
+    if _AUTO is None:
+        L = _lib.lib()
+        _AUTO = 'tc' if hasattr(L, 'gg_tc_supported') and L.gg_tc_supported() == 1 else 'simt'
+    return _AUTO
+
+
+_AUTO = None
 
 
 def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=None):
@@ -54,11 +70,27 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
     with torch.cuda.device(dev):
         # (c) node projections
         P = {}
+        use_tc = gemm_mode() == 'tc' and pk.C % 32 == 0 and max(pk.k1p.values()) <= 32
         for t in pk.node_types:
             x = xpad[t]
             n = x.shape[0]
             ht = None if h is None else h[t]
             P[t] = buf(('P', t), (n, pk.ncols[t]))
+            if use_tc:
+                k2 = 0 if ht is None else ht.shape[1]
+                kp = 32 + k2
+                if not hasattr(pk, 'tcW'):
+                    pk.tcW = {}
+                if t not in pk.tcW:
+                    from .packing import tc_weight_layout
+                    pk.tcW[t] = tc_weight_layout(pk, t)
+                whi, wlo = pk.tcW[t]
+                ahi, alo = buf(('Ahi', t), (n, kp)), buf(('Alo', t), (n, kp))
+                check(L.gg_split_tf32(ptr(x), x.stride(0), pk.k1p[t], ptr(ht), 0 if ht is None else ht.stride(0), k2,
+                                      n, ptr(ahi), ptr(alo), kp, 32, st), 'gg_split_tf32')
+                check(L.gg_node_proj_tc(ptr(ahi), ptr(alo), kp, ptr(whi), ptr(wlo), pk.ncols[t], ptr(pk.bcat[t]),
+                                        ptr(P[t]), pk.ncols[t], n, 0, st), 'gg_node_proj_tc')
+                continue
             check(L.gg_node_proj(ptr(x), x.stride(0), pk.k1p[t],
                                  ptr(ht), 0 if ht is None else ht.stride(0), 0 if ht is None else ht.shape[1],
                                  ptr(pk.Wcat[t]), pk.kin[t], ptr(pk.bcat[t]),

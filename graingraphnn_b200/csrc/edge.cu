@@ -111,7 +111,7 @@ __global__ void edge_head_kernel(const float* __restrict__ h, int ldh, const int
 
 // models.py:510-516 and test.py:401-402 (z += dz); the clamp of test.py:405-407 is the second kernel.
 __global__ void feature_update_kernel(float* __restrict__ xj, int ldj, int nj, const float* __restrict__ yj,
-                                      float* __restrict__ xg, int ldg, int ng, const float* __restrict__ yg, float dz) {
+                                      float* __restrict__ xg, int ldg, int ng, const float* __restrict__ yg, float dz, int last_g) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nj) {
         float* r = xj + (int64_t)i * ldj;
@@ -125,7 +125,7 @@ __global__ void feature_update_kernel(float* __restrict__ xj, int ldj, int nj, c
         const float ds = yg[2 * i], dv = yg[2 * i + 1];
         r[3] += ds / 20.0f;
         r[4] = dv;
-        r[ldg - 1] = ds;
+        r[last_g] = ds;
         r[2] += dz;
     }
 }
@@ -212,13 +212,13 @@ extern "C" int gg_edge_head(const float* h, int32_t ldh, int32_t C, const int64_
 }
 
 extern "C" int gg_feature_update(float* x_joint, int32_t ld_j, int32_t n_joint, const float* y_joint,
-                                 float* x_grain, int32_t ld_g, int32_t n_grain, const float* y_grain,
+                                 float* x_grain, int32_t ld_g, int32_t n_grain, int32_t n_grain_feat, const float* y_grain,
                                  float dz, float z_max, int32_t* scratch, void* stream) {
-    if (n_joint < 0 || n_grain < 1 || ld_j < 8 || ld_g < 6 || !scratch) return GG_EINVAL;
+    if (n_joint < 0 || n_grain < 1 || ld_j < 8 || n_grain_feat < 6 || ld_g < n_grain_feat || !scratch) return GG_EINVAL;
     if (!x_joint || !x_grain || !y_joint || !y_grain) return GG_EINVAL;
     cudaStream_t st = GG_STREAM(stream);
     const int n = n_joint + n_grain;
-    feature_update_kernel<<<(n + 255) / 256, 256, 0, st>>>(x_joint, ld_j, n_joint, y_joint, x_grain, ld_g, n_grain, y_grain, dz);
+    feature_update_kernel<<<(n + 255) / 256, 256, 0, st>>>(x_joint, ld_j, n_joint, y_joint, x_grain, ld_g, n_grain, y_grain, dz, n_grain_feat - 1);
     GG_LAUNCH_OK();
     z_probe_kernel<<<1, 1, 0, st>>>(x_grain, z_max, scratch);
     GG_LAUNCH_OK();

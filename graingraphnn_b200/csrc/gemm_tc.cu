@@ -1,0 +1,336 @@
+// gemm_tc.cu — kernel family (c) on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) with TMEM accumulators,
+// operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), warp-specialised persistent CTAs.
+//
+//   gg_split_tf32   : [X | h]  ->  A_hi, A_lo   (a = hi + lo, both representable in TF32; K padded to 32-float chunks)
+//   gg_node_proj_tc : P = A W^T + b  as  A_lo W_hi^T + A_hi W_lo^T + A_hi W_hi^T  ("3xTF32": fp32-grade accuracy,
+//                     error ~2^-22 relative per product, needed for the 1e-4 per-step parity bar that plain TF32 misses)
+//
+// Per CTA (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (tcgen05.ld -> +bias -> 128-bit global stores).  Tile = 128 rows x 256 columns, K streamed in
+// 32-float (128-byte) chunks through a 4-stage mbarrier ring; two 256-column TMEM accumulators double-buffer the
+// epilogue against the next tile's MMAs.  All three split terms accumulate into the same TMEM tile, smallest first.
+//
+// Roofline: tensor pipe. Algorithmic flops = 2 M N K; the kernel issues 3x that in TF32 MMAs.  The fp32 output
+// (N*4 bytes per row) makes it co-limited by HBM writes: 128 KB per tile vs 6144 MMA cycles.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;          // rows per tile  (UMMA M)
+constexpr int BN = 256;          // columns per tile (max UMMA N)
+constexpr int BK = 32;           // floats per K chunk = 128 bytes = one swizzle-128B row
+constexpr int kStages = 3;
+constexpr int A_BYTES = BM * BK * 4;     // 16 KB
+constexpr int B_BYTES = BN * BK * 4;     // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int OUT_CHUNK = 32;            // columns per epilogue chunk = one 128-byte swizzled row of the store box
+constexpr int OUT_BYTES = BM * OUT_CHUNK * 4;            // 16 KB staging per TMA store, double-buffered
+constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 2 * OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kThreads = 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1) |
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2, K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ the GEMM kernel
+__global__ void __launch_bounds__(kThreads, 1)
+node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                    const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, int M, int N, int Kp) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // swizzle-128B tiles need 1024-B alignment
+    const uint32_t out_base = smem_base + kStages * STAGE_BYTES;                 // 2 x 16 KB store staging (1024-B aligned)
+    const uint32_t bar_base = out_base + 2 * OUT_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
+    const int n_tiles = m_blocks * n_blocks;
+    const int chunks = Kp / BK, iters = 3 * chunks;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int m0 = (t / n_blocks) * BM, n0 = (t % n_blocks) * BN;
+                for (int it = 0; it < iters; ++it) {
+                    const int term = it / chunks, k0 = (it % chunks) * BK;
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    tma_load_2d(sa, term == 0 ? &tmA_lo : &tmA_hi, full_bar(stage), k0, m0);
+                    tma_load_2d(sb, term == 1 ? &tmW_lo : &tmW_hi, full_bar(stage), k0, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int n0 = (t % n_blocks) * BN;
+                int ncols = N - n0; ncols = ncols > BN ? BN : ncols; ncols = (ncols + 15) & ~15;
+                const uint32_t idesc = make_idesc(BM, ncols);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint64_t adesc = make_desc(sa), bdesc = make_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)                  // UMMA K = 8 tf32 = 32 bytes: advance start address by 2 (x16 B)
+                        umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) ? 1u : 0u);
+                    umma_commit(empty_bar(stage));                    // frees the smem slot when these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));                          // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> (+bias) -> swizzled smem staging -> TMA store =====
+        // Each thread owns one accumulator row; a direct global store would scatter 32 x 16 B per instruction
+        // (measured: ~1.5 TB/s chip-wide), so 32-column chunks are staged in shared memory in the 128-byte-swizzle
+        // layout of the store tensor map and written with one cp.async.bulk.tensor per chunk (OOB rows/cols clipped).
+        const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;                                  // row inside the tile
+        int acc = 0; uint32_t acc_phase = 0;
+        int obuf = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int m0 = (t / n_blocks) * BM, n0 = (t % n_blocks) * BN;
+            int ncols = N - n0; ncols = ncols > BN ? BN : ncols;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            for (int c0 = 0; c0 < ncols; c0 += OUT_CHUNK) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                // the staging buffer we are about to overwrite was read by the TMA store issued two chunks ago
+                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t srow = out_base + obuf * OUT_BYTES + (uint32_t)r * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    if (bias && c0 + 4 * j < ncols) {
+                        const float4 b = ldg4(bias + n0 + c0 + 4 * j);
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    const uint32_t dst = srow + (uint32_t)((j ^ (r & 7)) << 4);       // 128-byte swizzle: chunk ^= row % 8
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to TMA
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 128) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmOut), "r"(out_base + obuf * OUT_BYTES), "r"(n0 + c0), "r"(m0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                obuf ^= 1;
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ split kernel
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// one float4 of the padded row per thread: columns [0,K1p32) from X (zero beyond K1), then K2 columns of H
+__global__ void split_tf32_kernel(const float* __restrict__ X, int ldx, int K1, const float* __restrict__ H, int ldh, int K2,
+                                  int M, float* __restrict__ Ahi, float* __restrict__ Alo, int Kp, int K1p32) {
+    const int q4 = Kp >> 2;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)M * q4) return;
+    const int m = (int)(t / q4), c = (int)(t % q4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < K1p32) {
+        if (c < K1) v = ldg4(X + (size_t)m * ldx + c);            // K1 % 4 == 0 (padded feature rows)
+    } else if (H && c - K1p32 < K2) {
+        v = ldg4(H + (size_t)m * ldh + (c - K1p32));
+    }
+    float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z), to_tf32(v.w - hi.w));
+    *reinterpret_cast<float4*>(Ahi + (size_t)m * Kp + c) = hi;
+    *reinterpret_cast<float4*>(Alo + (size_t)m * Kp + c) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with row stride ld (floats); box = [box_rows x 32 floats], 128-byte swizzle
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    if ((ld & 3) || !gg_aligned16(base)) return GG_EALIGN;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GG_EARCH;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : GG_EINVAL;
+}
+
+}  // namespace
+
+extern "C" int gg_tc_supported(void) { return gg_device_is_sm100() && get_encode() != nullptr ? 1 : 0; }
+
+extern "C" int gg_split_tf32(const float* X, int32_t ldx, int32_t K1, const float* H, int32_t ldh, int32_t K2,
+                             int32_t M, float* A_hi, float* A_lo, int32_t Kp, int32_t K1p32, void* stream) {
+    if (M < 0 || K1 < 0 || K2 < 0 || Kp <= 0 || (Kp % BK) || (K1p32 % BK) || K1 > K1p32 || K1p32 + (H ? K2 : 0) > Kp) return GG_EINVAL;
+    if (M == 0) return 0;
+    if (!X || !A_hi || !A_lo) return GG_EINVAL;
+    if ((K1 & 3) || (K2 & 3) || (ldx & 3) || (H && (ldh & 3))) return GG_EALIGN;
+    if (!gg_aligned16(X) || (H && !gg_aligned16(H)) || !gg_aligned16(A_hi) || !gg_aligned16(A_lo)) return GG_EALIGN;
+    const int64_t n = (int64_t)M * (Kp / 4);
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, GG_STREAM(stream)>>>(X, ldx, K1, H, ldh, K2, M, A_hi, A_lo, Kp, K1p32);
+    GG_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, const float* W_hi, const float* W_lo,
+                               int32_t N, const float* bias, float* out, int32_t ldo, int32_t M, int32_t n_sms, void* stream) {
+    if (M < 0 || N < 0 || Kp <= 0 || (Kp % BK)) return GG_EINVAL;
+    if (M == 0 || N == 0) return 0;
+    if (!A_hi || !A_lo || !W_hi || !W_lo || !out) return GG_EINVAL;
+    if ((N & 3) || (ldo & 3) || !gg_aligned16(out) || (bias && !gg_aligned16(bias))) return GG_EALIGN;
+    if (!gg_aligned16(A_hi) || !gg_aligned16(A_lo) || !gg_aligned16(W_hi) || !gg_aligned16(W_lo)) return GG_EALIGN;
+    CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
+    int rc;
+    if ((rc = make_map(&mA_hi, A_hi, M, Kp, Kp, BM))) return rc;
+    if ((rc = make_map(&mA_lo, A_lo, M, Kp, Kp, BM))) return rc;
+    if ((rc = make_map(&mW_hi, W_hi, N, Kp, Kp, BN))) return rc;
+    if ((rc = make_map(&mW_lo, W_lo, N, Kp, Kp, BN))) return rc;
+    CUtensorMap mOut;
+    if ((rc = make_map(&mOut, out, M, N, ldo, BM))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(node_proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    if (n_sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < n_sms ? tiles : n_sms;
+    node_proj_tc_kernel<<<grid, kThreads, SMEM_BYTES, GG_STREAM(stream)>>>(mA_hi, mA_lo, mW_hi, mW_lo, mOut, bias, M, N, Kp);
+    GG_LAUNCH_OK();
+    return 0;
+}

@@ -155,7 +155,7 @@ class RolloutEngine:
     @torch.no_grad()
     def capture(self, span=6, warmup=2):
         """Capture the step into a CUDA graph (fixed topology): later step(span) calls replay it.
-        NOTE: capturing advances the rollout state by `warmup` + 1 steps."""
+        NOTE: the warm-up runs advance the rollout state by max(warmup, 1) steps; the capture itself executes nothing."""
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):

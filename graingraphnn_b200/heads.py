@@ -44,5 +44,5 @@ def feature_update(x_joint, x_grain, y_joint, y_grain, dz, z_max, scratch=None):
     assert x_joint.stride(1) == 1 and x_grain.stride(1) == 1
     with torch.cuda.device(x_joint.device):
         check(_lib.lib().gg_feature_update(ptr(x_joint), x_joint.stride(0), x_joint.shape[0], ptr(y_joint),
-                                           ptr(x_grain), x_grain.stride(0), x_grain.shape[0], ptr(y_grain),
+                                           ptr(x_grain), x_grain.stride(0), x_grain.shape[0], x_grain.shape[1], ptr(y_grain),
                                            float(dz), float(z_max), ptr(scratch), _stream()), 'gg_feature_update')

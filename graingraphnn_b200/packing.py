@@ -146,6 +146,30 @@ class PackedCell:
         return self
 
 
+def tf32_round(x):
+    """cvt.rna.tf32.f32 on a float32 tensor: round-to-nearest (ties away) to 10 mantissa bits, low 13 bits cleared."""
+    u = x.contiguous().view(torch.int32)
+    return ((u + 0x1000) & -8192).view(torch.float32)
+
+
+def split_tf32(w):
+    """w = hi + lo with both parts exactly representable in TF32 (operands of the 3xTF32 tensor-core GEMM)."""
+    hi = tf32_round(w)
+    return hi, tf32_round(w - hi)
+
+
+def tc_weight_layout(pk, t):
+    """Wcat[t] re-laid out for gg_node_proj_tc: K = [features padded to 32 | hidden], split into (hi, lo)."""
+    k1p, kin = pk.k1p[t], pk.kin[t]
+    k2 = kin - k1p
+    W = pk.Wcat[t]
+    out = torch.zeros(W.shape[0], 32 + k2, dtype=torch.float32, device=W.device)
+    out[:, :k1p] = W[:, :k1p]
+    out[:, 32:] = W[:, k1p:]
+    hi, lo = split_tf32(out)
+    return hi.contiguous(), lo.contiguous()
+
+
 def version_key(tensors):
     """Changes whenever any of the tensors is rebound, moved or modified in place (load_state_dict, .to(), optimizer)."""
     return tuple((t.data_ptr(), t._version, t.device.type, t.device.index) for t in tensors)

@@ -73,6 +73,20 @@ int gg_node_proj(const float* A1, int32_t lda1, int32_t K1,
                  const float* W, int32_t ldw, const float* bias /* nullable */,
                  float* out, int32_t ldo, int32_t M, int32_t N, void* stream);
 
+/* Tensor-core variant of gg_node_proj: tcgen05.mma kind::tf32 with TMEM accumulators, TMA-staged operands.
+ * fp32-grade accuracy through the 3xTF32 split  A W^T = A_lo W_hi^T + A_hi W_lo^T + A_hi W_hi^T.
+ *   gg_tc_supported : 1 when the device is sm_100 and the driver exposes cuTensorMapEncodeTiled.
+ *   gg_split_tf32   : builds A_hi, A_lo [M, Kp] (Kp % 32 == 0) from X (K1 columns, placed in [0, K1p32)) and h (K2 columns,
+ *                     placed from K1p32); every value is rounded to TF32 with cvt.rna, a = hi + lo up to 2^-22 |a|.
+ *   gg_node_proj_tc : out[M, N] = A W^T + bias; W_hi / W_lo are [N, Kp] with the same K layout. n_sms <= 0: all SMs.
+ */
+int gg_tc_supported(void);
+int gg_split_tf32(const float* X, int32_t ldx, int32_t K1, const float* H /* nullable */, int32_t ldh, int32_t K2,
+                  int32_t M, float* A_hi, float* A_lo, int32_t Kp, int32_t K1p32, void* stream);
+int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, const float* W_hi, const float* W_lo,
+                    int32_t N, const float* bias /* nullable */, float* out, int32_t ldo, int32_t M, int32_t n_sms,
+                    void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (b) fused periodic-attention gather.  One launch = one edge type, all G gates of one cell.
  *     Per target node i and gate g (PeriodConv.message, periodGATconv.py:204-236, applied to per-node
@@ -147,11 +161,11 @@ int gg_edge_head(const float* h, int32_t ldh, int32_t C, const int64_t* edge_ind
 
 /* ------------------------------------------------------------------------------------------------
  * (a12) in-place feature update, models.py:503-516 + test.py:401-407.
- *   x_j[:, :2] += y_j/5; x_j[:,6:8] = y_j; x_g[:,3] += y_g0/20; x_g[:,4] = y_g1; x_g[:,last] = y_g0;
+ *   x_j[:, :2] += y_j/5; x_j[:,6:8] = y_j; x_g[:,3] += y_g0/20; x_g[:,4] = y_g1; x_g[:,n_grain_feat-1] = y_g0;
  *   z += dz on both, then if x_g[0,2] > z_max: z = z_max everywhere.   scratch: device int32[1].
  * ---------------------------------------------------------------------------------------------- */
 int gg_feature_update(float* x_joint, int32_t ld_j, int32_t n_joint, const float* y_joint,
-                      float* x_grain, int32_t ld_g, int32_t n_grain, const float* y_grain,
+                      float* x_grain, int32_t ld_g, int32_t n_grain, int32_t n_grain_feat, const float* y_grain,
                       float dz, float z_max, int32_t* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
