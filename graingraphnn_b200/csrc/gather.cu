@@ -29,7 +29,7 @@ struct GatherParams {
     const int* rowptr; const int* col; const float* ea;
     const float* Wv3;
     int n_dst, G, quads, weighted;
-    float* agg; int ld_agg; float* ea_out;
+    float* agg; float* agg_lo; int ld_agg; float* ea_out;
     float sqrt_c;
 };
 
@@ -45,6 +45,12 @@ __device__ __forceinline__ float dot_group(const float4 (&a)[NV], const float4 (
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     return s;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
 }
 
 __device__ __forceinline__ float wrapf(float r) { return (float)((r < -0.5f) - (r > 0.5f)); }
@@ -175,6 +181,16 @@ pgat_gather_kernel(const GatherParams p) {
     }
     if (active) {
         float* orow = p.agg + (size_t)node * p.ld_agg + gcol;
+        if (p.agg_lo) {   // TF32 split for the tensor-core gate GEMM: agg = hi + lo, both TF32-representable
+            float* lrow = p.agg_lo + (size_t)node * p.ld_agg + gcol;
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {
+                const float4 hi = make_float4(tf32_rna(acc[r].x), tf32_rna(acc[r].y), tf32_rna(acc[r].z), tf32_rna(acc[r].w));
+                const float4 lo = make_float4(tf32_rna(acc[r].x - hi.x), tf32_rna(acc[r].y - hi.y), tf32_rna(acc[r].z - hi.z), tf32_rna(acc[r].w - hi.w));
+                *reinterpret_cast<float4*>(orow + 4 * (sub + 8 * r)) = hi;
+                *reinterpret_cast<float4*>(lrow + 4 * (sub + 8 * r)) = lo;
+            }
+        } else
 #pragma unroll
         for (int r = 0; r < NV; ++r) *reinterpret_cast<float4*>(orow + 4 * (sub + 8 * r)) = acc[r];
         if (sub == 0) p.ea_out[(size_t)node * p.G + gate] = ea_acc;
@@ -188,7 +204,7 @@ extern "C" int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off,
                               const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
                               const int32_t* rowptr, const int32_t* col, const float* eattr_csr,
                               const float* Wv3, int32_t n_dst, int32_t G, int32_t C, int32_t weighted,
-                              float* agg, int32_t ld_agg, float* ea, void* stream) {
+                              float* agg, float* agg_lo, int32_t ld_agg, float* ea, void* stream) {
     if (n_dst < 0 || G < 1 || G > 64 || C % 32 || C < 32 || C > 128) return GG_EINVAL;
     if (n_dst == 0) return 0;
     if (!P_src || !pos_src || !pos_dst || !rowptr || !Wv3 || !agg || !ea) return GG_EINVAL;
@@ -202,7 +218,8 @@ extern "C" int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off,
     p.pos_src = pos_src; p.ld_ps = ld_pos_src; p.pos_dst = pos_dst; p.ld_pd = ld_pos_dst;
     p.rowptr = rowptr; p.col = col; p.ea = eattr_csr; p.Wv3 = Wv3;
     p.n_dst = n_dst; p.G = G; p.quads = (G + 3) / 4; p.weighted = weighted ? 1 : 0;
-    p.agg = agg; p.ld_agg = ld_agg; p.ea_out = ea;
+    p.agg = agg; p.agg_lo = agg_lo; p.ld_agg = ld_agg; p.ea_out = ea;
+    if (agg_lo && !gg_aligned16(agg_lo)) return GG_EALIGN;
     p.sqrt_c = sqrtf((float)C);
     const int64_t units = (int64_t)n_dst * p.quads;
     const unsigned nb = (unsigned)((units + kWarpsPerBlock - 1) / kWarpsPerBlock);

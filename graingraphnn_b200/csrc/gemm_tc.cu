@@ -227,6 +227,238 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------ gate GEMM + LSTM
+// gg_gate_update_tc: per 128-node tile and gate g, D_g[128, C] (TMEM columns [g*C, (g+1)*C)) accumulates
+//   sum over K chunks of  A_chunk (agg of every incoming edge type, then X, then h)  x  Wall[g*C + n, k]   (3xTF32),
+// then the epilogue adds the rank-1 terms (lin_edge, lin_l2 bias, gate bias) and applies the LSTM update.
+constexpr int GK_STAGES = 6;
+constexpr int G_A_BYTES = BM * BK * 4;                  // 16 KB
+constexpr int G_B_BYTES = 128 * BK * 4;                 // up to C = 128 rows: 16 KB (TMA box is C rows)
+constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_SMEM_BYTES = GK_STAGES * G_STAGE_BYTES + 1024 + 256 + 5 * 4 * 128 * 4;   // + epilogue vectors (G*C <= 512 floats each)
+constexpr int kMaxIn = 2;
+
+struct GateMaps {
+    CUtensorMap agg_hi[kMaxIn], agg_lo[kMaxIn];
+    CUtensorMap a_hi, a_lo;         // [X padded to 32 | h]
+    CUtensorMap w_hi, w_lo;         // Wall [G*C, Ktot]
+};
+struct GateEpi {
+    const float* ea[kMaxIn]; const int* rowptr[kMaxIn]; const float* We[kMaxIn]; const float* b2[kMaxIn]; int weighted[kMaxIn];
+    const float* btot; const float* c_in; float* out_h; float* out_c;
+    int n_in, M, G, C, has_h, mode;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+
+template <int G, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + GK_STAGES * G_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (GK_STAGES + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * GK_STAGES), tempty_bar = tfull_bar + 8u;
+    const uint32_t tmem_slot = tempty_bar + 8u;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    // per-column epilogue vectors, staged once: [We0 | b2_0 | We1 | b2_1 | btot], each G*C floats
+    float* vecs = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = ep.C, CC = C / BK, GC = G * C;
+    const int n_in = ep.n_in;
+    const int n_tiles = (ep.M + BM - 1) / BM;
+    const int nck = n_in * CC + 1 + (ep.has_h ? CC : 0);             // K chunks per gate
+    const uint32_t stage_tx = (uint32_t)(G_A_BYTES + C * BK * 4);
+
+    for (int i = threadIdx.x; i < GC; i += kThreads) {
+        vecs[i] = __ldg(&ep.We[0][i]);
+        vecs[GC + i] = __ldg(&ep.b2[0][i]);
+        vecs[2 * GC + i] = n_in > 1 ? __ldg(&ep.We[1][i]) : 0.f;
+        vecs[3 * GC + i] = n_in > 1 ? __ldg(&ep.b2[1][i]) : 0.f;
+        vecs[4 * GC + i] = __ldg(&ep.btot[i]);
+    }
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < GK_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1); mbar_init(tempty_bar, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int m0 = t * BM;
+                for (int g = 0; g < G; ++g)
+                    for (int term = 0; term < 3; ++term)
+                        for (int ck = 0; ck < nck; ++ck) {
+                            const CUtensorMap* am;
+                            int acol;
+                            if (ck < n_in * CC) {
+                                const int e = ck / CC;
+                                am = term == 0 ? &maps.agg_lo[e] : &maps.agg_hi[e];
+                                acol = g * C + (ck % CC) * BK;
+                            } else {
+                                am = term == 0 ? &maps.a_lo : &maps.a_hi;
+                                acol = (ck - n_in * CC) * BK;
+                            }
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            mbar_expect_tx(full_bar(stage), stage_tx);
+                            const uint32_t sa = smem_base + stage * G_STAGE_BYTES, sb = sa + G_A_BYTES;
+                            tma_load_2d(sa, am, full_bar(stage), acol, m0);
+                            tma_load_2d(sb, term == 1 ? &maps.w_lo : &maps.w_hi, full_bar(stage), ck * BK, g * C);
+                            if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            const uint32_t idesc = make_idesc(BM, C);
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar, tphase ^ 1u);
+                tc_fence_after();
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(g * C);
+                    for (int it = 0; it < 3 * nck; ++it) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * G_STAGE_BYTES, sb = sa + G_A_BYTES;
+                        const uint64_t adesc = make_desc(sa), bdesc = make_desc(sb);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k)
+                            umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) ? 1u : 0u);
+                        umma_commit(empty_bar(stage));
+                        if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                umma_commit(tfull_bar);
+                tphase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: one accumulator row per thread, 16 columns of every gate at a time =====
+        const int q = warp & 3;
+        uint32_t tphase = 0;
+        const float* __restrict__ ea0p = ep.ea[0];
+        const float* __restrict__ ea1p = ep.ea[1];
+        const int* __restrict__ rp0 = ep.rowptr[0];
+        const int* __restrict__ rp1 = ep.rowptr[1];
+        const int w0 = ep.weighted[0], w1 = ep.weighted[1];
+        const float* __restrict__ c_in = ep.c_in;
+        float* __restrict__ out_h = ep.out_h;
+        float* __restrict__ out_c = ep.out_c;
+        const int M = ep.M;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int m = t * BM + q * 32 + lane;
+            const bool ok = m < M;
+            float cnt0 = 0.f, cnt1 = 0.f, ea0[G], ea1[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) { ea0[g] = 0.f; ea1[g] = 0.f; }
+            if (ok) {
+                const int d0 = __ldg(&rp0[m + 1]) - __ldg(&rp0[m]);
+                cnt0 = w0 ? (d0 > 0 ? 1.f : 0.f) : (float)d0;
+#pragma unroll
+                for (int g = 0; g < G; ++g) ea0[g] = __ldg(&ea0p[(size_t)m * G + g]);
+                if (n_in > 1) {
+                    const int d1 = __ldg(&rp1[m + 1]) - __ldg(&rp1[m]);
+                    cnt1 = w1 ? (d1 > 0 ? 1.f : 0.f) : (float)d1;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) ea1[g] = __ldg(&ea1p[(size_t)m * G + g]);
+                }
+            }
+            mbar_wait(tfull_bar, tphase);
+            tc_fence_after();
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                uint32_t v[G][16];
+#pragma unroll
+                for (int g = 0; g < G; ++g) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * C + c0), v[g]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float pre[G][16];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float* vg = vecs + g * C + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 we0 = *reinterpret_cast<const float4*>(vg + j);
+                        const float4 b20 = *reinterpret_cast<const float4*>(vg + GC + j);
+                        const float4 we1 = *reinterpret_cast<const float4*>(vg + 2 * GC + j);
+                        const float4 b21 = *reinterpret_cast<const float4*>(vg + 3 * GC + j);
+                        const float4 bt = *reinterpret_cast<const float4*>(vg + 4 * GC + j);
+                        pre[g][j + 0] = __uint_as_float(v[g][j + 0]) + fmaf(ea0[g], we0.x, cnt0 * b20.x) + fmaf(ea1[g], we1.x, cnt1 * b21.x) + bt.x;
+                        pre[g][j + 1] = __uint_as_float(v[g][j + 1]) + fmaf(ea0[g], we0.y, cnt0 * b20.y) + fmaf(ea1[g], we1.y, cnt1 * b21.y) + bt.y;
+                        pre[g][j + 2] = __uint_as_float(v[g][j + 2]) + fmaf(ea0[g], we0.z, cnt0 * b20.z) + fmaf(ea1[g], we1.z, cnt1 * b21.z) + bt.z;
+                        pre[g][j + 3] = __uint_as_float(v[g][j + 3]) + fmaf(ea0[g], we0.w, cnt0 * b20.w) + fmaf(ea1[g], we1.w, cnt1 * b21.w) + bt.w;
+                    }
+                }
+                if (!ok) continue;
+                if (MODE == GG_GATE_RAW || MODE == GG_GATE_RELU) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        float* o = out_h + (size_t)m * GC + g * C + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 w = make_float4(pre[g][j], pre[g][j + 1], pre[g][j + 2], pre[g][j + 3]);
+                            if (MODE == GG_GATE_RELU) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+                            *reinterpret_cast<float4*>(o + j) = w;
+                        }
+                    }
+                } else {
+                    constexpr bool lstm = MODE == GG_GATE_LSTM;       // gates (i,f,c,o); LSTM0: (i,c,o) with c_in = 0
+                    constexpr int gc = lstm ? 2 : 1, go = lstm ? 3 : 2;
+                    float cold[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) cold[j] = 0.f;
+                    if (lstm && c_in) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 c4 = ldg4(c_in + (size_t)m * C + c0 + j);
+                            cold[j] = c4.x; cold[j + 1] = c4.y; cold[j + 2] = c4.z; cold[j + 3] = c4.w;
+                        }
+                    }
+                    float hn[16], cn[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float c2 = sigmoidf_(pre[0][j]) * tanhf(pre[gc < G ? gc : 0][j]);
+                        if (lstm) c2 = sigmoidf_(pre[1 < G ? 1 : 0][j]) * cold[j] + c2;
+                        cn[j] = c2;
+                        hn[j] = sigmoidf_(pre[go < G ? go : 0][j]) * tanhf(c2);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        *reinterpret_cast<float4*>(out_h + (size_t)m * C + c0 + j) = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
+                        if (out_c) *reinterpret_cast<float4*>(out_c + (size_t)m * C + c0 + j) = make_float4(cn[j], cn[j + 1], cn[j + 2], cn[j + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar);
+            tphase ^= 1u;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ split kernel
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t u;
@@ -331,6 +563,68 @@ extern "C" int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp,
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < n_sms ? tiles : n_sms;
     node_proj_tc_kernel<<<grid, kThreads, SMEM_BYTES, GG_STREAM(stream)>>>(mA_hi, mA_lo, mW_hi, mW_lo, mOut, bias, M, N, Kp);
+    GG_LAUNCH_OK();
+    return 0;
+}
+
+// Tensor-core variant of gg_gate_update.  agg_hi/agg_lo: TF32 split of the aggregated values written by gg_pgat_gather
+// (agg_lo != NULL), A_hi/A_lo: the [X padded to 32 | h] split shared with gg_node_proj_tc, W_hi/W_lo: Wall [G*C, Ktot] with
+// Ktot = n_inputs*C + 32 (+ C when has_h), K layout [W2 of input 0 | W2 of input 1 | skip(X, 32) | skip(h)].
+extern "C" int gg_gate_update_tc(const gg_agg_input* inputs, const float* const* agg_lo, int32_t n_inputs,
+                                 const float* A_hi, const float* A_lo, int32_t Kp, int32_t has_h,
+                                 const float* W_hi, const float* W_lo, int32_t Ktot, const float* btot,
+                                 const float* c_in, float* out_h, float* out_c,
+                                 int32_t M, int32_t G, int32_t C, int32_t mode, int32_t n_sms, void* stream) {
+    if (M < 0 || G < 1 || G > 4 || C % 32 || C < 32 || C > 128 || n_inputs < 1 || n_inputs > kMaxIn) return GG_EINVAL;
+    if (mode < GG_GATE_RAW || mode > GG_GATE_LSTM0) return GG_EINVAL;
+    if ((mode == GG_GATE_LSTM && G != 4) || (mode == GG_GATE_LSTM0 && G != 3) || (mode == GG_GATE_RELU && G != 1)) return GG_EINVAL;
+    if (Kp != 32 + (has_h ? C : 0) || Ktot != n_inputs * C + Kp) return GG_EINVAL;
+    if (M == 0) return 0;
+    if (!inputs || !agg_lo || !A_hi || !A_lo || !W_hi || !W_lo || !btot || !out_h) return GG_EINVAL;
+    if (!gg_aligned16(out_h) || (out_c && !gg_aligned16(out_c)) || (c_in && !gg_aligned16(c_in))) return GG_EALIGN;
+    GateMaps maps;
+    GateEpi ep;
+    int rc;
+    for (int e = 0; e < n_inputs; ++e) {
+        const gg_agg_input& s = inputs[e];
+        if (!s.agg || !agg_lo[e] || !s.ea || !s.rowptr || !s.We || !s.b2) return GG_EINVAL;
+        if ((rc = make_map(&maps.agg_hi[e], s.agg, M, (int64_t)G * C, s.ld_agg, BM))) return rc;
+        if ((rc = make_map(&maps.agg_lo[e], agg_lo[e], M, (int64_t)G * C, s.ld_agg, BM))) return rc;
+        ep.ea[e] = s.ea; ep.rowptr[e] = s.rowptr; ep.We[e] = s.We; ep.b2[e] = s.b2; ep.weighted[e] = s.weighted;
+    }
+    for (int e = n_inputs; e < kMaxIn; ++e) {
+        maps.agg_hi[e] = maps.agg_hi[0]; maps.agg_lo[e] = maps.agg_lo[0];
+        ep.ea[e] = nullptr; ep.rowptr[e] = nullptr; ep.We[e] = nullptr; ep.b2[e] = nullptr; ep.weighted[e] = 0;
+    }
+    if ((rc = make_map(&maps.a_hi, A_hi, M, Kp, Kp, BM))) return rc;
+    if ((rc = make_map(&maps.a_lo, A_lo, M, Kp, Kp, BM))) return rc;
+    if ((rc = make_map(&maps.w_hi, W_hi, (int64_t)G * C, Ktot, Ktot, C))) return rc;
+    if ((rc = make_map(&maps.w_lo, W_lo, (int64_t)G * C, Ktot, Ktot, C))) return rc;
+    ep.btot = btot; ep.c_in = c_in; ep.out_h = out_h; ep.out_c = out_c;
+    ep.n_in = n_inputs; ep.M = M; ep.G = G; ep.C = C; ep.has_h = has_h ? 1 : 0; ep.mode = mode;
+    if (n_sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = (M + BM - 1) / BM;
+    const int grid = tiles < n_sms ? tiles : n_sms;
+    cudaStream_t st = GG_STREAM(stream);
+    cudaError_t err = cudaSuccess;
+#define GG_LAUNCH_GATE(GV, MV)                                                                                              \
+    do {                                                                                                                    \
+        err = cudaFuncSetAttribute(gate_update_tc_kernel<GV, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES); \
+        if (err != cudaSuccess) return (int)err;                                                                            \
+        gate_update_tc_kernel<GV, MV><<<grid, kThreads, G_SMEM_BYTES, st>>>(maps, ep);                                      \
+    } while (0)
+    if (mode == GG_GATE_LSTM) GG_LAUNCH_GATE(4, GG_GATE_LSTM);
+    else if (mode == GG_GATE_LSTM0) GG_LAUNCH_GATE(3, GG_GATE_LSTM0);
+    else if (mode == GG_GATE_RELU) GG_LAUNCH_GATE(1, GG_GATE_RELU);
+    else if (G == 1) GG_LAUNCH_GATE(1, GG_GATE_RAW);
+    else if (G == 2) GG_LAUNCH_GATE(2, GG_GATE_RAW);
+    else if (G == 3) GG_LAUNCH_GATE(3, GG_GATE_RAW);
+    else GG_LAUNCH_GATE(4, GG_GATE_RAW);
+#undef GG_LAUNCH_GATE
     GG_LAUNCH_OK();
     return 0;
 }

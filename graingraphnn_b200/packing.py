@@ -170,6 +170,27 @@ def tc_weight_layout(pk, t):
     return hi.contiguous(), lo.contiguous()
 
 
+def tc_gate_weight_layout(pk, t):
+    """Wall[t] [G*C, Ktot] for gg_gate_update_tc: per gate row block, K = [lin_l2 of each incoming edge type (C each) |
+    summed lin_skip on the features (padded to 32) | on the hidden state], split into (hi, lo)."""
+    C, G = pk.C, pk.G
+    k1p, kin = pk.k1p[t], pk.kin[t]
+    k2 = kin - k1p
+    ins = pk.into[t]
+    ktot = len(ins) * C + 32 + k2
+    dev = pk.Wskip[t].device
+    W = torch.zeros(G * C, ktot, dtype=torch.float32, device=dev)
+    for g in range(G):
+        rows = slice(g * C, (g + 1) * C)
+        for i, e in enumerate(ins):
+            W[rows, i * C:(i + 1) * C] = pk.W2[e][g]
+        off = len(ins) * C
+        W[rows, off:off + k1p] = pk.Wskip[t][rows, :k1p]
+        W[rows, off + 32:] = pk.Wskip[t][rows, k1p:]
+    hi, lo = split_tf32(W)
+    return hi.contiguous(), lo.contiguous(), ktot
+
+
 def version_key(tensors):
     """Changes whenever any of the tensors is rebound, moved or modified in place (load_state_dict, .to(), optimizer)."""
     return tuple((t.data_ptr(), t._version, t.device.type, t.device.index) for t in tensors)

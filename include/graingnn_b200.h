@@ -104,6 +104,7 @@ int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, const floa
  *             features; eattr_csr is a_e in CSR order.  Outputs: agg [n_dst, ld_agg] gate block, ea [n_dst, G].
  *     One warp per target node (8 lanes x C/8 channels per gate, 128-bit loads), no atomics; edges of a row
  *     are accumulated in CSR (= original) order, matching the sequential index_add_ of the CPU reference.
+ *     If agg_lo != NULL the aggregate is written as a TF32 split (agg = hi, agg_lo = lo, cvt.rna) for gg_gate_update_tc.
  *     All row pointers / leading dimensions / offsets must be multiples of 4 floats (GG_EALIGN otherwise).
  * ---------------------------------------------------------------------------------------------- */
 int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off, int32_t v_off,
@@ -111,7 +112,7 @@ int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off, int32_t v_
                    const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
                    const int32_t* rowptr, const int32_t* col, const float* eattr_csr,
                    const float* Wv3, int32_t n_dst, int32_t G, int32_t C, int32_t weighted,
-                   float* agg, int32_t ld_agg, float* ea, void* stream);
+                   float* agg, float* agg_lo /* nullable */, int32_t ld_agg, float* ea, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (c) post-aggregation gate GEMM fused with the LSTM update.  Per node m of one node type, gate g:
@@ -142,6 +143,18 @@ int gg_gate_update(const gg_agg_input* inputs_host, int32_t n_inputs,
                    const float* Wskip, int32_t ldw, const float* btot,
                    const float* c_in /* nullable */, float* out_h, float* out_c /* nullable */,
                    int32_t M, int32_t G, int32_t C, int32_t mode, void* stream);
+
+/* Tensor-core variant of gg_gate_update (tcgen05 kind::tf32, 3xTF32, TMEM accumulators: gate g in columns [g*C,(g+1)*C)).
+ *   inputs[e].agg / agg_lo[e]: TF32 split of the aggregate (gg_pgat_gather with agg_lo); A_hi/A_lo: the [X padded to 32 | h]
+ *   split shared with gg_node_proj_tc (Kp = 32 + C, or 32 when has_h == 0); W_hi/W_lo: Wall [G*C, Ktot], row g*C+n, K layout
+ *   [lin_l2 of input 0 (C) | lin_l2 of input 1 (C) | summed lin_skip on X (32) | on h (C)], Ktot = n_inputs*C + Kp.
+ *   inputs[e].W2 is ignored (it lives in Wall); We, b2, ea, rowptr, weighted are used by the epilogue. 1 <= n_inputs <= 2.
+ */
+int gg_gate_update_tc(const gg_agg_input* inputs_host, const float* const* agg_lo_host, int32_t n_inputs,
+                      const float* A_hi, const float* A_lo, int32_t Kp, int32_t has_h,
+                      const float* W_hi, const float* W_lo, int32_t Ktot, const float* btot,
+                      const float* c_in /* nullable */, float* out_h, float* out_c /* nullable */,
+                      int32_t M, int32_t G, int32_t C, int32_t mode, int32_t n_sms, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (d) heads.

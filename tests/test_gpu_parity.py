@@ -217,8 +217,10 @@ def test_pgc_cell_matches_golden():
 
 
 # ------------------------------------------------------------------------------------------------ models
+@pytest.mark.parametrize('gemm', ['tc', 'simt'])
 @pytest.mark.parametrize('name', ['c1', 'c2'])
-def test_regressor_and_classifier_forward_match_reference_golden(name):
+def test_regressor_and_classifier_forward_match_reference_golden(name, gemm, monkeypatch):
+    monkeypatch.setenv('GG_GEMM', gemm)      # tcgen05 3xTF32 GEMMs vs fp32 CUDA-core GEMMs: both must meet the bar
     x, ei, ea = load_graph(name)
     g = load_golden(name)
     R, C = models()
