@@ -267,13 +267,15 @@ def main():
         dist.all_reduce(tt)
         h2d, d2h = int(tt[0].item()), int(tt[1].item())
 
+    # ---- per-family device time of one eager step (all ranks take part: the step contains the halo exchanges) ----
+    bd = kernel_breakdown(eng, pk)
+    barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (rank 0, live CUDA events) -----------------------------------------
-    bd = kernel_breakdown(eng, pk)
     fam = {k: v['ms_total'] for k, v in bd.items()}
     total_fam = sum(fam.values())
     top = max(fam, key=fam.get)

@@ -46,9 +46,11 @@ def gemm_mode():
 _AUTO = None
 
 
-def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=None):
+def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=None, n_rows=None):
     """xpad[t]: [N_t, K1p] fp32 (x,y,z in columns 0..2); h[t]: [N_t, K2] or None; c[t]: [N_t, C] or None;
-    csr[e]: EdgeCSR; ea_csr[e]: [E] edge attribute in CSR order.  Returns (out_h, out_c) dicts."""
+    csr[e]: EdgeCSR; ea_csr[e]: [E] edge attribute in CSR order.  Returns (out_h, out_c) dicts.
+    n_rows[t] (optional): number of leading rows of node type t that results are computed for (the owned rows of a slab
+    partition; the rows behind them are halo copies that only serve as message sources)."""
     L = _lib.lib()
     C, G = pk.C, pk.G
     GC = G * C
@@ -100,6 +102,7 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
         for e in pk.edge_types:
             s, _, d = e
             nd = xpad[d].shape[0]
+            nd_out = nd if n_rows is None else n_rows[d]
             agg[e] = buf(('agg', e), (nd, GC))
             if use_tc:
                 agg_lo[e] = buf(('agg_lo', e), (nd, GC))
@@ -109,7 +112,7 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                                    ptr(P[d]), pk.ncols[d], pk.qoff[e], pk.qxoff[e],
                                    ptr(xpad[s]), xpad[s].stride(0), ptr(xpad[d]), xpad[d].stride(0),
                                    ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(pk.Wv3[e]),
-                                   nd, G, C, 1 if pk.weighted else 0, ptr(agg[e]), ptr(agg_lo[e]) if use_tc else None,
+                                   nd_out, G, C, 1 if pk.weighted else 0, ptr(agg[e]), ptr(agg_lo[e]) if use_tc else None,
                                    GC, ptr(ea[e]), st), 'gg_pgat_gather')
         # (c') gate GEMM + LSTM update per node type
         out_h = {} if out_h is None else out_h
@@ -118,6 +121,7 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
         for t in pk.node_types:
             x = xpad[t]
             n = x.shape[0]
+            n_out = n if n_rows is None else n_rows[t]
             ins = pk.into[t]
             if not ins:          # PyG HeteroConv emits nothing for a node type no edge type ends in
                 continue
@@ -143,13 +147,13 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                 ahi, alo = buf(('Ahi', t), (n, kp)), buf(('Alo', t), (n, kp))      # written by gg_split_tf32 above
                 check(L.gg_gate_update_tc(arr, lo_arr, len(ins), ptr(ahi), ptr(alo), kp, 0 if ht is None else 1,
                                           ptr(ghi), ptr(glo), ktot, ptr(pk.btot[t]), ptr(ct), ptr(out_h[t]),
-                                          ptr(out_c[t]) if lstm else None, n, G, C, mode, 0, st), 'gg_gate_update_tc')
+                                          ptr(out_c[t]) if lstm else None, n_out, G, C, mode, 0, st), 'gg_gate_update_tc')
                 continue
             check(L.gg_gate_update(arr, len(ins), ptr(x), x.stride(0), pk.k1p[t],
                                    ptr(ht), 0 if ht is None else ht.stride(0),
                                    ptr(pk.Wskip[t]), pk.kin[t], ptr(pk.btot[t]),
                                    ptr(ct), ptr(out_h[t]), ptr(out_c[t]) if lstm else None,
-                                   n, G, C, mode, st), 'gg_gate_update')
+                                   n_out, G, C, mode, st), 'gg_gate_update')
     return out_h, out_c
 
 

@@ -66,9 +66,11 @@ class RolloutEngine:
     def set_graph(self, x_dict, edge_index_dict, edge_attr_dict=None):
         """Copy features into padded resident buffers, build the CSR of every edge type, take (or compute) edge lengths."""
         self._graph = None
+        self._state = None
         for t in self.node_types:
             xt = x_dict[t].to(self.device, torch.float32)
-            buf = torch.zeros(xt.shape[0], pad4(xt.shape[1]), dtype=torch.float32, device=self.device)
+            buf = self.alloc_rows_x(t, xt.shape[0], pad4(xt.shape[1]))
+            buf.zero_()
             buf[:, :xt.shape[1]] = xt
             self.xbuf[t] = buf
             self.x[t] = buf[:, :xt.shape[1]]          # user-visible view; in-place edits land in the resident buffer
@@ -103,43 +105,59 @@ class RolloutEngine:
                        'gg_edge_length')
 
     # ---------------------------------------------------------------------------------------------------- step
-    def _model_forward(self, name):
-        pk_enc, pk_dec = self._pack()[name]
-        w = self._work
-        st = self._state.setdefault(name, {'he': {}, 'ce': {}, 'hd': {}, 'cd': {}})
-        self.exchange_x_hook()
-        run_cell(pk_enc, self.xbuf, None, None, self.csr, self.ea_csr, _lib.GG_GATE_LSTM0, st['he'], st['ce'], w)
-        self.exchange_h_hook(st['he'])
-        run_cell(pk_dec, self.xbuf, st['he'], st['ce'], self.csr, self.ea_csr, _lib.GG_GATE_LSTM, st['hd'], st['cd'], w)
-        return st['hd'], st['cd']
-
     _state = None
+    n_rows = None            # {node type: rows that per-node results are written for}; None = all (single-GPU engine)
 
-    def exchange_x_hook(self):      # overridden by the slab-partitioned engine (halo exchange of X rows)
-        pass
+    def alloc_rows_x(self, node_type, rows, width):
+        return torch.empty(rows, width, dtype=torch.float32, device=self.device)
 
-    def exchange_h_hook(self, h):   # overridden by the slab-partitioned engine (halo exchange of encoder h rows)
-        pass
+    def alloc_rows(self, node_type, width):
+        """Storage of a per-node tensor other ranks read (h of the encoder, ...); the partitioned engine overrides it."""
+        return torch.empty(self.xbuf[node_type].shape[0], width, dtype=torch.float32, device=self.device)
 
-    def _step_impl(self, span):
+    def _states(self, name):
+        st = self._state.get(name)
+        if st is None:
+            C = self.C
+            st = {'he': {t: self.alloc_rows(t, C) for t in self.node_types}, 'ce': {},
+                  'hd': {t: self.alloc_rows(t, C) for t in self.node_types}, 'cd': {}}
+            self._state[name] = st
+        return st
+
+    def _step_gen(self, span):
+        """One rollout step as a generator: yields, at each point where rows owned by other ranks are needed, the list of
+        {node type: tensor} whose halo rows must be refreshed before execution continues.  The single-GPU engine just
+        drains it; PartitionedEngine performs the exchanges (partition.py)."""
         if self._state is None:
             self._state = {}
         R, Cm = self.R, self.Cm
-        hd, _ = self._model_forward('R')
-        yj, _ = node_head(hd['joint'], R.linear['joint'].weight, R.linear['joint'].bias, [1, 1])
+        packs, w, nr = self._pack(), self._work, self.n_rows
+        sR, sC = self._states('R'), self._states('C')
+        # encoders of both models read only X (h0 = c0 = 0, models.py:237-238)
+        for name, st in (('R', sR), ('C', sC)):
+            run_cell(packs[name][0], self.xbuf, None, None, self.csr, self.ea_csr, _lib.GG_GATE_LSTM0, st['he'], st['ce'], w, nr)
+        yield [sR['he'], sC['he']]
+        for name, st in (('R', sR), ('C', sC)):
+            run_cell(packs[name][1], self.xbuf, st['he'], st['ce'], self.csr, self.ea_csr, _lib.GG_GATE_LSTM, st['hd'], st['cd'], w, nr)
+        yield [{'joint': sC['hd']['joint']}]                 # models.py:602 gathers h[src] of the joint-joint edges
+        nj = None if nr is None else nr['joint']
+        ng = None if nr is None else nr['grain']
+        hd = sR['hd']
+        yj, _ = node_head(hd['joint'], R.linear['joint'].weight, R.linear['joint'].bias, [1, 1], n_rows=nj)
         yg, area = node_head(hd['grain'], R.linear['grain'].weight, R.linear['grain'].bias, [1, 2],
-                             area_in=self.xbuf['grain'][:, 3], area_scale=20.0)
-        hc, _ = self._model_forward('C')
-        ev, ed = edge_head(hc['joint'], self.edge_index[ET_JJ], self.edge_attr[ET_JJ],
+                             area_in=self.xbuf['grain'][:, 3], area_scale=20.0, n_rows=ng)
+        ev, ed = edge_head(sC['hd']['joint'], self.edge_index[ET_JJ], self.edge_attr[ET_JJ],
                            Cm.lin1.weight, Cm.lin1.bias, Cm.lin2.weight, Cm.lin2.bias)
         feature_update(self.x['joint'], self.x['grain'], yj, yg, span / (self.train_frames + 1),
-                       self.train_frames / (self.train_frames + 1), self._scratch)
-        self.post_update_hook()
+                       self.train_frames / (self.train_frames + 1), self._scratch, n_joint=nj, n_grain=ng)
+        yield [self.xbuf]                                    # moved coordinates of the halo -> edge lengths, next step
         self.rebuild_edge_attr()
-        return {'joint': yj, 'grain': yg, 'grain_area': area, 'edge_event': ev, 'edge': ed}
+        self.pred = {'joint': yj, 'grain': yg, 'grain_area': area, 'edge_event': ev, 'edge': ed}
 
-    def post_update_hook(self):
-        pass
+    def _step_impl(self, span):
+        for _ in self._step_gen(span):
+            pass
+        return self.pred
 
     @torch.no_grad()
     def step(self, span=6):
@@ -149,7 +167,6 @@ class RolloutEngine:
             return self.pred
         with torch.cuda.device(self.device):
             out = self._step_impl(span)
-        self.pred = out
         return out
 
     @torch.no_grad()
@@ -166,7 +183,7 @@ class RolloutEngine:
         torch.cuda.current_stream(self.device).wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.pred = self._step_impl(span)
+            self._step_impl(span)
         self._graph = (span, g)
         return g
 

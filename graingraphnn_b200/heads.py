@@ -8,7 +8,7 @@ from ._lib import check, ptr
 from .graph import _stream
 
 
-def node_head(h, weight, bias, acts, area_in=None, area_scale=20.0):
+def node_head(h, weight, bias, acts, area_in=None, area_scale=20.0, n_rows=None):
     """y = act(W h + b) per node (models.py:433-452). acts: per output row 0 none / 1 tanh / 2 relu.
     With `area_in` ([N] strided view of x_grain[:, 3]) also returns tanh(raw y0)/area_scale + area_in (models.py:445)."""
     n, C = h.shape
@@ -19,7 +19,7 @@ def node_head(h, weight, bias, acts, area_in=None, area_scale=20.0):
     with torch.cuda.device(h.device):
         check(_lib.lib().gg_node_head(ptr(h), h.stride(0), C, ptr(weight), ptr(bias), n_out, a, ptr(y), n_out,
                                       ptr(area_in), 0 if area_in is None else area_in.stride(0), float(area_scale),
-                                      ptr(area), n, _stream()), 'gg_node_head')
+                                      ptr(area), n if n_rows is None else n_rows, _stream()), 'gg_node_head')
     return y, area
 
 
@@ -37,12 +37,13 @@ def edge_head(h_joint, edge_index, edge_attr, w1, b1, w2, b2, want_edge=True):
     return ev, ed
 
 
-def feature_update(x_joint, x_grain, y_joint, y_grain, dz, z_max, scratch=None):
+def feature_update(x_joint, x_grain, y_joint, y_grain, dz, z_max, scratch=None, n_joint=None, n_grain=None):
     """In place: models.py:510-516 + test.py:401-407.  x_* may be column-strided views of padded buffers."""
     if scratch is None:
         scratch = torch.empty(1, dtype=torch.int32, device=x_joint.device)
     assert x_joint.stride(1) == 1 and x_grain.stride(1) == 1
     with torch.cuda.device(x_joint.device):
-        check(_lib.lib().gg_feature_update(ptr(x_joint), x_joint.stride(0), x_joint.shape[0], ptr(y_joint),
-                                           ptr(x_grain), x_grain.stride(0), x_grain.shape[0], x_grain.shape[1], ptr(y_grain),
+        check(_lib.lib().gg_feature_update(ptr(x_joint), x_joint.stride(0), x_joint.shape[0] if n_joint is None else n_joint,
+                                           ptr(y_joint), ptr(x_grain), x_grain.stride(0),
+                                           x_grain.shape[0] if n_grain is None else n_grain, x_grain.shape[1], ptr(y_grain),
                                            float(dz), float(z_max), ptr(scratch), _stream()), 'gg_feature_update')
