@@ -82,17 +82,14 @@ class PackedCell:
                         w, b = (cw.wk, cw.bk) if role == 'k' else (cw.wv, cw.bv)
                         rows_w.append(_cols(w, k1, k1p, k2)); rows_b.append(_vec(b, C, w.device))
                     off += GC
-            for e in self.edge_types:              # target roles: Q gate block
-                if e[2] != t:
+            for e in self.edge_types:              # target roles: Q gate block, directly followed by its QX block
+                if e[2] != t:                      # ([Wk[:, :3]^T q (3), We . q (1)] per gate) so one bulk copy stages both
                     continue
                 self.qoff[e] = off
                 for g in self.gates:
                     cw = conv_of(g, e)
                     rows_w.append(_cols(cw.wq, k1, k1p, k2)); rows_b.append(_vec(cw.bq, C, cw.wq.device))
                 off += GC
-            for e in self.edge_types:              # target roles: QX block = [Wk[:, :3]^T q (3), We . q (1)] per gate
-                if e[2] != t:
-                    continue
                 self.qxoff[e] = off
                 for g in self.gates:
                     cw = conv_of(g, e)
