@@ -441,13 +441,9 @@ pgat_gather_tma_kernel(const GatherParams p) {
     for (int r = 0; r < NV; ++r) { st.q[r] = st.vp[r] = st.acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
     st.qx = make_float4(0.f, 0.f, 0.f, 0.f);
     st.pix = st.piy = st.piz = 0.f; st.m_run = -CUDART_INF_F; st.l_run = 0.f; st.ea_acc = 0.f;
-    uint32_t phase_bits = 0u;                                // bit s = parity the next wait on slot s expects
 
-    // phase 1 of edge e: wrap vector and score (log2 units)
-    auto score = [&](uint32_t sl, int e, float a, float& wx, float& wy, float& wz) -> float {
-        const float4 pj = lds4(sl + OFF_PJ + 16 * e);
-        wx = wrapf(pj.x - st.pix); wy = wrapf(pj.y - st.piy); wz = wrapf(pj.z - st.piz);
-        if (!w) return 0.f;
+    // phase 1 of edge e: score in log2 units (wrap vector w_e = (wx, wy, wz) already known)
+    auto score = [&](uint32_t sl, int e, float a, float wx, float wy, float wz) -> float {
         const uint32_t krow = sl + OFF_KV + e * (2 * ROWB) + lane_off;
         float d = 0.f;
 #pragma unroll
@@ -459,15 +455,16 @@ pgat_gather_tma_kernel(const GatherParams p) {
         d = fmaf(st.qx.x, wx, d); d = fmaf(st.qx.y, wy, d); d = fmaf(st.qx.z, wz, d); d = fmaf(st.qx.w, a, d);
         return d * sc2;
     };
-    // phase 2 of edge e: acc += pe * relu(V_j + Wv3 (w_e - p_i))
-    auto accumulate = [&](uint32_t sl, int e, float pe, float a, float wx, float wy, float wz) {
+    // phase 2 of edge e.  relu(v + vp) = max(v, -vp) + vp, so the loop accumulates pe * max(V_j + Wv3 w_e, nvp) with
+    // nvp = Wv3 p_i and the target adds vp * sum(pe) once at the end (2 instead of 3 instructions per channel and edge).
+    auto accumulate = [&](uint32_t sl, int e, float pe, float a, float wx, float wy, float wz, bool wrapped) {
         st.l_run += pe;
         st.ea_acc = fmaf(pe, a, st.ea_acc);
         const uint32_t vrow = sl + OFF_KV + e * (2 * ROWB) + rowb + lane_off;
         float4 v[NV];
 #pragma unroll
         for (int r = 0; r < NV; ++r) v[r] = lds4(vrow + 128 * r);
-        if (wx != 0.f || wy != 0.f || wz != 0.f) {           // edge crosses a periodic / patch boundary (warp-uniform)
+        if (wrapped) {                                       // edge crosses a periodic / patch boundary (warp-uniform)
 #pragma unroll
             for (int r = 0; r < NV; ++r) {
                 const float4 ax = lds4(wv_addr + 128 * r), ay = lds4(wv_addr + 16 * C + 128 * r), az = lds4(wv_addr + 32 * C + 128 * r);
@@ -479,29 +476,16 @@ pgat_gather_tma_kernel(const GatherParams p) {
         }
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
-            st.acc[r].x = fmaf(pe, fmaxf(v[r].x + st.vp[r].x, 0.f), st.acc[r].x);
-            st.acc[r].y = fmaf(pe, fmaxf(v[r].y + st.vp[r].y, 0.f), st.acc[r].y);
-            st.acc[r].z = fmaf(pe, fmaxf(v[r].z + st.vp[r].z, 0.f), st.acc[r].z);
-            st.acc[r].w = fmaf(pe, fmaxf(v[r].w + st.vp[r].w, 0.f), st.acc[r].w);
+            st.acc[r].x = fmaf(pe, fmaxf(v[r].x, st.vp[r].x), st.acc[r].x);
+            st.acc[r].y = fmaf(pe, fmaxf(v[r].y, st.vp[r].y), st.acc[r].y);
+            st.acc[r].z = fmaf(pe, fmaxf(v[r].z, st.vp[r].z), st.acc[r].z);
+            st.acc[r].w = fmaf(pe, fmaxf(v[r].w, st.vp[r].w), st.acc[r].w);
         }
     };
 
-    Item itC = cur.next(), itI;
-    int mjC, mjI; float maC, maI;
-    load_meta(itC, mjC, maC);
-    itI = cur.next();
-    load_meta(itI, mjI, maI);
-    if (itC.valid) issue(itC, mjC, 0);
-    int slot = 0;
-    while (itC.valid) {
-        Item itM = cur.next();
-        int mjM; float maM;
-        load_meta(itM, mjM, maM);                            // stage M: source ids of item k+2
-        if (itI.valid) issue(itI, mjI, slot ^ 1);            // stage I: bulk copies of item k+1
-        // ---- stage C: item k out of shared memory --------------------------------------------------------------
-        const uint32_t sl = slot_addr0 + slot * SLOT;
-        mbar_wait_(bar_addr0 + 8u * slot, (phase_bits >> slot) & 1u);
-        phase_bits ^= 1u << slot;
+    // one item out of slot SLOT_ID (compile-time, so every shared-memory address is base + immediate)
+    auto compute = [&](const Item& itC, float maC, const uint32_t sl, const uint32_t bar, const uint32_t parity) {
+        mbar_wait_(bar, parity);
         if (itC.first) {
             const float4 pi4 = lds4(sl + OFF_PI);
             st.pix = pi4.x; st.piy = pi4.y; st.piz = pi4.z;
@@ -511,58 +495,75 @@ pgat_gather_tma_kernel(const GatherParams p) {
                 st.qx = lds4(sl + rowb + 16 * gsel);
             }
 #pragma unroll
-            for (int r = 0; r < NV; ++r) {
+            for (int r = 0; r < NV; ++r) {   // vp holds nvp = Wv3 p_i  (V_j + Wv3 (w_e - p_i) > 0  <=>  V_j + Wv3 w_e > nvp)
                 const float4 ax = lds4(wv_addr + 128 * r), ay = lds4(wv_addr + 16 * C + 128 * r), az = lds4(wv_addr + 32 * C + 128 * r);
-                st.vp[r].x = -fmaf(az.x, st.piz, fmaf(ay.x, st.piy, ax.x * st.pix));
-                st.vp[r].y = -fmaf(az.y, st.piz, fmaf(ay.y, st.piy, ax.y * st.pix));
-                st.vp[r].z = -fmaf(az.z, st.piz, fmaf(ay.z, st.piy, ax.z * st.pix));
-                st.vp[r].w = -fmaf(az.w, st.piz, fmaf(ay.w, st.piy, ax.w * st.pix));
+                st.vp[r].x = fmaf(az.x, st.piz, fmaf(ay.x, st.piy, ax.x * st.pix));
+                st.vp[r].y = fmaf(az.y, st.piz, fmaf(ay.y, st.piy, ax.y * st.pix));
+                st.vp[r].z = fmaf(az.z, st.piz, fmaf(ay.z, st.piy, ax.z * st.pix));
+                st.vp[r].w = fmaf(az.w, st.piz, fmaf(ay.w, st.piy, ax.w * st.pix));
                 st.acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             st.m_run = -CUDART_INF_F; st.l_run = 0.f; st.ea_acc = 0.f;
         }
+        // wrap vector of edge `lane` (lanes < cnt), computed once and broadcast: periodGATconv.py:209-210
+        float lwx = 0.f, lwy = 0.f, lwz = 0.f;
+        if (lane < itC.cnt) {
+            const float4 pj = lds4(sl + OFF_PJ + 16 * lane);
+            lwx = wrapf(pj.x - st.pix); lwy = wrapf(pj.y - st.piy); lwz = wrapf(pj.z - st.piz);
+        }
+        const unsigned wrapped_mask = __ballot_sync(0xffffffffu, lwx != 0.f || lwy != 0.f || lwz != 0.f);
         float s[DCAP], a[DCAP], wx[DCAP], wy[DCAP], wz[DCAP];
         float m_new = st.m_run;
-        if (itC.cnt == DCAP) {                               // the common case, branch-free over the edges
+#pragma unroll
+        for (int e = 0; e < DCAP; ++e) {
+            a[e] = __shfl_sync(0xffffffffu, maC, e);
+            wx[e] = wy[e] = wz[e] = 0.f; s[e] = 0.f;
+        }
+        if (wrapped_mask) {                                  // rare: some edge of the item crosses a boundary
 #pragma unroll
             for (int e = 0; e < DCAP; ++e) {
-                a[e] = __shfl_sync(0xffffffffu, maC, e);
-                s[e] = score(sl, e, a[e], wx[e], wy[e], wz[e]);
-                m_new = fmaxf(m_new, s[e]);
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < DCAP; ++e) {
-                a[e] = __shfl_sync(0xffffffffu, maC, e);
-                s[e] = 0.f; wx[e] = wy[e] = wz[e] = 0.f;
-                if (e < itC.cnt) { s[e] = score(sl, e, a[e], wx[e], wy[e], wz[e]); m_new = fmaxf(m_new, s[e]); }
+                wx[e] = __shfl_sync(0xffffffffu, lwx, e); wy[e] = __shfl_sync(0xffffffffu, lwy, e); wz[e] = __shfl_sync(0xffffffffu, lwz, e);
             }
         }
-        if (w && m_new > st.m_run) {                         // online softmax: rescale what earlier chunks accumulated
-            if (st.m_run != -CUDART_INF_F) {
-                const float scale = ex2_approx(st.m_run - m_new);
-                st.l_run *= scale; st.ea_acc *= scale;
+        if (w) {
+            if (itC.cnt == DCAP) {                           // the common case, branch-free over the edges
 #pragma unroll
-                for (int r = 0; r < NV; ++r) { st.acc[r].x *= scale; st.acc[r].y *= scale; st.acc[r].z *= scale; st.acc[r].w *= scale; }
+                for (int e = 0; e < DCAP; ++e) { s[e] = score(sl, e, a[e], wx[e], wy[e], wz[e]); m_new = fmaxf(m_new, s[e]); }
+            } else {
+#pragma unroll
+                for (int e = 0; e < DCAP; ++e)
+                    if (e < itC.cnt) { s[e] = score(sl, e, a[e], wx[e], wy[e], wz[e]); m_new = fmaxf(m_new, s[e]); }
             }
-            st.m_run = m_new;
+            if (m_new > st.m_run) {                          // online softmax: rescale what earlier chunks accumulated
+                if (st.m_run != -CUDART_INF_F) {
+                    const float scale = ex2_approx(st.m_run - m_new);
+                    st.l_run *= scale; st.ea_acc *= scale;
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) { st.acc[r].x *= scale; st.acc[r].y *= scale; st.acc[r].z *= scale; st.acc[r].w *= scale; }
+                }
+                st.m_run = m_new;
+            }
         }
         if (itC.cnt == DCAP) {
 #pragma unroll
-            for (int e = 0; e < DCAP; ++e) accumulate(sl, e, w ? ex2_approx(s[e] - st.m_run) : 1.f, a[e], wx[e], wy[e], wz[e]);
+            for (int e = 0; e < DCAP; ++e)
+                accumulate(sl, e, w ? ex2_approx(s[e] - st.m_run) : 1.f, a[e], wx[e], wy[e], wz[e], (wrapped_mask >> e) & 1u);
         } else {
 #pragma unroll
             for (int e = 0; e < DCAP; ++e)
-                if (e < itC.cnt) accumulate(sl, e, w ? ex2_approx(s[e] - st.m_run) : 1.f, a[e], wx[e], wy[e], wz[e]);
+                if (e < itC.cnt) accumulate(sl, e, w ? ex2_approx(s[e] - st.m_run) : 1.f, a[e], wx[e], wy[e], wz[e], (wrapped_mask >> e) & 1u);
         }
         if (itC.last) {
             const float inv = w ? 1.0f / (st.l_run + 1e-16f) : 1.0f;      // PyG softmax: exp(s - max) / (sum + 1e-16)
+            const float lsum = st.l_run;
             if (active) {
                 float* orow = p.agg + (size_t)itC.node * p.ld_agg + grp * C + 4 * sub;
                 float* lrow = p.agg_lo ? p.agg_lo + (size_t)itC.node * p.ld_agg + grp * C + 4 * sub : nullptr;
 #pragma unroll
                 for (int r = 0; r < NV; ++r) {
-                    const float4 o = make_float4(st.acc[r].x * inv, st.acc[r].y * inv, st.acc[r].z * inv, st.acc[r].w * inv);
+                    // sum pe * relu(.) = sum pe * max(., nvp) - nvp * sum pe
+                    const float4 o = make_float4(fmaf(-st.vp[r].x, lsum, st.acc[r].x) * inv, fmaf(-st.vp[r].y, lsum, st.acc[r].y) * inv,
+                                                 fmaf(-st.vp[r].z, lsum, st.acc[r].z) * inv, fmaf(-st.vp[r].w, lsum, st.acc[r].w) * inv);
                     if (lrow) {   // TF32 split for the tensor-core gate GEMM: agg = hi + lo, both TF32-representable
                         const float4 hi = make_float4(tf32_rna(o.x), tf32_rna(o.y), tf32_rna(o.z), tf32_rna(o.w));
                         const float4 lo = make_float4(tf32_rna(o.x - hi.x), tf32_rna(o.y - hi.y), tf32_rna(o.z - hi.z), tf32_rna(o.w - hi.w));
@@ -576,9 +577,28 @@ pgat_gather_tma_kernel(const GatherParams p) {
             }
         }
         __syncwarp();                                        // every lane is done with this slot before it is refilled
-        itC = itI; mjC = mjI; maC = maI;
-        itI = itM; mjI = mjM; maI = maM;
-        slot ^= 1;
+    };
+
+    // 3-deep software pipeline, unrolled by two so that slot ids are compile-time constants:
+    //   stage M: source ids of item k+2 | stage I: bulk copies of item k+1 | stage C: compute item k
+    Item itA = cur.next(), itB, itN;
+    int mjA, mjB, mjN; float maA, maB, maN;
+    load_meta(itA, mjA, maA);
+    itB = cur.next();
+    load_meta(itB, mjB, maB);
+    if (itA.valid) issue(itA, mjA, 0);
+    uint32_t par = 0u;
+    while (itA.valid) {
+        itN = cur.next(); load_meta(itN, mjN, maN);
+        if (itB.valid) issue(itB, mjB, 1);
+        compute(itA, maA, slot_addr0, bar_addr0, par);
+        itA = itN; mjA = mjN; maA = maN;                     // A now holds item k+2 (to be issued into slot 0)
+        if (!itB.valid) break;
+        itN = cur.next(); load_meta(itN, mjN, maN);
+        if (itA.valid) issue(itA, mjA, 0);
+        compute(itB, maB, slot_addr0 + SLOT, bar_addr0 + 8u, par);
+        itB = itN; mjB = mjN; maB = maN;
+        par ^= 1u;
     }
 }
 
