@@ -98,21 +98,19 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                                  ptr(pk.Wcat[t]), pk.kin[t], ptr(pk.bcat[t]),
                                  ptr(P[t]), pk.ncols[t], n, pk.ncols[t], st), 'gg_node_proj')
         # (b) fused gather per edge type
-        agg, agg_lo, ea = {}, {}, {}
+        agg, ea = {}, {}
         for e in pk.edge_types:
             s, _, d = e
             nd = xpad[d].shape[0]
             nd_out = nd if n_rows is None else n_rows[d]
             agg[e] = buf(('agg', e), (nd, GC))
-            if use_tc:
-                agg_lo[e] = buf(('agg_lo', e), (nd, GC))
             ea[e] = buf(('ea', e), (nd, G))
             g = csr[e]
             check(L.gg_pgat_gather(ptr(P[s]), pk.ncols[s], pk.koff[e], pk.voff[e],
                                    ptr(P[d]), pk.ncols[d], pk.qoff[e], pk.qxoff[e],
                                    ptr(xpad[s]), xpad[s].stride(0), ptr(xpad[d]), xpad[d].stride(0),
                                    ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(pk.Wv3[e]),
-                                   nd_out, G, C, 1 if pk.weighted else 0, ptr(agg[e]), ptr(agg_lo[e]) if use_tc else None,
+                                   nd_out, G, C, 1 if pk.weighted else 0, ptr(agg[e]), None,
                                    GC, ptr(ea[e]), st), 'gg_pgat_gather')
         # (c') gate GEMM + LSTM update per node type
         out_h = {} if out_h is None else out_h
@@ -142,10 +140,8 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                     from .packing import tc_gate_weight_layout
                     pk.tcG[t] = tc_gate_weight_layout(pk, t)
                 ghi, glo, ktot = pk.tcG[t]
-                lo_arr = (ctypes.c_void_p * len(ins))(*[agg_lo[e].data_ptr() for e in ins])
-                kp = 32 + (0 if ht is None else ht.shape[1])
-                ahi, alo = buf(('Ahi', t), (n, kp)), buf(('Alo', t), (n, kp))      # written by gg_split_tf32 above
-                check(L.gg_gate_update_tc(arr, lo_arr, len(ins), ptr(ahi), ptr(alo), kp, 0 if ht is None else 1,
+                check(L.gg_gate_update_tc(arr, len(ins), ptr(x), x.stride(0), pk.k1p[t],
+                                          ptr(ht), 0 if ht is None else ht.stride(0),
                                           ptr(ghi), ptr(glo), ktot, ptr(pk.btot[t]), ptr(ct), ptr(out_h[t]),
                                           ptr(out_c[t]) if lstm else None, n_out, G, C, mode, 0, st), 'gg_gate_update_tc')
                 continue

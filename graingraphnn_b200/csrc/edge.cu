@@ -255,3 +255,39 @@ extern "C" int gg_scatter_rows(const float* src, int32_t ld_src, const int32_t* 
     GG_LAUNCH_OK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// (a7) SAGEConv mean aggregation (heterogclstm.py:52-54 -> PyG SAGEConv(aggr='mean')): out[i, :] = mean over the
+// in-edges of i of src[col[e], :], 0 for rows without in-edges.  One warp per target row, float4 columns, the row's
+// edges summed in CSR (= original) order and divided once, like scatter(..., reduce='mean') = sum / max(count, 1).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+segment_mean_kernel(const float* __restrict__ src, int ld_src, int width, const int* __restrict__ rowptr,
+                    const int* __restrict__ col, int n_dst, float* __restrict__ out, int ld_out) {
+    const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (row >= n_dst) return;
+    const int beg = __ldg(&rowptr[row]), end = __ldg(&rowptr[row + 1]);
+    const float inv = end > beg ? 1.0f / (float)(end - beg) : 0.f;
+    for (int c = 4 * lane; c < width; c += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = beg; e < end; ++e) {
+            const float4 v = ldg4(src + (size_t)__ldg(&col[e]) * ld_src + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)row * ld_out + c) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+}
+}  // namespace
+
+extern "C" int gg_segment_mean(const float* src, int32_t ld_src, int32_t width, const int32_t* rowptr, const int32_t* col,
+                               int32_t n_dst, float* out, int32_t ld_out, void* stream) {
+    if (n_dst < 0 || width < 0 || (width & 3)) return GG_EINVAL;
+    if (n_dst == 0 || width == 0) return 0;
+    if (!src || !rowptr || !col || !out) return GG_EINVAL;
+    if (!gg_aligned16(src) || !gg_aligned16(out) || (ld_src & 3) || (ld_out & 3)) return GG_EALIGN;
+    const unsigned nb = (unsigned)(((int64_t)n_dst * 32 + 255) / 256);
+    segment_mean_kernel<<<nb, 256, 0, GG_STREAM(stream)>>>(src, ld_src, width, rowptr, col, n_dst, out, ld_out);
+    GG_LAUNCH_OK();
+    return 0;
+}

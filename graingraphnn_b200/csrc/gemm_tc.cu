@@ -231,22 +231,31 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 // gg_gate_update_tc: per 128-node tile and gate g, D_g[128, C] (TMEM columns [g*C, (g+1)*C)) accumulates
 //   sum over K chunks of  A_chunk (agg of every incoming edge type, then X, then h)  x  Wall[g*C + n, k]   (3xTF32),
 // then the epilogue adds the rank-1 terms (lin_edge, lin_l2 bias, gate bias) and applies the LSTM update.
-constexpr int GK_STAGES = 6;
-constexpr int G_A_BYTES = BM * BK * 4;                  // 16 KB
-constexpr int G_B_BYTES = 128 * BK * 4;                 // up to C = 128 rows: 16 KB (TMA box is C rows)
-constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
-constexpr int G_SMEM_BYTES = GK_STAGES * G_STAGE_BYTES + 1024 + 256 + 5 * 4 * 128 * 4;   // + epilogue vectors (G*C <= 512 floats each)
+//
+// All A operands arrive as plain fp32 (the aggregate written by gg_pgat_gather, the node features, the hidden state):
+// the TF32 hi/lo split happens INSIDE the kernel.  TMA lands the fp32 [128 x 32] chunk in a ring slot, four converter
+// warps rewrite it in place as hi = rna_tf32(a) and put lo = a - hi into a 2-deep side ring (same 128-byte-swizzled
+// layout, the split is elementwise), then ONE stage feeds 12 MMAs: (lo, W_hi), (hi, W_lo), (hi, W_hi) x 4 k-steps.
+// Against loading pre-split operands per term this moves 16 KB instead of 48 KB of A per chunk from L2 and needs no
+// agg_lo / A_hi / A_lo tensors in HBM at all.
+//
+// Warp roles (384 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-7 epilogue | 8-11 hi/lo converters.
+constexpr int G_A_BYTES = BM * BK * 4;                  // 16 KB: fp32 chunk, rewritten in place as its TF32 hi part
+constexpr int G_W_BYTES = 128 * BK * 4;                 // up to C = 128 rows: 16 KB (the TMA box is C rows)
+constexpr int G_LO_RING = 2;
+constexpr int G_VEC_FLOATS = 5 * 4 * 128;               // epilogue vectors (5 x G*C <= 512 floats)
+constexpr int kGateThreads = 384;
 constexpr int kMaxIn = 2;
 
 struct GateMaps {
-    CUtensorMap agg_hi[kMaxIn], agg_lo[kMaxIn];
-    CUtensorMap a_hi, a_lo;         // [X padded to 32 | h]
+    CUtensorMap agg[kMaxIn];        // fp32 [M, G*C]
+    CUtensorMap x, h;               // fp32 [M, K1] (box 32 columns, zero-filled beyond K1) and [M, C]
     CUtensorMap w_hi, w_lo;         // Wall [G*C, Ktot]
 };
 struct GateEpi {
     const float* ea[kMaxIn]; const int* rowptr[kMaxIn]; const float* We[kMaxIn]; const float* b2[kMaxIn]; int weighted[kMaxIn];
     const float* btot; const float* c_in; float* out_h; float* out_c;
-    int n_in, M, G, C, has_h, mode;
+    int n_in, M, G, C, has_h, mode, stages;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -257,28 +266,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "r"(taddr));
 }
 
+// sigmoid / tanh through ex2.approx + rcp.approx (relative error ~2^-22 each; saturate correctly at +-inf)
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(-2.0f, fast_rcp(1.0f + fast_ex2(2.8853900817779268f * x)), 1.0f); }
+
 template <int G, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kGateThreads, 1)
 gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
     extern __shared__ uint8_t smem_raw[];
+    const int C = ep.C, CC = C / BK, GC = G * C;
+    const int S = ep.stages;
+    const uint32_t w_bytes = (uint32_t)C * BK * 4;                        // one W tile (hi or lo)
+    const uint32_t slot_bytes = G_A_BYTES + 2 * w_bytes;                  // [A fp32 -> hi | W_hi | W_lo], 1024-B multiples
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + GK_STAGES * G_STAGE_BYTES;
+    const uint32_t lo_base = smem_base + S * slot_bytes;
+    const uint32_t bar_base = lo_base + G_LO_RING * G_A_BYTES;
+    // barriers: full[S] | conv[S] | empty[S] | lo_free[2] | tfull | tempty
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (GK_STAGES + s); };
-    const uint32_t tfull_bar = bar_base + 8u * (2 * GK_STAGES), tempty_bar = tfull_bar + 8u;
+    auto conv_bar = [&](int s) { return bar_base + 8u * (S + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+    auto lofree_bar = [&](int j) { return bar_base + 8u * (3 * S + j); };
+    const uint32_t tfull_bar = bar_base + 8u * (3 * S + G_LO_RING), tempty_bar = tfull_bar + 8u;
     const uint32_t tmem_slot = tempty_bar + 8u;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     // per-column epilogue vectors, staged once: [We0 | b2_0 | We1 | b2_1 | btot], each G*C floats
     float* vecs = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int C = ep.C, CC = C / BK, GC = G * C;
     const int n_in = ep.n_in;
     const int n_tiles = (ep.M + BM - 1) / BM;
-    const int nck = n_in * CC + 1 + (ep.has_h ? CC : 0);             // K chunks per gate
-    const uint32_t stage_tx = (uint32_t)(G_A_BYTES + C * BK * 4);
+    const int nck = n_in * CC + 1 + (ep.has_h ? CC : 0);                 // K chunks per gate
+    const uint32_t stage_tx = (uint32_t)G_A_BYTES + 2u * w_bytes;
 
-    for (int i = threadIdx.x; i < GC; i += kThreads) {
+    for (int i = threadIdx.x; i < GC; i += kGateThreads) {
         vecs[i] = __ldg(&ep.We[0][i]);
         vecs[GC + i] = __ldg(&ep.b2[0][i]);
         vecs[2 * GC + i] = n_in > 1 ? __ldg(&ep.We[1][i]) : 0.f;
@@ -286,7 +308,8 @@ gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
         vecs[4 * GC + i] = __ldg(&ep.btot[i]);
     }
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < GK_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int j = 0; j < G_LO_RING; ++j) mbar_init(lofree_bar(j), 1);
         mbar_init(tfull_bar, 1); mbar_init(tempty_bar, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -300,55 +323,89 @@ gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
+        // ===== TMA producer: one fp32 A chunk + the matching W_hi / W_lo tiles per stage =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int m0 = t * BM;
                 for (int g = 0; g < G; ++g)
-                    for (int term = 0; term < 3; ++term)
-                        for (int ck = 0; ck < nck; ++ck) {
-                            const CUtensorMap* am;
-                            int acol;
-                            if (ck < n_in * CC) {
-                                const int e = ck / CC;
-                                am = term == 0 ? &maps.agg_lo[e] : &maps.agg_hi[e];
-                                acol = g * C + (ck % CC) * BK;
-                            } else {
-                                am = term == 0 ? &maps.a_lo : &maps.a_hi;
-                                acol = (ck - n_in * CC) * BK;
-                            }
-                            mbar_wait(empty_bar(stage), phase ^ 1u);
-                            mbar_expect_tx(full_bar(stage), stage_tx);
-                            const uint32_t sa = smem_base + stage * G_STAGE_BYTES, sb = sa + G_A_BYTES;
-                            tma_load_2d(sa, am, full_bar(stage), acol, m0);
-                            tma_load_2d(sb, term == 1 ? &maps.w_lo : &maps.w_hi, full_bar(stage), ck * BK, g * C);
-                            if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
-                        }
+                    for (int ck = 0; ck < nck; ++ck) {
+                        const CUtensorMap* am;
+                        int acol;
+                        if (ck < n_in * CC) { am = &maps.agg[ck / CC]; acol = g * C + (ck % CC) * BK; }
+                        else if (ck == n_in * CC) { am = &maps.x; acol = 0; }
+                        else { am = &maps.h; acol = (ck - n_in * CC - 1) * BK; }
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), stage_tx);
+                        const uint32_t sa = smem_base + stage * slot_bytes;
+                        tma_load_2d(sa, am, full_bar(stage), acol, m0);
+                        tma_load_2d(sa + G_A_BYTES, &maps.w_hi, full_bar(stage), ck * BK, g * C);
+                        tma_load_2d(sa + G_A_BYTES + w_bytes, &maps.w_lo, full_bar(stage), ck * BK, g * C);
+                        if (++stage == S) { stage = 0; phase ^= 1u; }
+                    }
             }
         }
     } else if (warp == 1) {
+        // ===== MMA issuer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, tphase = 0;
+            int lo = 0;
             const uint32_t idesc = make_idesc(BM, C);
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 mbar_wait(tempty_bar, tphase ^ 1u);
                 tc_fence_after();
                 for (int g = 0; g < G; ++g) {
                     const uint32_t tmem_d = tmem_base + (uint32_t)(g * C);
-                    for (int it = 0; it < 3 * nck; ++it) {
-                        mbar_wait(full_bar(stage), phase);
+                    for (int ck = 0; ck < nck; ++ck) {
+                        mbar_wait(conv_bar(stage), phase);          // TMA landed AND the chunk is split into hi / lo
                         tc_fence_after();
-                        const uint32_t sa = smem_base + stage * G_STAGE_BYTES, sb = sa + G_A_BYTES;
-                        const uint64_t adesc = make_desc(sa), bdesc = make_desc(sb);
+                        const uint32_t sa = smem_base + stage * slot_bytes;
+                        const uint64_t hdesc = make_desc(sa), ldesc = make_desc(lo_base + lo * G_A_BYTES);
+                        const uint64_t whdesc = make_desc(sa + G_A_BYTES), wldesc = make_desc(sa + G_A_BYTES + w_bytes);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k)
-                            umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) ? 1u : 0u);
+                        for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, ldesc + 2u * k, whdesc + 2u * k, idesc, (ck | k) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, hdesc + 2u * k, wldesc + 2u * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, hdesc + 2u * k, whdesc + 2u * k, idesc, 1u);
                         umma_commit(empty_bar(stage));
-                        if (++stage == GK_STAGES) { stage = 0; phase ^= 1u; }
+                        umma_commit(lofree_bar(lo));
+                        if (++stage == S) { stage = 0; phase ^= 1u; }
+                        lo ^= 1;
                     }
                 }
                 umma_commit(tfull_bar);
                 tphase ^= 1u;
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== converters: fp32 chunk -> (hi in place, lo into the side ring), 128 threads, 8 float4 each =====
+        const int ct = threadIdx.x - 256;
+        int stage = 0; uint32_t phase = 0;
+        int lo = 0; uint32_t lphase = 0u;                      // bit j = phase of lo-ring slot j
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int it = 0; it < G * nck; ++it) {
+                mbar_wait(full_bar(stage), phase);
+                mbar_wait(lofree_bar(lo), ((lphase >> lo) & 1u) ^ 1u);
+                const uint32_t sa = smem_base + stage * slot_bytes + 16u * ct;
+                const uint32_t la = lo_base + lo * G_A_BYTES + 16u * ct;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t a0, a1, a2, a3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(sa + 2048u * j));
+                    const uint32_t h0 = (a0 + 0x1000u) & 0xFFFFE000u, h1 = (a1 + 0x1000u) & 0xFFFFE000u;
+                    const uint32_t h2 = (a2 + 0x1000u) & 0xFFFFE000u, h3 = (a3 + 0x1000u) & 0xFFFFE000u;
+                    const float l0 = __uint_as_float(a0) - __uint_as_float(h0), l1 = __uint_as_float(a1) - __uint_as_float(h1);
+                    const float l2 = __uint_as_float(a2) - __uint_as_float(h2), l3 = __uint_as_float(a3) - __uint_as_float(h3);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 2048u * j), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(la + 2048u * j), "f"(l0), "f"(l1), "f"(l2), "f"(l3) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) mbar_arrive(conv_bar(stage));
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+                lphase ^= 1u << lo;
+                lo ^= 1;
             }
         }
     } else if (warp >= 4) {
@@ -434,10 +491,10 @@ gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
                     float hn[16], cn[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float c2 = sigmoidf_(pre[0][j]) * tanhf(pre[gc < G ? gc : 0][j]);
-                        if (lstm) c2 = sigmoidf_(pre[1 < G ? 1 : 0][j]) * cold[j] + c2;
+                        float c2 = fast_sigmoid(pre[0][j]) * fast_tanh(pre[gc < G ? gc : 0][j]);
+                        if (lstm) c2 = fmaf(fast_sigmoid(pre[1 < G ? 1 : 0][j]), cold[j], c2);
                         cn[j] = c2;
-                        hn[j] = sigmoidf_(pre[go < G ? go : 0][j]) * tanhf(c2);
+                        hn[j] = fast_sigmoid(pre[go < G ? go : 0][j]) * fast_tanh(c2);
                     }
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -567,55 +624,62 @@ extern "C" int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp,
     return 0;
 }
 
-// Tensor-core variant of gg_gate_update.  agg_hi/agg_lo: TF32 split of the aggregated values written by gg_pgat_gather
-// (agg_lo != NULL), A_hi/A_lo: the [X padded to 32 | h] split shared with gg_node_proj_tc, W_hi/W_lo: Wall [G*C, Ktot] with
-// Ktot = n_inputs*C + 32 (+ C when has_h), K layout [W2 of input 0 | W2 of input 1 | skip(X, 32) | skip(h)].
-extern "C" int gg_gate_update_tc(const gg_agg_input* inputs, const float* const* agg_lo, int32_t n_inputs,
-                                 const float* A_hi, const float* A_lo, int32_t Kp, int32_t has_h,
+// Tensor-core variant of gg_gate_update.  All A operands are plain fp32 and split into TF32 hi / lo inside the kernel:
+// inputs[e].agg [M, G*C] (gg_pgat_gather), X [M, K1 <= 32] (zero-extended to 32 columns by the TMA box), H [M, C] or NULL.
+// W_hi/W_lo: Wall [G*C, Ktot] with Ktot = n_inputs*C + 32 (+ C with H), K layout [W2 of input 0 | W2 of input 1 | skip(X, 32) | skip(h)].
+extern "C" int gg_gate_update_tc(const gg_agg_input* inputs, int32_t n_inputs,
+                                 const float* X, int32_t ldx, int32_t K1, const float* H, int32_t ldh,
                                  const float* W_hi, const float* W_lo, int32_t Ktot, const float* btot,
                                  const float* c_in, float* out_h, float* out_c,
                                  int32_t M, int32_t G, int32_t C, int32_t mode, int32_t n_sms, void* stream) {
     if (M < 0 || G < 1 || G > 4 || C % 32 || C < 32 || C > 128 || n_inputs < 1 || n_inputs > kMaxIn) return GG_EINVAL;
     if (mode < GG_GATE_RAW || mode > GG_GATE_LSTM0) return GG_EINVAL;
     if ((mode == GG_GATE_LSTM && G != 4) || (mode == GG_GATE_LSTM0 && G != 3) || (mode == GG_GATE_RELU && G != 1)) return GG_EINVAL;
-    if (Kp != 32 + (has_h ? C : 0) || Ktot != n_inputs * C + Kp) return GG_EINVAL;
+    if (K1 < 4 || K1 > 32 || (K1 & 3) || Ktot != n_inputs * C + 32 + (H ? C : 0)) return GG_EINVAL;
     if (M == 0) return 0;
-    if (!inputs || !agg_lo || !A_hi || !A_lo || !W_hi || !W_lo || !btot || !out_h) return GG_EINVAL;
+    if (!inputs || !X || !W_hi || !W_lo || !btot || !out_h) return GG_EINVAL;
     if (!gg_aligned16(out_h) || (out_c && !gg_aligned16(out_c)) || (c_in && !gg_aligned16(c_in))) return GG_EALIGN;
     GateMaps maps;
     GateEpi ep;
     int rc;
     for (int e = 0; e < n_inputs; ++e) {
         const gg_agg_input& s = inputs[e];
-        if (!s.agg || !agg_lo[e] || !s.ea || !s.rowptr || !s.We || !s.b2) return GG_EINVAL;
-        if ((rc = make_map(&maps.agg_hi[e], s.agg, M, (int64_t)G * C, s.ld_agg, BM))) return rc;
-        if ((rc = make_map(&maps.agg_lo[e], agg_lo[e], M, (int64_t)G * C, s.ld_agg, BM))) return rc;
+        if (!s.agg || !s.ea || !s.rowptr || !s.We || !s.b2) return GG_EINVAL;
+        if ((rc = make_map(&maps.agg[e], s.agg, M, (int64_t)G * C, s.ld_agg, BM))) return rc;
         ep.ea[e] = s.ea; ep.rowptr[e] = s.rowptr; ep.We[e] = s.We; ep.b2[e] = s.b2; ep.weighted[e] = s.weighted;
     }
     for (int e = n_inputs; e < kMaxIn; ++e) {
-        maps.agg_hi[e] = maps.agg_hi[0]; maps.agg_lo[e] = maps.agg_lo[0];
+        maps.agg[e] = maps.agg[0];
         ep.ea[e] = nullptr; ep.rowptr[e] = nullptr; ep.We[e] = nullptr; ep.b2[e] = nullptr; ep.weighted[e] = 0;
     }
-    if ((rc = make_map(&maps.a_hi, A_hi, M, Kp, Kp, BM))) return rc;
-    if ((rc = make_map(&maps.a_lo, A_lo, M, Kp, Kp, BM))) return rc;
+    if ((rc = make_map(&maps.x, X, M, K1, ldx, BM))) return rc;
+    if (H) { if ((rc = make_map(&maps.h, H, M, C, ldh, BM))) return rc; } else maps.h = maps.x;
     if ((rc = make_map(&maps.w_hi, W_hi, (int64_t)G * C, Ktot, Ktot, C))) return rc;
     if ((rc = make_map(&maps.w_lo, W_lo, (int64_t)G * C, Ktot, Ktot, C))) return rc;
     ep.btot = btot; ep.c_in = c_in; ep.out_h = out_h; ep.out_c = out_c;
-    ep.n_in = n_inputs; ep.M = M; ep.G = G; ep.C = C; ep.has_h = has_h ? 1 : 0; ep.mode = mode;
+    ep.n_in = n_inputs; ep.M = M; ep.G = G; ep.C = C; ep.has_h = H ? 1 : 0; ep.mode = mode;
     if (n_sms <= 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    // ring depth: as many [A | W_hi | W_lo] slots as fit beside the lo ring, the epilogue vectors and the barriers
+    const int slot_bytes = G_A_BYTES + 2 * C * BK * 4;
+    const int fixed = 1024 + G_LO_RING * G_A_BYTES + 256 + G_VEC_FLOATS * 4;
+    int stages = (227 * 1024 - fixed) / slot_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) return GG_EINVAL;
+    ep.stages = stages;
+    const int smem_bytes = fixed + stages * slot_bytes;
     const int tiles = (M + BM - 1) / BM;
     const int grid = tiles < n_sms ? tiles : n_sms;
     cudaStream_t st = GG_STREAM(stream);
     cudaError_t err = cudaSuccess;
 #define GG_LAUNCH_GATE(GV, MV)                                                                                              \
     do {                                                                                                                    \
-        err = cudaFuncSetAttribute(gate_update_tc_kernel<GV, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES); \
+        err = cudaFuncSetAttribute(gate_update_tc_kernel<GV, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
         if (err != cudaSuccess) return (int)err;                                                                            \
-        gate_update_tc_kernel<GV, MV><<<grid, kThreads, G_SMEM_BYTES, st>>>(maps, ep);                                      \
+        gate_update_tc_kernel<GV, MV><<<grid, kGateThreads, smem_bytes, st>>>(maps, ep);                                    \
     } while (0)
     if (mode == GG_GATE_LSTM) GG_LAUNCH_GATE(4, GG_GATE_LSTM);
     else if (mode == GG_GATE_LSTM0) GG_LAUNCH_GATE(3, GG_GATE_LSTM0);

@@ -145,16 +145,26 @@ int gg_gate_update(const gg_agg_input* inputs_host, int32_t n_inputs,
                    int32_t M, int32_t G, int32_t C, int32_t mode, void* stream);
 
 /* Tensor-core variant of gg_gate_update (tcgen05 kind::tf32, 3xTF32, TMEM accumulators: gate g in columns [g*C,(g+1)*C)).
- *   inputs[e].agg / agg_lo[e]: TF32 split of the aggregate (gg_pgat_gather with agg_lo); A_hi/A_lo: the [X padded to 32 | h]
- *   split shared with gg_node_proj_tc (Kp = 32 + C, or 32 when has_h == 0); W_hi/W_lo: Wall [G*C, Ktot], row g*C+n, K layout
- *   [lin_l2 of input 0 (C) | lin_l2 of input 1 (C) | summed lin_skip on X (32) | on h (C)], Ktot = n_inputs*C + Kp.
+ *   Every A operand is plain fp32 and is split into TF32 hi / lo INSIDE the kernel (converter warps, shared memory):
+ *   inputs[e].agg [M, G*C] as written by gg_pgat_gather (agg_lo == NULL), X [M, K1] with 4 <= K1 <= 32 (the TMA box
+ *   zero-extends it to 32 columns), H [M, C] or NULL (encoder).  W_hi/W_lo: Wall [G*C, Ktot], row g*C+n, K layout
+ *   [lin_l2 of input 0 (C) | lin_l2 of input 1 (C) | summed lin_skip on X (32) | on h (C)], Ktot = n_inputs*C + 32 (+ C).
  *   inputs[e].W2 is ignored (it lives in Wall); We, b2, ea, rowptr, weighted are used by the epilogue. 1 <= n_inputs <= 2.
+ *   X, H, agg rows must be 16-byte aligned with leading dimensions that are multiples of 4 floats.
  */
-int gg_gate_update_tc(const gg_agg_input* inputs_host, const float* const* agg_lo_host, int32_t n_inputs,
-                      const float* A_hi, const float* A_lo, int32_t Kp, int32_t has_h,
+int gg_gate_update_tc(const gg_agg_input* inputs_host, int32_t n_inputs,
+                      const float* X, int32_t ldx, int32_t K1, const float* H /* nullable */, int32_t ldh,
                       const float* W_hi, const float* W_lo, int32_t Ktot, const float* btot,
                       const float* c_in /* nullable */, float* out_h, float* out_c /* nullable */,
                       int32_t M, int32_t G, int32_t C, int32_t mode, int32_t n_sms, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a7) SAGEConv mean aggregation for HeteroGCLSTM / HeteroGC (heterogclstm.py:52-54, PyG SAGEConv aggr='mean'):
+ *      out[i, 0:width] = mean_{e -> i} src[col[e], 0:width], 0 for rows without in-edges.  width % 4 == 0.
+ *      The lin_l / lin_r GEMMs and the gate math that follow run in gg_gate_update on [mean_e0 | mean_e1 | X] and h.
+ * ---------------------------------------------------------------------------------------------- */
+int gg_segment_mean(const float* src, int32_t ld_src, int32_t width, const int32_t* rowptr, const int32_t* col,
+                    int32_t n_dst, float* out, int32_t ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (d) heads.

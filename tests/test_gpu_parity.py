@@ -216,6 +216,47 @@ def test_pgc_cell_matches_golden():
     assert torch.equal(cc['grain'].cpu(), c['grain'])
 
 
+def test_gclstm_sage_cell_matches_reference_golden():
+    """HeteroGCLSTM (SAGEConv gates, heterogclstm.py:125-196) with the state_dict the reference module produced."""
+    import os
+    from util import GOLDEN
+    from graingraphnn_b200.heterogclstm import HeteroGCLSTM
+    x, ei, ea = load_graph('c1')
+    g = load_golden('c1')
+    h, c = orc.encode_decode(orc.synth_state_dict('regressor', 1), x, ei, ea)
+    gsd = torch.load(os.path.join(GOLDEN, 'gclstm_state_dict.pt'))
+    cell = HeteroGCLSTM({'grain': 11, 'joint': 8}, 96, (['grain', 'joint'], list(ET)))
+    res = cell.load_state_dict(gsd)
+    assert not res.missing_keys and not res.unexpected_keys
+    hh, cc = cell.to(dev())(to_dev(x), to_dev(ei), to_dev(h), to_dev(c))
+    assert rel_err(hh['joint'], g['gclstm_h_joint']) < TOL and rel_err(cc['grain'], g['gclstm_c_grain']) < TOL
+    href, cref = orc.gclstm_cell({'cell.' + k: v for k, v in gsd.items()}, 'cell', x, ei, h, c)
+    assert all(rel_err(hh[t], href[t]) < TOL and rel_err(cc[t], cref[t]) < TOL for t in x)
+    # zero-initialised states (h_dict = c_dict = None, heterogclstm.py:101-109)
+    hh0, cc0 = cell(to_dev(x), to_dev(ei))
+    href0, cref0 = orc.gclstm_cell({'cell.' + k: v for k, v in gsd.items()}, 'cell', x, ei)
+    assert all(rel_err(hh0[t], href0[t]) < TOL and rel_err(cc0[t], cref0[t]) < TOL for t in x)
+
+
+def test_gc_sage_layer_matches_oracle_on_ragged_graph():
+    """HeteroGC = relu(HeteroConv{SAGEConv}(x)) (heterogclstm.py:236-275) incl. rows without in-edges (mean = 0)."""
+    from graingraphnn_b200.heterogclstm import HeteroGC
+    torch.manual_seed(3)
+    n = {'grain': 57, 'joint': 130}
+    x = {'grain': torch.rand(57, 11), 'joint': torch.rand(130, 8)}
+    ei = {ET[0]: random_graph(57, 130, 300, 1), ET[1]: random_graph(130, 57, 200, 2, hub=5), ET[2]: random_graph(130, 130, 390, 3)}
+    ei[ET[2]] = ei[ET[2]][:, ei[ET[2]][1] % 7 != 0]          # some joints receive nothing over this edge type
+    cell = HeteroGC(n_in := {'grain': 11, 'joint': 8}, 64, (['grain', 'joint'], list(ET)))
+    sd = cell.state_dict()
+    ref = {}
+    for et in ET:
+        o = orc.sage_conv(sd, 'conv_i.convs.' + '__'.join(et), x[et[0]], x[et[2]], ei[et])
+        ref[et[2]] = ref.get(et[2], 0) + o
+    out = cell.to(dev())(to_dev(x), to_dev(ei))
+    assert set(out) == {'grain', 'joint'} and out['joint'].shape == (130, 64)
+    assert all(rel_err(out[t], torch.relu(ref[t])) < TOL for t in n)
+
+
 # ------------------------------------------------------------------------------------------------ models
 @pytest.mark.parametrize('gemm', ['tc', 'simt'])
 @pytest.mark.parametrize('name', ['c1', 'c2'])

@@ -143,3 +143,25 @@ def test_packed_single_conv_matches_oracle(weighted):
     out, _ = emu_cell(pk, xpad, None, None, {et: (torch.from_numpy(rp), torch.from_numpy(col))},
                       {et: ea[ET[0]].reshape(-1)[torch.from_numpy(perm).long()]}, _lib.GG_GATE_RAW)
     assert rel_err(out['d'], ref) < 1e-6
+
+
+def test_sage_cells_have_the_reference_state_dict_layout():
+    """Keys / shapes / order of HeteroGCLSTM equal what the reference module produced (tests/golden/gclstm_state_dict.pt,
+    written by oracle/make_golden.py from /root/reference/heterogclstm.py); HeteroGC holds only conv_i."""
+    import os
+    from util import GOLDEN
+    from graingraphnn_b200.heterogclstm import HeteroGC, HeteroGCLSTM
+    gsd = torch.load(os.path.join(GOLDEN, 'gclstm_state_dict.pt'))
+    cell = HeteroGCLSTM({'grain': 11, 'joint': 8}, 96, (['grain', 'joint'], list(ET)))
+    sd = cell.state_dict()
+    assert list(sd.keys()) == list(gsd.keys())
+    assert all(sd[k].shape == gsd[k].shape for k in gsd)
+    assert not cell.load_state_dict(gsd).missing_keys
+    cell2 = copy.deepcopy(cell)
+    assert torch.equal(cell2.conv_o.conv(ET[1]).lin_l.weight, gsd['conv_o.convs.joint__pull__grain.lin_l.weight'])
+    gc = HeteroGC({'grain': 11, 'joint': 8}, 96, (['grain', 'joint'], list(ET)))
+    assert sorted(gc.state_dict()) == sorted(k for k in gsd if k.startswith('conv_i.')) or \
+        all(k.startswith('conv_i.') for k in gc.state_dict())
+    assert gc.conv_i.conv(ET[0]).lin_l.weight.shape == (96, 11) and gc.conv_i.conv(ET[0]).lin_r.weight.shape == (96, 8)
+    with pytest.raises(RuntimeError):
+        cell({'grain': torch.zeros(3, 11), 'joint': torch.zeros(4, 8)}, {})      # CPU tensors: no fallback
