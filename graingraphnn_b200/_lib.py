@@ -43,7 +43,7 @@ _OPTIONAL = {
     'gg_tc_supported': (_I, []),
     'gg_node_proj_tc': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P]),
     'gg_split_tf32': (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _P, _I, _I, _P]),
-    'gg_gate_update_tc': (_I, [POINTER(AggInput), _I, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'gg_gate_update_tc': (_I, [POINTER(AggInput), _I, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 
 

@@ -133,7 +133,7 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                 out_h[t] = torch.empty((n, C if lstm else GC), dtype=torch.float32, device=dev)
             if lstm and t not in out_c:
                 out_c[t] = torch.empty((n, C), dtype=torch.float32, device=dev)
-            if use_tc and 1 <= len(ins) <= 2:
+            if use_tc and 1 <= len(ins) <= 2 and (lstm or G == 1) and pk.k1p[t] <= 32 - (2 * G + 3):     # multi-gate RAW output stays on the fp32 SIMT kernel
                 if not hasattr(pk, 'tcG'):
                     pk.tcG = {}
                 if t not in pk.tcG:
@@ -142,7 +142,7 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                 ghi, glo, ktot = pk.tcG[t]
                 check(L.gg_gate_update_tc(arr, len(ins), ptr(x), x.stride(0), pk.k1p[t],
                                           ptr(ht), 0 if ht is None else ht.stride(0),
-                                          ptr(ghi), ptr(glo), ktot, ptr(pk.btot[t]), ptr(ct), ptr(out_h[t]),
+                                          ptr(ghi), ptr(glo), ktot, ptr(ct), ptr(out_h[t]),
                                           ptr(out_c[t]) if lstm else None, n_out, G, C, mode, 0, st), 'gg_gate_update_tc')
                 continue
             check(L.gg_gate_update(arr, len(ins), ptr(x), x.stride(0), pk.k1p[t],

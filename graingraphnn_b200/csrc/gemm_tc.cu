@@ -14,6 +14,8 @@
 // (N*4 bytes per row) makes it co-limited by HBM writes: 128 KB per tile vs 6144 MMA cycles.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+#include <stdio.h>
 
 namespace {
 
@@ -233,29 +235,37 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 // then the epilogue adds the rank-1 terms (lin_edge, lin_l2 bias, gate bias) and applies the LSTM update.
 //
 // All A operands arrive as plain fp32 (the aggregate written by gg_pgat_gather, the node features, the hidden state):
-// the TF32 hi/lo split happens INSIDE the kernel.  TMA lands the fp32 [128 x 32] chunk in a ring slot, four converter
-// warps rewrite it in place as hi = rna_tf32(a) and put lo = a - hi into a 2-deep side ring (same 128-byte-swizzled
-// layout, the split is elementwise), then ONE stage feeds 12 MMAs: (lo, W_hi), (hi, W_lo), (hi, W_hi) x 4 k-steps.
-// Against loading pre-split operands per term this moves 16 KB instead of 48 KB of A per chunk from L2 and needs no
-// agg_lo / A_hi / A_lo tensors in HBM at all.
+// the TF32 hi/lo split happens INSIDE the kernel and the split operand lives in TENSOR MEMORY.  TMA lands the fp32
+// [128 x 32] chunk in a ring slot; eight converter warps (thread = half a row) read it and tcgen05.st  hi = the fp32 word
+// itself (the tensor core reads only the upper 19 bits of a TF32 operand) and lo = a - trunc_tf32(a) into the 64 TMEM
+// columns of that stage; ONE stage then feeds 12 MMAs in the A-from-TMEM form (tcgen05.mma [d], [a_tmem], b_desc):
+// (lo, W_hi), (hi, W_lo), (hi, W_hi) x 4 k-steps.  The rank-1 terms of the pre-activation (lin_edge x ea, lin_l2 bias x
+// [deg > 0], biases) are injected by the converters into the unused columns of the feature chunk, so they are added by the
+// tensor core too and the epilogue sees finished pre-activations.
+// Why A in TMEM: with 4-byte operands and N = C = 96 an SS-form MMA reads 7 KB of shared memory per 48 tensor cycles, more
+// than the 128 B/clk an SM delivers (measured: the SS version scaled with the SM count at ~20 B/clk/SM of TMA traffic, a
+// per-SM limit).  With A in TMEM the tensor core only fetches W from shared memory, the converters write no shared memory,
+// and no agg_lo / A_hi / A_lo tensors exist in HBM.  Measured limits now (scripts/kernel_bench.py, clock64 traces): the
+// single MMA-issuing thread (~60 clk per N = 96 MMA + ~400 clk of wait/fence/commit per stage vs 576 tensor clk).
 //
-// Warp roles (384 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-7 epilogue | 8-11 hi/lo converters.
+// Warp roles (512 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-7 epilogue | 8-15 hi/lo converters
+// (two warps per TMEM lane quarter, 16 of the chunk's 32 columns each).  setmaxnreg moves registers to the epilogue warps,
+// which keep one row of the LSTM state (C values) in registers across the four gate passes.
 constexpr int G_A_BYTES = BM * BK * 4;                  // 16 KB: fp32 chunk, rewritten in place as its TF32 hi part
-constexpr int G_W_BYTES = 128 * BK * 4;                 // up to C = 128 rows: 16 KB (the TMA box is C rows)
-constexpr int G_LO_RING = 2;
-constexpr int G_VEC_FLOATS = 5 * 4 * 128;               // epilogue vectors (5 x G*C <= 512 floats)
-constexpr int kGateThreads = 384;
+constexpr int kGateThreads = 512;
 constexpr int kMaxIn = 2;
 
 struct GateMaps {
     CUtensorMap agg[kMaxIn];        // fp32 [M, G*C]
     CUtensorMap x, h;               // fp32 [M, K1] (box 32 columns, zero-filled beyond K1) and [M, C]
     CUtensorMap w_hi, w_lo;         // Wall [G*C, Ktot]
+    CUtensorMap out_h, out_c;       // stores: [M, C] (LSTM modes) or [M, G*C] (RAW / RELU), box 128 x 32
 };
 struct GateEpi {
-    const float* ea[kMaxIn]; const int* rowptr[kMaxIn]; const float* We[kMaxIn]; const float* b2[kMaxIn]; int weighted[kMaxIn];
-    const float* btot; const float* c_in; float* out_h; float* out_c;
+    const float* ea[kMaxIn]; const int* rowptr[kMaxIn]; int weighted[kMaxIn];
+    const float* c_in; const float* out_c;
     int n_in, M, G, C, has_h, mode, stages;
+
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -266,51 +276,68 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+// A-from-TMEM form: A = [128 lanes x 8 columns] of 32-bit TF32 values at a_tmem (row m in lane m, k in column k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
 // sigmoid / tanh through ex2.approx + rcp.approx (relative error ~2^-22 each; saturate correctly at +-inf)
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return fmaf(-2.0f, fast_rcp(1.0f + fast_ex2(2.8853900817779268f * x)), 1.0f); }
 
-template <int G, int MODE>
+// Gates are processed one per PASS; pass p accumulates in TMEM buffer p & 1 (C columns each), so the epilogue of one gate
+// overlaps the MMAs of the next and the rest of tensor memory (512 - 2C columns) holds a deep ring of split A chunks.
+// LSTM (i,f,c,o) runs i, c~, f, o:  u = s(i);  u *= tanh(c~);  u = s(f) c + u (= c');  h' = s(o) tanh(u).
+// LSTM0 (i,c~,o) runs i, c~, o with c = 0.  u lives in the epilogue thread's registers (one row, C values).
+template <int G, int MODE> struct GatePasses {
+    static constexpr bool lstm = MODE == GG_GATE_LSTM, lstm0 = MODE == GG_GATE_LSTM0;
+    static constexpr int n = G;
+    __host__ __device__ static constexpr int gate(int p) { return lstm ? (p == 1 ? 2 : (p == 2 ? 1 : p)) : p; }
+};
+
+template <int G, int MODE, int NV>
 __global__ void __launch_bounds__(kGateThreads, 1)
 gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
+    using PS = GatePasses<G, MODE>;
+    static_assert(G == 1 || MODE == GG_GATE_LSTM || MODE == GG_GATE_LSTM0, "RAW / RELU run one gate");
     extern __shared__ uint8_t smem_raw[];
-    const int C = ep.C, CC = C / BK, GC = G * C;
+    constexpr int C = 32 * NV, CC = NV;
     const int S = ep.stages;
     const uint32_t w_bytes = (uint32_t)C * BK * 4;                        // one W tile (hi or lo)
     const uint32_t slot_bytes = G_A_BYTES + 2 * w_bytes;                  // [A fp32 -> hi | W_hi | W_lo], 1024-B multiples
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t lo_base = smem_base + S * slot_bytes;
-    const uint32_t bar_base = lo_base + G_LO_RING * G_A_BYTES;
-    // barriers: full[S] | conv[S] | empty[S] | lo_free[2] | tfull | tempty
+    const uint32_t stage_base = smem_base + S * slot_bytes;               // epilogue staging: one [128 x 32] output chunk (16 KB)
+    const uint32_t bar_base = stage_base + OUT_BYTES;
+    constexpr uint32_t a_col0 = 2u * C;                                   // split-A ring behind the two accumulator buffers
+    // Split-A ring slot s belongs to shared-memory stage s (S <= (512 - 2C) / 64): full[s] can only fire after the producer saw
+    // empty[s], i.e. after the MMAs that read TMEM slot s retired, so the converters need no barrier of their own.
+    // barriers: full[S] | conv[S] | empty[S] | tfull[2] | tempty[2]
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto conv_bar = [&](int s) { return bar_base + 8u * (S + s); };
     auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
-    auto lofree_bar = [&](int j) { return bar_base + 8u * (3 * S + j); };
-    const uint32_t tfull_bar = bar_base + 8u * (3 * S + G_LO_RING), tempty_bar = tfull_bar + 8u;
-    const uint32_t tmem_slot = tempty_bar + 8u;
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * S + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * S + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * S + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    // per-column epilogue vectors, staged once: [We0 | b2_0 | We1 | b2_1 | btot], each G*C floats
-    float* vecs = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_in = ep.n_in;
     const int n_tiles = (ep.M + BM - 1) / BM;
     const int nck = n_in * CC + 1 + (ep.has_h ? CC : 0);                 // K chunks per gate
     const uint32_t stage_tx = (uint32_t)G_A_BYTES + 2u * w_bytes;
 
-    for (int i = threadIdx.x; i < GC; i += kGateThreads) {
-        vecs[i] = __ldg(&ep.We[0][i]);
-        vecs[GC + i] = __ldg(&ep.b2[0][i]);
-        vecs[2 * GC + i] = n_in > 1 ? __ldg(&ep.We[1][i]) : 0.f;
-        vecs[3 * GC + i] = n_in > 1 ? __ldg(&ep.b2[1][i]) : 0.f;
-        vecs[4 * GC + i] = __ldg(&ep.btot[i]);
-    }
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 4); mbar_init(empty_bar(s), 1); }
-        for (int j = 0; j < G_LO_RING; ++j) mbar_init(lofree_bar(j), 1);
-        mbar_init(tfull_bar, 1); mbar_init(tempty_bar, 128);
+        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 8); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -322,191 +349,221 @@ gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ===== TMA producer: one fp32 A chunk + the matching W_hi / W_lo tiles per stage =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            auto a_chunk = [&](int g, int ck, const CUtensorMap*& am, int& acol) {
+                if (ck < n_in * CC) { am = &maps.agg[ck / CC]; acol = g * C + (ck % CC) * BK; }
+                else if (ck == n_in * CC) { am = &maps.x; acol = 0; }
+                else { am = &maps.h; acol = (ck - n_in * CC - 1) * BK; }
+            };
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int m0 = t * BM;
-                for (int g = 0; g < G; ++g)
-                    for (int ck = 0; ck < nck; ++ck) {
-                        const CUtensorMap* am;
-                        int acol;
-                        if (ck < n_in * CC) { am = &maps.agg[ck / CC]; acol = g * C + (ck % CC) * BK; }
-                        else if (ck == n_in * CC) { am = &maps.x; acol = 0; }
-                        else { am = &maps.h; acol = (ck - n_in * CC - 1) * BK; }
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), stage_tx);
-                        const uint32_t sa = smem_base + stage * slot_bytes;
-                        tma_load_2d(sa, am, full_bar(stage), acol, m0);
-                        tma_load_2d(sa + G_A_BYTES, &maps.w_hi, full_bar(stage), ck * BK, g * C);
-                        tma_load_2d(sa + G_A_BYTES + w_bytes, &maps.w_lo, full_bar(stage), ck * BK, g * C);
-                        if (++stage == S) { stage = 0; phase ^= 1u; }
+#pragma unroll
+                for (int p = 0; p < PS::n; ++p) {
+                    {
+                        const int g = PS::gate(p);
+                        for (int ck = 0; ck < nck; ++ck) {
+                            const CUtensorMap* am; int acol;
+                            a_chunk(g, ck, am, acol);
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            const uint32_t sa = smem_base + stage * slot_bytes;
+                            mbar_expect_tx(full_bar(stage), stage_tx);
+                            tma_load_2d(sa, am, full_bar(stage), acol, m0);
+                            tma_load_2d(sa + G_A_BYTES, &maps.w_hi, full_bar(stage), ck * BK, g * C);
+                            tma_load_2d(sa + G_A_BYTES + w_bytes, &maps.w_lo, full_bar(stage), ck * BK, g * C);
+                            if (++stage == S) { stage = 0; phase ^= 1u; }
+                        }
                     }
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, tphase = 0;
-            int lo = 0;
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t bphase = 0;                           // bit b = phase of TMEM buffer b
             const uint32_t idesc = make_idesc(BM, C);
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                mbar_wait(tempty_bar, tphase ^ 1u);
-                tc_fence_after();
-                for (int g = 0; g < G; ++g) {
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(g * C);
-                    for (int ck = 0; ck < nck; ++ck) {
-                        mbar_wait(conv_bar(stage), phase);          // TMA landed AND the chunk is split into hi / lo
-                        tc_fence_after();
-                        const uint32_t sa = smem_base + stage * slot_bytes;
-                        const uint64_t hdesc = make_desc(sa), ldesc = make_desc(lo_base + lo * G_A_BYTES);
-                        const uint64_t whdesc = make_desc(sa + G_A_BYTES), wldesc = make_desc(sa + G_A_BYTES + w_bytes);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, ldesc + 2u * k, whdesc + 2u * k, idesc, (ck | k) ? 1u : 0u);
+                for (int p = 0; p < PS::n; ++p) {
+                    mbar_wait(tempty_bar(buf), ((bphase >> buf) & 1u) ^ 1u);      // epilogue has drained this buffer
+                    tc_fence_after();
+                    {
+                        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * C);
+                        for (int ck = 0; ck < nck; ++ck) {
+                            mbar_wait(conv_bar(stage), phase);          // TMA landed AND the chunk is split into hi / lo
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + stage * slot_bytes;
+                            const uint32_t ah = tmem_base + a_col0 + (uint32_t)(stage * 64), al = ah + 32u;
+                            const uint64_t whdesc = make_desc(sa + G_A_BYTES), wldesc = make_desc(sa + G_A_BYTES + w_bytes);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, hdesc + 2u * k, wldesc + 2u * k, idesc, 1u);
+                            for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, al + 8u * k, whdesc + 2u * k, idesc, (ck | k) ? 1u : 0u);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, hdesc + 2u * k, whdesc + 2u * k, idesc, 1u);
-                        umma_commit(empty_bar(stage));
-                        umma_commit(lofree_bar(lo));
-                        if (++stage == S) { stage = 0; phase ^= 1u; }
-                        lo ^= 1;
+                            for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, ah + 8u * k, wldesc + 2u * k, idesc, 1u);
+#pragma unroll
+                            for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, ah + 8u * k, whdesc + 2u * k, idesc, 1u);
+                            umma_commit(empty_bar(stage));      // frees the smem slot AND the TMEM ring slot
+                            if (++stage == S) { stage = 0; phase ^= 1u; }
+                        }
                     }
+                    umma_commit(tfull_bar(buf));
+                    bphase ^= 1u << buf;
+                    buf ^= 1;
                 }
-                umma_commit(tfull_bar);
-                tphase ^= 1u;
             }
         }
     } else if (warp >= 8) {
-        // ===== converters: fp32 chunk -> (hi in place, lo into the side ring), 128 threads, 8 float4 each =====
-        const int ct = threadIdx.x - 256;
+        // ===== converters: thread = half a row (16 columns) of the fp32 chunk -> TF32 hi / lo -> tensor memory (tcgen05.st).
+        // hi is the fp32 word itself: the tensor core reads only the upper 19 bits of a TF32 operand, i.e. hi = trunc_tf32(a);
+        // lo = a - trunc_tf32(a) is exact in fp32 (13 significant bits) and is in turn truncated by the hardware.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        const int q = warp & 3, r = q * 32 + lane, hf = (warp - 8) >> 2;
         int stage = 0; uint32_t phase = 0;
-        int lo = 0; uint32_t lphase = 0u;                      // bit j = phase of lo-ring slot j
+        constexpr int RB = 32 - (2 * G + 3);                   // rank-1 columns of the X chunk: [ea0[G] | cnt0 | ea1[G] | cnt1 | 1]
+        static_assert(RB >= 16, "the rank-1 columns must sit in the upper half of the feature chunk");
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            for (int it = 0; it < G * nck; ++it) {
-                mbar_wait(full_bar(stage), phase);
-                mbar_wait(lofree_bar(lo), ((lphase >> lo) & 1u) ^ 1u);
-                const uint32_t sa = smem_base + stage * slot_bytes + 16u * ct;
-                const uint32_t la = lo_base + lo * G_A_BYTES + 16u * ct;
+            // per-row inputs of the rank-1 terms (lin_edge, lin_l2 bias x [deg > 0], biases): they ride in the unused columns
+            // of the feature chunk, so the tensor core adds them with 3xTF32 accuracy and the epilogue only sees pre-activations
+            const int m = t * BM + r;
+            float ea0[G], ea1[G], cnt0 = 0.f, cnt1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint32_t a0, a1, a2, a3;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(sa + 2048u * j));
-                    const uint32_t h0 = (a0 + 0x1000u) & 0xFFFFE000u, h1 = (a1 + 0x1000u) & 0xFFFFE000u;
-                    const uint32_t h2 = (a2 + 0x1000u) & 0xFFFFE000u, h3 = (a3 + 0x1000u) & 0xFFFFE000u;
-                    const float l0 = __uint_as_float(a0) - __uint_as_float(h0), l1 = __uint_as_float(a1) - __uint_as_float(h1);
-                    const float l2 = __uint_as_float(a2) - __uint_as_float(h2), l3 = __uint_as_float(a3) - __uint_as_float(h3);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 2048u * j), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(la + 2048u * j), "f"(l0), "f"(l1), "f"(l2), "f"(l3) : "memory");
+            for (int g = 0; g < G; ++g) { ea0[g] = 0.f; ea1[g] = 0.f; }
+            if (hf == 1 && m < ep.M) {
+                const int d0 = __ldg(&ep.rowptr[0][m + 1]) - __ldg(&ep.rowptr[0][m]);
+                cnt0 = ep.weighted[0] ? (d0 > 0 ? 1.f : 0.f) : (float)d0;
+#pragma unroll
+                for (int g = 0; g < G; ++g) ea0[g] = __ldg(&ep.ea[0][(size_t)m * G + g]);
+                if (n_in > 1) {
+                    const int d1 = __ldg(&ep.rowptr[1][m + 1]) - __ldg(&ep.rowptr[1][m]);
+                    cnt1 = ep.weighted[1] ? (d1 > 0 ? 1.f : 0.f) : (float)d1;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) ea1[g] = __ldg(&ep.ea[1][(size_t)m * G + g]);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
+            }
+            for (int it = 0; it < G * nck; ++it) {
+                const bool xchunk = hf == 1 && (it % nck) == n_in * CC;
+                mbar_wait(full_bar(stage), phase);
+                const uint32_t srow = smem_base + stage * slot_bytes + (uint32_t)r * 128u;
+                uint32_t a[16], lw[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)                    // logical 16-byte chunk 4*hf + c sits at (4*hf + c) ^ (row % 8)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a[4 * c]), "=r"(a[4 * c + 1]), "=r"(a[4 * c + 2]), "=r"(a[4 * c + 3])
+                                 : "r"(srow + (uint32_t)(((4 * hf + c) ^ (r & 7)) << 4)));
+                if (xchunk) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) { a[RB - 16 + g] = __float_as_uint(ea0[g]); a[RB - 16 + G + 1 + g] = __float_as_uint(ea1[g]); }
+                    a[RB - 16 + G] = __float_as_uint(cnt0); a[RB - 16 + 2 * G + 1] = __float_as_uint(cnt1); a[15] = 0x3F800000u;
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) lw[c] = __float_as_uint(__uint_as_float(a[c]) - __uint_as_float(a[c] & 0xFFFFE000u));
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(stage * 64 + 16 * hf);
+                tmem_st16(ta, a);
+                tmem_st16(ta + 32u, lw);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(conv_bar(stage));
                 if (++stage == S) { stage = 0; phase ^= 1u; }
-                lphase ^= 1u << lo;
-                lo ^= 1;
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: one accumulator row per thread, 16 columns of every gate at a time =====
-        const int q = warp & 3;
-        uint32_t tphase = 0;
-        const float* __restrict__ ea0p = ep.ea[0];
-        const float* __restrict__ ea1p = ep.ea[1];
-        const int* __restrict__ rp0 = ep.rowptr[0];
-        const int* __restrict__ rp1 = ep.rowptr[1];
-        const int w0 = ep.weighted[0], w1 = ep.weighted[1];
+        // ===== epilogue: one accumulator row per thread; outputs leave through 128-byte-swizzled shared-memory staging and
+        // TMA stores (a thread-per-row global store scatters 16 B over 32 lines per instruction: measured LSU-bound at
+        // ~16 B/clk/SM, 3x the MMA time of a tile).  u = s(i) tanh(c~) of pass 0 stays in registers until pass 1. =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int q = warp & 3, r = q * 32 + lane;
+        int buf = 0; uint32_t bphase = 0;
         const float* __restrict__ c_in = ep.c_in;
-        float* __restrict__ out_h = ep.out_h;
-        float* __restrict__ out_c = ep.out_c;
+        const bool want_c = ep.out_c != nullptr;
         const int M = ep.M;
+        const uint32_t stage_row = stage_base + (uint32_t)r * 128u;
+        const bool leader = threadIdx.x == 128;
+        constexpr bool kLstmAny = PS::lstm || PS::lstm0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int m = t * BM + q * 32 + lane;
+            const int m0 = t * BM, m = m0 + r;
             const bool ok = m < M;
-            float cnt0 = 0.f, cnt1 = 0.f, ea0[G], ea1[G];
+            float u[kLstmAny ? C : 1];
 #pragma unroll
-            for (int g = 0; g < G; ++g) { ea0[g] = 0.f; ea1[g] = 0.f; }
-            if (ok) {
-                const int d0 = __ldg(&rp0[m + 1]) - __ldg(&rp0[m]);
-                cnt0 = w0 ? (d0 > 0 ? 1.f : 0.f) : (float)d0;
+            for (int p = 0; p < PS::n; ++p) {
+                mbar_wait(tfull_bar(buf), (bphase >> buf) & 1u);
+                tc_fence_after();
+                const uint32_t tbuf = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * C);
+                // what this pass writes: LSTM  p=2 -> c' (if wanted), p=3 -> h';  LSTM0  p=1 -> c', p=2 -> h';  RAW/RELU -> out
+                const bool is_c = (PS::lstm && p == 2) || (PS::lstm0 && p == 1);
+                const bool is_h = !kLstmAny || p == PS::n - 1;
+                const bool stores = ((is_c && want_c) || is_h);
 #pragma unroll
-                for (int g = 0; g < G; ++g) ea0[g] = __ldg(&ea0p[(size_t)m * G + g]);
-                if (n_in > 1) {
-                    const int d1 = __ldg(&rp1[m + 1]) - __ldg(&rp1[m]);
-                    cnt1 = w1 ? (d1 > 0 ? 1.f : 0.f) : (float)d1;
-#pragma unroll
-                    for (int g = 0; g < G; ++g) ea1[g] = __ldg(&ea1p[(size_t)m * G + g]);
-                }
-            }
-            mbar_wait(tfull_bar, tphase);
-            tc_fence_after();
-            for (int c0 = 0; c0 < C; c0 += 16) {
-                uint32_t v[G][16];
-#pragma unroll
-                for (int g = 0; g < G; ++g) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * C + c0), v[g]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float pre[G][16];
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float* vg = vecs + g * C + c0;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 we0 = *reinterpret_cast<const float4*>(vg + j);
-                        const float4 b20 = *reinterpret_cast<const float4*>(vg + GC + j);
-                        const float4 we1 = *reinterpret_cast<const float4*>(vg + 2 * GC + j);
-                        const float4 b21 = *reinterpret_cast<const float4*>(vg + 3 * GC + j);
-                        const float4 bt = *reinterpret_cast<const float4*>(vg + 4 * GC + j);
-                        pre[g][j + 0] = __uint_as_float(v[g][j + 0]) + fmaf(ea0[g], we0.x, cnt0 * b20.x) + fmaf(ea1[g], we1.x, cnt1 * b21.x) + bt.x;
-                        pre[g][j + 1] = __uint_as_float(v[g][j + 1]) + fmaf(ea0[g], we0.y, cnt0 * b20.y) + fmaf(ea1[g], we1.y, cnt1 * b21.y) + bt.y;
-                        pre[g][j + 2] = __uint_as_float(v[g][j + 2]) + fmaf(ea0[g], we0.z, cnt0 * b20.z) + fmaf(ea1[g], we1.z, cnt1 * b21.z) + bt.z;
-                        pre[g][j + 3] = __uint_as_float(v[g][j + 3]) + fmaf(ea0[g], we0.w, cnt0 * b20.w) + fmaf(ea1[g], we1.w, cnt1 * b21.w) + bt.w;
+                for (int c = 0; c < NV; ++c) {                         // 32-column chunk = one swizzled staging row
+                    if (stores) {
+                        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging is free again
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
                     }
-                }
-                if (!ok) continue;
-                if (MODE == GG_GATE_RAW || MODE == GG_GATE_RELU) {
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        float* o = out_h + (size_t)m * GC + g * C + c0;
+                    for (int half = 0; half < 2; ++half) {
+                        const int c0 = 32 * c + 16 * half;
+                        float pre[16], o[16];
+                        {
+                            uint32_t v[16];
+                            tmem_ld16(tbuf + (uint32_t)c0, v);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 w = make_float4(pre[g][j], pre[g][j + 1], pre[g][j + 2], pre[g][j + 3]);
-                            if (MODE == GG_GATE_RELU) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
-                            *reinterpret_cast<float4*>(o + j) = w;
+                            for (int i = 0; i < 16; ++i) pre[i] = __uint_as_float(v[i]);
+                        }
+                        if (!kLstmAny) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = MODE == GG_GATE_RELU ? fmaxf(pre[i], 0.f) : pre[i];
+                        } else if (p == 0) {                            // input gate
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) u[c0 + i] = fast_sigmoid(pre[i]);
+                        } else if (p == 1) {                            // candidate: u = s(i) tanh(c~)  (= c' when c = 0)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { u[c0 + i] *= fast_tanh(pre[i]); o[i] = u[c0 + i]; }
+                        } else if (PS::lstm && p == 2) {                // forget gate: c' = s(f) c + u
+                            if (c_in && ok) {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    const float4 c4 = ldg4(c_in + (size_t)m * C + c0 + i);
+                                    u[c0 + i] = fmaf(fast_sigmoid(pre[i]), c4.x, u[c0 + i]);
+                                    u[c0 + i + 1] = fmaf(fast_sigmoid(pre[i + 1]), c4.y, u[c0 + i + 1]);
+                                    u[c0 + i + 2] = fmaf(fast_sigmoid(pre[i + 2]), c4.z, u[c0 + i + 2]);
+                                    u[c0 + i + 3] = fmaf(fast_sigmoid(pre[i + 3]), c4.w, u[c0 + i + 3]);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = u[c0 + i];
+                        } else {                                        // output gate: h' = s(o) tanh(c')
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = fast_sigmoid(pre[i]) * fast_tanh(u[c0 + i]);
+                        }
+                        if (stores) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)                 // 16-byte chunk (4*half + i) of the row, 128-byte swizzle
+                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (uint32_t)(((4 * half + i) ^ (r & 7)) << 4)),
+                                             "f"(o[4 * i]), "f"(o[4 * i + 1]), "f"(o[4 * i + 2]), "f"(o[4 * i + 3]) : "memory");
                         }
                     }
-                } else {
-                    constexpr bool lstm = MODE == GG_GATE_LSTM;       // gates (i,f,c,o); LSTM0: (i,c,o) with c_in = 0
-                    constexpr int gc = lstm ? 2 : 1, go = lstm ? 3 : 2;
-                    float cold[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) cold[j] = 0.f;
-                    if (lstm && c_in) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 c4 = ldg4(c_in + (size_t)m * C + c0 + j);
-                            cold[j] = c4.x; cold[j + 1] = c4.y; cold[j + 2] = c4.z; cold[j + 3] = c4.w;
+                    if (stores) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (leader) {
+                            // RAW / RELU output is [M, G*C] (G = 1 here); the LSTM outputs are [M, C]
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(is_h ? &maps.out_h : &maps.out_c), "r"(stage_base), "r"(32 * c), "r"(m0) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                     }
-                    float hn[16], cn[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float c2 = fast_sigmoid(pre[0][j]) * fast_tanh(pre[gc < G ? gc : 0][j]);
-                        if (lstm) c2 = fmaf(fast_sigmoid(pre[1 < G ? 1 : 0][j]), cold[j], c2);
-                        cn[j] = c2;
-                        hn[j] = fast_sigmoid(pre[go < G ? go : 0][j]) * fast_tanh(c2);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        *reinterpret_cast<float4*>(out_h + (size_t)m * C + c0 + j) = make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]);
-                        if (out_c) *reinterpret_cast<float4*>(out_c + (size_t)m * C + c0 + j) = make_float4(cn[j], cn[j + 1], cn[j + 2], cn[j + 3]);
-                    }
                 }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(buf));
+                bphase ^= 1u << buf;
+                buf ^= 1;
             }
-            tc_fence_before();
-            mbar_arrive(tempty_bar);
-            tphase ^= 1u;
         }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -625,49 +682,57 @@ extern "C" int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp,
 }
 
 // Tensor-core variant of gg_gate_update.  All A operands are plain fp32 and split into TF32 hi / lo inside the kernel:
-// inputs[e].agg [M, G*C] (gg_pgat_gather), X [M, K1 <= 32] (zero-extended to 32 columns by the TMA box), H [M, C] or NULL.
-// W_hi/W_lo: Wall [G*C, Ktot] with Ktot = n_inputs*C + 32 (+ C with H), K layout [W2 of input 0 | W2 of input 1 | skip(X, 32) | skip(h)].
+// inputs[e].agg [M, G*C] (gg_pgat_gather), X [M, K1] (zero-extended to 32 columns by the TMA box), H [M, C] or NULL.
+// W_hi/W_lo: Wall [G*C, Ktot], Ktot = n_inputs*C + 32 (+ C with H), K layout
+//   [W2 of input 0 | W2 of input 1 | feature chunk (32) | skip(h)]; the feature chunk of gate g holds the summed lin_skip
+//   columns of X in [0, K1) and, from RB = 32 - (2G + 3): We_0[g] at RB + g (other gates' slots 0), b2_0[g] at RB + G,
+//   We_1[g] at RB + G + 1 + g, b2_1[g] at RB + 2G + 1, btot[g] at 31 - the kernel feeds [ea_0[0..G) | cnt_0 | ea_1[0..G) | cnt_1 | 1]
+//   in those columns (packing.tc_gate_weight_layout builds it).
 extern "C" int gg_gate_update_tc(const gg_agg_input* inputs, int32_t n_inputs,
                                  const float* X, int32_t ldx, int32_t K1, const float* H, int32_t ldh,
-                                 const float* W_hi, const float* W_lo, int32_t Ktot, const float* btot,
+                                 const float* W_hi, const float* W_lo, int32_t Ktot,
                                  const float* c_in, float* out_h, float* out_c,
                                  int32_t M, int32_t G, int32_t C, int32_t mode, int32_t n_sms, void* stream) {
     if (M < 0 || G < 1 || G > 4 || C % 32 || C < 32 || C > 128 || n_inputs < 1 || n_inputs > kMaxIn) return GG_EINVAL;
     if (mode < GG_GATE_RAW || mode > GG_GATE_LSTM0) return GG_EINVAL;
     if ((mode == GG_GATE_LSTM && G != 4) || (mode == GG_GATE_LSTM0 && G != 3) || (mode == GG_GATE_RELU && G != 1)) return GG_EINVAL;
-    if (K1 < 4 || K1 > 32 || (K1 & 3) || Ktot != n_inputs * C + 32 + (H ? C : 0)) return GG_EINVAL;
+    if (mode == GG_GATE_RAW && G != 1) return GG_EINVAL;      // multi-gate RAW output: use gg_gate_update (fp32 SIMT)
+    if (K1 < 4 || K1 > 32 - (2 * G + 3) || (K1 & 3) || Ktot != n_inputs * C + 32 + (H ? C : 0)) return GG_EINVAL;
     if (M == 0) return 0;
-    if (!inputs || !X || !W_hi || !W_lo || !btot || !out_h) return GG_EINVAL;
+    if (!inputs || !X || !W_hi || !W_lo || !out_h) return GG_EINVAL;
     if (!gg_aligned16(out_h) || (out_c && !gg_aligned16(out_c)) || (c_in && !gg_aligned16(c_in))) return GG_EALIGN;
     GateMaps maps;
     GateEpi ep;
     int rc;
     for (int e = 0; e < n_inputs; ++e) {
         const gg_agg_input& s = inputs[e];
-        if (!s.agg || !s.ea || !s.rowptr || !s.We || !s.b2) return GG_EINVAL;
+        if (!s.agg || !s.ea || !s.rowptr) return GG_EINVAL;
         if ((rc = make_map(&maps.agg[e], s.agg, M, (int64_t)G * C, s.ld_agg, BM))) return rc;
-        ep.ea[e] = s.ea; ep.rowptr[e] = s.rowptr; ep.We[e] = s.We; ep.b2[e] = s.b2; ep.weighted[e] = s.weighted;
+        ep.ea[e] = s.ea; ep.rowptr[e] = s.rowptr; ep.weighted[e] = s.weighted;
     }
     for (int e = n_inputs; e < kMaxIn; ++e) {
         maps.agg[e] = maps.agg[0];
-        ep.ea[e] = nullptr; ep.rowptr[e] = nullptr; ep.We[e] = nullptr; ep.b2[e] = nullptr; ep.weighted[e] = 0;
+        ep.ea[e] = nullptr; ep.rowptr[e] = nullptr; ep.weighted[e] = 0;
     }
     if ((rc = make_map(&maps.x, X, M, K1, ldx, BM))) return rc;
     if (H) { if ((rc = make_map(&maps.h, H, M, C, ldh, BM))) return rc; } else maps.h = maps.x;
     if ((rc = make_map(&maps.w_hi, W_hi, (int64_t)G * C, Ktot, Ktot, C))) return rc;
     if ((rc = make_map(&maps.w_lo, W_lo, (int64_t)G * C, Ktot, Ktot, C))) return rc;
-    ep.btot = btot; ep.c_in = c_in; ep.out_h = out_h; ep.out_c = out_c;
+    const bool lstm_any = mode == GG_GATE_LSTM || mode == GG_GATE_LSTM0;
+    if ((rc = make_map(&maps.out_h, out_h, M, lstm_any ? C : G * C, lstm_any ? C : G * C, BM))) return rc;
+    if (out_c) { if ((rc = make_map(&maps.out_c, out_c, M, C, C, BM))) return rc; } else maps.out_c = maps.out_h;
+    ep.c_in = c_in; ep.out_c = lstm_any ? out_c : nullptr;
     ep.n_in = n_inputs; ep.M = M; ep.G = G; ep.C = C; ep.has_h = H ? 1 : 0; ep.mode = mode;
     if (n_sms <= 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    // ring depth: as many [A | W_hi | W_lo] slots as fit beside the lo ring, the epilogue vectors and the barriers
+    // ring depth: as many [A | W_hi | W_lo] slots as fit beside the epilogue vectors and the barriers
     const int slot_bytes = G_A_BYTES + 2 * C * BK * 4;
-    const int fixed = 1024 + G_LO_RING * G_A_BYTES + 256 + G_VEC_FLOATS * 4;
+    const int fixed = 1024 + OUT_BYTES + 512;
     int stages = (227 * 1024 - fixed) / slot_bytes;
-    if (stages > 6) stages = 6;
+    if (stages > ((int)TMEM_COLS - 2 * C) / 64) stages = ((int)TMEM_COLS - 2 * C) / 64;   // TMEM: 2 accumulators + 64 columns per stage
     if (stages < 2) return GG_EINVAL;
     ep.stages = stages;
     const int smem_bytes = fixed + stages * slot_bytes;
@@ -675,20 +740,24 @@ extern "C" int gg_gate_update_tc(const gg_agg_input* inputs, int32_t n_inputs,
     const int grid = tiles < n_sms ? tiles : n_sms;
     cudaStream_t st = GG_STREAM(stream);
     cudaError_t err = cudaSuccess;
-#define GG_LAUNCH_GATE(GV, MV)                                                                                              \
-    do {                                                                                                                    \
-        err = cudaFuncSetAttribute(gate_update_tc_kernel<GV, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-        if (err != cudaSuccess) return (int)err;                                                                            \
-        gate_update_tc_kernel<GV, MV><<<grid, kGateThreads, smem_bytes, st>>>(maps, ep);                                    \
+#define GG_LAUNCH_GATE(GV, MV, NVV)                                                                                              \
+    do {                                                                                                                         \
+        err = cudaFuncSetAttribute(gate_update_tc_kernel<GV, MV, NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+        if (err != cudaSuccess) return (int)err;                                                                                 \
+        gate_update_tc_kernel<GV, MV, NVV><<<grid, kGateThreads, smem_bytes, st>>>(maps, ep);                                    \
     } while (0)
-    if (mode == GG_GATE_LSTM) GG_LAUNCH_GATE(4, GG_GATE_LSTM);
-    else if (mode == GG_GATE_LSTM0) GG_LAUNCH_GATE(3, GG_GATE_LSTM0);
-    else if (mode == GG_GATE_RELU) GG_LAUNCH_GATE(1, GG_GATE_RELU);
-    else if (G == 1) GG_LAUNCH_GATE(1, GG_GATE_RAW);
-    else if (G == 2) GG_LAUNCH_GATE(2, GG_GATE_RAW);
-    else if (G == 3) GG_LAUNCH_GATE(3, GG_GATE_RAW);
-    else GG_LAUNCH_GATE(4, GG_GATE_RAW);
-#undef GG_LAUNCH_GATE
+#define GG_LAUNCH_GATE_NV(GV, MV)                                                        \
+    switch (C / 32) {                                                                    \
+        case 1: GG_LAUNCH_GATE(GV, MV, 1); break;                                        \
+        case 2: GG_LAUNCH_GATE(GV, MV, 2); break;                                        \
+        case 3: GG_LAUNCH_GATE(GV, MV, 3); break;                                        \
+        default: GG_LAUNCH_GATE(GV, MV, 4); break;                                       \
+    }
+    if (mode == GG_GATE_LSTM) GG_LAUNCH_GATE_NV(4, GG_GATE_LSTM)
+    else if (mode == GG_GATE_LSTM0) GG_LAUNCH_GATE_NV(3, GG_GATE_LSTM0)
+    else if (mode == GG_GATE_RELU) GG_LAUNCH_GATE_NV(1, GG_GATE_RELU)
+    else GG_LAUNCH_GATE_NV(1, GG_GATE_RAW)
+#undef GG_LAUNCH_GATE_NV
     GG_LAUNCH_OK();
     return 0;
 }

@@ -169,11 +169,15 @@ def tc_weight_layout(pk, t):
 
 def tc_gate_weight_layout(pk, t):
     """Wall[t] [G*C, Ktot] for gg_gate_update_tc: per gate row block, K = [lin_l2 of each incoming edge type (C each) |
-    summed lin_skip on the features (padded to 32) | on the hidden state], split into (hi, lo)."""
+    feature chunk (32) | summed lin_skip on the hidden state], split into (hi, lo).  The feature chunk carries the summed
+    lin_skip columns of X and, in its tail (from RB = 32 - (2G+3)), the rank-1 terms the kernel feeds per node:
+    [ea_0[g] -> lin_edge_0 | cnt_0 -> lin_l2 bias_0 | ea_1[g] -> lin_edge_1 | cnt_1 -> lin_l2 bias_1 | 1 -> btot]."""
     C, G = pk.C, pk.G
     k1p, kin = pk.k1p[t], pk.kin[t]
     k2 = kin - k1p
     ins = pk.into[t]
+    rb = 32 - (2 * G + 3)
+    assert len(ins) <= 2 and k1p <= rb, (len(ins), k1p, rb)
     ktot = len(ins) * C + 32 + k2
     dev = pk.Wskip[t].device
     W = torch.zeros(G * C, ktot, dtype=torch.float32, device=dev)
@@ -183,6 +187,10 @@ def tc_gate_weight_layout(pk, t):
             W[rows, i * C:(i + 1) * C] = pk.W2[e][g]
         off = len(ins) * C
         W[rows, off:off + k1p] = pk.Wskip[t][rows, :k1p]
+        for i, e in enumerate(ins):
+            W[rows, off + rb + i * (G + 1) + g] = pk.We[e][g]
+            W[rows, off + rb + i * (G + 1) + G] = pk.b2[e][g]
+        W[rows, off + 31] = pk.btot[t][rows]
         W[rows, off + 32:] = pk.Wskip[t][rows, k1p:]
     hi, lo = split_tf32(W)
     return hi.contiguous(), lo.contiguous(), ktot

@@ -144,17 +144,23 @@ int gg_gate_update(const gg_agg_input* inputs_host, int32_t n_inputs,
                    const float* c_in /* nullable */, float* out_h, float* out_c /* nullable */,
                    int32_t M, int32_t G, int32_t C, int32_t mode, void* stream);
 
-/* Tensor-core variant of gg_gate_update (tcgen05 kind::tf32, 3xTF32, TMEM accumulators: gate g in columns [g*C,(g+1)*C)).
- *   Every A operand is plain fp32 and is split into TF32 hi / lo INSIDE the kernel (converter warps, shared memory):
- *   inputs[e].agg [M, G*C] as written by gg_pgat_gather (agg_lo == NULL), X [M, K1] with 4 <= K1 <= 32 (the TMA box
- *   zero-extends it to 32 columns), H [M, C] or NULL (encoder).  W_hi/W_lo: Wall [G*C, Ktot], row g*C+n, K layout
- *   [lin_l2 of input 0 (C) | lin_l2 of input 1 (C) | summed lin_skip on X (32) | on h (C)], Ktot = n_inputs*C + 32 (+ C).
- *   inputs[e].W2 is ignored (it lives in Wall); We, b2, ea, rowptr, weighted are used by the epilogue. 1 <= n_inputs <= 2.
- *   X, H, agg rows must be 16-byte aligned with leading dimensions that are multiples of 4 floats.
+/* Tensor-core variant of gg_gate_update (tcgen05 kind::tf32 in the A-from-TMEM form, 3xTF32, accumulators in TMEM).
+ *   Every A operand is plain fp32 and is split into TF32 hi / lo INSIDE the kernel (converter warps -> tensor memory):
+ *   inputs[e].agg [M, G*C] as written by gg_pgat_gather (agg_lo == NULL), X [M, K1] with 4 <= K1 <= 32 - (2G+3) (the TMA
+ *   box zero-extends it to 32 columns), H [M, C] or NULL (encoder).  Modes: LSTM (G=4), LSTM0 (G=3), RAW / RELU (G=1).
+ *   W_hi/W_lo: TF32 split of Wall [G*C, Ktot], row g*C+n, Ktot = n_inputs*C + 32 (+ C with H), K layout
+ *     [lin_l2 of input 0 (C) | lin_l2 of input 1 (C) | feature chunk (32) | summed lin_skip on h (C)].
+ *   Feature chunk of gate g: summed lin_skip on X in columns [0, K1); the rank-1 terms ride in its tail, RB = 32-(2G+3):
+ *     col RB+g: lin_edge of input 0 (gate g only) | RB+G: lin_l2 bias of input 0 | RB+G+1+g: lin_edge of input 1 |
+ *     RB+2G+1: lin_l2 bias of input 1 | 31: summed lin_skip bias + gate bias;
+ *   the kernel supplies [ea_0[0..G) | cnt_0 | ea_1[0..G) | cnt_1 | 1] there per node (cnt = [deg>0] weighted, deg otherwise),
+ *   so inputs[e].W2 / We / b2 are not read (they live in Wall); ea, rowptr, weighted are.  1 <= n_inputs <= 2.
+ *   X, H, agg, out rows must be 16-byte aligned with leading dimensions that are multiples of 4 floats; out_h is [M, C]
+ *   (LSTM modes; out_c [M, C] nullable) or [M, G*C] (RAW / RELU), both dense.
  */
 int gg_gate_update_tc(const gg_agg_input* inputs_host, int32_t n_inputs,
                       const float* X, int32_t ldx, int32_t K1, const float* H /* nullable */, int32_t ldh,
-                      const float* W_hi, const float* W_lo, int32_t Ktot, const float* btot,
+                      const float* W_hi, const float* W_lo, int32_t Ktot,
                       const float* c_in /* nullable */, float* out_h, float* out_c /* nullable */,
                       int32_t M, int32_t G, int32_t C, int32_t mode, int32_t n_sms, void* stream);
 
