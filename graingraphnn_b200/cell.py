@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from ._lib import AggInput, check, ptr
-from .graph import _stream
+from .graph import _stream, edge_wrap
 
 
 def require_cuda(t, what):
@@ -46,11 +46,12 @@ def gemm_mode():
 _AUTO = None
 
 
-def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=None, n_rows=None):
+def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=None, n_rows=None, wrap=None):
     """xpad[t]: [N_t, K1p] fp32 (x,y,z in columns 0..2); h[t]: [N_t, K2] or None; c[t]: [N_t, C] or None;
     csr[e]: EdgeCSR; ea_csr[e]: [E] edge attribute in CSR order.  Returns (out_h, out_c) dicts.
     n_rows[t] (optional): number of leading rows of node type t that results are computed for (the owned rows of a slab
-    partition; the rows behind them are halo copies that only serve as message sources)."""
+    partition; the rows behind them are halo copies that only serve as message sources).
+    wrap[e] (optional): per-edge wrap codes of gg_edge_wrap for the positions in xpad; computed here when absent."""
     L = _lib.lib()
     C, G = pk.C, pk.G
     GC = G * C
@@ -106,12 +107,12 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
             agg[e] = buf(('agg', e), (nd, GC))
             ea[e] = buf(('ea', e), (nd, G))
             g = csr[e]
+            wr = wrap[e] if wrap is not None else edge_wrap(g, xpad[s], xpad[d])
             check(L.gg_pgat_gather(ptr(P[s]), pk.ncols[s], pk.koff[e], pk.voff[e],
                                    ptr(P[d]), pk.ncols[d], pk.qoff[e], pk.qxoff[e],
                                    ptr(xpad[s]), xpad[s].stride(0), ptr(xpad[d]), xpad[d].stride(0),
-                                   ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(pk.Wv3[e]),
-                                   nd_out, G, C, 1 if pk.weighted else 0, ptr(agg[e]), None,
-                                   GC, ptr(ea[e]), st), 'gg_pgat_gather')
+                                   ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(g.items), ptr(g.item_ptr), ptr(wr), ptr(pk.Wv3[e]),
+                                   nd_out, G, C, 1 if pk.weighted else 0, ptr(agg[e]), GC, ptr(ea[e]), st), 'gg_pgat_gather')
         # (c') gate GEMM + LSTM update per node type
         out_h = {} if out_h is None else out_h
         out_c = {} if out_c is None else out_c

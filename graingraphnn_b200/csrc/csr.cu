@@ -103,6 +103,26 @@ __global__ void csr_sort_rows(const int64_t* __restrict__ src, int n_dst, const 
     for (int i = b; i < e; ++i) col[i] = (int)src[perm[i]];
 }
 
+// work items of the gather kernel: node i contributes max(1, ceil(deg_i / dcap)) chunks of <= dcap in-edges
+__global__ void items_count(const int* __restrict__ rowptr, int n_dst, int dcap, int* __restrict__ cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_dst) return;
+    if (i == n_dst) { cnt[i] = 0; return; }
+    const int deg = rowptr[i + 1] - rowptr[i];
+    cnt[i] = deg == 0 ? 1 : (deg + dcap - 1) / dcap;
+}
+__global__ void items_fill(const int* __restrict__ rowptr, const int* __restrict__ item_ptr, int n_dst, int dcap, int4* __restrict__ items) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_dst) return;
+    const int b = rowptr[i], e = rowptr[i + 1];
+    int o = item_ptr[i];
+    if (b == e) { items[o] = make_int4(i, b, 0x300, 0); return; }          // no in-edges: one empty item, first and last
+    for (int pos = b; pos < e; pos += dcap, ++o) {
+        const int c = min(dcap, e - pos);
+        items[o] = make_int4(i, pos, c | (pos == b ? 0x100 : 0) | (pos + c >= e ? 0x200 : 0), 0);
+    }
+}
+
 __global__ void permute_f32(const float* __restrict__ src, const int* __restrict__ perm, float* __restrict__ out, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = __ldg(&src[perm[i]]);
@@ -154,5 +174,26 @@ extern "C" int gg_permute_f32(const float* src, const int32_t* perm, float* out,
     if (n == 0) return 0;
     permute_f32<<<(unsigned)((n + 255) / 256), 256, 0, GG_STREAM(stream)>>>(src, perm, out, n);
     GG_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int gg_csr_items(const int32_t* rowptr, int32_t n_dst, int32_t dcap, int32_t* item_ptr, int32_t* items,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_dst < 0 || dcap < 1 || dcap > 255 || !rowptr || !item_ptr || !workspace) return GG_EINVAL;
+    if (n_dst > 0 && !items) return GG_EINVAL;
+    if (workspace_bytes < gg_csr_workspace_bytes(0, n_dst)) return GG_ENOSPC;
+    if (items && !gg_aligned16(items)) return GG_EALIGN;
+    cudaStream_t st = GG_STREAM(stream);
+    const int n = n_dst + 1;
+    const int tiles = (n + kScanTile - 1) / kScanTile;
+    int* count = static_cast<int*>(workspace);
+    int* tile_sum = count + n;
+    items_count<<<(n + 255) / 256, 256, 0, st>>>(rowptr, n_dst, dcap, count); GG_LAUNCH_OK();
+    scan_tiles<<<tiles, 256, 0, st>>>(count, item_ptr, n, tile_sum); GG_LAUNCH_OK();
+    if (tiles > 1) {
+        scan_tile_sums<<<1, 1024, 0, st>>>(tile_sum, tiles); GG_LAUNCH_OK();
+        scan_add_offsets<<<tiles, 256, 0, st>>>(item_ptr, n, tile_sum); GG_LAUNCH_OK();
+    }
+    if (n_dst > 0) { items_fill<<<(n_dst + 255) / 256, 256, 0, st>>>(rowptr, item_ptr, n_dst, dcap, reinterpret_cast<int4*>(items)); GG_LAUNCH_OK(); }
     return 0;
 }

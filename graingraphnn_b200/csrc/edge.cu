@@ -291,3 +291,33 @@ extern "C" int gg_segment_mean(const float* src, int32_t ld_src, int32_t width, 
     GG_LAUNCH_OK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// per-edge periodic wrap of the source displacement (periodGATconv.py:209-210): r = p_j - p_i; +1 where r < -0.5,
+// -1 where r > 0.5, per coordinate.  2 bits per coordinate (0: none, 1: +1, 2: -1), x | y << 2 | z << 4, CSR order.
+// Computed once per step / forward and shared by every gate, cell and model that reads the same positions.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ int wrap_code2(float r) { return (r < -0.5f) ? 1 : ((r > 0.5f) ? 2 : 0); }
+__global__ void edge_wrap_kernel(const float* __restrict__ ps, int ld_ps, const float* __restrict__ pd, int ld_pd,
+                                 const int* __restrict__ rowptr, const int* __restrict__ col, int n_dst, int* __restrict__ wrap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_dst) return;
+    const float x = __ldg(pd + (size_t)i * ld_pd), y = __ldg(pd + (size_t)i * ld_pd + 1), z = __ldg(pd + (size_t)i * ld_pd + 2);
+    const int b = __ldg(&rowptr[i]), e = __ldg(&rowptr[i + 1]);
+    for (int k = b; k < e; ++k) {
+        const float* pj = ps + (size_t)__ldg(&col[k]) * ld_ps;
+        wrap[k] = wrap_code2(__ldg(pj) - x) | (wrap_code2(__ldg(pj + 1) - y) << 2) | (wrap_code2(__ldg(pj + 2) - z) << 4);
+    }
+}
+}  // namespace
+
+extern "C" int gg_edge_wrap(const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
+                            const int32_t* rowptr, const int32_t* col, int32_t n_dst, int32_t* wrap_csr, void* stream) {
+    if (n_dst < 0 || ld_pos_src < 3 || ld_pos_dst < 3) return GG_EINVAL;
+    if (n_dst == 0) return 0;
+    if (!pos_src || !pos_dst || !rowptr || !col || !wrap_csr) return GG_EINVAL;
+    edge_wrap_kernel<<<(n_dst + 255) / 256, 256, 0, GG_STREAM(stream)>>>(pos_src, ld_pos_src, pos_dst, ld_pos_dst, rowptr, col, n_dst, wrap_csr);
+    GG_LAUNCH_OK();
+    return 0;
+}

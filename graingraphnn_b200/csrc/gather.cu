@@ -39,9 +39,10 @@ struct GatherParams {
     const float* pos_src; int ld_ps;
     const float* pos_dst; int ld_pd;
     const int* rowptr; const int* col; const float* ea;
+    const int* items; const int* item_ptr; const int* wrap;   // flat work list (+ per-node offsets) and per-edge wrap codes (TMA path)
     const float* Wv3;
     int n_dst, G, quads, weighted;
-    float* agg; float* agg_lo; int ld_agg; float* ea_out;
+    float* agg; int ld_agg; float* ea_out;
     float inv_sqrt_c;
 };
 
@@ -53,12 +54,6 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {      // read-onc
 }
 __device__ __forceinline__ void stg4_stream(float* p, const float4& v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
 }
 
 __device__ __forceinline__ float group_sum8(float s) {
@@ -243,34 +238,25 @@ pgat_gather_kernel(const GatherParams p) {
     }
     if (active) {
         float* orow = p.agg + (size_t)node * p.ld_agg + gcol;
-        if (p.agg_lo) {   // TF32 split for the tensor-core gate GEMM: agg = hi + lo, both TF32-representable
-            float* lrow = p.agg_lo + (size_t)node * p.ld_agg + gcol;
 #pragma unroll
-            for (int r = 0; r < NV; ++r) {
-                const float4 hi = make_float4(tf32_rna(acc[r].x), tf32_rna(acc[r].y), tf32_rna(acc[r].z), tf32_rna(acc[r].w));
-                const float4 lo = make_float4(tf32_rna(acc[r].x - hi.x), tf32_rna(acc[r].y - hi.y), tf32_rna(acc[r].z - hi.z), tf32_rna(acc[r].w - hi.w));
-                stg4_stream(orow + 4 * (sub + 8 * r), hi);
-                stg4_stream(lrow + 4 * (sub + 8 * r), lo);
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < NV; ++r) stg4_stream(orow + 4 * (sub + 8 * r), acc[r]);
-        }
+        for (int r = 0; r < NV; ++r) stg4_stream(orow + 4 * (sub + 8 * r), acc[r]);
         if (sub == 0) p.ea_out[(size_t)node * p.G + gate] = ea_acc;
     }
 }
 
 
 // =====================================================================================================================
-// TMA-staged variant (the default on sm_100): every warp runs its own double-buffered bulk-copy pipeline.
+// TMA-staged variant (the default on sm_100): every warp runs its own double-buffered bulk-copy pipeline over a FLAT list
+// of work items.
 //
-// Work item = (target node, gate quad, chunk of <= DCAP in-edges).  For item k+1 twelve lanes each issue ONE
-// cp.async.bulk (UBLKCP) — the Q row, the QX block and position of the target, and per edge the position, K row and
-// V row of the source — into the warp's shared-memory slot (k+1)&1, completing on that slot's mbarrier, while the warp
-// computes item k out of slot k&1.  The source ids of item k+2 are fetched (plain loads) in the same iteration, so
-// the dependent chain rowptr -> col -> row address never stalls the warp: 3-deep software pipeline, no cross-warp
-// synchronisation.  Registers hold only the per-target state (Q, -Wv3 p_i, accumulators), so 10 warps x 2 slots x 10.6 KB
-// fill the 227 KB of shared memory of one persistent CTA per SM and keep ~100 KB of loads in flight per SM.
+// Work item = (target node, chunk of <= DCAP in-edges), precomputed once per topology by gg_csr_items as int4
+// {node, first edge, count | first << 8 | last << 9, -}.  The periodic wrap of every edge is precomputed once per step by
+// gg_edge_wrap (2 bits per coordinate), so the kernel touches no source positions.  Per item the warp issues ONE
+// cp.async.bulk per edge (the K|V row pair of the source, 3 KB) into its shared-memory slot (k+1)&1, completing on that
+// slot's mbarrier, while it computes item k out of slot k&1; Q | QX and the target position of item k+1 travel by plain
+// 128-bit loads into a second register set, and the descriptors / source ids of items k+3 / k+2 are fetched in the same
+// iteration, so the dependent chain item -> col -> row address never stalls the warp (4-deep software pipeline, no
+// cross-warp synchronisation).  Wv3 lives in registers.  12 warps x 2 slots x 9 KB per persistent CTA.
 // =====================================================================================================================
 constexpr int DCAP = 3;               // in-edges per item (joints of a grain network have exactly 3)
 
@@ -297,45 +283,6 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
         }
     } while (!done);
 }
-
-struct Item { int node, ebeg, cnt, first, last, valid; };
-
-// warp-uniform walk over this warp's target nodes and their edge chunks; the rowptr pair of the NEXT node is always
-// already requested when the current one starts.
-struct Cursor {
-    int node, stride, n_nodes;
-    int end, pos, started;
-    int nbeg, nend;
-    const int* rowptr;
-    __device__ __forceinline__ void prefetch(int n) {
-        if (n < n_nodes) { nbeg = __ldg(&rowptr[n]); nend = __ldg(&rowptr[n + 1]); }
-    }
-    __device__ __forceinline__ void init(int first, int stride_, int n_nodes_, const int* rp) {
-        node = first; stride = stride_; n_nodes = n_nodes_; rowptr = rp; started = 0;
-        nbeg = nend = 0;
-        prefetch(node);
-        pos = nbeg; end = nend;
-        prefetch(node + stride);
-    }
-    __device__ __forceinline__ Item next() {
-        Item it;
-        it.valid = 0; it.node = 0; it.ebeg = 0; it.cnt = 0; it.first = 0; it.last = 0;
-        if (node >= n_nodes) return it;
-        if (started && pos >= end) {                       // move to the next node
-            node += stride;
-            if (node >= n_nodes) return it;
-            pos = nbeg; end = nend; started = 0;
-            prefetch(node + stride);
-        }
-        it.valid = 1;
-        it.node = node;
-        it.ebeg = pos; it.cnt = min(DCAP, end - pos);
-        it.first = !started; it.last = pos + it.cnt >= end;
-        pos += it.cnt; started = 1;
-        return it;
-    }
-};
-
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
     float4 r;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
@@ -346,282 +293,245 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// periodGATconv.py:210: +1 where r < -0.5, -1 where r > 0.5
-__device__ __forceinline__ float wrapf(float r) { return (r < -0.5f ? 1.f : 0.f) - (r > 0.5f ? 1.f : 0.f); }
 
-// One edge of an item out of the staged slot.  Phase 1 (score) and phase 2 (accumulate) are separate calls.
-template <int NV>
-struct TmaGatherState {
-    float4 q[NV], vp[NV], acc[NV];
-    float4 qx;
-    float pix, piy, piz, m_run, l_run, ea_acc;
-};
+struct Meta { int col, wrap; float ea; };            // per lane: edge `lane` of an item (lanes >= cnt: unused)
 
 template <int NV>
 __global__ void __launch_bounds__(384, 1)
 pgat_gather_tma_kernel(const GatherParams p) {
     constexpr int C = 32 * NV;
-    constexpr int ROWB = 4 * C * 4;                         // one row of 4 gates x C floats
-    // slot layout: [Q row | QX (64 B)] [P_i 16 B | P_j 3 x 16 B] [edge 0: K row | V row] [edge 1 ...] [edge 2 ...]
-    constexpr int OFF_PI = ROWB + 64, OFF_PJ = ROWB + 80, OFF_KV = ROWB + 128;
-    constexpr int SLOT = ROWB * (1 + 2 * DCAP) + 128;
+    constexpr int ROWB = 4 * C * 4;                         // one row of 4 gates x C floats (bytes)
+    constexpr int SLOT = DCAP * 2 * ROWB;                   // per edge: [K row | V row]
     constexpr float LOG2E = 1.4426950408889634f;
     extern __shared__ __align__(128) uint8_t smem[];
     const int n_warps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = p.G, GC = G * C;                          // G <= 4 here (host dispatch)
-    float* s_wv = reinterpret_cast<float*>(smem);           // [3][4*C], zero beyond G*C
-    constexpr uint32_t WVB = 3 * 4 * C * 4;
-    uint8_t* my = smem + WVB + (size_t)warp * (2 * SLOT);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WVB + (size_t)n_warps * (2 * SLOT)) + 2 * warp;
-
-    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
-        const bool in = i < GC;
-        s_wv[i] = in ? __ldg(&p.Wv3[(size_t)i * 4 + 0]) : 0.f;
-        s_wv[4 * C + i] = in ? __ldg(&p.Wv3[(size_t)i * 4 + 1]) : 0.f;
-        s_wv[8 * C + i] = in ? __ldg(&p.Wv3[(size_t)i * 4 + 2]) : 0.f;
-    }
+    uint8_t* my = smem + (size_t)warp * (2 * SLOT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)n_warps * (2 * SLOT)) + 2 * warp;
     if (lane == 0) {
         mbar_init_(smem_addr(&bars[0]), 1);
         mbar_init_(smem_addr(&bars[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
 
     const int grp = lane >> 3, sub = lane & 7;
     const bool active = grp < G;
     const int gsel = active ? grp : 0;                      // idle 8-lane groups (G < 4) shadow gate 0 and store nothing
     const uint32_t slot_addr0 = smem_addr(my);
     const uint32_t bar_addr0 = smem_addr(&bars[0]);
-    const uint32_t wv_addr = smem_addr(s_wv) + 4u * (grp * C + 4 * sub);
     const uint32_t lane_off = 4u * (gsel * C + 4 * sub);    // byte offset of this lane's first float4 inside a staged row
     const uint32_t rowb = (uint32_t)GC * 4u;                // bytes of one K / V / Q row
     const int w = p.weighted;
     const bool kv_adjacent = w && p.v_off == p.k_off + GC;  // one copy brings K|V
-    const bool qx_adjacent = w && p.qx_off == p.q_off + GC; // one copy brings Q|QX
     const float sc2 = p.inv_sqrt_c * LOG2E;                 // scores are kept in log2 units: exp(x) = ex2(x log2 e)
 
-    Cursor cur;
-    cur.init(blockIdx.x * n_warps + warp, gridDim.x * n_warps, p.n_dst, p.rowptr);
+    // x, y, z columns of lin_value for this lane's channels (zero for idle groups): Wv3 is [G*C][4]
+    float4 wvx[NV], wvy[NV], wvz[NV];
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        float4 t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = active ? ldg4(p.Wv3 + (size_t)(grp * C + 4 * (sub + 8 * r) + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wvx[r] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
+        wvy[r] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
+        wvz[r] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
+    }
 
-    auto load_meta = [&](const Item& it, int& mj, float& ma) {
-        mj = 0; ma = 0.f;
-        if (it.valid && lane < it.cnt) { mj = __ldg(&p.col[it.ebeg + lane]); ma = __ldg(&p.ea[it.ebeg + lane]); }
-    };
-    auto issue = [&](const Item& it, int mj, int slot) {
-        const uint32_t base = slot_addr0 + slot * SLOT, bar = bar_addr0 + 8u * slot;
-        const uint32_t tx = (uint32_t)it.cnt * (16u + rowb + (w ? rowb : 0u)) + (it.first ? 16u + (w ? rowb + 16u * G : 0u) : 0u);
-        if (lane == 0) mbar_expect_tx_(bar, tx);
-        __syncwarp();
-        if (lane < it.cnt) {                                             // per edge: position and K|V rows of the source
-            const float* prow = p.P_src + (size_t)mj * p.ld_src;
-            const uint32_t kv = base + OFF_KV + lane * (2 * ROWB);
-            bulk_g2s(base + OFF_PJ + 16 * lane, p.pos_src + (size_t)mj * p.ld_ps, 16, bar);
-            if (kv_adjacent) {
-                bulk_g2s(kv, prow + p.k_off, 2 * rowb, bar);
-            } else {
-                if (w) bulk_g2s(kv, prow + p.k_off, rowb, bar);
-                bulk_g2s(kv + rowb, prow + p.v_off, rowb, bar);
-            }
-        } else if (lane == DCAP && it.first) {
-            bulk_g2s(base + OFF_PI, p.pos_dst + (size_t)it.node * p.ld_pd, 16, bar);
-        } else if (lane == DCAP + 1 && it.first && w) {
-            const float* qrow = p.P_dst + (size_t)it.node * p.ld_dst;
-            if (qx_adjacent) {
-                bulk_g2s(base, qrow + p.q_off, rowb + 16u * G, bar);
-            } else {
-                bulk_g2s(base, qrow + p.q_off, rowb, bar);
-                bulk_g2s(base + rowb, qrow + p.qx_off, 16u * G, bar);
-            }
+    // this warp owns a contiguous block of target nodes, hence a contiguous range of the item list (all chunks of a node
+    // stay in one warp: the softmax state lives in registers)
+    const int4* __restrict__ items = reinterpret_cast<const int4*>(p.items);
+    const int64_t W = (int64_t)gridDim.x * n_warps, gw = (int64_t)blockIdx.x * n_warps + warp;
+    const int64_t per = (p.n_dst + W - 1) / W;
+    const int64_t node0 = gw * per < p.n_dst ? gw * per : p.n_dst, node1 = node0 + per < p.n_dst ? node0 + per : p.n_dst;
+    int64_t idx = __ldg(&p.item_ptr[node0]);
+    const int64_t n_items = __ldg(&p.item_ptr[node1]);
+    constexpr int64_t W1 = 1;
+
+    auto load_desc = [&](int64_t i) -> int4 { return i < n_items ? __ldg(items + i) : make_int4(-1, 0, 0, 0); };
+    auto load_meta = [&](const int4& d) -> Meta {
+        Meta m; m.col = 0; m.wrap = 0; m.ea = 0.f;
+        if (d.x >= 0 && lane < (d.z & 0xff)) {
+            m.col = __ldg(&p.col[d.y + lane]); m.ea = __ldg(&p.ea[d.y + lane]); m.wrap = __ldg(&p.wrap[d.y + lane]);
         }
+        return m;
     };
-
-    TmaGatherState<NV> st;
+    // register set of the NEXT item's target: Q row chunks, QX, position
+    float4 qn[NV], qxn = make_float4(0.f, 0.f, 0.f, 0.f);
+    float pnx = 0.f, pny = 0.f, pnz = 0.f;
 #pragma unroll
-    for (int r = 0; r < NV; ++r) { st.q[r] = st.vp[r] = st.acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
-    st.qx = make_float4(0.f, 0.f, 0.f, 0.f);
-    st.pix = st.piy = st.piz = 0.f; st.m_run = -CUDART_INF_F; st.l_run = 0.f; st.ea_acc = 0.f;
-
-    // phase 1 of edge e: score in log2 units (wrap vector w_e = (wx, wy, wz) already known)
-    auto score = [&](uint32_t sl, int e, float a, float wx, float wy, float wz) -> float {
-        const uint32_t krow = sl + OFF_KV + e * (2 * ROWB) + lane_off;
-        float d = 0.f;
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const float4 k = lds4(krow + 128 * r);
-            d = fmaf(st.q[r].x, k.x, d); d = fmaf(st.q[r].y, k.y, d); d = fmaf(st.q[r].z, k.z, d); d = fmaf(st.q[r].w, k.w, d);
-        }
-        d = group_sum8(d);
-        d = fmaf(st.qx.x, wx, d); d = fmaf(st.qx.y, wy, d); d = fmaf(st.qx.z, wz, d); d = fmaf(st.qx.w, a, d);
-        return d * sc2;
-    };
-    // phase 2 of edge e.  relu(v + vp) = max(v, -vp) + vp, so the loop accumulates pe * max(V_j + Wv3 w_e, nvp) with
-    // nvp = Wv3 p_i and the target adds vp * sum(pe) once at the end (2 instead of 3 instructions per channel and edge).
-    auto accumulate = [&](uint32_t sl, int e, float pe, float a, float wx, float wy, float wz, bool wrapped) {
-        st.l_run += pe;
-        st.ea_acc = fmaf(pe, a, st.ea_acc);
-        const uint32_t vrow = sl + OFF_KV + e * (2 * ROWB) + rowb + lane_off;
-        float4 v[NV];
-#pragma unroll
-        for (int r = 0; r < NV; ++r) v[r] = lds4(vrow + 128 * r);
-        if (wrapped) {                                       // edge crosses a periodic / patch boundary (warp-uniform)
-#pragma unroll
-            for (int r = 0; r < NV; ++r) {
-                const float4 ax = lds4(wv_addr + 128 * r), ay = lds4(wv_addr + 16 * C + 128 * r), az = lds4(wv_addr + 32 * C + 128 * r);
-                v[r].x += fmaf(az.x, wz, fmaf(ay.x, wy, ax.x * wx));
-                v[r].y += fmaf(az.y, wz, fmaf(ay.y, wy, ax.y * wx));
-                v[r].z += fmaf(az.z, wz, fmaf(ay.z, wy, ax.z * wx));
-                v[r].w += fmaf(az.w, wz, fmaf(ay.w, wy, ax.w * wx));
+    for (int r = 0; r < NV; ++r) qn[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto issue = [&](const int4& d, const Meta& m, int slot) {
+        const int cnt = d.z & 0xff;
+        if (cnt > 0) {
+            const uint32_t base = slot_addr0 + slot * SLOT, bar = bar_addr0 + 8u * slot;
+            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)cnt * (w ? 2u * rowb : rowb));
+            __syncwarp();
+            if (lane < cnt) {                                            // per edge: K|V rows of the source
+                const float* prow = p.P_src + (size_t)m.col * p.ld_src;
+                const uint32_t kv = base + lane * (2 * ROWB);
+                if (kv_adjacent) {
+                    bulk_g2s(kv, prow + p.k_off, 2 * rowb, bar);
+                } else {
+                    if (w) bulk_g2s(kv, prow + p.k_off, rowb, bar);
+                    bulk_g2s(kv + rowb, prow + p.v_off, rowb, bar);
+                }
             }
         }
+        if (d.z & 0x100) {                                               // first chunk of a target: its Q | QX and position
+            const float* pd = p.pos_dst + (size_t)d.x * p.ld_pd;
+            pnx = __ldg(pd); pny = __ldg(pd + 1); pnz = __ldg(pd + 2);
+            if (w) {
+                const float* qrow = p.P_dst + (size_t)d.x * p.ld_dst;
 #pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            st.acc[r].x = fmaf(pe, fmaxf(v[r].x, st.vp[r].x), st.acc[r].x);
-            st.acc[r].y = fmaf(pe, fmaxf(v[r].y, st.vp[r].y), st.acc[r].y);
-            st.acc[r].z = fmaf(pe, fmaxf(v[r].z, st.vp[r].z), st.acc[r].z);
-            st.acc[r].w = fmaf(pe, fmaxf(v[r].w, st.vp[r].w), st.acc[r].w);
+                for (int r = 0; r < NV; ++r) qn[r] = ldg4_stream(qrow + p.q_off + gsel * C + 4 * (sub + 8 * r));
+                qxn = ldg4(qrow + p.qx_off + 4 * gsel);
+            }
         }
     };
 
-    // one item out of slot SLOT_ID (compile-time, so every shared-memory address is base + immediate)
-    auto compute = [&](const Item& itC, float maC, const uint32_t sl, const uint32_t bar, const uint32_t parity) {
-        mbar_wait_(bar, parity);
-        if (itC.first) {
-            const float4 pi4 = lds4(sl + OFF_PI);
-            st.pix = pi4.x; st.piy = pi4.y; st.piz = pi4.z;
+    // per-target state
+    float4 q[NV], vp[NV], acc[NV], qx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float m_run = -CUDART_INF_F, l_run = 0.f, ea_acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) { q[r] = vp[r] = acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+    auto wrapv = [](int code) -> float { return code == 0 ? 0.f : (code == 1 ? 1.f : -1.f); };   // gg_edge_wrap: 1 -> +1, 2 -> -1
+
+    int4 d0 = load_desc(idx), d1 = load_desc(idx + W1), d2 = load_desc(idx + 2 * W1);
+    Meta m0 = load_meta(d0), m1 = load_meta(d1);
+    if (d0.x >= 0) issue(d0, m0, 0);
+    uint32_t par = 0u;                                       // bit s = phase of slot s
+    int slot = 0;
+    while (d0.x >= 0) {
+        const int4 d3 = load_desc(idx + 3 * W1);
+        const Meta m2 = load_meta(d2);
+        const int cnt = d0.z & 0xff;
+        if (d0.z & 0x100) {                                  // adopt the prefetched target registers (before they are reused)
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {                   // vp = Wv3 p_i:  V_j + Wv3 (w_e - p_i) > 0  <=>  V_j + Wv3 w_e > vp
+                q[r] = qn[r];
+                vp[r].x = fmaf(wvz[r].x, pnz, fmaf(wvy[r].x, pny, wvx[r].x * pnx));
+                vp[r].y = fmaf(wvz[r].y, pnz, fmaf(wvy[r].y, pny, wvx[r].y * pnx));
+                vp[r].z = fmaf(wvz[r].z, pnz, fmaf(wvy[r].z, pny, wvx[r].z * pnx));
+                vp[r].w = fmaf(wvz[r].w, pnz, fmaf(wvy[r].w, pny, wvx[r].w * pnx));
+                acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            qx = qxn;
+            m_run = -CUDART_INF_F; l_run = 0.f; ea_acc = 0.f;
+        }
+        if (d1.x >= 0) issue(d1, m1, slot ^ 1);
+
+        // ---------------------------------------------------------------- compute item d0 out of `slot`
+        const uint32_t sl = slot_addr0 + slot * SLOT;
+        if (cnt > 0) {
+            mbar_wait_(bar_addr0 + 8u * slot, (par >> slot) & 1u);
+            par ^= 1u << slot;
+            float a[DCAP], s[DCAP];
+            int wc[DCAP];
+#pragma unroll
+            for (int e = 0; e < DCAP; ++e) { a[e] = __shfl_sync(0xffffffffu, m0.ea, e); wc[e] = __shfl_sync(0xffffffffu, m0.wrap, e); s[e] = 0.f; }
+            float m_new = m_run;
             if (w) {
 #pragma unroll
-                for (int r = 0; r < NV; ++r) st.q[r] = lds4(sl + lane_off + 128 * r);
-                st.qx = lds4(sl + rowb + 16 * gsel);
-            }
+                for (int e = 0; e < DCAP; ++e) {
+                    if (e < cnt) {                           // warp-uniform
+                        const uint32_t krow = sl + e * (2 * ROWB) + lane_off;
+                        float dd = 0.f, d2_ = 0.f;           // two partial sums: shorter dependency chains
 #pragma unroll
-            for (int r = 0; r < NV; ++r) {   // vp holds nvp = Wv3 p_i  (V_j + Wv3 (w_e - p_i) > 0  <=>  V_j + Wv3 w_e > nvp)
-                const float4 ax = lds4(wv_addr + 128 * r), ay = lds4(wv_addr + 16 * C + 128 * r), az = lds4(wv_addr + 32 * C + 128 * r);
-                st.vp[r].x = fmaf(az.x, st.piz, fmaf(ay.x, st.piy, ax.x * st.pix));
-                st.vp[r].y = fmaf(az.y, st.piz, fmaf(ay.y, st.piy, ax.y * st.pix));
-                st.vp[r].z = fmaf(az.z, st.piz, fmaf(ay.z, st.piy, ax.z * st.pix));
-                st.vp[r].w = fmaf(az.w, st.piz, fmaf(ay.w, st.piy, ax.w * st.pix));
-                st.acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            st.m_run = -CUDART_INF_F; st.l_run = 0.f; st.ea_acc = 0.f;
-        }
-        // wrap vector of edge `lane` (lanes < cnt), computed once and broadcast: periodGATconv.py:209-210
-        float lwx = 0.f, lwy = 0.f, lwz = 0.f;
-        if (lane < itC.cnt) {
-            const float4 pj = lds4(sl + OFF_PJ + 16 * lane);
-            lwx = wrapf(pj.x - st.pix); lwy = wrapf(pj.y - st.piy); lwz = wrapf(pj.z - st.piz);
-        }
-        const unsigned wrapped_mask = __ballot_sync(0xffffffffu, lwx != 0.f || lwy != 0.f || lwz != 0.f);
-        float s[DCAP], a[DCAP], wx[DCAP], wy[DCAP], wz[DCAP];
-        float m_new = st.m_run;
-#pragma unroll
-        for (int e = 0; e < DCAP; ++e) {
-            a[e] = __shfl_sync(0xffffffffu, maC, e);
-            wx[e] = wy[e] = wz[e] = 0.f; s[e] = 0.f;
-        }
-        if (wrapped_mask) {                                  // rare: some edge of the item crosses a boundary
-#pragma unroll
-            for (int e = 0; e < DCAP; ++e) {
-                wx[e] = __shfl_sync(0xffffffffu, lwx, e); wy[e] = __shfl_sync(0xffffffffu, lwy, e); wz[e] = __shfl_sync(0xffffffffu, lwz, e);
-            }
-        }
-        if (w) {
-            if (itC.cnt == DCAP) {                           // the common case, branch-free over the edges
-#pragma unroll
-                for (int e = 0; e < DCAP; ++e) { s[e] = score(sl, e, a[e], wx[e], wy[e], wz[e]); m_new = fmaxf(m_new, s[e]); }
-            } else {
-#pragma unroll
-                for (int e = 0; e < DCAP; ++e)
-                    if (e < itC.cnt) { s[e] = score(sl, e, a[e], wx[e], wy[e], wz[e]); m_new = fmaxf(m_new, s[e]); }
-            }
-            if (m_new > st.m_run) {                          // online softmax: rescale what earlier chunks accumulated
-                if (st.m_run != -CUDART_INF_F) {
-                    const float scale = ex2_approx(st.m_run - m_new);
-                    st.l_run *= scale; st.ea_acc *= scale;
-#pragma unroll
-                    for (int r = 0; r < NV; ++r) { st.acc[r].x *= scale; st.acc[r].y *= scale; st.acc[r].z *= scale; st.acc[r].w *= scale; }
-                }
-                st.m_run = m_new;
-            }
-        }
-        if (itC.cnt == DCAP) {
-#pragma unroll
-            for (int e = 0; e < DCAP; ++e)
-                accumulate(sl, e, w ? ex2_approx(s[e] - st.m_run) : 1.f, a[e], wx[e], wy[e], wz[e], (wrapped_mask >> e) & 1u);
-        } else {
-#pragma unroll
-            for (int e = 0; e < DCAP; ++e)
-                if (e < itC.cnt) accumulate(sl, e, w ? ex2_approx(s[e] - st.m_run) : 1.f, a[e], wx[e], wy[e], wz[e], (wrapped_mask >> e) & 1u);
-        }
-        if (itC.last) {
-            const float inv = w ? 1.0f / (st.l_run + 1e-16f) : 1.0f;      // PyG softmax: exp(s - max) / (sum + 1e-16)
-            const float lsum = st.l_run;
-            if (active) {
-                float* orow = p.agg + (size_t)itC.node * p.ld_agg + grp * C + 4 * sub;
-                float* lrow = p.agg_lo ? p.agg_lo + (size_t)itC.node * p.ld_agg + grp * C + 4 * sub : nullptr;
-#pragma unroll
-                for (int r = 0; r < NV; ++r) {
-                    // sum pe * relu(.) = sum pe * max(., nvp) - nvp * sum pe
-                    const float4 o = make_float4(fmaf(-st.vp[r].x, lsum, st.acc[r].x) * inv, fmaf(-st.vp[r].y, lsum, st.acc[r].y) * inv,
-                                                 fmaf(-st.vp[r].z, lsum, st.acc[r].z) * inv, fmaf(-st.vp[r].w, lsum, st.acc[r].w) * inv);
-                    if (lrow) {   // TF32 split for the tensor-core gate GEMM: agg = hi + lo, both TF32-representable
-                        const float4 hi = make_float4(tf32_rna(o.x), tf32_rna(o.y), tf32_rna(o.z), tf32_rna(o.w));
-                        const float4 lo = make_float4(tf32_rna(o.x - hi.x), tf32_rna(o.y - hi.y), tf32_rna(o.z - hi.z), tf32_rna(o.w - hi.w));
-                        stg4_stream(orow + 32 * r, hi);
-                        stg4_stream(lrow + 32 * r, lo);
-                    } else {
-                        stg4_stream(orow + 32 * r, o);
+                        for (int r = 0; r < NV; ++r) {
+                            const float4 k = lds4(krow + 128 * r);
+                            dd = fmaf(q[r].x, k.x, dd); d2_ = fmaf(q[r].y, k.y, d2_); dd = fmaf(q[r].z, k.z, dd); d2_ = fmaf(q[r].w, k.w, d2_);
+                        }
+                        dd = group_sum8(dd + d2_);
+                        if (wc[e]) {                         // periodGATconv.py:209-211: the wrapped displacement enters the key
+                            dd = fmaf(qx.x, wrapv(wc[e] & 3), dd); dd = fmaf(qx.y, wrapv((wc[e] >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((wc[e] >> 4) & 3), dd);
+                        }
+                        dd = fmaf(qx.w, a[e], dd);
+                        s[e] = dd * sc2;
+                        m_new = fmaxf(m_new, s[e]);
                     }
                 }
-                if (sub == 0) p.ea_out[(size_t)itC.node * G + grp] = st.ea_acc * inv;
+                if (m_new > m_run) {                         // online softmax: rescale what earlier chunks accumulated
+                    if (m_run != -CUDART_INF_F) {
+                        const float scale = ex2_approx(m_run - m_new);
+                        l_run *= scale; ea_acc *= scale;
+#pragma unroll
+                        for (int r = 0; r < NV; ++r) { acc[r].x *= scale; acc[r].y *= scale; acc[r].z *= scale; acc[r].w *= scale; }
+                    }
+                    m_run = m_new;
+                }
+            }
+            // relu(v + Wv3 (w_e - p_i)) = max(V_j + Wv3 w_e, vp) - vp: accumulate pe * max(., vp); the target subtracts vp * sum(pe) once
+#pragma unroll
+            for (int e = 0; e < DCAP; ++e) {
+                if (e < cnt) {
+                    const float pe = w ? ex2_approx(s[e] - m_run) : 1.f;
+                    l_run += pe;
+                    ea_acc = fmaf(pe, a[e], ea_acc);
+                    const uint32_t vrow = sl + e * (2 * ROWB) + rowb + lane_off;
+                    float4 v[NV];
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) v[r] = lds4(vrow + 128 * r);
+                    if (wc[e]) {                             // edge crosses a periodic / patch boundary (warp-uniform, rare)
+                        const float tx = wrapv(wc[e] & 3), ty = wrapv((wc[e] >> 2) & 3), tz = wrapv((wc[e] >> 4) & 3);
+#pragma unroll
+                        for (int r = 0; r < NV; ++r) {
+                            v[r].x += fmaf(wvz[r].x, tz, fmaf(wvy[r].x, ty, wvx[r].x * tx));
+                            v[r].y += fmaf(wvz[r].y, tz, fmaf(wvy[r].y, ty, wvx[r].y * tx));
+                            v[r].z += fmaf(wvz[r].z, tz, fmaf(wvy[r].z, ty, wvx[r].z * tx));
+                            v[r].w += fmaf(wvz[r].w, tz, fmaf(wvy[r].w, ty, wvx[r].w * tx));
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) {
+                        acc[r].x = fmaf(pe, fmaxf(v[r].x, vp[r].x), acc[r].x);
+                        acc[r].y = fmaf(pe, fmaxf(v[r].y, vp[r].y), acc[r].y);
+                        acc[r].z = fmaf(pe, fmaxf(v[r].z, vp[r].z), acc[r].z);
+                        acc[r].w = fmaf(pe, fmaxf(v[r].w, vp[r].w), acc[r].w);
+                    }
+                }
+            }
+        }
+        if (d0.z & 0x200) {                                  // last chunk of the target: normalise and store
+            const float inv = w ? 1.0f / (l_run + 1e-16f) : 1.0f;      // PyG softmax: exp(s - max) / (sum + 1e-16)
+            if (active) {
+                float* orow = p.agg + (size_t)d0.x * p.ld_agg + grp * C + 4 * sub;
+#pragma unroll
+                for (int r = 0; r < NV; ++r)                 // sum pe * relu(.) = sum pe * max(., vp) - vp * sum pe
+                    stg4_stream(orow + 32 * r, make_float4(fmaf(-vp[r].x, l_run, acc[r].x) * inv, fmaf(-vp[r].y, l_run, acc[r].y) * inv,
+                                                           fmaf(-vp[r].z, l_run, acc[r].z) * inv, fmaf(-vp[r].w, l_run, acc[r].w) * inv));
+                if (sub == 0) p.ea_out[(size_t)d0.x * G + grp] = ea_acc * inv;
             }
         }
         __syncwarp();                                        // every lane is done with this slot before it is refilled
-    };
-
-    // 3-deep software pipeline, unrolled by two so that slot ids are compile-time constants:
-    //   stage M: source ids of item k+2 | stage I: bulk copies of item k+1 | stage C: compute item k
-    Item itA = cur.next(), itB, itN;
-    int mjA, mjB, mjN; float maA, maB, maN;
-    load_meta(itA, mjA, maA);
-    itB = cur.next();
-    load_meta(itB, mjB, maB);
-    if (itA.valid) issue(itA, mjA, 0);
-    uint32_t par = 0u;
-    while (itA.valid) {
-        itN = cur.next(); load_meta(itN, mjN, maN);
-        if (itB.valid) issue(itB, mjB, 1);
-        compute(itA, maA, slot_addr0, bar_addr0, par);
-        itA = itN; mjA = mjN; maA = maN;                     // A now holds item k+2 (to be issued into slot 0)
-        if (!itB.valid) break;
-        itN = cur.next(); load_meta(itN, mjN, maN);
-        if (itA.valid) issue(itA, mjA, 0);
-        compute(itB, maB, slot_addr0 + SLOT, bar_addr0 + 8u, par);
-        itB = itN; mjB = mjN; maB = maN;
-        par ^= 1u;
+        d0 = d1; m0 = m1; d1 = d2; m1 = m2; d2 = d3;
+        idx += W1;
+        slot ^= 1;
     }
 }
 
-static int tma_gather_warps(int C, int quads, size_t* smem_out) {
-    const size_t rowb = (size_t)4 * C * 4;
-    const size_t slot = rowb * (1 + 2 * DCAP) + 128;
-    (void)quads;
-    const size_t wv = (size_t)3 * 4 * C * 4;
+static int tma_gather_warps(int C, size_t* smem_out) {
+    const size_t slot = (size_t)DCAP * 2 * 4 * C * 4;
     const size_t budget = 227 * 1024;
     int warps = 12;                                          // __launch_bounds__(384)
-    while (warps > 0 && wv + (size_t)warps * (2 * slot + 16) > budget) --warps;
-    *smem_out = wv + (size_t)warps * (2 * slot + 16);
+    while (warps > 0 && (size_t)warps * (2 * slot + 16) > budget) --warps;
+    *smem_out = (size_t)warps * (2 * slot + 16);
     return warps;
 }
 
 }  // namespace
 
+extern "C" int gg_gather_dcap(void) { return DCAP; }
+
 extern "C" int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off, int32_t v_off,
                               const float* P_dst, int32_t ld_dst, int32_t q_off, int32_t qx_off,
                               const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
                               const int32_t* rowptr, const int32_t* col, const float* eattr_csr,
+                              const int32_t* items, const int32_t* item_ptr, const int32_t* wrap_csr,
                               const float* Wv3, int32_t n_dst, int32_t G, int32_t C, int32_t weighted,
-                              float* agg, float* agg_lo, int32_t ld_agg, float* ea, void* stream) {
+                              float* agg, int32_t ld_agg, float* ea, void* stream) {
     if (n_dst < 0 || G < 1 || G > 64 || C % 32 || C < 32 || C > 128) return GG_EINVAL;
     if (n_dst == 0) return 0;
     if (!P_src || !pos_src || !pos_dst || !rowptr || !Wv3 || !agg || !ea) return GG_EINVAL;
@@ -634,24 +544,25 @@ extern "C" int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off,
     p.P_dst = P_dst; p.ld_dst = ld_dst; p.q_off = q_off; p.qx_off = qx_off;
     p.pos_src = pos_src; p.ld_ps = ld_pos_src; p.pos_dst = pos_dst; p.ld_pd = ld_pos_dst;
     p.rowptr = rowptr; p.col = col; p.ea = eattr_csr; p.Wv3 = Wv3;
+    p.items = items; p.item_ptr = item_ptr; p.wrap = wrap_csr;
     p.n_dst = n_dst; p.G = G; p.quads = (G + 3) / 4; p.weighted = weighted ? 1 : 0;
-    p.agg = agg; p.agg_lo = agg_lo; p.ld_agg = ld_agg; p.ea_out = ea;
-    if (agg_lo && !gg_aligned16(agg_lo)) return GG_EALIGN;
+    p.agg = agg; p.ld_agg = ld_agg; p.ea_out = ea;
     p.inv_sqrt_c = 1.0f / sqrtf((float)C);
     const int64_t units = (int64_t)n_dst * p.quads;
     cudaStream_t st = GG_STREAM(stream);
     cudaError_t err = cudaSuccess;
-    // TMA-staged pipeline (default): needs 16-byte aligned position rows for the bulk copies and room for >= 4 warps
+    // TMA-staged pipeline (default): needs the flat item list (gg_csr_items), the per-edge wrap codes (gg_edge_wrap) and G <= 4
     static const int force_ldg = []() { const char* e = getenv("GG_GATHER"); return e && e[0] == 'l' ? 1 : 0; }();
     size_t tma_smem = 0;
-    const int tma_warps = tma_gather_warps(C, p.quads, &tma_smem);
-    const bool tma_ok = !force_ldg && tma_warps >= 4 && p.quads == 1 && n_dst < (1 << 30) && !((ld_pos_src | ld_pos_dst) & 3) && ld_pos_src >= 4 && ld_pos_dst >= 4 && gg_aligned16(pos_src) && gg_aligned16(pos_dst)
-                        && (!weighted || !(qx_off & 3)) && gg_device_is_sm100();
+    const int tma_warps = tma_gather_warps(C, &tma_smem);
+    const bool tma_ok = !force_ldg && items && item_ptr && wrap_csr && tma_warps >= 4 && p.quads == 1 && gg_device_is_sm100();
     if (tma_ok) {
         static int n_sms = 0;
         if (n_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); }
+        static const int sm_cap = []() { const char* e = getenv("GG_GATHER_SMS"); return e ? atoi(e) : 0; }();   // experiments
+        const int use_sms = sm_cap > 0 && sm_cap < n_sms ? sm_cap : n_sms;
         const int64_t want = ((int64_t)n_dst + tma_warps - 1) / tma_warps;
-        const unsigned grid = (unsigned)(want < n_sms ? want : n_sms);
+        const unsigned grid = (unsigned)(want < use_sms ? want : use_sms);
 #define GG_GATHER_TMA(NV)                                                                                          \
     do {                                                                                                           \
         err = cudaFuncSetAttribute(pgat_gather_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem); \

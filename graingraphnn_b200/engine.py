@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from .cell import run_cell
-from .graph import build_csr, edge_length
+from .graph import build_csr, edge_length, edge_wrap
 from .heads import edge_head, feature_update, node_head
 from .models import GrainNN_classifier, GrainNN_regressor
 from .packing import pad4
@@ -35,7 +35,7 @@ class RolloutEngine:
         self.train_frames = 120
         self._graph = None
         self._work = {}
-        self.x, self.xbuf, self.edge_index, self.edge_attr, self.ea_csr, self.csr = {}, {}, {}, {}, {}, {}
+        self.x, self.xbuf, self.edge_index, self.edge_attr, self.ea_csr, self.csr, self.wrap = {}, {}, {}, {}, {}, {}, {}
         self.pred = {}
         self._scratch = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._packs = None
@@ -84,6 +84,7 @@ class RolloutEngine:
             self.csr[e] = build_csr(ei, self.xbuf[e[0]].shape[0], self.xbuf[e[2]].shape[0])
             self.edge_attr[e] = torch.empty(ei.shape[1], 1, dtype=torch.float32, device=self.device)
             self.ea_csr[e] = torch.empty(ei.shape[1], dtype=torch.float32, device=self.device)
+            self.wrap[e] = torch.empty(max(ei.shape[1], 1), dtype=torch.int32, device=self.device)
         if edge_attr_dict is None:
             self.rebuild_edge_attr()
         else:
@@ -92,9 +93,16 @@ class RolloutEngine:
                 self.edge_attr[e].copy_(edge_attr_dict[e].to(self.device, torch.float32).reshape(-1, 1))
                 _lib.check(L.gg_permute_f32(_lib.ptr(self.edge_attr[e]), _lib.ptr(self.csr[e].perm), _lib.ptr(self.ea_csr[e]),
                                             self.ea_csr[e].numel(), torch.cuda.current_stream().cuda_stream), 'gg_permute_f32')
+            self.rebuild_edge_wrap()
+
+    def rebuild_edge_wrap(self):
+        """Per-edge periodic wrap codes (periodGATconv.py:209-210) of the CURRENT coordinates, shared by all 48 convs of a step."""
+        for e in self.edge_types:
+            edge_wrap(self.csr[e], self.xbuf[e[0]], self.xbuf[e[2]], self.wrap[e])
 
     def rebuild_edge_attr(self):
-        """test.py:562-575 for every edge type, written in original and CSR order."""
+        """test.py:562-575 for every edge type, written in original and CSR order (+ the wrap codes of the new coordinates)."""
+        self.rebuild_edge_wrap()
         L = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
         for e in self.edge_types:
@@ -135,10 +143,10 @@ class RolloutEngine:
         sR, sC = self._states('R'), self._states('C')
         # encoders of both models read only X (h0 = c0 = 0, models.py:237-238)
         for name, st in (('R', sR), ('C', sC)):
-            run_cell(packs[name][0], self.xbuf, None, None, self.csr, self.ea_csr, _lib.GG_GATE_LSTM0, st['he'], st['ce'], w, nr)
+            run_cell(packs[name][0], self.xbuf, None, None, self.csr, self.ea_csr, _lib.GG_GATE_LSTM0, st['he'], st['ce'], w, nr, self.wrap)
         yield [sR['he'], sC['he']]
         for name, st in (('R', sR), ('C', sC)):
-            run_cell(packs[name][1], self.xbuf, st['he'], st['ce'], self.csr, self.ea_csr, _lib.GG_GATE_LSTM, st['hd'], st['cd'], w, nr)
+            run_cell(packs[name][1], self.xbuf, st['he'], st['ce'], self.csr, self.ea_csr, _lib.GG_GATE_LSTM, st['hd'], st['cd'], w, nr, self.wrap)
         yield [{'joint': sC['hd']['joint']}]                 # models.py:602 gathers h[src] of the joint-joint edges
         nj = None if nr is None else nr['joint']
         ng = None if nr is None else nr['grain']
@@ -193,9 +201,12 @@ class RolloutEngine:
         return {t: self.x[t].detach().cpu().contiguous() for t in self.node_types}
 
     def load_features(self, host_x):
-        """H2D: overwrite the resident node features from (ideally pinned) host tensors."""
+        """H2D: overwrite the resident node features from (ideally pinned) host tensors, then refresh what derives from the
+        coordinates (edge lengths, wrap codes), as test.py:556-575 does after the region-centre update."""
         for t in self.node_types:
             self.x[t].copy_(host_x[t], non_blocking=True)
+        with torch.cuda.device(self.device):
+            self.rebuild_edge_attr()
 
     def fetch_predictions(self, pred, out=None, keys=('joint', 'grain', 'grain_area', 'edge_event')):
         """D2H of the step outputs the host topology update consumes (models.py:626-628, test.py:418) into pinned buffers."""

@@ -18,13 +18,15 @@ def _stream():
 
 
 class EdgeCSR:
-    """rowptr[n_dst+1], col[E] (source ids), perm[E] (original edge ids) — int32, on the edge_index device."""
+    """rowptr[n_dst+1], col[E] (source ids), perm[E] (original edge ids) — int32, on the edge_index device;
+    items[*, 4] / item_ptr[n_dst+1]: flat work list of the gather kernel (gg_csr_items)."""
 
-    __slots__ = ('rowptr', 'col', 'perm', 'n_src', 'n_dst', 'n_edges')
+    __slots__ = ('rowptr', 'col', 'perm', 'n_src', 'n_dst', 'n_edges', 'items', 'item_ptr')
 
-    def __init__(self, rowptr, col, perm, n_src, n_dst, n_edges):
+    def __init__(self, rowptr, col, perm, n_src, n_dst, n_edges, items=None, item_ptr=None):
         self.rowptr, self.col, self.perm = rowptr, col, perm
         self.n_src, self.n_dst, self.n_edges = n_src, n_dst, n_edges
+        self.items, self.item_ptr = items, item_ptr
 
 
 def build_csr(edge_index, n_src, n_dst, validate=True):
@@ -46,9 +48,25 @@ def build_csr(edge_index, n_src, n_dst, validate=True):
     with torch.cuda.device(dev):
         check(L.gg_csr_build(ptr(ei), E, n_src, n_dst, ptr(rowptr), ptr(col), ptr(perm), ptr(status),
                              ptr(ws), ws_bytes, _stream()), 'gg_csr_build')
+    # flat work list of the gather kernel: <= n_dst + E / dcap items of <= dcap consecutive in-edges
+    dcap = L.gg_gather_dcap()
+    item_ptr = torch.empty(n_dst + 1, dtype=torch.int32, device=dev)
+    items = torch.empty(n_dst + E // dcap + 1, 4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(L.gg_csr_items(ptr(rowptr), n_dst, dcap, ptr(item_ptr), ptr(items), ptr(ws), ws_bytes, _stream()), 'gg_csr_items')
     if validate and int(status.item()) != 0:
         raise IndexError('edge_index holds an endpoint outside [0, N) (gg_csr_build: GG_ERANGE)')
-    return EdgeCSR(rowptr, col, perm, n_src, n_dst, E)
+    return EdgeCSR(rowptr, col, perm, n_src, n_dst, E, items, item_ptr)
+
+
+def edge_wrap(csr, x_src, x_dst, out=None):
+    """Per-edge periodic wrap codes (periodGATconv.py:209-210) in CSR order from the CURRENT positions (columns 0..2)."""
+    if out is None:
+        out = torch.empty(max(csr.n_edges, 1), dtype=torch.int32, device=x_dst.device)
+    with torch.cuda.device(x_dst.device):
+        check(_lib.lib().gg_edge_wrap(ptr(x_src), x_src.stride(0), ptr(x_dst), x_dst.stride(0), ptr(csr.rowptr), ptr(csr.col),
+                                      csr.n_dst, ptr(out), _stream()), 'gg_edge_wrap')
+    return out
 
 
 class CSRCache:

@@ -104,15 +104,32 @@ int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, const floa
  *             features; eattr_csr is a_e in CSR order.  Outputs: agg [n_dst, ld_agg] gate block, ea [n_dst, G].
  *     One warp per target node (8 lanes x C/8 channels per gate, 128-bit loads), no atomics; edges of a row
  *     are accumulated in CSR (= original) order, matching the sequential index_add_ of the CPU reference.
- *     If agg_lo != NULL the aggregate is written as a TF32 split (agg = hi, agg_lo = lo, cvt.rna) for gg_gate_update_tc.
+ *     Fast path (sm_100, G <= 4): pass the flat work list of gg_csr_items (items, item_ptr) and the per-edge wrap codes of
+ *     gg_edge_wrap (wrap_csr, computed from the CURRENT positions); the kernel then stages K|V rows with cp.async.bulk and
+ *     never reads source positions.  With items == NULL or wrap_csr == NULL the 128-bit-load kernel runs and derives the
+ *     wraps from pos_src / pos_dst itself.
  *     All row pointers / leading dimensions / offsets must be multiples of 4 floats (GG_EALIGN otherwise).
  * ---------------------------------------------------------------------------------------------- */
 int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off, int32_t v_off,
                    const float* P_dst, int32_t ld_dst, int32_t q_off, int32_t qx_off,
                    const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
                    const int32_t* rowptr, const int32_t* col, const float* eattr_csr,
+                   const int32_t* items /* nullable */, const int32_t* item_ptr /* nullable */, const int32_t* wrap_csr /* nullable */,
                    const float* Wv3, int32_t n_dst, int32_t G, int32_t C, int32_t weighted,
-                   float* agg, float* agg_lo /* nullable */, int32_t ld_agg, float* ea, void* stream);
+                   float* agg, int32_t ld_agg, float* ea, void* stream);
+
+/* Work list of the fast gather path: node i contributes max(1, ceil(deg_i / dcap)) items of <= dcap consecutive in-edges,
+ * items[k] = {node, first CSR edge, count | first << 8 | last << 9, 0} (int32 x 4, 16-byte aligned), item_ptr[n_dst + 1] =
+ * exclusive scan of the per-node item counts (item_ptr[n_dst] = number of items <= n_dst + E / dcap).
+ * dcap must be gg_gather_dcap().  workspace: gg_csr_workspace_bytes(0, n_dst). */
+int gg_gather_dcap(void);
+int gg_csr_items(const int32_t* rowptr, int32_t n_dst, int32_t dcap, int32_t* item_ptr, int32_t* items,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Periodic wrap of every edge (periodGATconv.py:209-210), CSR order: r = p_src - p_dst per coordinate, code 1 where
+ * r < -0.5 (+1), 2 where r > 0.5 (-1), else 0; wrap_csr[e] = cx | cy << 2 | cz << 4.  pos_* point at column 0 (x,y,z). */
+int gg_edge_wrap(const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
+                 const int32_t* rowptr, const int32_t* col, int32_t n_dst, int32_t* wrap_csr, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (c) post-aggregation gate GEMM fused with the LSTM update.  Per node m of one node type, gate g:
