@@ -29,7 +29,7 @@ _PROTOS = {
     'gg_permute_f32': (_I, [_P, _P, _P, _L, _P]),
     'gg_edge_length': (_I, [_P, _I, _P, _I, _P, _L, _P, _P, _P, _P]),
     'gg_node_proj': (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _I, _I, _I, _P]),
-    'gg_pgat_gather': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P]),
+    'gg_pgat_gather': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P]),
     'gg_gather_dcap': (_I, []),
     'gg_csr_items': (_I, [_P, _I, _I, _P, _P, _P, _S, _P]),
     'gg_edge_wrap': (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _P]),

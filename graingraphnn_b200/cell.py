@@ -46,6 +46,14 @@ def gemm_mode():
 _AUTO = None
 
 
+def raw_gather_available():
+    """True when gg_pgat_gather will run its bulk-copy kernel, the only one that implements raw-score mode."""
+    if os.environ.get('GG_GATHER', '').lower().startswith('l'):
+        return False
+    L = _lib.lib()
+    return hasattr(L, 'gg_tc_supported') and L.gg_tc_supported() == 1
+
+
 def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=None, n_rows=None, wrap=None):
     """xpad[t]: [N_t, K1p] fp32 (x,y,z in columns 0..2); h[t]: [N_t, K2] or None; c[t]: [N_t, C] or None;
     csr[e]: EdgeCSR; ea_csr[e]: [E] edge attribute in CSR order.  Returns (out_h, out_c) dicts.
@@ -111,7 +119,7 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
             check(L.gg_pgat_gather(ptr(P[s]), pk.ncols[s], pk.koff[e], pk.voff[e],
                                    ptr(P[d]), pk.ncols[d], pk.qoff[e], pk.qxoff[e],
                                    ptr(xpad[s]), xpad[s].stride(0), ptr(xpad[d]), xpad[d].stride(0),
-                                   ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(g.items), ptr(g.item_ptr), ptr(wr), ptr(pk.Wv3[e]),
+                                   ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(g.items), ptr(g.item_ptr), ptr(wr), pk.raw_k, ptr(pk.Wv3[e]),
                                    nd_out, G, C, 1 if pk.weighted else 0, ptr(agg[e]), GC, ptr(ea[e]), st), 'gg_pgat_gather')
         # (c') gate GEMM + LSTM update per node type
         out_h = {} if out_h is None else out_h

@@ -39,7 +39,7 @@ struct GatherParams {
     const float* pos_src; int ld_ps;
     const float* pos_dst; int ld_pd;
     const int* rowptr; const int* col; const float* ea;
-    int nb; const int* items; const int* item_ptr; const int* wrap;   // flat work list (+ per-node offsets) and per-edge wrap codes (TMA path)
+    int nb, raw_k; const int* items; const int* item_ptr; const int* wrap;   // flat work list (+ per-node offsets) and per-edge wrap codes (TMA path)
     const float* Wv3;
     int n_dst, G, quads, weighted;
     float* agg; int ld_agg; float* ea_out;
@@ -296,12 +296,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct Meta { int col, wrap; float ea; };            // per lane: edge `lane` of an item (lanes >= cnt: unused)
 
-template <int NV>
+// RAW: raw-score mode (cells without hidden state): the staged source row is [raw features (16 floats) | V row], the target
+// carries Q' = [Wk[:, :F]^T q | We . q] (16 floats per gate) and the score is the 16-term dot product x_j . Q' (the last term
+// multiplies the edge length), computed redundantly by the 8 lanes of a gate group: no key rows, no shuffles.
+template <int NV, bool RAW>
 __global__ void __launch_bounds__(384, 1)
 pgat_gather_tma_kernel(const GatherParams p) {
     constexpr int C = 32 * NV;
     constexpr int ROWB = 4 * C * 4;                         // one row of 4 gates x C floats (bytes)
-    constexpr int SLOT = DCAP * 2 * ROWB;                   // per edge: [K row | V row]
+    constexpr int SLOT = DCAP * 2 * ROWB;                   // per edge: [K row | V row]   (RAW: [16 raw floats | V row])
+    constexpr int NQ = RAW ? 4 : NV;                        // float4 registers of the target's query
     constexpr float LOG2E = 1.4426950408889634f;
     extern __shared__ __align__(128) uint8_t smem[];
     const int n_warps = blockDim.x >> 5;
@@ -324,7 +328,8 @@ pgat_gather_tma_kernel(const GatherParams p) {
     const uint32_t lane_off = 4u * (gsel * C + 4 * sub);    // byte offset of this lane's first float4 inside a staged row
     const uint32_t rowb = (uint32_t)GC * 4u;                // bytes of one K / V / Q row
     const int w = p.weighted;
-    const bool kv_adjacent = w && p.v_off == p.k_off + GC;  // one copy brings K|V
+    const bool kv_adjacent = w && p.v_off == p.k_off + (RAW ? 16 : GC);  // one copy brings K|V (RAW: raw features | V)
+    const uint32_t kbytes = RAW ? 64u : rowb;               // bytes staged in front of the V row
     const float sc2 = p.inv_sqrt_c * LOG2E;                 // scores are kept in log2 units: exp(x) = ex2(x log2 e)
 
     // x, y, z columns of lin_value for this lane's channels (zero for idle groups): Wv3 is [G*C][4]
@@ -375,24 +380,24 @@ pgat_gather_tma_kernel(const GatherParams p) {
         return m;
     };
     // register set of the NEXT item's target: Q row chunks, QX, position
-    float4 qn[NV], qxn = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 qn[NQ], qxn = make_float4(0.f, 0.f, 0.f, 0.f);
     float pnx = 0.f, pny = 0.f, pnz = 0.f;
 #pragma unroll
-    for (int r = 0; r < NV; ++r) qn[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < NQ; ++r) qn[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     auto issue_copies = [&](const int4& d, const Meta& m, int slot) {
         const int cnt = d.z & 0xff;
         if (cnt > 0) {
             const uint32_t base = slot_addr0 + slot * SLOT, bar = bar_addr0 + 8u * slot;
-            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)cnt * (w ? 2u * rowb : rowb));
+            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)cnt * (w ? kbytes + rowb : rowb));
             __syncwarp();
             if (lane < cnt) {                                            // per edge: K|V rows of the source
                 const float* prow = p.P_src + (size_t)m.col * p.ld_src;
                 const uint32_t kv = base + lane * (2 * ROWB);
                 if (kv_adjacent) {
-                    bulk_g2s(kv, prow + p.k_off, 2 * rowb, bar);
+                    bulk_g2s(kv, prow + p.k_off, kbytes + rowb, bar);
                 } else {
-                    if (w) bulk_g2s(kv, prow + p.k_off, rowb, bar);
-                    bulk_g2s(kv + rowb, prow + p.v_off, rowb, bar);
+                    if (w) bulk_g2s(kv, prow + p.k_off, kbytes, bar);
+                    bulk_g2s(kv + kbytes, prow + p.v_off, rowb, bar);
                 }
             }
         }
@@ -403,18 +408,25 @@ pgat_gather_tma_kernel(const GatherParams p) {
             pnx = __ldg(pd); pny = __ldg(pd + 1); pnz = __ldg(pd + 2);
             if (w) {
                 const float* qrow = p.P_dst + (size_t)d.x * p.ld_dst;
+                if (RAW) {
 #pragma unroll
-                for (int r = 0; r < NV; ++r) qn[r] = ldg4_stream(qrow + p.q_off + gsel * C + 4 * (sub + 8 * r));
-                qxn = ldg4(qrow + p.qx_off + 4 * gsel);
+                    for (int r = 0; r < NQ; ++r) qn[r] = ldg4(qrow + p.q_off + gsel * 16 + 4 * r);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NQ; ++r) qn[r] = ldg4_stream(qrow + p.q_off + gsel * C + 4 * (sub + 8 * r));
+                    qxn = ldg4(qrow + p.qx_off + 4 * gsel);
+                }
             }
         }
     };
 
     // per-target state
-    float4 q[NV], vp[NV], acc[NV], qx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 q[NQ], vp[NV], acc[NV], qx = make_float4(0.f, 0.f, 0.f, 0.f);
     float m_run = -CUDART_INF_F, l_run = 0.f, ea_acc = 0.f;
 #pragma unroll
-    for (int r = 0; r < NV; ++r) { q[r] = vp[r] = acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int r = 0; r < NV; ++r) { vp[r] = acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto wrapv = [](int code) -> float { return code == 0 ? 0.f : (code == 1 ? 1.f : -1.f); };   // gg_edge_wrap: 1 -> +1, 2 -> -1
 
@@ -430,15 +442,16 @@ pgat_gather_tma_kernel(const GatherParams p) {
         if (d1.x >= 0) issue_copies(d1, m1, slot ^ 1);       // the next item's rows are in flight before anything can stall
         if (d0.z & 0x100) {                                  // adopt the prefetched target registers (before they are reused)
 #pragma unroll
+            for (int r = 0; r < NQ; ++r) q[r] = qn[r];
+#pragma unroll
             for (int r = 0; r < NV; ++r) {                   // vp = Wv3 p_i:  V_j + Wv3 (w_e - p_i) > 0  <=>  V_j + Wv3 w_e > vp
-                q[r] = qn[r];
                 vp[r].x = fmaf(wvz[r].x, pnz, fmaf(wvy[r].x, pny, wvx[r].x * pnx));
                 vp[r].y = fmaf(wvz[r].y, pnz, fmaf(wvy[r].y, pny, wvx[r].y * pnx));
                 vp[r].z = fmaf(wvz[r].z, pnz, fmaf(wvy[r].z, pny, wvx[r].z * pnx));
                 vp[r].w = fmaf(wvz[r].w, pnz, fmaf(wvy[r].w, pny, wvx[r].w * pnx));
                 acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            qx = qxn;
+            qx = RAW ? q[0] : qxn;                           // RAW: Q'[0:3] = Wk3^T q
             m_run = -CUDART_INF_F; l_run = 0.f; ea_acc = 0.f;
         }
         if (d1.x >= 0) prefetch_target(d1);
@@ -457,18 +470,29 @@ pgat_gather_tma_kernel(const GatherParams p) {
 #pragma unroll
                 for (int e = 0; e < DCAP; ++e) {
                     if (e < cnt) {                           // warp-uniform
-                        const uint32_t krow = sl + e * (2 * ROWB) + lane_off;
                         float dd = 0.f, d2_ = 0.f;           // two partial sums: shorter dependency chains
+                        if (RAW) {
+                            const uint32_t xrow = sl + e * (2 * ROWB);          // same 64 bytes for every lane (broadcast)
+                            float4 x0 = lds4(xrow), x1 = lds4(xrow + 16), x2 = lds4(xrow + 32), x3 = lds4(xrow + 48);
+                            x3.w = a[e];                                         // Q'[15] = We . q multiplies the edge length
+                            dd = fmaf(q[0].x, x0.x, dd); d2_ = fmaf(q[0].y, x0.y, d2_); dd = fmaf(q[0].z, x0.z, dd); d2_ = fmaf(q[0].w, x0.w, d2_);
+                            dd = fmaf(q[1].x, x1.x, dd); d2_ = fmaf(q[1].y, x1.y, d2_); dd = fmaf(q[1].z, x1.z, dd); d2_ = fmaf(q[1].w, x1.w, d2_);
+                            dd = fmaf(q[2].x, x2.x, dd); d2_ = fmaf(q[2].y, x2.y, d2_); dd = fmaf(q[2].z, x2.z, dd); d2_ = fmaf(q[2].w, x2.w, d2_);
+                            dd = fmaf(q[3].x, x3.x, dd); d2_ = fmaf(q[3].y, x3.y, d2_); dd = fmaf(q[3].z, x3.z, dd); d2_ = fmaf(q[3].w, x3.w, d2_);
+                            dd += d2_;
+                        } else {
+                            const uint32_t krow = sl + e * (2 * ROWB) + lane_off;
 #pragma unroll
-                        for (int r = 0; r < NV; ++r) {
-                            const float4 k = lds4(krow + 128 * r);
-                            dd = fmaf(q[r].x, k.x, dd); d2_ = fmaf(q[r].y, k.y, d2_); dd = fmaf(q[r].z, k.z, dd); d2_ = fmaf(q[r].w, k.w, d2_);
+                            for (int r = 0; r < NV; ++r) {
+                                const float4 k = lds4(krow + 128 * r);
+                                dd = fmaf(q[r].x, k.x, dd); d2_ = fmaf(q[r].y, k.y, d2_); dd = fmaf(q[r].z, k.z, dd); d2_ = fmaf(q[r].w, k.w, d2_);
+                            }
+                            dd = group_sum8(dd + d2_);
                         }
-                        dd = group_sum8(dd + d2_);
                         if (wc[e]) {                         // periodGATconv.py:209-211: the wrapped displacement enters the key
                             dd = fmaf(qx.x, wrapv(wc[e] & 3), dd); dd = fmaf(qx.y, wrapv((wc[e] >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((wc[e] >> 4) & 3), dd);
                         }
-                        dd = fmaf(qx.w, a[e], dd);
+                        if (!RAW) dd = fmaf(qx.w, a[e], dd);
                         s[e] = dd * sc2;
                         m_new = fmaxf(m_new, s[e]);
                     }
@@ -490,7 +514,7 @@ pgat_gather_tma_kernel(const GatherParams p) {
                     const float pe = w ? ex2_approx(s[e] - m_run) : 1.f;
                     l_run += pe;
                     ea_acc = fmaf(pe, a[e], ea_acc);
-                    const uint32_t vrow = sl + e * (2 * ROWB) + rowb + lane_off;
+                    const uint32_t vrow = sl + e * (2 * ROWB) + kbytes + lane_off;
                     float4 v[NV];
 #pragma unroll
                     for (int r = 0; r < NV; ++r) v[r] = lds4(vrow + 128 * r);
@@ -548,7 +572,7 @@ extern "C" int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off,
                               const float* P_dst, int32_t ld_dst, int32_t q_off, int32_t qx_off,
                               const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
                               const int32_t* rowptr, const int32_t* col, const float* eattr_csr,
-                              const int32_t* items, const int32_t* item_ptr, const int32_t* wrap_csr,
+                              const int32_t* items, const int32_t* item_ptr, const int32_t* wrap_csr, int32_t raw_k,
                               const float* Wv3, int32_t n_dst, int32_t G, int32_t C, int32_t weighted,
                               float* agg, int32_t ld_agg, float* ea, void* stream) {
     if (n_dst < 0 || G < 1 || G > 64 || C % 32 || C < 32 || C > 128) return GG_EINVAL;
@@ -563,7 +587,8 @@ extern "C" int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off,
     p.P_dst = P_dst; p.ld_dst = ld_dst; p.q_off = q_off; p.qx_off = qx_off;
     p.pos_src = pos_src; p.ld_ps = ld_pos_src; p.pos_dst = pos_dst; p.ld_pd = ld_pos_dst;
     p.rowptr = rowptr; p.col = col; p.ea = eattr_csr; p.Wv3 = Wv3;
-    p.items = items; p.item_ptr = item_ptr; p.wrap = wrap_csr;
+    p.items = items; p.item_ptr = item_ptr; p.wrap = wrap_csr; p.raw_k = raw_k;
+    if (raw_k != 0 && (raw_k != 16 || !weighted || v_off != k_off + 16)) return GG_EINVAL;
     static const int nb_env = []() { const char* e = getenv("GG_GATHER_NB"); return e ? atoi(e) : 0; }();
     p.nb = nb_env > 0 ? nb_env : 8;                          // measured on B200, 250k targets: 1: 4.25 | 4: 3.87 | 8: 3.70 | 16: 3.96 | 64: 5.50 ms per step
     p.n_dst = n_dst; p.G = G; p.quads = (G + 3) / 4; p.weighted = weighted ? 1 : 0;
@@ -584,22 +609,32 @@ extern "C" int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off,
         const int use_sms = sm_cap > 0 && sm_cap < n_sms ? sm_cap : n_sms;
         const int64_t want = ((int64_t)n_dst + tma_warps - 1) / tma_warps;
         const unsigned grid = (unsigned)(want < use_sms ? want : use_sms);
-#define GG_GATHER_TMA(NV)                                                                                          \
+#define GG_GATHER_TMA(NV, RW)                                                                                        \
     do {                                                                                                           \
-        err = cudaFuncSetAttribute(pgat_gather_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem); \
+        err = cudaFuncSetAttribute(pgat_gather_tma_kernel<NV, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem); \
         if (err != cudaSuccess) return (int)err;                                                                   \
-        pgat_gather_tma_kernel<NV><<<grid, tma_warps * 32, tma_smem, st>>>(p);                                     \
+        pgat_gather_tma_kernel<NV, RW><<<grid, tma_warps * 32, tma_smem, st>>>(p);                                 \
     } while (0)
-        switch (C / 32) {
-            case 1: GG_GATHER_TMA(1); break;
-            case 2: GG_GATHER_TMA(2); break;
-            case 3: GG_GATHER_TMA(3); break;
-            default: GG_GATHER_TMA(4); break;
+        if (raw_k) {
+            switch (C / 32) {
+                case 1: GG_GATHER_TMA(1, true); break;
+                case 2: GG_GATHER_TMA(2, true); break;
+                case 3: GG_GATHER_TMA(3, true); break;
+                default: GG_GATHER_TMA(4, true); break;
+            }
+        } else {
+            switch (C / 32) {
+                case 1: GG_GATHER_TMA(1, false); break;
+                case 2: GG_GATHER_TMA(2, false); break;
+                case 3: GG_GATHER_TMA(3, false); break;
+                default: GG_GATHER_TMA(4, false); break;
+            }
         }
 #undef GG_GATHER_TMA
         GG_LAUNCH_OK();
         return 0;
     }
+    if (raw_k) return GG_EINVAL;                 // raw-score mode exists in the bulk-copy kernel only
     const unsigned nb = (unsigned)((units + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const size_t smem = (size_t)3 * p.quads * 4 * C * sizeof(float);
     if (smem > 200 * 1024) return GG_EINVAL;

@@ -15,7 +15,7 @@ from torch import nn
 from torch.nn import Parameter
 
 from . import _lib
-from .cell import _as_f32c, pad_features, require_cuda, run_cell
+from .cell import _as_f32c, pad_features, raw_gather_available, require_cuda, run_cell
 from .graph import GLOBAL_CSR_CACHE, permute_to_csr
 from .nn import HeteroConv, glorot_
 from .packing import ConvWeights, PackedCell, version_key
@@ -74,21 +74,26 @@ class _PGCBase(nn.Module):
     def _weights(self, gates):
         return {(g, e): ConvWeights(getattr(self, f'conv_{g}').conv(e)) for g in gates for e in self.metadata[1]}
 
-    def packed(self, gates, with_h, device, edge_types=None):
+    def packed(self, gates, with_h, device, edge_types=None, raw=None):
+        """raw: pack for the raw-score gather (no key projection; cells without hidden state only).  None = whenever the fast
+        gather path will take it (sm_100 device, <= 4 gates, <= 15 padded features per node type)."""
         edge_types = tuple(self.metadata[1]) if edge_types is None else tuple(edge_types)
+        if raw is None:
+            raw = (not with_h) and len(gates) <= 4 and str(device).startswith('cuda') and raw_gather_available() \
+                and all((f + 3) // 4 * 4 <= PackedCell.RAW_K - 1 for f in self.in_channels_dict.values())
         cws = self._weights(gates)
         tensors = [t for cw in cws.values() for t in cw.tensors()]
         tensors += [getattr(self, f'b_{g}')[t] for g in gates for t in self.in_channels_dict]
-        key = (tuple(gates), with_h, str(device), edge_types, version_key(tensors))
-        slot = (tuple(gates), with_h, edge_types)
+        key = (tuple(gates), with_h, str(device), edge_types, bool(raw), version_key(tensors))
+        slot = (tuple(gates), with_h, edge_types, bool(raw))
         hit = self._packs.get(slot)
         if hit is None or hit[0] != key:
             C = self.out_channels
             in_dims = {t: (f, C) for t, f in self.in_channels_dict.items()}
             pk = PackedCell(edge_types, gates, in_dims, C, lambda g, e: cws[(g, e)],
                             gate_bias=lambda g, t: getattr(self, f'b_{g}')[t],
-                            weighted=self.conv_class.weighted, device=device)
-            if not with_h:   # h == 0: only the feature columns of every weight matter (K = K1p)
+                            weighted=self.conv_class.weighted, device=device, raw_scores=bool(raw))
+            if not with_h and not raw:   # h == 0: only the feature columns of every weight matter (K = K1p)
                 for t in pk.node_types:
                     k1p = pk.k1p[t]
                     pk.Wcat[t] = pk.Wcat[t][:, :k1p].contiguous()

@@ -6,6 +6,9 @@ All re-associations are linear and exact in real arithmetic (SURVEY.md §7 "Alge
     collapses into the 4 scalars QX = [Wk[:, :3]^T q, We . q] per target and gate).
   * lin_l2, lin_edge and lin_skip move behind the aggregation (sum_e alpha_e = 1).
   * all gates of a cell share one projection GEMM; lin_skip of the edge types that end in the same node type are summed.
+  * "raw scores" (cells without hidden state, i.e. the encoder, models.py:237-238): q_i . (Wk x_j) = x_j . (Wk^T q_i), so the
+    key projection disappears altogether: the target carries Q'_i = [Wk[:, :F]^T q_i (F <= 15 source features) | We . q_i]
+    (16 floats per gate instead of C + 4) and the source row only its raw features next to V.
 Packing runs once per weight version (on whatever device the parameters live on) in float64, then rounds to fp32.
 """
 import torch
@@ -34,8 +37,9 @@ class ConvWeights:
 
 
 def _cols(w, k1, k1p, k2):
-    """[out, k1+k2] -> [out, k1p+k2] with zero columns inserted after the first k1."""
-    w = w.detach().double()
+    """[out, k1+k2] -> [out, k1p+k2] with zero columns inserted after the first k1 (a wider w is cut to its first k1+k2
+    columns: the hidden-state columns of a cell that runs without hidden state)."""
+    w = w.detach().double()[:, :k1 + k2]
     assert w.shape[1] == k1 + k2, (tuple(w.shape), k1, k2)
     out = torch.zeros(w.shape[0], k1p + k2, dtype=torch.float64, device=w.device)
     out[:, :k1] = w[:, :k1]
@@ -54,9 +58,16 @@ class PackedCell:
     in_dims[node_type] = (K1, K2): widths of the two input pieces (X and h); K2 may be 0.
     """
 
-    def __init__(self, edge_types, gates, in_dims, C, conv_of, gate_bias=None, weighted=True, device=None):
+    RAW_K = 16          # floats of the raw-feature block / of Q' per gate in raw-score mode
+
+    def __init__(self, edge_types, gates, in_dims, C, conv_of, gate_bias=None, weighted=True, device=None, raw_scores=False):
         self.edge_types, self.gates, self.C, self.G = list(edge_types), list(gates), C, len(gates)
         self.weighted = bool(weighted)
+        self.raw_k = self.RAW_K if raw_scores else 0
+        if raw_scores:      # h == 0: only the feature columns of every weight act; the hidden columns are dropped here
+            in_dims = {t: (k[0], 0) for t, k in in_dims.items()}
+            assert all(pad4(k[0]) <= self.RAW_K - 1 for k in in_dims.values()), 'raw-score mode needs <= 15 (padded) features'
+            self._full_k2 = C
         self.in_dims = dict(in_dims)
         self.node_types = list(self.in_dims)
         G = self.G
@@ -75,6 +86,19 @@ class PackedCell:
             for e in self.edge_types:              # source roles: K and V gate blocks
                 if e[0] != t:
                     continue
+                if self.raw_k:                     # raw-score mode: [raw features (16) | V gate block], one bulk copy per edge
+                    self.koff[e] = off
+                    dev0 = conv_of(self.gates[0], e).wv.device
+                    eye = torch.zeros(self.raw_k, k1p + k2, dtype=torch.float64, device=dev0)
+                    eye[:k1p, :k1p] = torch.eye(k1p, dtype=torch.float64, device=dev0)
+                    rows_w.append(eye); rows_b.append(torch.zeros(self.raw_k, dtype=torch.float64, device=dev0))
+                    off += self.raw_k
+                    self.voff[e] = off
+                    for g in self.gates:
+                        cw = conv_of(g, e)
+                        rows_w.append(_cols(cw.wv, k1, k1p, k2)); rows_b.append(_vec(cw.bv, C, cw.wv.device))
+                    off += GC
+                    continue
                 for role, store in (('k', self.koff), ('v', self.voff)):
                     store[e] = off
                     for g in self.gates:
@@ -84,6 +108,18 @@ class PackedCell:
                     off += GC
             for e in self.edge_types:              # target roles: Q gate block, directly followed by its QX block
                 if e[2] != t:                      # ([Wk[:, :3]^T q (3), We . q (1)] per gate) so one bulk copy stages both
+                    continue
+                if self.raw_k:                     # Q'[g] = [Wk[:, :F_src]^T q (padded to 15) | We . q]: 16 floats per gate
+                    self.qoff[e] = self.qxoff[e] = off
+                    fs = self.in_dims[e[0]][0]
+                    for g in self.gates:
+                        cw = conv_of(g, e)
+                        wq, bq = _cols(cw.wq, k1, k1p, k2), _vec(cw.bq, C, cw.wq.device)
+                        m = torch.zeros(C, self.raw_k, dtype=torch.float64, device=wq.device)
+                        m[:, :fs] = cw.wk.detach().double()[:, :fs]
+                        m[:, self.raw_k - 1] = cw.we.detach().double().reshape(C)
+                        rows_w.append(m.t() @ wq); rows_b.append(m.t() @ bq)
+                    off += self.raw_k * G
                     continue
                 self.qoff[e] = off
                 for g in self.gates:

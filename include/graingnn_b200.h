@@ -108,6 +108,9 @@ int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, const floa
  *     gg_edge_wrap (wrap_csr, computed from the CURRENT positions); the kernel then stages K|V rows with cp.async.bulk and
  *     never reads source positions.  With items == NULL or wrap_csr == NULL the 128-bit-load kernel runs and derives the
  *     wraps from pos_src / pos_dst itself.
+ *     raw_k = 16 (fast path only, cells without hidden state, weighted): raw-score mode.  q_i . (Wk x_j) = x_j . (Wk^T q_i), so
+ *     no key rows exist: P_src holds [raw features of the source (16 floats, zero padded) @k_off | V block @v_off = k_off+16]
+ *     and P_dst holds Q'_i = [Wk[:, :F]^T q_i (15) | We . q_i] per gate (G*16 floats @q_off; qx_off unused).  raw_k = 0: classic.
  *     All row pointers / leading dimensions / offsets must be multiples of 4 floats (GG_EALIGN otherwise).
  * ---------------------------------------------------------------------------------------------- */
 int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off, int32_t v_off,
@@ -115,6 +118,7 @@ int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off, int32_t v_
                    const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
                    const int32_t* rowptr, const int32_t* col, const float* eattr_csr,
                    const int32_t* items /* nullable */, const int32_t* item_ptr /* nullable */, const int32_t* wrap_csr /* nullable */,
+                   int32_t raw_k,
                    const float* Wv3, int32_t n_dst, int32_t G, int32_t C, int32_t weighted,
                    float* agg, int32_t ld_agg, float* ea, void* stream);
 

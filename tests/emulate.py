@@ -25,13 +25,21 @@ def emu_gather(pk, e, P_src, P_dst, pos_src, pos_dst, rowptr, col, ea_csr):
     w = pos_src[src, :3] - pos_dst[dst, :3]
     w = (w < -0.5).to(P_src.dtype) - (w > 0.5).to(P_src.dtype)
     t = w - pos_dst[dst, :3]
+    rk = getattr(pk, 'raw_k', 0)
     for g in range(G):
-        K = P_src[src, pk.koff[e] + g * C: pk.koff[e] + (g + 1) * C]
         V = P_src[src, pk.voff[e] + g * C: pk.voff[e] + (g + 1) * C]
-        Q = P_dst[dst, pk.qoff[e] + g * C: pk.qoff[e] + (g + 1) * C]
-        QX = P_dst[dst, pk.qxoff[e] + 4 * g: pk.qxoff[e] + 4 * g + 4]
+        if rk:      # raw-score mode: the source row carries its raw features, the target Q' = [Wk^T q | We . q] (16 per gate)
+            xj = P_src[src, pk.koff[e]: pk.koff[e] + rk].clone()
+            xj[:, rk - 1] = ea_csr
+            Qp = P_dst[dst, pk.qoff[e] + rk * g: pk.qoff[e] + rk * (g + 1)]
+            raw_s = (Qp * xj).sum(1) + (Qp[:, :3] * w).sum(1)
+        else:
+            K = P_src[src, pk.koff[e] + g * C: pk.koff[e] + (g + 1) * C]
+            Q = P_dst[dst, pk.qoff[e] + g * C: pk.qoff[e] + (g + 1) * C]
+            QX = P_dst[dst, pk.qxoff[e] + 4 * g: pk.qxoff[e] + 4 * g + 4]
+            raw_s = (Q * K).sum(1) + (QX[:, :3] * w).sum(1) + QX[:, 3] * ea_csr
         if pk.weighted:
-            s = ((Q * K).sum(1) + (QX[:, :3] * w).sum(1) + QX[:, 3] * ea_csr) / math.sqrt(C)
+            s = raw_s / math.sqrt(C)
             m = torch.full((nd,), float('-inf'), dtype=s.dtype).scatter_reduce(0, dst, s, 'amax')
             p = (s - m[dst]).exp()
             den = torch.zeros(nd, dtype=s.dtype).index_add_(0, dst, p)

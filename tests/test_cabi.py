@@ -36,7 +36,7 @@ def test_error_strings_and_argument_checks_without_gpu():
     assert b'aligned' in L.gg_error_string(-3)
     # argument validation happens before any CUDA call, so it is testable on a CPU-only box
     assert L.gg_csr_build(None, -1, 0, 0, None, None, None, None, None, 0, None) == -1
-    assert L.gg_pgat_gather(None, 0, 0, 0, None, 0, 0, 0, None, 0, None, 0, None, None, None, None, None, None, None, 5, 4, 100, 1, None, 0, None, None) == -1
+    assert L.gg_pgat_gather(None, 0, 0, 0, None, 0, 0, 0, None, 0, None, 0, None, None, None, None, None, None, 0, None, 5, 4, 100, 1, None, 0, None, None) == -1
     assert L.gg_gather_dcap() == 3 and L.gg_csr_items(None, -1, 3, None, None, None, 0, None) == -1
     assert L.gg_edge_wrap(None, 0, None, 0, None, None, 5, None, None) == -1
     assert L.gg_node_proj(None, 0, 0, None, 0, 0, None, 0, None, None, 0, 0, 0, None) == 0   # empty problem is a no-op

@@ -109,15 +109,21 @@ def test_packed_cell_algebra_matches_oracle(cls, gates, mode):
     assert all(rel_err(hh[t], href[t]) < 1e-6 for t in x)
 
 
-def test_packed_encoder_drops_forget_gate_and_hidden_columns():
+@pytest.mark.parametrize('raw', [False, True])
+def test_packed_encoder_drops_forget_gate_and_hidden_columns(raw):
+    """Encoder packing (h = c = 0): classic layout and the raw-score layout (no key projection, Q' of 16 floats per gate)."""
     x, ei, ea = load_graph('c1', torch.float64)
     sd = orc.synth_state_dict('classifier', 2)
     C = GrainNN_classifier(hyper())
     C.load_state_dict(sd)
     cell = C.gclstm_encoder.cell_list[0]
-    pk = cell.packed(('i', 'c', 'o'), False, 'cpu')
+    pk = cell.packed(('i', 'c', 'o'), False, 'cpu', raw=raw)
     assert pk.G == 3 and pk.Wcat['grain'].shape[1] == 12 and pk.Wcat['joint'].shape[1] == 8
-    assert pk.ncols['joint'] == 6 * 3 * 96 + 2 * 3 * 4 and pk.ncols['grain'] == 3 * 3 * 96 + 3 * 4
+    if raw:
+        assert pk.raw_k == 16 and pk.ncols['joint'] == 2 * (16 + 3 * 96) + 2 * 3 * 16 and pk.ncols['grain'] == 16 + 3 * 96 + 3 * 16
+        assert all(pk.voff[e] == pk.koff[e] + 16 for e in ET)
+    else:
+        assert pk.raw_k == 0 and pk.ncols['joint'] == 6 * 3 * 96 + 2 * 3 * 4 and pk.ncols['grain'] == 3 * 3 * 96 + 3 * 4
     csr = _csr(ei, x)
     eac = {e: ea[e].reshape(-1)[csr[e][2]] for e in ET}
     xpad = {t: pad_features(x[t].float(), pk.k1p[t]).double() for t in x}
