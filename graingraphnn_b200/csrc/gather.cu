@@ -296,12 +296,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct Meta { int col, wrap; float ea; };            // per lane: edge `lane` of an item (lanes >= cnt: unused)
 
-// RAW: raw-score mode (cells without hidden state): the staged source row is [raw features (16 floats) | V row], the target
-// carries Q' = [Wk[:, :F]^T q | We . q] (16 floats per gate) and the score is the 16-term dot product x_j . Q' (the last term
-// multiplies the edge length), computed redundantly by the 8 lanes of a gate group: no key rows, no shuffles.
-template <int NV, bool RAW>
+template <int NV>
 __global__ void __launch_bounds__(384, 1)
 pgat_gather_tma_kernel(const GatherParams p) {
+    constexpr bool RAW = false;                             // raw-score mode has its own kernel (pgat_gather_raw_kernel)
     constexpr int C = 32 * NV;
     constexpr int ROWB = 4 * C * 4;                         // one row of 4 gates x C floats (bytes)
     constexpr int SLOT = DCAP * 2 * ROWB;                   // per edge: [K row | V row]   (RAW: [16 raw floats | V row])
@@ -555,6 +553,250 @@ pgat_gather_tma_kernel(const GatherParams p) {
     }
 }
 
+// =====================================================================================================================
+// Raw-score variant (cells without hidden state, i.e. the encoder): q_i . (Wk x_j) = x_j . (Wk^T q_i), so no key rows exist.
+// The staged source row is [raw features (16 floats) | V row]; the target carries Q' = [Wk[:, :F]^T q | We . q] (16 floats per
+// gate) and the score is the 16-term dot product x_j . Q' (the last term multiplies the edge length), computed redundantly by
+// the 8 lanes of a gate group: no key rows, no shuffles.  An item needs ~5 KB of shared memory instead of 9 KB, which buys a
+// THIRD slot per warp: two items are in flight while one is computed (the classic kernel is bound by DRAM latency with one
+// item of lookahead).  Q' and the target position travel in the slot too (bulk copies), so no register set is tied up.
+// =====================================================================================================================
+constexpr int RAW_NSLOT = 3;
+
+template <int NV>
+__global__ void __launch_bounds__(384, 1)
+pgat_gather_raw_kernel(const GatherParams p) {
+    constexpr int C = 32 * NV;
+    constexpr int ROWB = 4 * C * 4;                         // V row of 4 gates (bytes)
+    constexpr int ES = 64 + ROWB;                           // per edge: [16 raw floats | V row]
+    constexpr int HDR = 320;                                // [Q' of 4 gates (256 B) | target position (16 B) | pad]
+    constexpr int SLOT = HDR + DCAP * ES;
+    constexpr int D = RAW_NSLOT - 1;                        // items in flight ahead of the one being computed
+    constexpr float LOG2E = 1.4426950408889634f;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int n_warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = p.G, GC = G * C;
+    uint8_t* my = smem + (size_t)warp * (RAW_NSLOT * SLOT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)n_warps * (RAW_NSLOT * SLOT)) + RAW_NSLOT * warp;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < RAW_NSLOT; ++i) mbar_init_(smem_addr(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int grp = lane >> 3, sub = lane & 7;
+    const bool active = grp < G;
+    const int gsel = active ? grp : 0;
+    const uint32_t slot_addr0 = smem_addr(my);
+    const uint32_t bar_addr0 = smem_addr(&bars[0]);
+    const uint32_t lane_off = 4u * (gsel * C + 4 * sub);
+    const uint32_t rowb = (uint32_t)GC * 4u;
+    const float sc2 = p.inv_sqrt_c * LOG2E;
+
+    float4 wvx[NV], wvy[NV], wvz[NV];
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        float4 t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = active ? ldg4(p.Wv3 + (size_t)(grp * C + 4 * (sub + 8 * r) + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wvx[r] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
+        wvy[r] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
+        wvz[r] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
+    }
+
+    // block-cyclic ownership of the item list (see pgat_gather_tma_kernel)
+    const int NB = p.nb;
+    const int4* __restrict__ items = reinterpret_cast<const int4*>(p.items);
+    const int64_t W = (int64_t)gridDim.x * n_warps, gw = (int64_t)blockIdx.x * n_warps + warp;
+    const int64_t n_blocks = ((int64_t)p.n_dst + NB - 1) / NB;
+    int64_t blk = gw;
+    int cur = 0, cur_end = 0, nxt = 0, nxt_end = 0;
+    auto block_range = [&](int64_t b, int& lo, int& hi) {
+        lo = hi = 0;
+        if (b < n_blocks) {
+            const int64_t n0 = b * NB, n1 = n0 + NB < p.n_dst ? n0 + NB : p.n_dst;
+            lo = __ldg(&p.item_ptr[n0]); hi = __ldg(&p.item_ptr[n1]);
+        }
+    };
+    block_range(blk, cur, cur_end);
+    block_range(blk + W, nxt, nxt_end);
+    auto load_desc = [&]() -> int4 {
+        while (cur >= cur_end) {
+            if (blk >= n_blocks) return make_int4(-1, 0, 0, 0);
+            blk += W; cur = nxt; cur_end = nxt_end;
+            block_range(blk + W, nxt, nxt_end);
+        }
+        return __ldg(items + cur++);
+    };
+    auto load_meta = [&](const int4& d) -> Meta {
+        Meta m; m.col = 0; m.wrap = 0; m.ea = 0.f;
+        if (d.x >= 0 && lane < (d.z & 0xff)) {
+            m.col = __ldg(&p.col[d.y + lane]); m.ea = __ldg(&p.ea[d.y + lane]); m.wrap = __ldg(&p.wrap[d.y + lane]);
+        }
+        return m;
+    };
+    auto issue = [&](const int4& d, const Meta& m, int slot) {
+        if (d.x < 0) return;
+        const int cnt = d.z & 0xff;
+        const bool first = d.z & 0x100;
+        const uint32_t tx = (uint32_t)cnt * (64u + rowb) + (first ? 64u * G + 16u : 0u);
+        if (tx == 0) return;
+        const uint32_t base = slot_addr0 + slot * SLOT, bar = bar_addr0 + 8u * slot;
+        if (lane == 0) mbar_expect_tx_(bar, tx);
+        __syncwarp();
+        if (lane < cnt) {                                                // per edge: [raw features | V] of the source
+            bulk_g2s(base + HDR + lane * ES, p.P_src + (size_t)m.col * p.ld_src + p.k_off, 64u + rowb, bar);
+        } else if (lane == DCAP && first) {
+            bulk_g2s(base, p.P_dst + (size_t)d.x * p.ld_dst + p.q_off, 64u * G, bar);
+        } else if (lane == DCAP + 1 && first) {
+            bulk_g2s(base + 256, p.pos_dst + (size_t)d.x * p.ld_pd, 16, bar);
+        }
+    };
+
+    float4 q[4], vp[NV], acc[NV];
+    float m_run = -CUDART_INF_F, l_run = 0.f, ea_acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) { vp[r] = acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto wrapv = [](int code) -> float { return code == 0 ? 0.f : (code == 1 ? 1.f : -1.f); };
+
+    // descriptor / metadata queues: d[i], m[i] belong to the item i positions ahead of the one being computed
+    int4 d[D + 2];
+    Meta m[D + 1];
+#pragma unroll
+    for (int i = 0; i < D + 2; ++i) d[i] = load_desc();
+#pragma unroll
+    for (int i = 0; i < D + 1; ++i) m[i] = load_meta(d[i]);
+#pragma unroll
+    for (int i = 0; i < D; ++i) issue(d[i], m[i], i);
+    uint32_t par = 0u;
+    int slot = 0;
+    while (d[0].x >= 0) {
+        const int4 d_new = load_desc();
+        const Meta m_new = load_meta(d[D + 1]);
+        { int s2 = slot + D; if (s2 >= RAW_NSLOT) s2 -= RAW_NSLOT; issue(d[D], m[D], s2); }   // slot of the item computed last
+
+        const int4 d0 = d[0];
+        const Meta m0 = m[0];
+        const int cnt = d0.z & 0xff;
+        const bool first = d0.z & 0x100;
+        const uint32_t sl = slot_addr0 + slot * SLOT;
+        if (cnt > 0 || first) {
+            mbar_wait_(bar_addr0 + 8u * slot, (par >> slot) & 1u);
+            par ^= 1u << slot;
+        }
+        if (first) {
+            const float4 pi = lds4(sl + 256);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) q[r] = lds4(sl + gsel * 64 + 16 * r);
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {                   // vp = Wv3 p_i
+                vp[r].x = fmaf(wvz[r].x, pi.z, fmaf(wvy[r].x, pi.y, wvx[r].x * pi.x));
+                vp[r].y = fmaf(wvz[r].y, pi.z, fmaf(wvy[r].y, pi.y, wvx[r].y * pi.x));
+                vp[r].z = fmaf(wvz[r].z, pi.z, fmaf(wvy[r].z, pi.y, wvx[r].z * pi.x));
+                vp[r].w = fmaf(wvz[r].w, pi.z, fmaf(wvy[r].w, pi.y, wvx[r].w * pi.x));
+                acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            m_run = -CUDART_INF_F; l_run = 0.f; ea_acc = 0.f;
+        }
+        if (cnt > 0) {
+            float a[DCAP], s[DCAP];
+            int wc[DCAP];
+#pragma unroll
+            for (int e = 0; e < DCAP; ++e) { a[e] = __shfl_sync(0xffffffffu, m0.ea, e); wc[e] = __shfl_sync(0xffffffffu, m0.wrap, e); s[e] = 0.f; }
+            float m_new_ = m_run;
+#pragma unroll
+            for (int e = 0; e < DCAP; ++e) {
+                if (e < cnt) {                               // warp-uniform
+                    const uint32_t xrow = sl + HDR + e * ES;                 // same 64 bytes for every lane (broadcast)
+                    float4 x0 = lds4(xrow), x1 = lds4(xrow + 16), x2 = lds4(xrow + 32), x3 = lds4(xrow + 48);
+                    x3.w = a[e];                                             // Q'[15] = We . q multiplies the edge length
+                    float dd = 0.f, d2_ = 0.f;
+                    dd = fmaf(q[0].x, x0.x, dd); d2_ = fmaf(q[0].y, x0.y, d2_); dd = fmaf(q[0].z, x0.z, dd); d2_ = fmaf(q[0].w, x0.w, d2_);
+                    dd = fmaf(q[1].x, x1.x, dd); d2_ = fmaf(q[1].y, x1.y, d2_); dd = fmaf(q[1].z, x1.z, dd); d2_ = fmaf(q[1].w, x1.w, d2_);
+                    dd = fmaf(q[2].x, x2.x, dd); d2_ = fmaf(q[2].y, x2.y, d2_); dd = fmaf(q[2].z, x2.z, dd); d2_ = fmaf(q[2].w, x2.w, d2_);
+                    dd = fmaf(q[3].x, x3.x, dd); d2_ = fmaf(q[3].y, x3.y, d2_); dd = fmaf(q[3].z, x3.z, dd); d2_ = fmaf(q[3].w, x3.w, d2_);
+                    dd += d2_;
+                    if (wc[e]) {                             // Q'[0:3] = Wk3^T q meets the wrap vector (periodGATconv.py:209-211)
+                        dd = fmaf(q[0].x, wrapv(wc[e] & 3), dd); dd = fmaf(q[0].y, wrapv((wc[e] >> 2) & 3), dd); dd = fmaf(q[0].z, wrapv((wc[e] >> 4) & 3), dd);
+                    }
+                    s[e] = dd * sc2;
+                    m_new_ = fmaxf(m_new_, s[e]);
+                }
+            }
+            if (m_new_ > m_run) {                            // online softmax: rescale what earlier chunks accumulated
+                if (m_run != -CUDART_INF_F) {
+                    const float scale = ex2_approx(m_run - m_new_);
+                    l_run *= scale; ea_acc *= scale;
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) { acc[r].x *= scale; acc[r].y *= scale; acc[r].z *= scale; acc[r].w *= scale; }
+                }
+                m_run = m_new_;
+            }
+#pragma unroll
+            for (int e = 0; e < DCAP; ++e) {
+                if (e < cnt) {
+                    const float pe = ex2_approx(s[e] - m_run);
+                    l_run += pe;
+                    ea_acc = fmaf(pe, a[e], ea_acc);
+                    const uint32_t vrow = sl + HDR + e * ES + 64 + lane_off;
+                    float4 v[NV];
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) v[r] = lds4(vrow + 128 * r);
+                    if (wc[e]) {
+                        const float tx = wrapv(wc[e] & 3), ty = wrapv((wc[e] >> 2) & 3), tz = wrapv((wc[e] >> 4) & 3);
+#pragma unroll
+                        for (int r = 0; r < NV; ++r) {
+                            v[r].x += fmaf(wvz[r].x, tz, fmaf(wvy[r].x, ty, wvx[r].x * tx));
+                            v[r].y += fmaf(wvz[r].y, tz, fmaf(wvy[r].y, ty, wvx[r].y * tx));
+                            v[r].z += fmaf(wvz[r].z, tz, fmaf(wvy[r].z, ty, wvx[r].z * tx));
+                            v[r].w += fmaf(wvz[r].w, tz, fmaf(wvy[r].w, ty, wvx[r].w * tx));
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) {
+                        acc[r].x = fmaf(pe, fmaxf(v[r].x, vp[r].x), acc[r].x);
+                        acc[r].y = fmaf(pe, fmaxf(v[r].y, vp[r].y), acc[r].y);
+                        acc[r].z = fmaf(pe, fmaxf(v[r].z, vp[r].z), acc[r].z);
+                        acc[r].w = fmaf(pe, fmaxf(v[r].w, vp[r].w), acc[r].w);
+                    }
+                }
+            }
+        }
+        if (d0.z & 0x200) {                                  // last chunk of the target: normalise and store
+            const float inv = 1.0f / (l_run + 1e-16f);       // PyG softmax: exp(s - max) / (sum + 1e-16)
+            if (active) {
+                float* orow = p.agg + (size_t)d0.x * p.ld_agg + grp * C + 4 * sub;
+#pragma unroll
+                for (int r = 0; r < NV; ++r)
+                    stg4_stream(orow + 32 * r, make_float4(fmaf(-vp[r].x, l_run, acc[r].x) * inv, fmaf(-vp[r].y, l_run, acc[r].y) * inv,
+                                                           fmaf(-vp[r].z, l_run, acc[r].z) * inv, fmaf(-vp[r].w, l_run, acc[r].w) * inv));
+                if (sub == 0) p.ea_out[(size_t)d0.x * G + grp] = ea_acc * inv;
+            }
+        }
+        __syncwarp();                                        // every lane is done with this slot before it is refilled
+#pragma unroll
+        for (int i = 0; i < D + 1; ++i) d[i] = d[i + 1];
+        d[D + 1] = d_new;
+#pragma unroll
+        for (int i = 0; i < D; ++i) m[i] = m[i + 1];
+        m[D] = m_new;
+        if (++slot == RAW_NSLOT) slot = 0;
+    }
+}
+
+static int raw_gather_warps(int C, size_t* smem_out) {
+    const size_t slot = 320 + (size_t)DCAP * (64 + 4 * C * 4);
+    const size_t per_warp = RAW_NSLOT * slot + 8 * RAW_NSLOT;
+    int warps = 12;                                          // __launch_bounds__(384)
+    while (warps > 0 && (size_t)warps * per_warp > 227 * 1024) --warps;
+    *smem_out = (size_t)warps * per_warp;
+    return warps;
+}
+
 static int tma_gather_warps(int C, size_t* smem_out) {
     const size_t slot = (size_t)DCAP * 2 * 4 * C * 4;
     const size_t budget = 227 * 1024;
@@ -609,25 +851,36 @@ extern "C" int gg_pgat_gather(const float* P_src, int32_t ld_src, int32_t k_off,
         const int use_sms = sm_cap > 0 && sm_cap < n_sms ? sm_cap : n_sms;
         const int64_t want = ((int64_t)n_dst + tma_warps - 1) / tma_warps;
         const unsigned grid = (unsigned)(want < use_sms ? want : use_sms);
-#define GG_GATHER_TMA(NV, RW)                                                                                        \
+#define GG_GATHER_TMA(NV)                                                                                          \
     do {                                                                                                           \
-        err = cudaFuncSetAttribute(pgat_gather_tma_kernel<NV, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem); \
+        err = cudaFuncSetAttribute(pgat_gather_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem); \
         if (err != cudaSuccess) return (int)err;                                                                   \
-        pgat_gather_tma_kernel<NV, RW><<<grid, tma_warps * 32, tma_smem, st>>>(p);                                 \
+        pgat_gather_tma_kernel<NV><<<grid, tma_warps * 32, tma_smem, st>>>(p);                                     \
     } while (0)
         if (raw_k) {
+            size_t raw_smem = 0;
+            const int raw_warps = raw_gather_warps(C, &raw_smem);
+            const int64_t want_r = ((int64_t)n_dst + raw_warps - 1) / raw_warps;
+            const unsigned grid_r = (unsigned)(want_r < use_sms ? want_r : use_sms);
+#define GG_GATHER_RAW(NV)                                                                                          \
+    do {                                                                                                           \
+        err = cudaFuncSetAttribute(pgat_gather_raw_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raw_smem); \
+        if (err != cudaSuccess) return (int)err;                                                                   \
+        pgat_gather_raw_kernel<NV><<<grid_r, raw_warps * 32, raw_smem, st>>>(p);                                   \
+    } while (0)
             switch (C / 32) {
-                case 1: GG_GATHER_TMA(1, true); break;
-                case 2: GG_GATHER_TMA(2, true); break;
-                case 3: GG_GATHER_TMA(3, true); break;
-                default: GG_GATHER_TMA(4, true); break;
+                case 1: GG_GATHER_RAW(1); break;
+                case 2: GG_GATHER_RAW(2); break;
+                case 3: GG_GATHER_RAW(3); break;
+                default: GG_GATHER_RAW(4); break;
             }
+#undef GG_GATHER_RAW
         } else {
             switch (C / 32) {
-                case 1: GG_GATHER_TMA(1, false); break;
-                case 2: GG_GATHER_TMA(2, false); break;
-                case 3: GG_GATHER_TMA(3, false); break;
-                default: GG_GATHER_TMA(4, false); break;
+                case 1: GG_GATHER_TMA(1); break;
+                case 2: GG_GATHER_TMA(2); break;
+                case 3: GG_GATHER_TMA(3); break;
+                default: GG_GATHER_TMA(4); break;
             }
         }
 #undef GG_GATHER_TMA
