@@ -54,6 +54,22 @@ def raw_gather_available():
     return hasattr(L, 'gg_tc_supported') and L.gg_tc_supported() == 1
 
 
+def tiled_ecap(pk, e):
+    """Tile size of the warp-specialised gather for edge type e of this pack, 0 when that kernel does not apply (unweighted
+    sum variant, G > 4, operand blocks not adjacent, not an sm_100 device, GG_GATHER=ldg|items)."""
+    mode = os.environ.get('GG_GATHER', '').lower()
+    if mode.startswith('l') or mode.startswith('i') or not pk.weighted or pk.G > 4 or pk.C % 32:
+        return 0
+    if pk.voff[e] != pk.koff[e] + (pk.raw_k if pk.raw_k else pk.G * pk.C):
+        return 0
+    if not pk.raw_k and pk.qxoff[e] != pk.qoff[e] + pk.G * pk.C:
+        return 0
+    L = _lib.lib()
+    if not (hasattr(L, 'gg_tc_supported') and L.gg_tc_supported() == 1):
+        return 0
+    return int(L.gg_gather_tile_ecap(pk.G, pk.C, pk.raw_k))
+
+
 def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=None, n_rows=None, wrap=None):
     """xpad[t]: [N_t, K1p] fp32 (x,y,z in columns 0..2); h[t]: [N_t, K2] or None; c[t]: [N_t, C] or None;
     csr[e]: EdgeCSR; ea_csr[e]: [E] edge attribute in CSR order.  Returns (out_h, out_c) dicts.
@@ -116,6 +132,15 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
             ea[e] = buf(('ea', e), (nd, G))
             g = csr[e]
             wr = wrap[e] if wrap is not None else edge_wrap(g, xpad[s], xpad[d])
+            ecap = tiled_ecap(pk, e)
+            if ecap:
+                tiles, cta_ptr, n_ctas = g.tiles(ecap)      # builds nz / nzptr on first use
+                check(L.gg_pgat_gather_tiled(ptr(P[s]), pk.ncols[s], pk.koff[e], ptr(P[d]), pk.ncols[d], pk.qoff[e],
+                                             ptr(xpad[d]), xpad[d].stride(0), ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(wr),
+                                             ptr(g.nz), ptr(g.nzptr), ptr(tiles), ptr(cta_ptr), n_ctas,
+                                             ecap, g.n_edges, pk.raw_k, ptr(pk.Wv3[e]), nd_out, G, C, ptr(agg[e]), GC, ptr(ea[e]), st),
+                      'gg_pgat_gather_tiled')
+                continue
             check(L.gg_pgat_gather(ptr(P[s]), pk.ncols[s], pk.koff[e], pk.voff[e],
                                    ptr(P[d]), pk.ncols[d], pk.qoff[e], pk.qxoff[e],
                                    ptr(xpad[s]), xpad[s].stride(0), ptr(xpad[d]), xpad[d].stride(0),

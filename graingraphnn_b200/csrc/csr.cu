@@ -123,6 +123,75 @@ __global__ void items_fill(const int* __restrict__ rowptr, const int* __restrict
     }
 }
 
+// ---- tile index of the warp-specialised gather (gather_tiled.cu) ------------------------------------------------
+// nz_flag / scan / nz_fill: the targets WITH in-edges, ascending (nz), and where their rows start (nzptr, nzptr[NZ] = E)
+__global__ void nz_flag(const int* __restrict__ rowptr, int n_dst, int* __restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_dst) return;
+    flag[i] = (i < n_dst && rowptr[i + 1] > rowptr[i]) ? 1 : 0;
+}
+__global__ void nz_fill(const int* __restrict__ rowptr, const int* __restrict__ pos, int n_dst, int* __restrict__ nz,
+                        int* __restrict__ nzptr, int* __restrict__ nz_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_dst) return;
+    const int o = pos[i];
+    if (i == n_dst) { nzptr[o] = rowptr[n_dst]; nz_count[0] = o; return; }
+    const int b = rowptr[i];
+    if (rowptr[i + 1] > b) { nz[o] = i; nzptr[o] = b; }
+}
+// Units and tiles (see gather_tiled.cu).  Unit k = targets (indices into nz) whose first in-edge lies in [k B, (k+1) B); its
+// edges [nzptr[i_lo], nzptr[i_hi]) are cut into tiles of <= ecap edges.  Units are laid out CTA-major: slot b * Uc + k' holds
+// unit k = b + k' * n_ctas, so an exclusive scan over the slots orders the tiles by CTA, then by unit, then by position.
+__device__ __forceinline__ int nz_lower_bound(const int* __restrict__ nzptr, int nzc, int x) {   // first i in [0, nzc] with nzptr[i] >= x
+    int lo = 0, hi = nzc;                            // nzptr[nzc] = E >= every x asked for
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&nzptr[mid]) >= x) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ int nz_owner(const int* __restrict__ nzptr, int nzc, int e) {         // largest i in [0, nzc) with nzptr[i] <= e
+    int lo = 0, hi = nzc - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&nzptr[mid]) <= e) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__global__ void unit_tiles_count(const int* __restrict__ nzptr, const int* __restrict__ nz_count, int E, int B, int ecap,
+                                 int n_units, int n_ctas, int Uc, int* __restrict__ cnt) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot > n_ctas * Uc) return;
+    int nt = 0;
+    const int k = Uc > 0 ? slot / Uc + (slot % Uc) * n_ctas : n_units;
+    if (slot < n_ctas * Uc && k < n_units) {
+        const int nzc = nz_count[0];
+        const int i_lo = nz_lower_bound(nzptr, nzc, k * B), i_hi = nz_lower_bound(nzptr, nzc, min((k + 1) * B, E));
+        if (i_lo < i_hi) nt = (__ldg(&nzptr[i_hi]) - __ldg(&nzptr[i_lo]) + ecap - 1) / ecap;
+    }
+    cnt[slot] = nt;
+}
+__global__ void unit_tiles_fill(const int* __restrict__ nzptr, const int* __restrict__ nz_count, int E, int B, int ecap,
+                                int n_units, int n_ctas, int Uc, const int* __restrict__ pos, int4* __restrict__ tiles,
+                                int* __restrict__ cta_ptr) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot > n_ctas * Uc) return;
+    if (Uc == 0) { for (int b = 0; b <= n_ctas; ++b) cta_ptr[b] = 0; return; }     // no edges: slot 0 is the only thread
+    if (slot == n_ctas * Uc) { cta_ptr[n_ctas] = pos[slot]; return; }
+    if (slot % Uc == 0) cta_ptr[slot / Uc] = pos[slot];
+    const int k = slot / Uc + (slot % Uc) * n_ctas;
+    if (k >= n_units) return;
+    const int nzc = nz_count[0];
+    const int i_lo = nz_lower_bound(nzptr, nzc, k * B), i_hi = nz_lower_bound(nzptr, nzc, min((k + 1) * B, E));
+    if (i_lo >= i_hi) return;
+    const int lo = __ldg(&nzptr[i_lo]), hi = __ldg(&nzptr[i_hi]);
+    int o = pos[slot];
+    for (int e0 = lo; e0 < hi; e0 += ecap, ++o) {
+        const int ne = min(ecap, hi - e0);
+        tiles[o] = make_int4(e0, ne, nz_owner(nzptr, nzc, e0), nz_owner(nzptr, nzc, e0 + ne - 1));
+    }
+}
+
 __global__ void permute_f32(const float* __restrict__ src, const int* __restrict__ perm, float* __restrict__ out, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = __ldg(&src[perm[i]]);
@@ -195,5 +264,62 @@ extern "C" int gg_csr_items(const int32_t* rowptr, int32_t n_dst, int32_t dcap, 
         scan_add_offsets<<<tiles, 256, 0, st>>>(item_ptr, n, tile_sum); GG_LAUNCH_OK();
     }
     if (n_dst > 0) { items_fill<<<(n_dst + 255) / 256, 256, 0, st>>>(rowptr, item_ptr, n_dst, dcap, reinterpret_cast<int4*>(items)); GG_LAUNCH_OK(); }
+    return 0;
+}
+
+extern "C" int gg_csr_compact(const int32_t* rowptr, int32_t n_dst, int32_t* nz, int32_t* nzptr, int32_t* nz_count,
+                              int32_t* scratch, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_dst < 0 || !rowptr || !nzptr || !nz_count || !scratch || !workspace) return GG_EINVAL;
+    if (n_dst > 0 && !nz) return GG_EINVAL;
+    if (workspace_bytes < gg_csr_workspace_bytes(0, n_dst)) return GG_ENOSPC;
+    cudaStream_t st = GG_STREAM(stream);
+    const int n = n_dst + 1;
+    const int tiles = (n + kScanTile - 1) / kScanTile;
+    int* flag = static_cast<int*>(workspace);
+    int* tile_sum = flag + n;
+    nz_flag<<<(n + 255) / 256, 256, 0, st>>>(rowptr, n_dst, flag); GG_LAUNCH_OK();
+    scan_tiles<<<tiles, 256, 0, st>>>(flag, scratch, n, tile_sum); GG_LAUNCH_OK();
+    if (tiles > 1) {
+        scan_tile_sums<<<1, 1024, 0, st>>>(tile_sum, tiles); GG_LAUNCH_OK();
+        scan_add_offsets<<<tiles, 256, 0, st>>>(scratch, n, tile_sum); GG_LAUNCH_OK();
+    }
+    nz_fill<<<(n + 255) / 256, 256, 0, st>>>(rowptr, scratch, n_dst, nz, nzptr, nz_count); GG_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int64_t gg_csr_tiles_capacity(int64_t n_edges, int32_t ecap, int32_t n_ctas) {
+    if (n_edges < 0 || ecap < 1 || n_ctas < 1) return 0;
+    const int64_t B = 8LL * ecap, n_units = (n_edges + B - 1) / B;
+    return n_units + n_edges / ecap + 1;              // every unit ends in at most one partial tile
+}
+
+extern "C" size_t gg_csr_tiles_scratch_ints(int64_t n_edges, int32_t ecap, int32_t n_ctas) {
+    if (n_edges < 0 || ecap < 1 || n_ctas < 1) return 0;
+    const int64_t B = 8LL * ecap, n_units = (n_edges + B - 1) / B, Uc = (n_units + n_ctas - 1) / n_ctas;
+    const int64_t n = (int64_t)n_ctas * Uc + 1;
+    return (size_t)(2 * n + (n + kScanTile - 1) / kScanTile + 64);
+}
+
+extern "C" int gg_csr_tiles(const int32_t* nzptr, const int32_t* nz_count, int64_t n_edges, int32_t ecap, int32_t n_ctas,
+                            int32_t* tiles, int32_t* cta_ptr, int32_t* scratch, void* stream) {
+    if (n_edges < 0 || n_edges > 0x7fffffffLL || ecap < 1 || n_ctas < 1 || !nzptr || !nz_count || !cta_ptr || !scratch) return GG_EINVAL;
+    if (n_edges > 0 && (!tiles || !gg_aligned16(tiles))) return GG_EINVAL;
+    cudaStream_t st = GG_STREAM(stream);
+    const int B = 8 * ecap;
+    const int n_units = (int)((n_edges + B - 1) / B);
+    const int Uc = (n_units + n_ctas - 1) / n_ctas;
+    const int n = n_ctas * Uc + 1;
+    const int scan_blocks = (n + kScanTile - 1) / kScanTile;
+    int* cnt = scratch;
+    int* pos = cnt + n;
+    int* tile_sum = pos + n;
+    unit_tiles_count<<<(n + 127) / 128, 128, 0, st>>>(nzptr, nz_count, (int)n_edges, B, ecap, n_units, n_ctas, Uc, cnt); GG_LAUNCH_OK();
+    scan_tiles<<<scan_blocks, 256, 0, st>>>(cnt, pos, n, tile_sum); GG_LAUNCH_OK();
+    if (scan_blocks > 1) {
+        scan_tile_sums<<<1, 1024, 0, st>>>(tile_sum, scan_blocks); GG_LAUNCH_OK();
+        scan_add_offsets<<<scan_blocks, 256, 0, st>>>(pos, n, tile_sum); GG_LAUNCH_OK();
+    }
+    unit_tiles_fill<<<(n + 127) / 128, 128, 0, st>>>(nzptr, nz_count, (int)n_edges, B, ecap, n_units, n_ctas, Uc, pos,
+                                                     reinterpret_cast<int4*>(tiles), cta_ptr); GG_LAUNCH_OK();
     return 0;
 }

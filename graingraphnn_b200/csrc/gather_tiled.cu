@@ -1,0 +1,518 @@
+// gather_tiled.cu — kernel family (b), warp-specialised form: fused periodic-attention gather / segment softmax / aggregate
+// (PeriodConv.message + PyG softmax + scatter-add, periodGATconv.py:204-236, :174) for ONE edge type and ALL gates of a cell.
+//
+// Why this form: the per-warp pipelines of gather.cu spend ~350 of their ~570 instructions per target on bookkeeping (work-list
+// queues, address arithmetic, copy issue loops) and run 3 warps per scheduler, so they are bound by instruction issue at ~30 %
+// of the HBM roofline although every copy has landed before it is waited for (ncu: profiles/r1_gather_v4_ncu_summary.csv).
+// Here the irregular part lives in dedicated producer warps and the consumers execute straight-line arithmetic out of shared
+// memory:
+//
+//   * Targets are grouped into UNITS by the CSR position of their first in-edge (unit k: first edge in [k B, (k+1) B), B = 8 ECAP)
+//     and the edges of a unit are cut into TILES of ECAP consecutive in-edges (the last one shorter) — independent of where
+//     target rows begin and end, so any in-degree works with a fixed shared-memory slot count.  gg_csr_compact lists the targets
+//     with in-edges (nz, nzptr); gg_csr_tiles emits the tile list {first edge, edges, first target, last target} ordered by
+//     CTA: unit k belongs to CTA k mod n_ctas (neighbouring units, which share source rows, are in flight together on
+//     different SMs and meet in L2), and cta_ptr[b] .. cta_ptr[b + 1] are the tiles of CTA b in processing order.
+//   * Persistent CTA per SM.  NP producer warps: per tile, one cp.async.bulk per edge brings the source row
+//     ([K|V], or [raw features|V] in raw-score mode) into the stage, one per starting target brings Q|QX (or Q') and one its
+//     position; edge lengths, wrap codes and the target list are written to the stage by the producer lanes.  Everything of a
+//     tile completes on ONE mbarrier (expect_tx); NS stages, full/empty barrier pair per stage.
+//   * NC consumer warps: target i (index in the compacted list) belongs to warp i mod NC in EVERY tile, so a row that straddles a
+//     tile boundary (always inside one unit, hence inside one CTA) stays with its warp and the online-softmax state (running
+//     max, denominator, accumulators) simply stays in registers across tiles.  8 lanes per gate, 128-bit shared-memory loads, no atomics, edges of a row accumulate in CSR order.
+//   * Targets without in-edges get their zero rows from a short pass at the end.
+//
+// Algorithmic bytes per launch: see gather.cu (identical data, identical arithmetic).
+#include "common.cuh"
+#include <math_constants.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int NP = 4;                 // producer warps (one warpgroup)
+constexpr int NC = 12;                // consumer warps
+constexpr int kThreads = 32 * (NP + NC);
+constexpr int CH = 3;                 // edges per softmax chunk (joints have exactly 3 in-edges)
+
+struct TiledParams {
+    const float* P_src; int ld_src, k_off;
+    const float* P_dst; int ld_dst, q_off;
+    const float* pos_dst; int ld_pd;
+    const int* rowptr; const int* col; const float* ea; const int* wrap;
+    const int* nz; const int* nzptr; const int4* tiles; const int* cta_ptr;
+    const float* Wv3;
+    int n_dst, n_edges, G, ecap, hcap, nstage;
+    float* agg; int ld_agg; float* ea_out;
+    float inv_sqrt_c;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    long long t0 = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && (++spins & 0xfffu) == 0) {              // a lost copy must surface as an error, not as a hung GPU
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 8000000000LL) __trap();
+        }
+    } while (!done);
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ int lds1i(uint32_t addr) {
+    int r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float lds1f(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts1i(uint32_t addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts1f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void stg4_stream(float* p, const float4& v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float group_sum8(float s) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    return s;
+}
+__device__ __forceinline__ float wrapv(int code) { return code == 0 ? 0.f : (code == 1 ? 1.f : -1.f); }   // gg_edge_wrap: 1 -> +1, 2 -> -1
+
+// shared-memory layout of one stage (byte offsets; every block 16-byte aligned)
+struct StageLayout {
+    uint32_t es, qb, hb, hdr, ea, wrap, tn, te, info, bytes;
+};
+__host__ __device__ inline StageLayout stage_layout(int G, int C, bool raw, int ecap, int hcap) {
+    StageLayout L;
+    const uint32_t gc4 = (uint32_t)G * C * 4u;
+    L.es = raw ? 64u + gc4 : 2u * gc4;                      // one edge: [raw16 | V] or [K | V]
+    L.qb = raw ? 64u * G : gc4 + 16u * G;                   // one starting target: Q' (16 per gate) or Q | QX
+    L.hb = L.qb + 16u;                                      // ... followed by its position (x, y, z, -)
+    L.hdr = (uint32_t)ecap * L.es;
+    L.ea = L.hdr + (uint32_t)hcap * L.hb;
+    const uint32_t e4 = (((uint32_t)ecap * 4u) + 15u) & ~15u;
+    L.wrap = L.ea + e4;
+    L.tn = L.wrap + e4;
+    L.te = L.tn + e4;
+    L.info = L.te + ((((uint32_t)ecap + 1u) * 4u + 15u) & ~15u);
+    L.bytes = (L.info + 16u + 127u) & ~127u;
+    return L;
+}
+
+template <int NV, bool RAW>
+__global__ void __launch_bounds__(kThreads, 1)
+pgat_gather_tiled_kernel(const TiledParams p) {
+    constexpr int C = 32 * NV;
+    constexpr int NQ = RAW ? 4 : NV;                         // float4 registers of the target's query
+    constexpr float LOG2E = 1.4426950408889634f;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = p.G, GC = G * C;
+    const int ECAP = p.ecap, HCAP = p.hcap, NS = p.nstage;
+    const StageLayout L = stage_layout(G, C, RAW, ECAP, HCAP);
+    const uint32_t smem0 = smem_addr(smem);
+    const uint32_t bar0 = smem0 + (uint32_t)NS * L.bytes;    // full[NS] | empty[NS]
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (NS + s); };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init_(full_bar(s), 1); mbar_init_(empty_bar(s), NC); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int grid = gridDim.x;
+    const int f0 = __ldg(&p.cta_ptr[blockIdx.x]), n_tiles = __ldg(&p.cta_ptr[blockIdx.x + 1]) - f0;   // this CTA's tiles
+
+    if (warp < NP) {
+        // =========================================================================================== producers
+        // Producer w serves the CTA's tiles w, w + NP, ... (local index t; stage t mod NS).  Tile descriptors are read two
+        // tiles ahead and the per-edge / per-target metadata one tile ahead, so the chain tiles -> col -> row address is
+        // never waited for.
+        struct Meta { int col[2], wrap[2], tn[2], te[2], te_end; float ea[2]; };
+        auto load_desc = [&](int t) -> int4 {                       // {first edge, edges, first target, last target}
+            return t < n_tiles ? __ldg(&p.tiles[f0 + t]) : make_int4(0, 0, 0, -1);
+        };
+        auto load_meta = [&](const int4& d) -> Meta {
+            Meta m;
+            const int e0 = d.x, ne = d.y, cnt = d.w - d.z + 1;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int s = lane + 32 * r;
+                m.col[r] = 0; m.wrap[r] = 0; m.ea[r] = 0.f; m.tn[r] = 0; m.te[r] = 0;
+                if (s < ne) { m.col[r] = __ldg(&p.col[e0 + s]); m.ea[r] = __ldg(&p.ea[e0 + s]); m.wrap[r] = __ldg(&p.wrap[e0 + s]); }
+                if (s < cnt) { m.tn[r] = __ldg(&p.nz[d.z + s]); m.te[r] = __ldg(&p.nzptr[d.z + s]); }
+            }
+            m.te_end = (lane == 0 && cnt > 0) ? __ldg(&p.nzptr[d.w + 1]) : 0;
+            return m;
+        };
+        // A producer may run at most NS tiles ahead of the consumers: a parity wait cannot tell "two phases behind" from "done",
+        // so only min(NP, NS) producers are active (producer w moves from tile t to t + np <= t + NS, whose stage was last used
+        // by a tile <= t, already handed back in order).
+        const int np = NP < NS ? NP : NS;
+        if (warp >= np) return;
+        int t = warp;
+        int4 d_cur = load_desc(t), d_nxt = load_desc(t + np);
+        Meta m_cur = load_meta(d_cur);
+        for (; t < n_tiles; t += np) {
+            const int4 d_n2 = load_desc(t + 2 * np);
+            const Meta m_nxt = load_meta(d_nxt);
+            const int e0 = d_cur.x, ne = d_cur.y;
+            const int cnt = d_cur.w - d_cur.z + 1;
+            const int stage = t % NS;
+            const uint32_t phase = (uint32_t)(t / NS) & 1u;
+            const int fs = __shfl_sync(0xffffffffu, m_cur.te[0], 0) >= e0 ? 1 : 0;     // does the first target START in this tile?
+            const int n_hdr = min(cnt - (1 - fs), HCAP);
+            const uint32_t base = smem0 + (uint32_t)stage * L.bytes, bar = full_bar(stage);
+            mbar_wait_(empty_bar(stage), phase ^ 1u);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int s = lane + 32 * r;
+                if (s < ne) { sts1f(base + L.ea + 4u * s, m_cur.ea[r]); sts1i(base + L.wrap + 4u * s, m_cur.wrap[r]); }
+                if (s < cnt) { sts1i(base + L.tn + 4u * s, m_cur.tn[r]); sts1i(base + L.te + 4u * s, m_cur.te[r]); }
+            }
+            if (lane == 0) {
+                sts1i(base + L.te + 4u * cnt, m_cur.te_end);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + L.info), "r"(e0), "r"(cnt | (fs << 16)), "r"(ne), "r"(d_cur.z) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)ne * L.es + (uint32_t)n_hdr * L.hb);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int s = lane + 32 * r;
+                if (s < ne) bulk_g2s(base + (uint32_t)s * L.es, p.P_src + (size_t)m_cur.col[r] * p.ld_src + p.k_off, L.es, bar);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int h = lane + 32 * r - (1 - fs);                      // header slot of target j = lane + 32 r
+                if (lane + 32 * r < cnt && h >= 0 && h < HCAP) {
+                    const uint32_t hd = base + L.hdr + (uint32_t)h * L.hb;
+                    bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn[r] * p.ld_dst + p.q_off, L.qb, bar);
+                    bulk_g2s(hd + L.qb, p.pos_dst + (size_t)m_cur.tn[r] * p.ld_pd, 16u, bar);
+                }
+            }
+            d_cur = d_nxt; d_nxt = d_n2; m_cur = m_nxt;
+        }
+        return;
+    }
+
+    // =============================================================================================== consumers
+    const int cw = warp - NP;
+    const int grp = lane >> 3, sub = lane & 7;
+    const bool active = grp < G;
+    const int gsel = active ? grp : 0;                       // idle 8-lane groups (G < 4) shadow gate 0 and store nothing
+    const uint32_t lane_off = 4u * (gsel * C + 4 * sub);     // byte offset of this lane's first float4 inside a staged row
+    const uint32_t v_off = RAW ? 64u : (uint32_t)GC * 4u;    // V row behind the raw features / the K row
+    const float sc2 = p.inv_sqrt_c * LOG2E;                  // scores are kept in log2 units: exp(x) = ex2(x log2 e)
+
+    // x, y, z columns of lin_value for this lane's channels (zero for idle groups): Wv3 is [G*C][4]
+    float4 wvx[NV], wvy[NV], wvz[NV];
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        float4 t4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t4[i] = active ? ldg4(p.Wv3 + (size_t)(grp * C + 4 * (sub + 8 * r) + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wvx[r] = make_float4(t4[0].x, t4[1].x, t4[2].x, t4[3].x);
+        wvy[r] = make_float4(t4[0].y, t4[1].y, t4[2].y, t4[3].y);
+        wvz[r] = make_float4(t4[0].z, t4[1].z, t4[2].z, t4[3].z);
+    }
+
+    // per-target state (survives tile boundaries)
+    float4 q[NQ], vp[NV], acc[NV], qx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float m_run = -CUDART_INF_F, l_run = 0.f, ea_acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) { vp[r] = acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int stage = 0; uint32_t phase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t base = smem0 + (uint32_t)stage * L.bytes;
+        mbar_wait_(full_bar(stage), phase);
+        int e0, cnt, ne, i_first;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(cnt), "=r"(ne), "=r"(i_first) : "r"(base + L.info));
+        const int fs = cnt >> 16;
+        cnt &= 0xffff;
+        const int e1 = e0 + ne;
+        int j = cw - i_first % NC;
+        if (j < 0) j += NC;
+        for (; j < cnt; j += NC) {
+            const int node = lds1i(base + L.tn + 4u * j);
+            const int a = lds1i(base + L.te + 4u * j), b = lds1i(base + L.te + 4u * j + 4u);
+            if (node >= p.n_dst) continue;                   // rows behind the owned ones (slab partition) are not computed
+            const int lo = max(a, e0) - e0, hi = min(b, e1) - e0;
+            if (a >= e0) {
+                // ---- the target starts here: its query, position, fresh softmax state
+                const int h = j - (1 - fs);
+                float4 pi;
+                if (h < HCAP) {
+                    const uint32_t hd = base + L.hdr + (uint32_t)h * L.hb;
+                    if (RAW) {
+#pragma unroll
+                        for (int r = 0; r < NQ; ++r) q[r] = lds4(hd + gsel * 64 + 16 * r);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NQ; ++r) q[r] = lds4(hd + lane_off + 128 * r);
+                        qx = lds4(hd + (uint32_t)GC * 4u + 16u * gsel);
+                    }
+                    pi = lds4(hd + L.qb);
+                } else {                                      // more starting targets than header slots (runs of in-degree < 3): plain loads
+                    const float* qrow = p.P_dst + (size_t)node * p.ld_dst + p.q_off;
+                    if (RAW) {
+#pragma unroll
+                        for (int r = 0; r < NQ; ++r) q[r] = ldg4(qrow + gsel * 16 + 4 * r);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NQ; ++r) q[r] = ldg4(qrow + gsel * C + 4 * (sub + 8 * r));
+                        qx = ldg4(qrow + GC + 4 * gsel);
+                    }
+                    pi = ldg4(p.pos_dst + (size_t)node * p.ld_pd);
+                }
+                if (RAW) qx = q[0];                           // Q'[0:3] = Wk3^T q
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {                // vp = Wv3 p_i:  V_j + Wv3 (w_e - p_i) > 0  <=>  V_j + Wv3 w_e > vp
+                    vp[r].x = fmaf(wvz[r].x, pi.z, fmaf(wvy[r].x, pi.y, wvx[r].x * pi.x));
+                    vp[r].y = fmaf(wvz[r].y, pi.z, fmaf(wvy[r].y, pi.y, wvx[r].y * pi.x));
+                    vp[r].z = fmaf(wvz[r].z, pi.z, fmaf(wvy[r].z, pi.y, wvx[r].z * pi.x));
+                    vp[r].w = fmaf(wvz[r].w, pi.z, fmaf(wvy[r].w, pi.y, wvx[r].w * pi.x));
+                    acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                m_run = -CUDART_INF_F; l_run = 0.f; ea_acc = 0.f;
+            }
+            for (int s0 = lo; s0 < hi; s0 += CH) {
+                const int n_e = min(CH, hi - s0);             // warp-uniform
+                float ae[CH], sc[CH];
+                int wc[CH];
+                float m_new = m_run;
+#pragma unroll
+                for (int e = 0; e < CH; ++e) {
+                    sc[e] = 0.f; ae[e] = 0.f; wc[e] = 0;
+                    if (e < n_e) {
+                        ae[e] = lds1f(base + L.ea + 4u * (s0 + e));
+                        wc[e] = lds1i(base + L.wrap + 4u * (s0 + e));
+                        const uint32_t row = base + (uint32_t)(s0 + e) * L.es;
+                        float dd = 0.f, d2 = 0.f;             // two partial sums: shorter dependency chains
+                        if (RAW) {
+                            float4 x0 = lds4(row), x1 = lds4(row + 16), x2 = lds4(row + 32), x3 = lds4(row + 48);   // broadcast
+                            x3.w = ae[e];                     // Q'[15] = We . q multiplies the edge length
+                            dd = fmaf(q[0].x, x0.x, dd); d2 = fmaf(q[0].y, x0.y, d2); dd = fmaf(q[0].z, x0.z, dd); d2 = fmaf(q[0].w, x0.w, d2);
+                            dd = fmaf(q[1].x, x1.x, dd); d2 = fmaf(q[1].y, x1.y, d2); dd = fmaf(q[1].z, x1.z, dd); d2 = fmaf(q[1].w, x1.w, d2);
+                            dd = fmaf(q[2].x, x2.x, dd); d2 = fmaf(q[2].y, x2.y, d2); dd = fmaf(q[2].z, x2.z, dd); d2 = fmaf(q[2].w, x2.w, d2);
+                            dd = fmaf(q[3].x, x3.x, dd); d2 = fmaf(q[3].y, x3.y, d2); dd = fmaf(q[3].z, x3.z, dd); d2 = fmaf(q[3].w, x3.w, d2);
+                            dd += d2;
+                        } else {
+                            const uint32_t krow = row + lane_off;
+#pragma unroll
+                            for (int r = 0; r < NV; ++r) {
+                                const float4 kk = lds4(krow + 128 * r);
+                                dd = fmaf(q[r].x, kk.x, dd); d2 = fmaf(q[r].y, kk.y, d2); dd = fmaf(q[r].z, kk.z, dd); d2 = fmaf(q[r].w, kk.w, d2);
+                            }
+                            dd = group_sum8(dd + d2);
+                            dd = fmaf(qx.w, ae[e], dd);
+                        }
+                        if (wc[e]) {                          // periodGATconv.py:209-211: the wrapped displacement enters the key
+                            dd = fmaf(qx.x, wrapv(wc[e] & 3), dd); dd = fmaf(qx.y, wrapv((wc[e] >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((wc[e] >> 4) & 3), dd);
+                        }
+                        sc[e] = dd * sc2;
+                        m_new = fmaxf(m_new, sc[e]);
+                    }
+                }
+                if (m_new > m_run) {                          // online softmax: rescale what earlier chunks accumulated
+                    if (m_run != -CUDART_INF_F) {
+                        const float scale = ex2_approx(m_run - m_new);
+                        l_run *= scale; ea_acc *= scale;
+#pragma unroll
+                        for (int r = 0; r < NV; ++r) { acc[r].x *= scale; acc[r].y *= scale; acc[r].z *= scale; acc[r].w *= scale; }
+                    }
+                    m_run = m_new;
+                }
+                // relu(v + Wv3 (w_e - p_i)) = max(V_j + Wv3 w_e, vp) - vp: accumulate pe * max(., vp); vp * sum(pe) is subtracted once
+#pragma unroll
+                for (int e = 0; e < CH; ++e) {
+                    if (e < n_e) {
+                        const float pe = ex2_approx(sc[e] - m_run);
+                        l_run += pe;
+                        ea_acc = fmaf(pe, ae[e], ea_acc);
+                        const uint32_t vrow = base + (uint32_t)(s0 + e) * L.es + v_off + lane_off;
+                        float4 v[NV];
+#pragma unroll
+                        for (int r = 0; r < NV; ++r) v[r] = lds4(vrow + 128 * r);
+                        if (wc[e]) {                          // edge crosses a periodic / patch boundary (warp-uniform, rare)
+                            const float tx = wrapv(wc[e] & 3), ty = wrapv((wc[e] >> 2) & 3), tz = wrapv((wc[e] >> 4) & 3);
+#pragma unroll
+                            for (int r = 0; r < NV; ++r) {
+                                v[r].x += fmaf(wvz[r].x, tz, fmaf(wvy[r].x, ty, wvx[r].x * tx));
+                                v[r].y += fmaf(wvz[r].y, tz, fmaf(wvy[r].y, ty, wvx[r].y * tx));
+                                v[r].z += fmaf(wvz[r].z, tz, fmaf(wvy[r].z, ty, wvx[r].z * tx));
+                                v[r].w += fmaf(wvz[r].w, tz, fmaf(wvy[r].w, ty, wvx[r].w * tx));
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < NV; ++r) {
+                            acc[r].x = fmaf(pe, fmaxf(v[r].x, vp[r].x), acc[r].x);
+                            acc[r].y = fmaf(pe, fmaxf(v[r].y, vp[r].y), acc[r].y);
+                            acc[r].z = fmaf(pe, fmaxf(v[r].z, vp[r].z), acc[r].z);
+                            acc[r].w = fmaf(pe, fmaxf(v[r].w, vp[r].w), acc[r].w);
+                        }
+                    }
+                }
+            }
+            if (b <= e1) {
+                // ---- the target ends here: normalise and store (PyG softmax: exp(s - max) / (sum + 1e-16))
+                const float inv = 1.0f / (l_run + 1e-16f);
+                if (active) {
+                    float* orow = p.agg + (size_t)node * p.ld_agg + grp * C + 4 * sub;
+#pragma unroll
+                    for (int r = 0; r < NV; ++r)              // sum pe * relu(.) = sum pe * max(., vp) - vp * sum pe
+                        stg4_stream(orow + 32 * r, make_float4(fmaf(-vp[r].x, l_run, acc[r].x) * inv, fmaf(-vp[r].y, l_run, acc[r].y) * inv,
+                                                               fmaf(-vp[r].z, l_run, acc[r].z) * inv, fmaf(-vp[r].w, l_run, acc[r].w) * inv));
+                    if (sub == 0) p.ea_out[(size_t)node * G + grp] = ea_acc * inv;
+                }
+            }
+        }
+        __syncwarp();                                         // every lane is done with the stage before it is handed back
+        if (lane == 0) mbar_arrive_(empty_bar(stage));
+        if (++stage == NS) { stage = 0; phase ^= 1u; }
+    }
+
+    // ---- targets without in-edges: zero rows (PyG scatter-add leaves them 0)
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t b0 = ((int64_t)blockIdx.x * NC + cw) * 32; b0 < p.n_dst; b0 += (int64_t)grid * NC * 32) {
+        const int n = (int)b0 + lane;
+        const bool empty = n < p.n_dst && __ldg(&p.rowptr[n + 1]) == __ldg(&p.rowptr[n]);
+        unsigned mask = __ballot_sync(0xffffffffu, empty);
+        while (mask) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int node = (int)b0 + bit;
+            if (active) {
+                float* orow = p.agg + (size_t)node * p.ld_agg + grp * C + 4 * sub;
+#pragma unroll
+                for (int r = 0; r < NV; ++r) stg4_stream(orow + 32 * r, z4);
+                if (sub == 0) p.ea_out[(size_t)node * G + grp] = 0.f;
+            }
+        }
+    }
+}
+
+// tile geometry for (G, C, raw): the largest stage count / tile size that fits 227 KB
+struct TileCfg { int ecap, hcap, nstage; };
+TileCfg tile_config(int G, int C, bool raw) {
+    TileCfg c{0, 0, 0};
+    if (G < 1 || G > 4 || C % 32 || C < 32 || C > 128) return c;
+    const int budget = 227 * 1024 - 256;
+    // candidates, best first: three stages of as many edges as fit (multiple of 6: joints have 3 in-edges, grains ~6), else two
+    for (int ns = 3; ns >= 2; --ns) {
+        for (int ecap = 60; ecap >= 12; ecap -= 6) {
+            const int hcap = ecap / 3 + 2;
+            const StageLayout L = stage_layout(G, C, raw, ecap, hcap);
+            if ((long long)ns * L.bytes <= budget) { c.ecap = ecap; c.hcap = hcap; c.nstage = ns; return c; }
+        }
+    }
+    return c;
+}
+
+}  // namespace
+
+extern "C" int gg_gather_tile_ecap(int32_t G, int32_t C, int32_t raw_k) {
+    return tile_config(G, C, raw_k != 0).ecap;
+}
+
+// number of persistent CTAs the tile lists are laid out for: one per SM (GG_GATHER_SMS caps it for experiments)
+extern "C" int gg_gather_ctas(void) {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) return 0;
+        const char* e = getenv("GG_GATHER_SMS");
+        const int cap = e ? atoi(e) : 0;
+        n = cap > 0 && cap < sms ? cap : sms;
+    }
+    return n;
+}
+
+extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t k_off,
+                                    const float* P_dst, int32_t ld_dst, int32_t q_off,
+                                    const float* pos_dst, int32_t ld_pos_dst,
+                                    const int32_t* rowptr, const int32_t* col, const float* eattr_csr, const int32_t* wrap_csr,
+                                    const int32_t* nz, const int32_t* nzptr, const int32_t* tiles, const int32_t* cta_ptr,
+                                    int32_t n_ctas, int32_t ecap, int64_t n_edges,
+                                    int32_t raw_k, const float* Wv3, int32_t n_dst, int32_t G, int32_t C,
+                                    float* agg, int32_t ld_agg, float* ea, void* stream) {
+    if (n_dst < 0 || n_edges < 0 || n_edges > 0x7fffffffLL || (raw_k != 0 && raw_k != 16)) return GG_EINVAL;
+    const TileCfg cfg = tile_config(G, C, raw_k != 0);
+    if (cfg.ecap == 0 || ecap != cfg.ecap) return GG_EINVAL;
+    if (n_dst == 0) return 0;
+    if (!P_src || !P_dst || !pos_dst || !rowptr || !Wv3 || !agg || !ea) return GG_EINVAL;
+    if (!cta_ptr || n_ctas < 1) return GG_EINVAL;
+    if (n_edges > 0 && (!col || !eattr_csr || !wrap_csr || !nz || !nzptr || !tiles || !gg_aligned16(tiles))) return GG_EINVAL;
+    if ((ld_src | k_off | ld_dst | q_off | ld_agg | ld_pos_dst) & 3) return GG_EALIGN;
+    if (!gg_aligned16(P_src) || !gg_aligned16(P_dst) || !gg_aligned16(pos_dst) || !gg_aligned16(agg) || !gg_aligned16(Wv3)) return GG_EALIGN;
+    if (!gg_device_is_sm100()) return GG_EARCH;
+    TiledParams p;
+    p.P_src = P_src; p.ld_src = ld_src; p.k_off = k_off;
+    p.P_dst = P_dst; p.ld_dst = ld_dst; p.q_off = q_off;
+    p.pos_dst = pos_dst; p.ld_pd = ld_pos_dst;
+    p.rowptr = rowptr; p.col = col; p.ea = eattr_csr; p.wrap = wrap_csr;
+    p.nz = nz; p.nzptr = nzptr; p.tiles = reinterpret_cast<const int4*>(tiles); p.cta_ptr = cta_ptr;
+    p.Wv3 = Wv3;
+    p.n_dst = n_dst; p.n_edges = (int)n_edges;
+    p.G = G; p.ecap = cfg.ecap; p.hcap = cfg.hcap; p.nstage = cfg.nstage;
+    p.agg = agg; p.ld_agg = ld_agg; p.ea_out = ea;
+    p.inv_sqrt_c = 1.0f / sqrtf((float)C);
+    const StageLayout L = stage_layout(G, C, raw_k != 0, cfg.ecap, cfg.hcap);
+    const size_t smem = (size_t)cfg.nstage * L.bytes + 16 * cfg.nstage;
+    const unsigned grid = (unsigned)n_ctas;                  // the tile list is ordered for exactly this many CTAs
+    cudaStream_t st = GG_STREAM(stream);
+    cudaError_t err = cudaSuccess;
+#define GG_TILED(NV, RAWV)                                                                                                        \
+    do {                                                                                                                          \
+        err = cudaFuncSetAttribute(pgat_gather_tiled_kernel<NV, RAWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (err != cudaSuccess) return (int)err;                                                                                  \
+        pgat_gather_tiled_kernel<NV, RAWV><<<grid, kThreads, smem, st>>>(p);                                                      \
+    } while (0)
+    if (raw_k) {
+        switch (C / 32) {
+            case 1: GG_TILED(1, true); break;
+            case 2: GG_TILED(2, true); break;
+            case 3: GG_TILED(3, true); break;
+            default: GG_TILED(4, true); break;
+        }
+    } else {
+        switch (C / 32) {
+            case 1: GG_TILED(1, false); break;
+            case 2: GG_TILED(2, false); break;
+            case 3: GG_TILED(3, false); break;
+            default: GG_TILED(4, false); break;
+        }
+    }
+#undef GG_TILED
+    GG_LAUNCH_OK();
+    return 0;
+}

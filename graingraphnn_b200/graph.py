@@ -21,12 +21,41 @@ class EdgeCSR:
     """rowptr[n_dst+1], col[E] (source ids), perm[E] (original edge ids) — int32, on the edge_index device;
     items[*, 4] / item_ptr[n_dst+1]: flat work list of the gather kernel (gg_csr_items)."""
 
-    __slots__ = ('rowptr', 'col', 'perm', 'n_src', 'n_dst', 'n_edges', 'items', 'item_ptr')
+    __slots__ = ('rowptr', 'col', 'perm', 'n_src', 'n_dst', 'n_edges', 'items', 'item_ptr', 'nz', 'nzptr', 'nz_count', '_tiles')
 
     def __init__(self, rowptr, col, perm, n_src, n_dst, n_edges, items=None, item_ptr=None):
         self.rowptr, self.col, self.perm = rowptr, col, perm
         self.n_src, self.n_dst, self.n_edges = n_src, n_dst, n_edges
         self.items, self.item_ptr = items, item_ptr
+        self.nz = self.nzptr = self.nz_count = None
+        self._tiles = {}
+
+    def tiles(self, ecap):
+        """Tile index of the warp-specialised gather (gg_csr_compact + gg_csr_tiles) for tiles of `ecap` in-edges: (tiles [*, 4],
+        cta_ptr [n_ctas + 1], n_ctas), built on first use per tile size, then reused until the topology changes."""
+        t = self._tiles.get(ecap)
+        if t is None:
+            L = _lib.lib()
+            dev = self.rowptr.device
+            with torch.cuda.device(dev):
+                if self.nz is None:
+                    self.nz = torch.empty(max(self.n_dst, 1), dtype=torch.int32, device=dev)
+                    self.nzptr = torch.empty(self.n_dst + 1, dtype=torch.int32, device=dev)
+                    self.nz_count = torch.empty(1, dtype=torch.int32, device=dev)
+                    scratch = torch.empty(self.n_dst + 1, dtype=torch.int32, device=dev)
+                    ws_bytes = L.gg_csr_workspace_bytes(0, self.n_dst)
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                    check(L.gg_csr_compact(ptr(self.rowptr), self.n_dst, ptr(self.nz), ptr(self.nzptr), ptr(self.nz_count),
+                                           ptr(scratch), ptr(ws), ws_bytes, _stream()), 'gg_csr_compact')
+                n_ctas = L.gg_gather_ctas()
+                tl = torch.empty(max(L.gg_csr_tiles_capacity(self.n_edges, ecap, n_ctas), 1), 4, dtype=torch.int32, device=dev)
+                cta_ptr = torch.empty(n_ctas + 1, dtype=torch.int32, device=dev)
+                scr = torch.empty(L.gg_csr_tiles_scratch_ints(self.n_edges, ecap, n_ctas), dtype=torch.int32, device=dev)
+                check(L.gg_csr_tiles(ptr(self.nzptr), ptr(self.nz_count), self.n_edges, ecap, n_ctas, ptr(tl), ptr(cta_ptr), ptr(scr),
+                                     _stream()), 'gg_csr_tiles')
+                t = (tl, cta_ptr, n_ctas)
+            self._tiles[ecap] = t
+        return t
 
 
 def build_csr(edge_index, n_src, n_dst, validate=True):

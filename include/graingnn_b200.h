@@ -130,6 +130,37 @@ int gg_gather_dcap(void);
 int gg_csr_items(const int32_t* rowptr, int32_t n_dst, int32_t dcap, int32_t* item_ptr, int32_t* items,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Warp-specialised form of (b) (gather_tiled.cu; sm_100, weighted, G <= 4): same arithmetic and outputs as gg_pgat_gather on
+ * the same layout (K|V adjacent at k_off, or raw16|V in raw-score mode; Q|QX adjacent at q_off, or Q'), driven by the TILE
+ * index instead of the item list: the CSR edge array is cut into tiles of ecap = gg_gather_tile_ecap(G, C, raw_k) consecutive
+ * in-edges (0 = this shape is not supported), producer warps stage each tile with cp.async.bulk, consumer warps compute.
+ *   gg_csr_compact: nz[NZ] = targets with in-edges (ascending), nzptr[NZ + 1] = where their rows start (nzptr[NZ] = E),
+ *                   nz_count[0] = NZ;  nz / nzptr sized n_dst / n_dst + 1, scratch int32[n_dst + 1],
+ *                   workspace gg_csr_workspace_bytes(0, n_dst).
+ *   gg_csr_tiles:   targets are grouped into units by the CSR position of their first in-edge (unit k: [8 ecap k, 8 ecap (k+1)))
+ *                   and each unit's edges are cut into tiles of <= ecap edges; tiles[f] = {first CSR edge, edges, index in nz of
+ *                   the target owning the first edge, ... the last edge} (int32 x 4, 16-byte aligned), ordered by CTA (unit k
+ *                   belongs to CTA k mod n_ctas), cta_ptr[n_ctas + 1] = where each CTA's tiles start.  tiles holds
+ *                   gg_csr_tiles_capacity(E, ecap, n_ctas) entries, scratch gg_csr_tiles_scratch_ints(...) int32.
+ *                   n_ctas must be gg_gather_ctas() (one persistent CTA per SM) and is the grid gg_pgat_gather_tiled launches.
+ * Replaces PyG propagate + utils.softmax + scatter-add (periodGATconv.py:174, :204-236) like gg_pgat_gather. */
+int gg_gather_tile_ecap(int32_t G, int32_t C, int32_t raw_k);
+int gg_csr_compact(const int32_t* rowptr, int32_t n_dst, int32_t* nz, int32_t* nzptr, int32_t* nz_count,
+                   int32_t* scratch, void* workspace, size_t workspace_bytes, void* stream);
+int gg_gather_ctas(void);
+int64_t gg_csr_tiles_capacity(int64_t n_edges, int32_t ecap, int32_t n_ctas);
+size_t gg_csr_tiles_scratch_ints(int64_t n_edges, int32_t ecap, int32_t n_ctas);
+int gg_csr_tiles(const int32_t* nzptr, const int32_t* nz_count, int64_t n_edges, int32_t ecap, int32_t n_ctas,
+                 int32_t* tiles, int32_t* cta_ptr, int32_t* scratch, void* stream);
+int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t k_off,
+                         const float* P_dst, int32_t ld_dst, int32_t q_off,
+                         const float* pos_dst, int32_t ld_pos_dst,
+                         const int32_t* rowptr, const int32_t* col, const float* eattr_csr, const int32_t* wrap_csr,
+                         const int32_t* nz, const int32_t* nzptr, const int32_t* tiles, const int32_t* cta_ptr,
+                         int32_t n_ctas, int32_t ecap, int64_t n_edges,
+                         int32_t raw_k, const float* Wv3, int32_t n_dst, int32_t G, int32_t C,
+                         float* agg, int32_t ld_agg, float* ea, void* stream);
+
 /* Periodic wrap of every edge (periodGATconv.py:209-210), CSR order: r = p_src - p_dst per coordinate, code 1 where
  * r < -0.5 (+1), 2 where r > 0.5 (-1), else 0; wrap_csr[e] = cx | cy << 2 | cz << 4.  pos_* point at column 0 (x,y,z). */
 int gg_edge_wrap(const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,

@@ -6,8 +6,8 @@ timeout 600 python -m pytest tests -m gpu -q -x --timeout 120 2>&1 | tail -15
 timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -c 2500 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
 if [ -n "$GG_AB" ]; then
-GG_GATHER=ldg timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_ldg.json 2>> gpurun_out/bench_n1.err
-tail -c 900 gpurun_out/bench_n1_ldg.json
+GG_GATHER=items timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_items.json 2>> gpurun_out/bench_n1.err
+tail -c 900 gpurun_out/bench_n1_items.json
 fi
 if [ -n "$GG_PROFILE" ]; then
 KREG='regex:pgat_gather|node_proj|gate_update|split_tf32|edge_length|edge_head|node_head|feature_update|z_probe|z_clamp|permute_kernel'

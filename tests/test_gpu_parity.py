@@ -188,6 +188,54 @@ def test_pgclstm_cell_encoder_and_decoder_states():
         assert rel_err(v, g[k]) < TOL, k
 
 
+def ragged_hetero_graph(seed, ng=220, nj=400):
+    """Edge lists that exercise the tile logic of the warp-specialised gather: a row of 300 in-edges (spans several tiles),
+    rows without in-edges, a long run of rows with a single in-edge (more starting targets than header slots)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for et in ET:
+        ns, nd = (ng if et[0] == 'grain' else nj), (ng if et[2] == 'grain' else nj)
+        src = torch.randint(0, ns, (3 * nd,), generator=g)
+        dst = torch.randint(0, nd, (3 * nd,), generator=g)
+        hub = torch.full((300,), 7, dtype=torch.int64)
+        ones = torch.arange(40, 140)                                   # a run of in-degree ~1 rows
+        keep = (dst < 40) | (dst >= 140)
+        src, dst = src[keep], dst[keep]
+        keep = (dst != 150) & (dst != 151) & (dst != nd - 1)           # rows without in-edges (the last row among them)
+        src, dst = src[keep], dst[keep]
+        src = torch.cat([src, torch.randint(0, ns, (300,), generator=g), torch.randint(0, ns, (100,), generator=g)])
+        dst = torch.cat([dst, hub, ones])
+        perm = torch.randperm(src.numel(), generator=g)
+        out[et] = torch.stack([src[perm], dst[perm]])
+    return out
+
+
+@pytest.mark.parametrize('gather', ['tiled', 'items'])
+def test_pgclstm_cell_on_ragged_graph(gather, monkeypatch):
+    """Encoder form (no state: raw-score gather, 3 live gates) and decoder form (4 gates) of the cell on a ragged graph,
+    through the warp-specialised gather and through the per-warp item-list gather."""
+    from graingraphnn_b200.heteropgclstm import HeteroPGCLSTM
+    monkeypatch.setenv('GG_GATHER', gather)
+    torch.manual_seed(5)
+    ng, nj = 220, 400
+    x = {'grain': torch.rand(ng, 11), 'joint': torch.rand(nj, 8)}
+    ei = ragged_hetero_graph(11, ng, nj)
+    ea = {e: torch.rand(ei[e].shape[1], 1) * 0.2 for e in ET}
+    sd = orc.synth_state_dict('regressor', 4)
+    pre = 'gclstm_decoder.cell_list.0.'
+    cell = HeteroPGCLSTM({'grain': 11, 'joint': 8}, 96, (['grain', 'joint'], list(ET)))
+    cell.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    cell = cell.to(dev())
+    h0 = {t: torch.rand(v.shape[0], 96) - 0.5 for t, v in x.items()}
+    c0 = {t: torch.rand(v.shape[0], 96) - 0.5 for t, v in x.items()}
+    for hh0, cc0 in ((None, None), (h0, c0)):
+        href, cref = orc.pgclstm_cell(sd, pre[:-1], x, ei, ea, hh0, cc0)
+        hh, cc = cell(to_dev(x), to_dev(ei), to_dev(ea), None if hh0 is None else to_dev(hh0), None if cc0 is None else to_dev(cc0))
+        for t in x:
+            assert torch.isfinite(hh[t]).all()
+            assert rel_err(hh[t], href[t]) < TOL and rel_err(cc[t], cref[t]) < TOL, (t, hh0 is None)
+
+
 def test_pgclstm_cell_with_h_but_without_c():
     from graingraphnn_b200.heteropgclstm import HeteroPGCLSTM
     x, ei, ea = load_graph('c1')
