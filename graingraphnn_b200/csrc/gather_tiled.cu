@@ -103,11 +103,35 @@ __device__ __forceinline__ float group_sum8(float s) {
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     return s;
 }
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2): a float4 travels as two 64-bit registers
+typedef unsigned long long u64;
+struct P4 { u64 lo, hi; };
+__device__ __forceinline__ u64 pack2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fmax2(u64 a, u64 b) {           // no packed max on sm_100: two FMNMX on the halves
+    float ax, ay, bx, by;
+    unpack2(a, ax, ay); unpack2(b, bx, by);
+    return pack2(fmaxf(ax, bx), fmaxf(ay, by));
+}
+__device__ __forceinline__ float hsum2(u64 a, u64 b) { float ax, ay, bx, by; unpack2(a, ax, ay); unpack2(b, bx, by); return (ax + ay) + (bx + by); }
+__device__ __forceinline__ P4 lds4p(uint32_t addr) {
+    P4 r;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r.lo), "=l"(r.hi) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ P4 ldg4p(const float* p) { const float4 v = ldg4(p); P4 r; r.lo = pack2(v.x, v.y); r.hi = pack2(v.z, v.w); return r; }
+__device__ __forceinline__ void lds2(uint32_t addr, int& a, int& b) { asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr)); }
+__device__ __forceinline__ void sts2(uint32_t addr, int a, int b) { asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory"); }
+__device__ __forceinline__ void stg4p_stream(float* p, u64 a, u64 b) {
+    asm volatile("st.global.cs.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
 __device__ __forceinline__ float wrapv(int code) { return code == 0 ? 0.f : (code == 1 ? 1.f : -1.f); }   // gg_edge_wrap: 1 -> +1, 2 -> -1
 
 // shared-memory layout of one stage (byte offsets; every block 16-byte aligned)
 struct StageLayout {
-    uint32_t es, qb, hb, hdr, ea, wrap, tn, te, info, bytes;
+    uint32_t es, qb, hb, hdr, td, em, info, bytes;
 };
 __host__ __device__ inline StageLayout stage_layout(int G, int C, bool raw, int ecap, int hcap) {
     StageLayout L;
@@ -116,12 +140,10 @@ __host__ __device__ inline StageLayout stage_layout(int G, int C, bool raw, int 
     L.qb = raw ? 64u * G : gc4 + 16u * G;                   // one starting target: Q' (16 per gate) or Q | QX
     L.hb = L.qb + 16u;                                      // ... followed by its position (x, y, z, -)
     L.hdr = (uint32_t)ecap * L.es;
-    L.ea = L.hdr + (uint32_t)hcap * L.hb;
-    const uint32_t e4 = (((uint32_t)ecap * 4u) + 15u) & ~15u;
-    L.wrap = L.ea + e4;
-    L.tn = L.wrap + e4;
-    L.te = L.tn + e4;
-    L.info = L.te + ((((uint32_t)ecap + 1u) * 4u + 15u) & ~15u);
+    L.td = L.hdr + (uint32_t)hcap * L.hb;                   // per target of the tile: {node, lo | hi << 8 | starts << 16 | ends << 17 | header slot << 24}
+    const uint32_t e8 = (((uint32_t)ecap * 8u) + 15u) & ~15u;
+    L.em = L.td + e8;                                       // per edge: {edge length, wrap code}
+    L.info = L.em + e8;                                     // {targets, index of the first one in nz, -, -}
     L.bytes = (L.info + 16u + 127u) & ~127u;
     return L;
 }
@@ -142,7 +164,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (NS + s); };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init_(full_bar(s), 1); mbar_init_(empty_bar(s), NC); }
+        for (int s = 0; s < NS; ++s) { mbar_init_(full_bar(s), NP); mbar_init_(empty_bar(s), NC); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -151,73 +173,57 @@ pgat_gather_tiled_kernel(const TiledParams p) {
 
     if (warp < NP) {
         // =========================================================================================== producers
-        // Producer w serves the CTA's tiles w, w + NP, ... (local index t; stage t mod NS).  Tile descriptors are read two
-        // tiles ahead and the per-edge / per-target metadata one tile ahead, so the chain tiles -> col -> row address is
-        // never waited for.
-        struct Meta { int col[2], wrap[2], tn[2], te[2], te_end; float ea[2]; };
-        auto load_desc = [&](int t) -> int4 {                       // {first edge, edges, first target, last target}
+        // All NP producer warps work on EVERY tile, in order (so none can run more than one stage ring ahead: a parity wait
+        // cannot tell "two phases behind" from "done"): slot s / target j of a tile belongs to warp s mod NP, lane s / NP, which
+        // spreads the warp-serial issue of the bulk copies (~50 clk each) over NP warps.  Tile descriptors are read two tiles
+        // ahead and the per-edge / per-target metadata one tile ahead, so the chain tiles -> col -> row address is never waited for.
+        struct Meta { int col, wrap, tn, ta, tb, t0; float ea; };
+        const int mine = warp + NP * lane;                           // the slot and the target this lane serves in every tile
+        auto load_desc = [&](int t) -> int4 {                        // {first edge, edges, first target, last target}
             return t < n_tiles ? __ldg(&p.tiles[f0 + t]) : make_int4(0, 0, 0, -1);
         };
         auto load_meta = [&](const int4& d) -> Meta {
             Meta m;
             const int e0 = d.x, ne = d.y, cnt = d.w - d.z + 1;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int s = lane + 32 * r;
-                m.col[r] = 0; m.wrap[r] = 0; m.ea[r] = 0.f; m.tn[r] = 0; m.te[r] = 0;
-                if (s < ne) { m.col[r] = __ldg(&p.col[e0 + s]); m.ea[r] = __ldg(&p.ea[e0 + s]); m.wrap[r] = __ldg(&p.wrap[e0 + s]); }
-                if (s < cnt) { m.tn[r] = __ldg(&p.nz[d.z + s]); m.te[r] = __ldg(&p.nzptr[d.z + s]); }
-            }
-            m.te_end = (lane == 0 && cnt > 0) ? __ldg(&p.nzptr[d.w + 1]) : 0;
+            m.col = 0; m.wrap = 0; m.ea = 0.f; m.tn = 0; m.ta = 0; m.tb = 0; m.t0 = 0;
+            if (mine < ne) { m.col = __ldg(&p.col[e0 + mine]); m.ea = __ldg(&p.ea[e0 + mine]); m.wrap = __ldg(&p.wrap[e0 + mine]); }
+            if (mine < cnt) { m.tn = __ldg(&p.nz[d.z + mine]); m.ta = __ldg(&p.nzptr[d.z + mine]); m.tb = __ldg(&p.nzptr[d.z + mine + 1]); }
+            if (cnt > 0) m.t0 = __ldg(&p.nzptr[d.z]);
             return m;
         };
-        // A producer may run at most NS tiles ahead of the consumers: a parity wait cannot tell "two phases behind" from "done",
-        // so only min(NP, NS) producers are active (producer w moves from tile t to t + np <= t + NS, whose stage was last used
-        // by a tile <= t, already handed back in order).
-        const int np = NP < NS ? NP : NS;
-        if (warp >= np) return;
-        int t = warp;
-        int4 d_cur = load_desc(t), d_nxt = load_desc(t + np);
+        int4 d_cur = load_desc(0), d_nxt = load_desc(1);
         Meta m_cur = load_meta(d_cur);
-        for (; t < n_tiles; t += np) {
-            const int4 d_n2 = load_desc(t + 2 * np);
+        int stage = 0; uint32_t phase = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int4 d_n2 = load_desc(t + 2);
             const Meta m_nxt = load_meta(d_nxt);
-            const int e0 = d_cur.x, ne = d_cur.y;
+            const int e0 = d_cur.x, ne = d_cur.y, e1 = e0 + ne;
             const int cnt = d_cur.w - d_cur.z + 1;
-            const int stage = t % NS;
-            const uint32_t phase = (uint32_t)(t / NS) & 1u;
-            const int fs = __shfl_sync(0xffffffffu, m_cur.te[0], 0) >= e0 ? 1 : 0;     // does the first target START in this tile?
-            const int n_hdr = min(cnt - (1 - fs), HCAP);
+            const int fs = m_cur.t0 >= e0 ? 1 : 0;                           // does the first target START in this tile?
             const uint32_t base = smem0 + (uint32_t)stage * L.bytes, bar = full_bar(stage);
+            // what the consumer needs to know about target `mine`
+            const int starts = m_cur.ta >= e0 ? 1 : 0, ends = m_cur.tb <= e1 ? 1 : 0;
+            const int h = mine - (1 - fs);
+            const bool has_hdr = mine < cnt && starts && h < HCAP;           // else: continuing row, or more starts than header slots
+            const int n_hdr = __popc(__ballot_sync(0xffffffffu, has_hdr));
+            const int n_rows = ne > warp ? (ne - warp + NP - 1) / NP : 0;
             mbar_wait_(empty_bar(stage), phase ^ 1u);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int s = lane + 32 * r;
-                if (s < ne) { sts1f(base + L.ea + 4u * s, m_cur.ea[r]); sts1i(base + L.wrap + 4u * s, m_cur.wrap[r]); }
-                if (s < cnt) { sts1i(base + L.tn + 4u * s, m_cur.tn[r]); sts1i(base + L.te + 4u * s, m_cur.te[r]); }
-            }
-            if (lane == 0) {
-                sts1i(base + L.te + 4u * cnt, m_cur.te_end);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + L.info), "r"(e0), "r"(cnt | (fs << 16)), "r"(ne), "r"(d_cur.z) : "memory");
-            }
+            if (mine < ne) sts2(base + L.em + 8u * mine, __float_as_int(m_cur.ea), m_cur.wrap);
+            if (mine < cnt)
+                sts2(base + L.td + 8u * mine, m_cur.tn,
+                     (max(m_cur.ta, e0) - e0) | ((min(m_cur.tb, e1) - e0) << 8) | (starts << 16) | (ends << 17) | ((has_hdr ? h : 255) << 24));
+            if (threadIdx.x == 0) sts2(base + L.info, cnt, d_cur.z);
             __syncwarp();
-            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)ne * L.es + (uint32_t)n_hdr * L.hb);
+            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)n_rows * L.es + (uint32_t)n_hdr * L.hb);
             __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int s = lane + 32 * r;
-                if (s < ne) bulk_g2s(base + (uint32_t)s * L.es, p.P_src + (size_t)m_cur.col[r] * p.ld_src + p.k_off, L.es, bar);
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int h = lane + 32 * r - (1 - fs);                      // header slot of target j = lane + 32 r
-                if (lane + 32 * r < cnt && h >= 0 && h < HCAP) {
-                    const uint32_t hd = base + L.hdr + (uint32_t)h * L.hb;
-                    bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn[r] * p.ld_dst + p.q_off, L.qb, bar);
-                    bulk_g2s(hd + L.qb, p.pos_dst + (size_t)m_cur.tn[r] * p.ld_pd, 16u, bar);
-                }
+            if (mine < ne) bulk_g2s(base + (uint32_t)mine * L.es, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, L.es, bar);
+            if (has_hdr) {
+                const uint32_t hd = base + L.hdr + (uint32_t)h * L.hb;
+                bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn * p.ld_dst + p.q_off, L.qb, bar);
+                bulk_g2s(hd + L.qb, p.pos_dst + (size_t)m_cur.tn * p.ld_pd, 16u, bar);
             }
             d_cur = d_nxt; d_nxt = d_n2; m_cur = m_nxt;
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
         return;
     }
@@ -230,55 +236,55 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     const uint32_t lane_off = 4u * (gsel * C + 4 * sub);     // byte offset of this lane's first float4 inside a staged row
     const uint32_t v_off = RAW ? 64u : (uint32_t)GC * 4u;    // V row behind the raw features / the K row
     const float sc2 = p.inv_sqrt_c * LOG2E;                  // scores are kept in log2 units: exp(x) = ex2(x log2 e)
+    const int me = sub % 3;                                  // raw-score mode: the edge of a chunk this lane scores (lanes 0..2 of a group publish)
+    const int src0 = lane & 24;                              // lane `sub == 0` of this gate group
 
-    // x, y, z columns of lin_value for this lane's channels (zero for idle groups): Wv3 is [G*C][4]
-    float4 wvx[NV], wvy[NV], wvz[NV];
+    // x, y, z columns of lin_value for this lane's channels (zero for idle groups): Wv3 is [G*C][4]; packed pairs
+    P4 wvx[NV], wvy[NV], wvz[NV];
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
         float4 t4[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) t4[i] = active ? ldg4(p.Wv3 + (size_t)(grp * C + 4 * (sub + 8 * r) + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        wvx[r] = make_float4(t4[0].x, t4[1].x, t4[2].x, t4[3].x);
-        wvy[r] = make_float4(t4[0].y, t4[1].y, t4[2].y, t4[3].y);
-        wvz[r] = make_float4(t4[0].z, t4[1].z, t4[2].z, t4[3].z);
+        wvx[r].lo = pack2(t4[0].x, t4[1].x); wvx[r].hi = pack2(t4[2].x, t4[3].x);
+        wvy[r].lo = pack2(t4[0].y, t4[1].y); wvy[r].hi = pack2(t4[2].y, t4[3].y);
+        wvz[r].lo = pack2(t4[0].z, t4[1].z); wvz[r].hi = pack2(t4[2].z, t4[3].z);
     }
 
     // per-target state (survives tile boundaries)
-    float4 q[NQ], vp[NV], acc[NV], qx = make_float4(0.f, 0.f, 0.f, 0.f);
+    P4 q[NQ], vp[NV], acc[NV];
+    float4 qx = make_float4(0.f, 0.f, 0.f, 0.f);
     float m_run = -CUDART_INF_F, l_run = 0.f, ea_acc = 0.f;
 #pragma unroll
-    for (int r = 0; r < NV; ++r) { vp[r] = acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int r = 0; r < NV; ++r) { vp[r].lo = vp[r].hi = 0ull; acc[r].lo = acc[r].hi = 0ull; }
 #pragma unroll
-    for (int r = 0; r < NQ; ++r) q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < NQ; ++r) q[r].lo = q[r].hi = 0ull;
 
     int stage = 0; uint32_t phase = 0;
     for (int t = 0; t < n_tiles; ++t) {
         const uint32_t base = smem0 + (uint32_t)stage * L.bytes;
         mbar_wait_(full_bar(stage), phase);
-        int e0, cnt, ne, i_first;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(cnt), "=r"(ne), "=r"(i_first) : "r"(base + L.info));
-        const int fs = cnt >> 16;
-        cnt &= 0xffff;
-        const int e1 = e0 + ne;
+        int cnt, i_first;
+        lds2(base + L.info, cnt, i_first);
         int j = cw - i_first % NC;
         if (j < 0) j += NC;
         for (; j < cnt; j += NC) {
-            const int node = lds1i(base + L.tn + 4u * j);
-            const int a = lds1i(base + L.te + 4u * j), b = lds1i(base + L.te + 4u * j + 4u);
+            int node, td;
+            lds2(base + L.td + 8u * j, node, td);
             if (node >= p.n_dst) continue;                   // rows behind the owned ones (slab partition) are not computed
-            const int lo = max(a, e0) - e0, hi = min(b, e1) - e0;
-            if (a >= e0) {
+            const int lo = td & 0xff, hi = (td >> 8) & 0xff;
+            if (td & 0x10000) {
                 // ---- the target starts here: its query, position, fresh softmax state
-                const int h = j - (1 - fs);
+                const int hs = (td >> 24) & 0xff;
                 float4 pi;
-                if (h < HCAP) {
-                    const uint32_t hd = base + L.hdr + (uint32_t)h * L.hb;
+                if (hs != 255) {
+                    const uint32_t hd = base + L.hdr + (uint32_t)hs * L.hb;
                     if (RAW) {
 #pragma unroll
-                        for (int r = 0; r < NQ; ++r) q[r] = lds4(hd + gsel * 64 + 16 * r);
+                        for (int r = 0; r < NQ; ++r) q[r] = lds4p(hd + gsel * 64 + 16 * r);
                     } else {
 #pragma unroll
-                        for (int r = 0; r < NQ; ++r) q[r] = lds4(hd + lane_off + 128 * r);
+                        for (int r = 0; r < NQ; ++r) q[r] = lds4p(hd + lane_off + 128 * r);
                         qx = lds4(hd + (uint32_t)GC * 4u + 16u * gsel);
                     }
                     pi = lds4(hd + L.qb);
@@ -286,69 +292,79 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                     const float* qrow = p.P_dst + (size_t)node * p.ld_dst + p.q_off;
                     if (RAW) {
 #pragma unroll
-                        for (int r = 0; r < NQ; ++r) q[r] = ldg4(qrow + gsel * 16 + 4 * r);
+                        for (int r = 0; r < NQ; ++r) q[r] = ldg4p(qrow + gsel * 16 + 4 * r);
                     } else {
 #pragma unroll
-                        for (int r = 0; r < NQ; ++r) q[r] = ldg4(qrow + gsel * C + 4 * (sub + 8 * r));
+                        for (int r = 0; r < NQ; ++r) q[r] = ldg4p(qrow + gsel * C + 4 * (sub + 8 * r));
                         qx = ldg4(qrow + GC + 4 * gsel);
                     }
                     pi = ldg4(p.pos_dst + (size_t)node * p.ld_pd);
                 }
-                if (RAW) qx = q[0];                           // Q'[0:3] = Wk3^T q
+                if (RAW) { unpack2(q[0].lo, qx.x, qx.y); float dummy; unpack2(q[0].hi, qx.z, dummy); }   // Q'[0:3] = Wk3^T q
+                const u64 px = pack2(pi.x, pi.x), py = pack2(pi.y, pi.y), pz = pack2(pi.z, pi.z);
 #pragma unroll
                 for (int r = 0; r < NV; ++r) {                // vp = Wv3 p_i:  V_j + Wv3 (w_e - p_i) > 0  <=>  V_j + Wv3 w_e > vp
-                    vp[r].x = fmaf(wvz[r].x, pi.z, fmaf(wvy[r].x, pi.y, wvx[r].x * pi.x));
-                    vp[r].y = fmaf(wvz[r].y, pi.z, fmaf(wvy[r].y, pi.y, wvx[r].y * pi.x));
-                    vp[r].z = fmaf(wvz[r].z, pi.z, fmaf(wvy[r].z, pi.y, wvx[r].z * pi.x));
-                    vp[r].w = fmaf(wvz[r].w, pi.z, fmaf(wvy[r].w, pi.y, wvx[r].w * pi.x));
-                    acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vp[r].lo = ffma2(wvz[r].lo, pz, ffma2(wvy[r].lo, py, fmul2(wvx[r].lo, px)));
+                    vp[r].hi = ffma2(wvz[r].hi, pz, ffma2(wvy[r].hi, py, fmul2(wvx[r].hi, px)));
+                    acc[r].lo = acc[r].hi = 0ull;
                 }
                 m_run = -CUDART_INF_F; l_run = 0.f; ea_acc = 0.f;
             }
             for (int s0 = lo; s0 < hi; s0 += CH) {
-                const int n_e = min(CH, hi - s0);             // warp-uniform
+                const int n_e = hi - s0;                      // >= 1, warp-uniform; slots beyond the row are clamped to its last edge
+                const int sl[CH] = {s0, s0 + (n_e > 1 ? 1 : 0), s0 + (n_e > 2 ? 2 : (n_e > 1 ? 1 : 0))};
                 float ae[CH], sc[CH];
                 int wc[CH];
-                float m_new = m_run;
 #pragma unroll
-                for (int e = 0; e < CH; ++e) {
-                    sc[e] = 0.f; ae[e] = 0.f; wc[e] = 0;
-                    if (e < n_e) {
-                        ae[e] = lds1f(base + L.ea + 4u * (s0 + e));
-                        wc[e] = lds1i(base + L.wrap + 4u * (s0 + e));
-                        const uint32_t row = base + (uint32_t)(s0 + e) * L.es;
-                        float dd = 0.f, d2 = 0.f;             // two partial sums: shorter dependency chains
-                        if (RAW) {
-                            float4 x0 = lds4(row), x1 = lds4(row + 16), x2 = lds4(row + 32), x3 = lds4(row + 48);   // broadcast
-                            x3.w = ae[e];                     // Q'[15] = We . q multiplies the edge length
-                            dd = fmaf(q[0].x, x0.x, dd); d2 = fmaf(q[0].y, x0.y, d2); dd = fmaf(q[0].z, x0.z, dd); d2 = fmaf(q[0].w, x0.w, d2);
-                            dd = fmaf(q[1].x, x1.x, dd); d2 = fmaf(q[1].y, x1.y, d2); dd = fmaf(q[1].z, x1.z, dd); d2 = fmaf(q[1].w, x1.w, d2);
-                            dd = fmaf(q[2].x, x2.x, dd); d2 = fmaf(q[2].y, x2.y, d2); dd = fmaf(q[2].z, x2.z, dd); d2 = fmaf(q[2].w, x2.w, d2);
-                            dd = fmaf(q[3].x, x3.x, dd); d2 = fmaf(q[3].y, x3.y, d2); dd = fmaf(q[3].z, x3.z, dd); d2 = fmaf(q[3].w, x3.w, d2);
-                            dd += d2;
-                        } else {
-                            const uint32_t krow = row + lane_off;
+                for (int e = 0; e < CH; ++e) { int ai; lds2(base + L.em + 8u * sl[e], ai, wc[e]); ae[e] = __int_as_float(ai); }
+                const int wc_any = wc[0] | wc[1] | wc[2];
+                if (RAW) {
+                    // each lane scores ONE edge of the chunk (edge `me`) for its gate; lanes 0..2 of the group publish
+                    const float my_ae = me == 0 ? ae[0] : (me == 1 ? ae[1] : ae[2]);
+                    const uint32_t row = base + (uint32_t)(me == 0 ? sl[0] : (me == 1 ? sl[1] : sl[2])) * L.es;
+                    const P4 x0 = lds4p(row), x1 = lds4p(row + 16), x2 = lds4p(row + 32);
+                    P4 x3 = lds4p(row + 48);
+                    { float x14, x15; unpack2(x3.hi, x14, x15); x3.hi = pack2(x14, my_ae); }    // Q'[15] = We . q multiplies the edge length
+                    u64 da = fmul2(q[0].lo, x0.lo), db = fmul2(q[0].hi, x0.hi);
+                    da = ffma2(q[1].lo, x1.lo, da); db = ffma2(q[1].hi, x1.hi, db);
+                    da = ffma2(q[2].lo, x2.lo, da); db = ffma2(q[2].hi, x2.hi, db);
+                    da = ffma2(q[3].lo, x3.lo, da); db = ffma2(q[3].hi, x3.hi, db);
+                    float dd = hsum2(da, db);
+                    if (wc_any) {                             // periodGATconv.py:209-211: the wrapped displacement enters the key
+                        const int my_wc = me == 0 ? wc[0] : (me == 1 ? wc[1] : wc[2]);
+                        dd = fmaf(qx.x, wrapv(my_wc & 3), dd); dd = fmaf(qx.y, wrapv((my_wc >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((my_wc >> 4) & 3), dd);
+                    }
+                    dd *= sc2;
 #pragma unroll
-                            for (int r = 0; r < NV; ++r) {
-                                const float4 kk = lds4(krow + 128 * r);
-                                dd = fmaf(q[r].x, kk.x, dd); d2 = fmaf(q[r].y, kk.y, d2); dd = fmaf(q[r].z, kk.z, dd); d2 = fmaf(q[r].w, kk.w, d2);
-                            }
-                            dd = group_sum8(dd + d2);
-                            dd = fmaf(qx.w, ae[e], dd);
+                    for (int e = 0; e < CH; ++e) sc[e] = __shfl_sync(0xffffffffu, dd, src0 + e);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < CH; ++e) {
+                        const uint32_t krow = base + (uint32_t)sl[e] * L.es + lane_off;
+                        u64 da = 0ull, db = 0ull;
+#pragma unroll
+                        for (int r = 0; r < NV; ++r) {
+                            const P4 kk = lds4p(krow + 128 * r);
+                            da = ffma2(q[r].lo, kk.lo, da); db = ffma2(q[r].hi, kk.hi, db);
                         }
-                        if (wc[e]) {                          // periodGATconv.py:209-211: the wrapped displacement enters the key
+                        float dd = group_sum8(hsum2(da, db));
+                        dd = fmaf(qx.w, ae[e], dd);
+                        if (wc[e]) {
                             dd = fmaf(qx.x, wrapv(wc[e] & 3), dd); dd = fmaf(qx.y, wrapv((wc[e] >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((wc[e] >> 4) & 3), dd);
                         }
                         sc[e] = dd * sc2;
-                        m_new = fmaxf(m_new, sc[e]);
                     }
                 }
+                if (n_e < 2) sc[1] = -CUDART_INF_F;
+                if (n_e < 3) sc[2] = -CUDART_INF_F;
+                const float m_new = fmaxf(fmaxf(m_run, sc[0]), fmaxf(sc[1], sc[2]));
                 if (m_new > m_run) {                          // online softmax: rescale what earlier chunks accumulated
                     if (m_run != -CUDART_INF_F) {
                         const float scale = ex2_approx(m_run - m_new);
+                        const u64 s2 = pack2(scale, scale);
                         l_run *= scale; ea_acc *= scale;
 #pragma unroll
-                        for (int r = 0; r < NV; ++r) { acc[r].x *= scale; acc[r].y *= scale; acc[r].z *= scale; acc[r].w *= scale; }
+                        for (int r = 0; r < NV; ++r) { acc[r].lo = fmul2(acc[r].lo, s2); acc[r].hi = fmul2(acc[r].hi, s2); }
                     }
                     m_run = m_new;
                 }
@@ -357,41 +373,39 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 for (int e = 0; e < CH; ++e) {
                     if (e < n_e) {
                         const float pe = ex2_approx(sc[e] - m_run);
+                        const u64 pe2 = pack2(pe, pe);
                         l_run += pe;
                         ea_acc = fmaf(pe, ae[e], ea_acc);
-                        const uint32_t vrow = base + (uint32_t)(s0 + e) * L.es + v_off + lane_off;
-                        float4 v[NV];
+                        const uint32_t vrow = base + (uint32_t)sl[e] * L.es + v_off + lane_off;
+                        P4 v[NV];
 #pragma unroll
-                        for (int r = 0; r < NV; ++r) v[r] = lds4(vrow + 128 * r);
+                        for (int r = 0; r < NV; ++r) v[r] = lds4p(vrow + 128 * r);
                         if (wc[e]) {                          // edge crosses a periodic / patch boundary (warp-uniform, rare)
-                            const float tx = wrapv(wc[e] & 3), ty = wrapv((wc[e] >> 2) & 3), tz = wrapv((wc[e] >> 4) & 3);
+                            const float fx = wrapv(wc[e] & 3), fy = wrapv((wc[e] >> 2) & 3), fz = wrapv((wc[e] >> 4) & 3);
+                            const u64 tx = pack2(fx, fx), ty = pack2(fy, fy), tz = pack2(fz, fz);
 #pragma unroll
                             for (int r = 0; r < NV; ++r) {
-                                v[r].x += fmaf(wvz[r].x, tz, fmaf(wvy[r].x, ty, wvx[r].x * tx));
-                                v[r].y += fmaf(wvz[r].y, tz, fmaf(wvy[r].y, ty, wvx[r].y * tx));
-                                v[r].z += fmaf(wvz[r].z, tz, fmaf(wvy[r].z, ty, wvx[r].z * tx));
-                                v[r].w += fmaf(wvz[r].w, tz, fmaf(wvy[r].w, ty, wvx[r].w * tx));
+                                v[r].lo = ffma2(wvz[r].lo, tz, ffma2(wvy[r].lo, ty, ffma2(wvx[r].lo, tx, v[r].lo)));
+                                v[r].hi = ffma2(wvz[r].hi, tz, ffma2(wvy[r].hi, ty, ffma2(wvx[r].hi, tx, v[r].hi)));
                             }
                         }
 #pragma unroll
                         for (int r = 0; r < NV; ++r) {
-                            acc[r].x = fmaf(pe, fmaxf(v[r].x, vp[r].x), acc[r].x);
-                            acc[r].y = fmaf(pe, fmaxf(v[r].y, vp[r].y), acc[r].y);
-                            acc[r].z = fmaf(pe, fmaxf(v[r].z, vp[r].z), acc[r].z);
-                            acc[r].w = fmaf(pe, fmaxf(v[r].w, vp[r].w), acc[r].w);
+                            acc[r].lo = ffma2(pe2, fmax2(v[r].lo, vp[r].lo), acc[r].lo);
+                            acc[r].hi = ffma2(pe2, fmax2(v[r].hi, vp[r].hi), acc[r].hi);
                         }
                     }
                 }
             }
-            if (b <= e1) {
+            if (td & 0x20000) {
                 // ---- the target ends here: normalise and store (PyG softmax: exp(s - max) / (sum + 1e-16))
                 const float inv = 1.0f / (l_run + 1e-16f);
                 if (active) {
                     float* orow = p.agg + (size_t)node * p.ld_agg + grp * C + 4 * sub;
+                    const u64 nl2 = pack2(-l_run, -l_run), inv2 = pack2(inv, inv);
 #pragma unroll
                     for (int r = 0; r < NV; ++r)              // sum pe * relu(.) = sum pe * max(., vp) - vp * sum pe
-                        stg4_stream(orow + 32 * r, make_float4(fmaf(-vp[r].x, l_run, acc[r].x) * inv, fmaf(-vp[r].y, l_run, acc[r].y) * inv,
-                                                               fmaf(-vp[r].z, l_run, acc[r].z) * inv, fmaf(-vp[r].w, l_run, acc[r].w) * inv));
+                        stg4p_stream(orow + 32 * r, fmul2(ffma2(vp[r].lo, nl2, acc[r].lo), inv2), fmul2(ffma2(vp[r].hi, nl2, acc[r].hi), inv2));
                     if (sub == 0) p.ea_out[(size_t)node * G + grp] = ea_acc * inv;
                 }
             }
