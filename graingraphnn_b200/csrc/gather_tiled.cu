@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int NP = 4;                 // producer warps (one warpgroup)
+constexpr int NP = 4;                 // producer warps (exactly one warpgroup: setmaxnreg is per warpgroup)
 constexpr int NC = 12;                // consumer warps
 constexpr int kThreads = 32 * (NP + NC);
 constexpr int CH = 3;                 // edges per softmax chunk (joints have exactly 3 in-edges)
@@ -41,7 +41,7 @@ struct TiledParams {
     const int* rowptr; const int* col; const float* ea; const int* wrap;
     const int* nz; const int* nzptr; const int4* tiles; const int* cta_ptr;
     const float* Wv3;
-    int n_dst, n_edges, G, ecap, hcap, nstage;
+    int n_dst, n_edges;
     float* agg; int ld_agg; float* ea_out;
     float inv_sqrt_c;
 };
@@ -129,38 +129,54 @@ __device__ __forceinline__ void stg4p_stream(float* p, u64 a, u64 b) {
 }
 __device__ __forceinline__ float wrapv(int code) { return code == 0 ? 0.f : (code == 1 ? 1.f : -1.f); }   // gg_edge_wrap: 1 -> +1, 2 -> -1
 
-// shared-memory layout of one stage (byte offsets; every block 16-byte aligned)
-struct StageLayout {
-    uint32_t es, qb, hb, hdr, td, em, info, bytes;
-};
-__host__ __device__ inline StageLayout stage_layout(int G, int C, bool raw, int ecap, int hcap) {
-    StageLayout L;
-    const uint32_t gc4 = (uint32_t)G * C * 4u;
-    L.es = raw ? 64u + gc4 : 2u * gc4;                      // one edge: [raw16 | V] or [K | V]
-    L.qb = raw ? 64u * G : gc4 + 16u * G;                   // one starting target: Q' (16 per gate) or Q | QX
-    L.hb = L.qb + 16u;                                      // ... followed by its position (x, y, z, -)
-    L.hdr = (uint32_t)ecap * L.es;
-    L.td = L.hdr + (uint32_t)hcap * L.hb;                   // per target of the tile: {node, lo | hi << 8 | starts << 16 | ends << 17 | header slot << 24}
+// Tile geometry and shared-memory layout of one stage (byte offsets; every block 16-byte aligned), fixed at compile time per
+// (width, gates, mode) so that every address in the consumer loop is a constant offset.
+//   rows [ECAP x ES] | headers [HCAP x HB] | target descriptors [ECAP x 8] | edge metadata [ECAP x 8] | info [16]
+constexpr uint32_t cfg_es(int G, int C, bool raw) { return raw ? 64u + (uint32_t)G * C * 4u : 2u * (uint32_t)G * C * 4u; }   // [raw16 | V] or [K | V]
+constexpr uint32_t cfg_qb(int G, int C, bool raw) { return raw ? 64u * G : (uint32_t)G * C * 4u + 16u * G; }                 // Q' (16 per gate) or Q | QX
+constexpr uint32_t cfg_stage_bytes(int G, int C, bool raw, int ecap, int hcap) {
     const uint32_t e8 = (((uint32_t)ecap * 8u) + 15u) & ~15u;
-    L.em = L.td + e8;                                       // per edge: {edge length, wrap code}
-    L.info = L.em + e8;                                     // {targets, index of the first one in nz, -, -}
-    L.bytes = (L.info + 16u + 127u) & ~127u;
-    return L;
+    return ((uint32_t)ecap * cfg_es(G, C, raw) + (uint32_t)hcap * (cfg_qb(G, C, raw) + 16u) + 2u * e8 + 16u + 127u) & ~127u;
 }
+constexpr int cfg_hcap(int ecap) { return ecap / 3 + 2; }
+// the largest tile (multiple of 6 edges: joints have 3 in-edges, grains ~6) that fits 227 KB with three stages, else with two;
+// what = 0: ECAP, 1: stages
+constexpr int cfg_pick(int G, int C, bool raw, int what) {
+    for (int ns = 3; ns >= 2; --ns)
+        for (int ecap = 60; ecap >= 12; ecap -= 6)
+            if ((long long)ns * cfg_stage_bytes(G, C, raw, ecap, cfg_hcap(ecap)) <= 227 * 1024 - 256) return what == 0 ? ecap : ns;
+    return 0;
+}
+template <int NV, int G_, bool RAW>
+struct TCfg {
+    static constexpr int C = 32 * NV, G = G_, GC = G * C;
+    static constexpr int ECAP = cfg_pick(G, C, RAW, 0), NS = cfg_pick(G, C, RAW, 1), HCAP = cfg_hcap(ECAP);
+    static constexpr uint32_t ES = cfg_es(G, C, RAW), QB = cfg_qb(G, C, RAW), HB = QB + 16u;
+    static constexpr uint32_t HDR = (uint32_t)ECAP * ES;
+    static constexpr uint32_t TD = HDR + (uint32_t)HCAP * HB;            // {node, lo | hi << 8 | starts << 16 | ends << 17 | header slot << 24}
+    static constexpr uint32_t E8 = (((uint32_t)ECAP * 8u) + 15u) & ~15u;
+    static constexpr uint32_t EM = TD + E8;                              // {edge length, wrap code}
+    static constexpr uint32_t INFO = EM + E8;                            // {targets, index of the first one in nz, -, -}
+    static constexpr uint32_t BYTES = cfg_stage_bytes(G, C, RAW, ECAP, HCAP);
+    static_assert(ECAP >= 12 && ECAP <= 60 && NS >= 2, "tile does not fit");
+    static_assert(BYTES == ((INFO + 16u + 127u) & ~127u), "layout");
+};
+// shapes with a compiled kernel: the encoder (3 live gates, raw scores), the decoder (4 gates), single convolutions (1 gate)
+constexpr bool cfg_supported(int G, bool raw) { return raw ? G == 3 : (G == 4 || G == 1); }
 
-template <int NV, bool RAW>
+template <int NV, int G, bool RAW>
 __global__ void __launch_bounds__(kThreads, 1)
 pgat_gather_tiled_kernel(const TiledParams p) {
-    constexpr int C = 32 * NV;
+    using K = TCfg<NV, G, RAW>;
+    constexpr int C = 32 * NV, GC = G * C;
     constexpr int NQ = RAW ? 4 : NV;                         // float4 registers of the target's query
     constexpr float LOG2E = 1.4426950408889634f;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = p.G, GC = G * C;
-    const int ECAP = p.ecap, HCAP = p.hcap, NS = p.nstage;
-    const StageLayout L = stage_layout(G, C, RAW, ECAP, HCAP);
+    constexpr int ECAP = K::ECAP, HCAP = K::HCAP, NS = K::NS;
+    (void)ECAP;
     const uint32_t smem0 = smem_addr(smem);
-    const uint32_t bar0 = smem0 + (uint32_t)NS * L.bytes;    // full[NS] | empty[NS]
+    const uint32_t bar0 = smem0 + (uint32_t)NS * K::BYTES;    // full[NS] | empty[NS]
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (NS + s); };
     if (threadIdx.x == 0) {
@@ -177,6 +193,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
         // cannot tell "two phases behind" from "done"): slot s / target j of a tile belongs to warp s mod NP, lane s / NP, which
         // spreads the warp-serial issue of the bulk copies (~50 clk each) over NP warps.  Tile descriptors are read two tiles
         // ahead and the per-edge / per-target metadata one tile ahead, so the chain tiles -> col -> row address is never waited for.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");          // registers go to the consumer warpgroups
         struct Meta { int col, wrap, tn, ta, tb, t0; float ea; };
         const int mine = warp + NP * lane;                           // the slot and the target this lane serves in every tile
         auto load_desc = [&](int t) -> int4 {                        // {first edge, edges, first target, last target}
@@ -200,7 +217,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             const int e0 = d_cur.x, ne = d_cur.y, e1 = e0 + ne;
             const int cnt = d_cur.w - d_cur.z + 1;
             const int fs = m_cur.t0 >= e0 ? 1 : 0;                           // does the first target START in this tile?
-            const uint32_t base = smem0 + (uint32_t)stage * L.bytes, bar = full_bar(stage);
+            const uint32_t base = smem0 + (uint32_t)stage * K::BYTES, bar = full_bar(stage);
             // what the consumer needs to know about target `mine`
             const int starts = m_cur.ta >= e0 ? 1 : 0, ends = m_cur.tb <= e1 ? 1 : 0;
             const int h = mine - (1 - fs);
@@ -208,19 +225,19 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             const int n_hdr = __popc(__ballot_sync(0xffffffffu, has_hdr));
             const int n_rows = ne > warp ? (ne - warp + NP - 1) / NP : 0;
             mbar_wait_(empty_bar(stage), phase ^ 1u);
-            if (mine < ne) sts2(base + L.em + 8u * mine, __float_as_int(m_cur.ea), m_cur.wrap);
+            if (mine < ne) sts2(base + K::EM + 8u * mine, __float_as_int(m_cur.ea), m_cur.wrap);
             if (mine < cnt)
-                sts2(base + L.td + 8u * mine, m_cur.tn,
+                sts2(base + K::TD + 8u * mine, m_cur.tn,
                      (max(m_cur.ta, e0) - e0) | ((min(m_cur.tb, e1) - e0) << 8) | (starts << 16) | (ends << 17) | ((has_hdr ? h : 255) << 24));
-            if (threadIdx.x == 0) sts2(base + L.info, cnt, d_cur.z);
+            if (threadIdx.x == 0) sts2(base + K::INFO, cnt, d_cur.z);
             __syncwarp();
-            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)n_rows * L.es + (uint32_t)n_hdr * L.hb);
+            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)n_rows * K::ES + (uint32_t)n_hdr * K::HB);
             __syncwarp();
-            if (mine < ne) bulk_g2s(base + (uint32_t)mine * L.es, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, L.es, bar);
+            if (mine < ne) bulk_g2s(base + (uint32_t)mine * K::ES, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, K::ES, bar);
             if (has_hdr) {
-                const uint32_t hd = base + L.hdr + (uint32_t)h * L.hb;
-                bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn * p.ld_dst + p.q_off, L.qb, bar);
-                bulk_g2s(hd + L.qb, p.pos_dst + (size_t)m_cur.tn * p.ld_pd, 16u, bar);
+                const uint32_t hd = base + K::HDR + (uint32_t)h * K::HB;
+                bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn * p.ld_dst + p.q_off, K::QB, bar);
+                bulk_g2s(hd + K::QB, p.pos_dst + (size_t)m_cur.tn * p.ld_pd, 16u, bar);
             }
             d_cur = d_nxt; d_nxt = d_n2; m_cur = m_nxt;
             if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -229,6 +246,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     }
 
     // =============================================================================================== consumers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");             // 4 x 32 x 56 + 12 x 32 x 152 = 64 K registers
     const int cw = warp - NP;
     const int grp = lane >> 3, sub = lane & 7;
     const bool active = grp < G;
@@ -262,15 +280,15 @@ pgat_gather_tiled_kernel(const TiledParams p) {
 
     int stage = 0; uint32_t phase = 0;
     for (int t = 0; t < n_tiles; ++t) {
-        const uint32_t base = smem0 + (uint32_t)stage * L.bytes;
+        const uint32_t base = smem0 + (uint32_t)stage * K::BYTES;
         mbar_wait_(full_bar(stage), phase);
         int cnt, i_first;
-        lds2(base + L.info, cnt, i_first);
+        lds2(base + K::INFO, cnt, i_first);
         int j = cw - i_first % NC;
         if (j < 0) j += NC;
         for (; j < cnt; j += NC) {
             int node, td;
-            lds2(base + L.td + 8u * j, node, td);
+            lds2(base + K::TD + 8u * j, node, td);
             if (node >= p.n_dst) continue;                   // rows behind the owned ones (slab partition) are not computed
             const int lo = td & 0xff, hi = (td >> 8) & 0xff;
             if (td & 0x10000) {
@@ -278,7 +296,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 const int hs = (td >> 24) & 0xff;
                 float4 pi;
                 if (hs != 255) {
-                    const uint32_t hd = base + L.hdr + (uint32_t)hs * L.hb;
+                    const uint32_t hd = base + K::HDR + (uint32_t)hs * K::HB;
                     if (RAW) {
 #pragma unroll
                         for (int r = 0; r < NQ; ++r) q[r] = lds4p(hd + gsel * 64 + 16 * r);
@@ -287,7 +305,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                         for (int r = 0; r < NQ; ++r) q[r] = lds4p(hd + lane_off + 128 * r);
                         qx = lds4(hd + (uint32_t)GC * 4u + 16u * gsel);
                     }
-                    pi = lds4(hd + L.qb);
+                    pi = lds4(hd + K::QB);
                 } else {                                      // more starting targets than header slots (runs of in-degree < 3): plain loads
                     const float* qrow = p.P_dst + (size_t)node * p.ld_dst + p.q_off;
                     if (RAW) {
@@ -316,12 +334,12 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 float ae[CH], sc[CH];
                 int wc[CH];
 #pragma unroll
-                for (int e = 0; e < CH; ++e) { int ai; lds2(base + L.em + 8u * sl[e], ai, wc[e]); ae[e] = __int_as_float(ai); }
+                for (int e = 0; e < CH; ++e) { int ai; lds2(base + K::EM + 8u * sl[e], ai, wc[e]); ae[e] = __int_as_float(ai); }
                 const int wc_any = wc[0] | wc[1] | wc[2];
                 if (RAW) {
                     // each lane scores ONE edge of the chunk (edge `me`) for its gate; lanes 0..2 of the group publish
                     const float my_ae = me == 0 ? ae[0] : (me == 1 ? ae[1] : ae[2]);
-                    const uint32_t row = base + (uint32_t)(me == 0 ? sl[0] : (me == 1 ? sl[1] : sl[2])) * L.es;
+                    const uint32_t row = base + (uint32_t)(me == 0 ? sl[0] : (me == 1 ? sl[1] : sl[2])) * K::ES;
                     const P4 x0 = lds4p(row), x1 = lds4p(row + 16), x2 = lds4p(row + 32);
                     P4 x3 = lds4p(row + 48);
                     { float x14, x15; unpack2(x3.hi, x14, x15); x3.hi = pack2(x14, my_ae); }    // Q'[15] = We . q multiplies the edge length
@@ -340,7 +358,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 } else {
 #pragma unroll
                     for (int e = 0; e < CH; ++e) {
-                        const uint32_t krow = base + (uint32_t)sl[e] * L.es + lane_off;
+                        const uint32_t krow = base + (uint32_t)sl[e] * K::ES + lane_off;
                         u64 da = 0ull, db = 0ull;
 #pragma unroll
                         for (int r = 0; r < NV; ++r) {
@@ -376,7 +394,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                         const u64 pe2 = pack2(pe, pe);
                         l_run += pe;
                         ea_acc = fmaf(pe, ae[e], ea_acc);
-                        const uint32_t vrow = base + (uint32_t)sl[e] * L.es + v_off + lane_off;
+                        const uint32_t vrow = base + (uint32_t)sl[e] * K::ES + v_off + lane_off;
                         P4 v[NV];
 #pragma unroll
                         for (int r = 0; r < NV; ++r) v[r] = lds4p(vrow + 128 * r);
@@ -435,27 +453,15 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     }
 }
 
-// tile geometry for (G, C, raw): the largest stage count / tile size that fits 227 KB
-struct TileCfg { int ecap, hcap, nstage; };
-TileCfg tile_config(int G, int C, bool raw) {
-    TileCfg c{0, 0, 0};
-    if (G < 1 || G > 4 || C % 32 || C < 32 || C > 128) return c;
-    const int budget = 227 * 1024 - 256;
-    // candidates, best first: three stages of as many edges as fit (multiple of 6: joints have 3 in-edges, grains ~6), else two
-    for (int ns = 3; ns >= 2; --ns) {
-        for (int ecap = 60; ecap >= 12; ecap -= 6) {
-            const int hcap = ecap / 3 + 2;
-            const StageLayout L = stage_layout(G, C, raw, ecap, hcap);
-            if ((long long)ns * L.bytes <= budget) { c.ecap = ecap; c.hcap = hcap; c.nstage = ns; return c; }
-        }
-    }
-    return c;
+int host_ecap(int G, int C, bool raw) {
+    if (G < 1 || G > 4 || C % 32 || C < 32 || C > 128 || !cfg_supported(G, raw)) return 0;
+    return cfg_pick(G, C, raw, 0);
 }
 
 }  // namespace
 
 extern "C" int gg_gather_tile_ecap(int32_t G, int32_t C, int32_t raw_k) {
-    return tile_config(G, C, raw_k != 0).ecap;
+    return host_ecap(G, C, raw_k != 0);
 }
 
 // number of persistent CTAs the tile lists are laid out for: one per SM (GG_GATHER_SMS caps it for experiments)
@@ -480,8 +486,8 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
                                     int32_t raw_k, const float* Wv3, int32_t n_dst, int32_t G, int32_t C,
                                     float* agg, int32_t ld_agg, float* ea, void* stream) {
     if (n_dst < 0 || n_edges < 0 || n_edges > 0x7fffffffLL || (raw_k != 0 && raw_k != 16)) return GG_EINVAL;
-    const TileCfg cfg = tile_config(G, C, raw_k != 0);
-    if (cfg.ecap == 0 || ecap != cfg.ecap) return GG_EINVAL;
+    const int my_ecap = host_ecap(G, C, raw_k != 0);
+    if (my_ecap == 0 || ecap != my_ecap) return GG_EINVAL;
     if (n_dst == 0) return 0;
     if (!P_src || !P_dst || !pos_dst || !rowptr || !Wv3 || !agg || !ea) return GG_EINVAL;
     if (!cta_ptr || n_ctas < 1) return GG_EINVAL;
@@ -497,35 +503,30 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
     p.nz = nz; p.nzptr = nzptr; p.tiles = reinterpret_cast<const int4*>(tiles); p.cta_ptr = cta_ptr;
     p.Wv3 = Wv3;
     p.n_dst = n_dst; p.n_edges = (int)n_edges;
-    p.G = G; p.ecap = cfg.ecap; p.hcap = cfg.hcap; p.nstage = cfg.nstage;
     p.agg = agg; p.ld_agg = ld_agg; p.ea_out = ea;
     p.inv_sqrt_c = 1.0f / sqrtf((float)C);
-    const StageLayout L = stage_layout(G, C, raw_k != 0, cfg.ecap, cfg.hcap);
-    const size_t smem = (size_t)cfg.nstage * L.bytes + 16 * cfg.nstage;
     const unsigned grid = (unsigned)n_ctas;                  // the tile list is ordered for exactly this many CTAs
     cudaStream_t st = GG_STREAM(stream);
     cudaError_t err = cudaSuccess;
-#define GG_TILED(NV, RAWV)                                                                                                        \
-    do {                                                                                                                          \
-        err = cudaFuncSetAttribute(pgat_gather_tiled_kernel<NV, RAWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        if (err != cudaSuccess) return (int)err;                                                                                  \
-        pgat_gather_tiled_kernel<NV, RAWV><<<grid, kThreads, smem, st>>>(p);                                                      \
+#define GG_TILED(NV, GV, RAWV)                                                                                                      \
+    do {                                                                                                                            \
+        using KC = TCfg<NV, GV, RAWV>;                                                                                              \
+        const size_t smem = (size_t)KC::NS * KC::BYTES + 16 * KC::NS;                                                               \
+        err = cudaFuncSetAttribute(pgat_gather_tiled_kernel<NV, GV, RAWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (err != cudaSuccess) return (int)err;                                                                                    \
+        pgat_gather_tiled_kernel<NV, GV, RAWV><<<grid, kThreads, smem, st>>>(p);                                                    \
     } while (0)
-    if (raw_k) {
-        switch (C / 32) {
-            case 1: GG_TILED(1, true); break;
-            case 2: GG_TILED(2, true); break;
-            case 3: GG_TILED(3, true); break;
-            default: GG_TILED(4, true); break;
-        }
-    } else {
-        switch (C / 32) {
-            case 1: GG_TILED(1, false); break;
-            case 2: GG_TILED(2, false); break;
-            case 3: GG_TILED(3, false); break;
-            default: GG_TILED(4, false); break;
-        }
+#define GG_TILED_NV(GV, RAWV)                        \
+    switch (C / 32) {                                \
+        case 1: GG_TILED(1, GV, RAWV); break;        \
+        case 2: GG_TILED(2, GV, RAWV); break;        \
+        case 3: GG_TILED(3, GV, RAWV); break;        \
+        default: GG_TILED(4, GV, RAWV); break;       \
     }
+    if (raw_k) { GG_TILED_NV(3, true) }
+    else if (G == 4) { GG_TILED_NV(4, false) }
+    else { GG_TILED_NV(1, false) }
+#undef GG_TILED_NV
 #undef GG_TILED
     GG_LAUNCH_OK();
     return 0;
