@@ -116,6 +116,21 @@ def cpu_reference_run(steps, warmup, sample_patches=(3, 3)):
             'steps_per_s': steps / dt}
 
 
+def ncu_traffic(n_grains, launches):
+    """dram__bytes_read.sum + dram__bytes_write.sum per gather launch (mean over the launches of one step) from the committed
+    `ncu --set full` capture of this very workload (profiles/gather_traffic.json, written by scripts/ncu_traffic.py); None when
+    the capture is of another size."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'gather_traffic.json')
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        if d.get('n_grains') == n_grains and d.get('launches') == launches:
+            return d['dram_bytes_per_launch']
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def kernel_breakdown(eng, peak):
     """Per-family device time of ONE eager step, CUDA events on the launching stream (torch's current stream)."""
     from graingraphnn_b200 import _lib, cell, heads, graph
@@ -128,7 +143,7 @@ def kernel_breakdown(eng, peak):
 
         def __getattr__(self, name):
             fn = getattr(self._inner, name)
-            if not name.startswith('gg_') or name in ('gg_error_string', 'gg_csr_workspace_bytes'):
+            if name not in _lib.KERNELS_PER_CALL:          # queries (gg_version, gg_gather_tile_ecap, ...) launch nothing
                 return fn
 
             def wrapped(*a):
@@ -145,7 +160,8 @@ def kernel_breakdown(eng, peak):
     try:
         saved = eng._graph
         eng._graph = None
-        eng.step(SPAN)
+        torch.cuda._sleep(40_000_000)       # ~20 ms of device idle: the whole step is enqueued behind it, so the events bracket
+        eng.step(SPAN)                      # back-to-back kernels and not the host's launch cadence
         torch.cuda.synchronize()
         eng._graph = saved
     finally:
@@ -276,6 +292,10 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel (rank 0, live CUDA events) -----------------------------------------
+    if 'gg_pgat_gather_tiled' in bd:                       # both entry points are kernel family (b)
+        t = bd.pop('gg_pgat_gather_tiled')
+        g = bd.setdefault('gg_pgat_gather', {'calls': 0, 'ms_total': 0.0, 'ms_each': []})
+        g['calls'] += t['calls']; g['ms_total'] += t['ms_total']; g['ms_each'] += t['ms_each']
     fam = {k: v['ms_total'] for k, v in bd.items()}
     total_fam = sum(fam.values())
     top = max(fam, key=fam.get)
@@ -291,6 +311,10 @@ def main():
         roof = {'kernel': top, 'bound': bound, 'achieved': achieved, 'peak': peak, 'unit': unit, 'frac': achieved / peak,
                 'traffic': None, 'peak_source': pk['source'] + (' (sustained bf16 cuBLAS)' if bound == 'tensor' else ' (copy)'),
                 'launches_per_step': bd[top]['calls'], 'ms_per_step': fam[top], 'share_of_step': fam[top] / total_fam}
+        if top == 'gg_pgat_gather':
+            # per-launch figures like `traffic`: algorithmic bytes and time of the average launch of the step
+            roof['achieved_bytes_per_launch'] = amount / bd[top]['calls']
+            roof['traffic'] = ncu_traffic(ng_total, bd[top]['calls'])
     else:
         roof = {'kernel': top, 'bound': 'hbm', 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None, 'traffic': None}
     roof['breakdown_ms'] = {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}

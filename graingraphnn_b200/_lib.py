@@ -51,7 +51,7 @@ _PROTOS = {
 # entry points of the tcgen05 path (gemm_tc.cu); bound when present
 _OPTIONAL = {
     'gg_tc_supported': (_I, []),
-    'gg_node_proj_tc': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P]),
+    'gg_node_proj_tc': (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P]),
     'gg_split_tf32': (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _P, _I, _I, _P]),
     'gg_gate_update_tc': (_I, [POINTER(AggInput), _I, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }

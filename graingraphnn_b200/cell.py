@@ -115,7 +115,7 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                 ahi, alo = buf(('Ahi', t), (n, kp)), buf(('Alo', t), (n, kp))
                 check(L.gg_split_tf32(ptr(x), x.stride(0), pk.k1p[t], ptr(ht), 0 if ht is None else ht.stride(0), k2,
                                       n, ptr(ahi), ptr(alo), kp, 32, st), 'gg_split_tf32')
-                check(L.gg_node_proj_tc(ptr(ahi), ptr(alo), kp, ptr(whi), ptr(wlo), pk.ncols[t], ptr(pk.bcat[t]),
+                check(L.gg_node_proj_tc(ptr(ahi), ptr(alo), kp, pk.k1p[t], ptr(whi), ptr(wlo), pk.ncols[t], ptr(pk.bcat[t]),
                                         ptr(P[t]), pk.ncols[t], n, 0, st), 'gg_node_proj_tc')
                 continue
             check(L.gg_node_proj(ptr(x), x.stride(0), pk.k1p[t],

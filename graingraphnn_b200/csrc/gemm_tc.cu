@@ -94,7 +94,7 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
 __global__ void __launch_bounds__(kThreads, 1)
 node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                    const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, int M, int N, int Kp) {
+                    const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, int M, int N, int Kp, int k_first_steps) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // swizzle-128B tiles need 1024-B alignment
     const uint32_t out_base = smem_base + kStages * STAGE_BYTES;                 // 2 x 16 KB store staging (1024-B aligned)
@@ -164,9 +164,12 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint64_t adesc = make_desc(sa), bdesc = make_desc(sb);
+                    // UMMA K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B).  The first chunk holds the node features
+                    // zero-padded to 32 columns: only its k_first_steps leading K steps can contribute.
+                    const int ks = (it % chunks == 0) ? k_first_steps : BK / 8;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)                  // UMMA K = 8 tf32 = 32 bytes: advance start address by 2 (x16 B)
-                        umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / 8; ++k)
+                        if (k < ks) umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) ? 1u : 0u);
                     umma_commit(empty_bar(stage));                    // frees the smem slot when these MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -648,9 +651,9 @@ extern "C" int gg_split_tf32(const float* X, int32_t ldx, int32_t K1, const floa
     return 0;
 }
 
-extern "C" int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, const float* W_hi, const float* W_lo,
+extern "C" int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, int32_t k_first, const float* W_hi, const float* W_lo,
                                int32_t N, const float* bias, float* out, int32_t ldo, int32_t M, int32_t n_sms, void* stream) {
-    if (M < 0 || N < 0 || Kp <= 0 || (Kp % BK)) return GG_EINVAL;
+    if (M < 0 || N < 0 || Kp <= 0 || (Kp % BK) || k_first < 1 || k_first > BK) return GG_EINVAL;
     if (M == 0 || N == 0) return 0;
     if (!A_hi || !A_lo || !W_hi || !W_lo || !out) return GG_EINVAL;
     if ((N & 3) || (ldo & 3) || !gg_aligned16(out) || (bias && !gg_aligned16(bias))) return GG_EALIGN;
@@ -676,7 +679,7 @@ extern "C" int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp,
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < n_sms ? tiles : n_sms;
-    node_proj_tc_kernel<<<grid, kThreads, SMEM_BYTES, GG_STREAM(stream)>>>(mA_hi, mA_lo, mW_hi, mW_lo, mOut, bias, M, N, Kp);
+    node_proj_tc_kernel<<<grid, kThreads, SMEM_BYTES, GG_STREAM(stream)>>>(mA_hi, mA_lo, mW_hi, mW_lo, mOut, bias, M, N, Kp, (k_first + 7) / 8);
     GG_LAUNCH_OK();
     return 0;
 }

@@ -79,11 +79,12 @@ int gg_node_proj(const float* A1, int32_t lda1, int32_t K1,
  *   gg_split_tf32   : builds A_hi, A_lo [M, Kp] (Kp % 32 == 0) from X (K1 columns, placed in [0, K1p32)) and h (K2 columns,
  *                     placed from K1p32); every value is rounded to TF32 with cvt.rna, a = hi + lo up to 2^-22 |a|.
  *   gg_node_proj_tc : out[M, N] = A W^T + bias; W_hi / W_lo are [N, Kp] with the same K layout. n_sms <= 0: all SMs.
+ *                     k_first (1..32): columns [k_first, 32) of A are zero (feature padding) - their MMAs are not issued.
  */
 int gg_tc_supported(void);
 int gg_split_tf32(const float* X, int32_t ldx, int32_t K1, const float* H /* nullable */, int32_t ldh, int32_t K2,
                   int32_t M, float* A_hi, float* A_lo, int32_t Kp, int32_t K1p32, void* stream);
-int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, const float* W_hi, const float* W_lo,
+int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, int32_t k_first, const float* W_hi, const float* W_lo,
                     int32_t N, const float* bias /* nullable */, float* out, int32_t ldo, int32_t M, int32_t n_sms,
                     void* stream);
 

@@ -61,7 +61,7 @@ def bench_proj(sms, M=249120, N=2336, K2=96):
     whi, wlo = split_tf32(torch.randn(N, kp, device=d) * 0.05)
     bias, out = torch.randn(N, device=d), torch.empty(M, N, device=d)
     for n in sms:
-        us = timeit(lambda: check(L.gg_node_proj_tc(ptr(ahi), ptr(alo), kp, ptr(whi), ptr(wlo), N, ptr(bias), ptr(out), N, M, n, st), 'gg_node_proj_tc'))
+        us = timeit(lambda: check(L.gg_node_proj_tc(ptr(ahi), ptr(alo), kp, 8, ptr(whi), ptr(wlo), N, ptr(bias), ptr(out), N, M, n, st), 'gg_node_proj_tc'))
         print(f'proj M={M} N={N} Kp={kp} sms={n:3d}: {us:8.1f} us   out {M * N * 4 / us / 1e6:5.2f} TB/s   {2 * M * N * kp * 3 / us / 1e6:7.1f} TF/s tf32 issued')
 
 

@@ -162,10 +162,12 @@ def test_tcgen05_node_proj_matches_fp32(M, N, K2):
     st = torch.cuda.current_stream().cuda_stream
     check(L.gg_split_tf32(ptr(xd), K1, K1, ptr(hd), K2, K2, M, ptr(ahi), ptr(alo), kp, 32, st), 'gg_split_tf32')
     assert rel_err(ahi + alo, a) < 1e-6
-    check(L.gg_node_proj_tc(ptr(ahi), ptr(alo), kp, ptr(whi), ptr(wlo), N, ptr(bd), ptr(out), N, M, 0, st), 'gg_node_proj_tc')
-    torch.cuda.synchronize()
-    assert torch.isfinite(out).all()
-    assert rel_err(out, ref) < 2e-6, rel_err(out, ref)
+    for k_first in (K1, 32):             # with and without skipping the MMAs of the zero padding behind the features
+        out.fill_(float('nan'))
+        check(L.gg_node_proj_tc(ptr(ahi), ptr(alo), kp, k_first, ptr(whi), ptr(wlo), N, ptr(bd), ptr(out), N, M, 0, st), 'gg_node_proj_tc')
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        assert rel_err(out, ref) < 2e-6, rel_err(out, ref)
     # the fp32 CUDA-core kernel on the same (unsplit) operands
     Wd = torch.cat([W[:, :K1], W[:, 32:]], 1).contiguous().to(d)
     out2 = torch.empty(M, N, device=d)
