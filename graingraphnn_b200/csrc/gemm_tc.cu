@@ -7,7 +7,7 @@
 //
 // Per CTA (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (tcgen05.ld -> +bias -> 128-bit global stores).  Tile = 128 rows x 256 columns, K streamed in
-// 32-float (128-byte) chunks through a 4-stage mbarrier ring; two 256-column TMEM accumulators double-buffer the
+// 32-float (128-byte) chunks through two mbarrier rings (A tiles, W tiles: every operand tile is fetched once per chunk); two 256-column TMEM accumulators double-buffer the
 // epilogue against the next tile's MMAs.  All three split terms accumulate into the same TMEM tile, smallest first.
 //
 // Roofline: tensor pipe. Algorithmic flops = 2 M N K; the kernel issues 3x that in TF32 MMAs.  The fp32 output
@@ -22,13 +22,14 @@ namespace {
 constexpr int BM = 128;          // rows per tile  (UMMA M)
 constexpr int BN = 256;          // columns per tile (max UMMA N)
 constexpr int BK = 32;           // floats per K chunk = 128 bytes = one swizzle-128B row
-constexpr int kStages = 3;
 constexpr int A_BYTES = BM * BK * 4;     // 16 KB
 constexpr int B_BYTES = BN * BK * 4;     // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int kRingA = 4, kRingB = 4;    // node projection: separate rings of A (16 KB) and W (32 KB) chunk tiles
+constexpr int kOutBufs = 2;              // node projection: store staging buffers (the TMA store of a chunk takes ~1 us to drain)
 constexpr int OUT_CHUNK = 32;            // columns per epilogue chunk = one 128-byte swizzled row of the store box
 constexpr int OUT_BYTES = BM * OUT_CHUNK * 4;            // 16 KB staging per TMA store, double-buffered
-constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 2 * OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = kRingA * A_BYTES + kRingB * B_BYTES + kOutBufs * OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "node projection shared memory");
 constexpr int kThreads = 256;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -97,22 +98,29 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, int M, int N, int Kp, int k_first_steps) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // swizzle-128B tiles need 1024-B alignment
-    const uint32_t out_base = smem_base + kStages * STAGE_BYTES;                 // 2 x 16 KB store staging (1024-B aligned)
-    const uint32_t bar_base = out_base + 2 * OUT_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    // Operand rings: the three split terms of a K chunk are issued as (A_lo, W_hi), (A_hi, W_hi), (A_hi, W_lo), so every operand
+    // tile is fetched ONCE per chunk (A_lo, W_hi, A_hi, W_lo: 96 KB instead of 3 x 48 KB) — the kernel is bound by the ~60 B/clk an
+    // SM pulls from L2 through TMA, not by the tensor pipe.  A tiles and W tiles live in separate rings with their own barriers.
+    const uint32_t ringA = smem_base, ringB = smem_base + kRingA * A_BYTES;
+    const uint32_t out_base = ringB + kRingB * B_BYTES;                          // 2 x 16 KB store staging (1024-B aligned)
+    const uint32_t bar_base = out_base + kOutBufs * OUT_BYTES;
+    auto fullA = [&](int s) { return bar_base + 8u * s; };
+    auto emptyA = [&](int s) { return bar_base + 8u * (kRingA + s); };
+    auto fullB = [&](int s) { return bar_base + 8u * (2 * kRingA + s); };
+    auto emptyB = [&](int s) { return bar_base + 8u * (2 * kRingA + kRingB + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kRingA + 2 * kRingB + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kRingA + 2 * kRingB + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kRingA + 2 * kRingB + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
     const int n_tiles = m_blocks * n_blocks;
-    const int chunks = Kp / BK, iters = 3 * chunks;
+    const int chunks = Kp / BK;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kRingA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < kRingB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
@@ -133,24 +141,34 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            auto load_a = [&](const CUtensorMap* map, int k0, int m0) {
+                mbar_wait(emptyA(sa), pa ^ 1u);
+                mbar_expect_tx(fullA(sa), A_BYTES);
+                tma_load_2d(ringA + sa * A_BYTES, map, fullA(sa), k0, m0);
+                if (++sa == kRingA) { sa = 0; pa ^= 1u; }
+            };
+            auto load_b = [&](const CUtensorMap* map, int k0, int n0) {
+                mbar_wait(emptyB(sb), pb ^ 1u);
+                mbar_expect_tx(fullB(sb), B_BYTES);
+                tma_load_2d(ringB + sb * B_BYTES, map, fullB(sb), k0, n0);
+                if (++sb == kRingB) { sb = 0; pb ^= 1u; }
+            };
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int m0 = (t / n_blocks) * BM, n0 = (t % n_blocks) * BN;
-                for (int it = 0; it < iters; ++it) {
-                    const int term = it / chunks, k0 = (it % chunks) * BK;
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    tma_load_2d(sa, term == 0 ? &tmA_lo : &tmA_hi, full_bar(stage), k0, m0);
-                    tma_load_2d(sb, term == 1 ? &tmW_lo : &tmW_hi, full_bar(stage), k0, n0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                for (int c = 0; c < chunks; ++c) {
+                    const int k0 = c * BK;
+                    load_a(&tmA_lo, k0, m0);
+                    load_b(&tmW_hi, k0, n0);
+                    load_a(&tmA_hi, k0, m0);
+                    load_b(&tmW_lo, k0, n0);
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int n0 = (t % n_blocks) * BN;
@@ -159,19 +177,33 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int it = 0; it < iters; ++it) {
-                    mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    const uint64_t adesc = make_desc(sa), bdesc = make_desc(sb);
+                for (int c = 0; c < chunks; ++c) {
                     // UMMA K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B).  The first chunk holds the node features
                     // zero-padded to 32 columns: only its k_first_steps leading K steps can contribute.
-                    const int ks = (it % chunks == 0) ? k_first_steps : BK / 8;
+                    const int ks = c == 0 ? k_first_steps : BK / 8;
+                    auto group = [&](uint32_t a_addr, uint32_t b_addr, bool first) {
+                        const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(b_addr);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)
-                        if (k < ks) umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) ? 1u : 0u);
-                    umma_commit(empty_bar(stage));                    // frees the smem slot when these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        for (int k = 0; k < BK / 8; ++k)
+                            if (k < ks) umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                    };
+                    // (A_lo, W_hi)
+                    const int a_lo = sa; mbar_wait(fullA(sa), pa); if (++sa == kRingA) { sa = 0; pa ^= 1u; }
+                    const int b_hi = sb; mbar_wait(fullB(sb), pb); if (++sb == kRingB) { sb = 0; pb ^= 1u; }
+                    tc_fence_after();
+                    group(ringA + a_lo * A_BYTES, ringB + b_hi * B_BYTES, c == 0);
+                    umma_commit(emptyA(a_lo));                        // A_lo is free when these MMAs retire
+                    // (A_hi, W_hi)
+                    const int a_hi = sa; mbar_wait(fullA(sa), pa); if (++sa == kRingA) { sa = 0; pa ^= 1u; }
+                    tc_fence_after();
+                    group(ringA + a_hi * A_BYTES, ringB + b_hi * B_BYTES, false);
+                    umma_commit(emptyB(b_hi));
+                    // (A_hi, W_lo)
+                    const int b_lo = sb; mbar_wait(fullB(sb), pb); if (++sb == kRingB) { sb = 0; pb ^= 1u; }
+                    tc_fence_after();
+                    group(ringA + a_hi * A_BYTES, ringB + b_lo * B_BYTES, false);
+                    umma_commit(emptyA(a_hi));
+                    umma_commit(emptyB(b_lo));
                 }
                 umma_commit(tfull_bar(acc));                          // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -194,8 +226,8 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             for (int c0 = 0; c0 < ncols; c0 += OUT_CHUNK) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                // the staging buffer we are about to overwrite was read by the TMA store issued two chunks ago
-                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                // the staging buffer we are about to overwrite was read by the TMA store issued kOutBufs chunks ago
+                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kOutBufs - 1) : "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const uint32_t srow = out_base + obuf * OUT_BYTES + (uint32_t)r * 128u;
 #pragma unroll
@@ -216,7 +248,7 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                                  ::"l"(&tmOut), "r"(out_base + obuf * OUT_BYTES), "r"(n0 + c0), "r"(m0) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                obuf ^= 1;
+                if (++obuf == kOutBufs) obuf = 0;
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
