@@ -27,6 +27,15 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#ifdef GG_TILED_PROFILE
+__device__ unsigned long long g_tiled_prof[8];   // [0] consumer wait, [1] consumer busy, [2] producer wait, [3] producer issue, [4] consumer warps, [5] producer warps
+#define GG_PROF_T0() long long prof_t = clock64()
+#define GG_PROF_ADD(var) do { const long long now_ = clock64(); var += now_ - prof_t; prof_t = now_; } while (0)
+#else
+#define GG_PROF_T0() do {} while (0)
+#define GG_PROF_ADD(var) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int NP = 4;                 // producer warps (exactly one warpgroup: setmaxnreg is per warpgroup)
@@ -217,6 +226,9 @@ pgat_gather_tiled_kernel(const TiledParams p) {
         int4 d_cur = load_desc(0), d_nxt = load_desc(1);
         Meta m_cur = load_meta(d_cur);
         int stage = 0; uint32_t phase = 0;
+        long long prof_wait = 0, prof_busy = 0;
+        (void)prof_wait; (void)prof_busy;
+        GG_PROF_T0();
         for (int t = 0; t < n_tiles; ++t) {
             const int4 d_n2 = load_desc(t + 2);
             const Meta m_nxt = load_meta(d_nxt);
@@ -230,7 +242,9 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             const bool has_hdr = mine < cnt && starts && h < HCAP;           // else: continuing row, or more starts than header slots
             const int n_hdr = __popc(__ballot_sync(0xffffffffu, has_hdr));
             const int n_rows = ne > warp ? (ne - warp + NP - 1) / NP : 0;
+            GG_PROF_ADD(prof_busy);
             mbar_wait_(empty_bar(stage), phase ^ 1u);
+            GG_PROF_ADD(prof_wait);
             if (mine < ne) sts2(base + K::EM + 8u * mine, __float_as_int(m_cur.ea), m_cur.wrap);
             if (mine < cnt)
                 sts2(base + K::TD + 8u * mine, m_cur.tn,
@@ -248,6 +262,10 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             d_cur = d_nxt; d_nxt = d_n2; m_cur = m_nxt;
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
+#ifdef GG_TILED_PROFILE
+        GG_PROF_ADD(prof_busy);
+        if (lane == 0) { atomicAdd(&g_tiled_prof[2], (unsigned long long)prof_wait); atomicAdd(&g_tiled_prof[3], (unsigned long long)prof_busy); atomicAdd(&g_tiled_prof[5], 1ull); }
+#endif
         return;
     }
 
@@ -285,9 +303,14 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     for (int r = 0; r < NQ; ++r) q[r].lo = q[r].hi = 0ull;
 
     int stage = 0; uint32_t phase = 0;
+    long long prof_wait = 0, prof_busy = 0;
+    (void)prof_wait; (void)prof_busy;
+    GG_PROF_T0();
     for (int t = 0; t < n_tiles; ++t) {
         const uint32_t base = smem0 + (uint32_t)stage * K::BYTES;
+        GG_PROF_ADD(prof_busy);
         mbar_wait_(full_bar(stage), phase);
+        GG_PROF_ADD(prof_wait);
         int cnt, i_first;
         lds2(base + K::INFO, cnt, i_first);
         int j = cw - i_first % NC;
@@ -439,6 +462,10 @@ pgat_gather_tiled_kernel(const TiledParams p) {
         if (++stage == NS) { stage = 0; phase ^= 1u; }
     }
 
+#ifdef GG_TILED_PROFILE
+    GG_PROF_ADD(prof_busy);
+    if (lane == 0) { atomicAdd(&g_tiled_prof[0], (unsigned long long)prof_wait); atomicAdd(&g_tiled_prof[1], (unsigned long long)prof_busy); atomicAdd(&g_tiled_prof[4], 1ull); }
+#endif
     // ---- targets without in-edges: zero rows (PyG scatter-add leaves them 0)
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t b0 = ((int64_t)blockIdx.x * NC + cw) * 32; b0 < p.n_dst; b0 += (int64_t)grid * NC * 32) {
@@ -536,4 +563,19 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
 #undef GG_TILED
     GG_LAUNCH_OK();
     return 0;
+}
+
+// Debug builds (-DGG_TILED_PROFILE): cycles the consumer / producer warps spent waiting and working since the last call, summed
+// over warps: out[0..5] = consumer wait, consumer busy, producer wait, producer busy, consumer warps, producer warps.
+extern "C" int gg_gather_tiled_profile(unsigned long long* out) {
+#ifdef GG_TILED_PROFILE
+    unsigned long long z[8] = {0};
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_tiled_prof, sizeof(z)) != cudaSuccess) return GG_EINVAL;
+    cudaMemcpyToSymbol(g_tiled_prof, z, sizeof(z));
+    return 0;
+#else
+    (void)out;
+    return GG_EINVAL;
+#endif
 }

@@ -13,7 +13,8 @@ if [ -n "$GG_PROFILE" ]; then
 KREG='regex:pgat_gather|node_proj|gate_update|split_tf32|edge_length|edge_head|node_head|feature_update|z_probe|z_clamp|permute_kernel'
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:pgat_gather -s 24 -c 3 -o gpurun_out/prof_gather \
+# the 12 gather launches of ONE step (3 warm-up steps x 12 launches are skipped), full metric set + source
+timeout 800 ncu --set full --clock-control none --import-source on -k regex:pgat_gather -s 36 -c 12 -o gpurun_out/prof_gather_step \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_gather.log 2>&1
 fi
 ls -la gpurun_out

@@ -52,8 +52,11 @@ def main():
                     got[torch.from_numpy(np.asarray(gid))] = val
                 same = bool(torch.equal(got, ref[k]))
                 if not same:
-                    err = float((got - ref[k]).abs().max())
-                    print(f'step {s} {k}: MISMATCH max abs err {err}', flush=True)
+                    # Rows whose in-edges straddle a tile boundary of the gather are summed in different chunks on the slab and
+                    # on the undivided graph (the tiling follows the CSR position): equal to rounding, not bit for bit.
+                    err = float((got - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-30))
+                    same = err < 1e-5
+                    print(f'step {s} {k}: not bit-identical, max rel err {err:.3e} ({"within" if same else "OUTSIDE"} 1e-5)', flush=True)
                 ok &= same
         print(f'MGPU {"OK" if ok else "FAIL"} world={world} transport={eng.halo.transport} '
               f'halo_bytes_per_exchange={eng.halo.bytes_sent_per_exchange[:3]} counts={eng.counts()}', flush=True)
