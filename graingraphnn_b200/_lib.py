@@ -38,7 +38,7 @@ _PROTOS = {
     'gg_csr_tiles_capacity': (_L, [_L, _I, _I]),
     'gg_csr_tiles_scratch_ints': (_S, [_L, _I, _I]),
     'gg_csr_tiles': (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P]),
-    'gg_pgat_gather_tiled': (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P, _I, _I, _I, _P, _I, _P, _P]),
+    'gg_pgat_gather_tiled': (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P, _I, _I, _I, _P, _I, _P, _P]),
     'gg_edge_wrap': (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _P]),
     'gg_gate_update': (_I, [POINTER(AggInput), _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'gg_node_head': (_I, [_P, _I, _I, _P, _P, _I, POINTER(c_int32), _P, _I, _P, _I, _F, _P, _I, _P]),

@@ -64,6 +64,8 @@ def tiled_ecap(pk, e):
         return 0
     if not pk.raw_k and pk.qxoff[e] != pk.qoff[e] + pk.G * pk.C:
         return 0
+    if pk.posoff.get(e) != (pk.qoff[e] + pk.raw_k * pk.G if pk.raw_k else pk.qxoff[e] + 4 * pk.G):
+        return 0                                   # the target's position must sit right behind its Q | QX (Q') block
     L = _lib.lib()
     if not (hasattr(L, 'gg_tc_supported') and L.gg_tc_supported() == 1):
         return 0
@@ -136,7 +138,7 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
             if ecap:
                 tiles, cta_ptr, n_ctas = g.tiles(ecap)      # builds nz / nzptr on first use
                 check(L.gg_pgat_gather_tiled(ptr(P[s]), pk.ncols[s], pk.koff[e], ptr(P[d]), pk.ncols[d], pk.qoff[e],
-                                             ptr(xpad[d]), xpad[d].stride(0), ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(wr),
+                                             ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(wr),
                                              ptr(g.nz), ptr(g.nzptr), ptr(tiles), ptr(cta_ptr), n_ctas,
                                              ecap, g.n_edges, pk.raw_k, ptr(pk.Wv3[e]), nd_out, G, C, ptr(agg[e]), GC, ptr(ea[e]), st),
                       'gg_pgat_gather_tiled')

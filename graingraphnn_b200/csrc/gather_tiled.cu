@@ -14,8 +14,8 @@
 //     CTA: unit k belongs to CTA k mod n_ctas (neighbouring units, which share source rows, are in flight together on
 //     different SMs and meet in L2), and cta_ptr[b] .. cta_ptr[b + 1] are the tiles of CTA b in processing order.
 //   * Persistent CTA per SM.  NP producer warps: per tile, one cp.async.bulk per edge brings the source row
-//     ([K|V], or [raw features|V] in raw-score mode) into the stage, one per starting target brings Q|QX (or Q') and one its
-//     position; edge lengths, wrap codes and the target list are written to the stage by the producer lanes.  Everything of a
+//     ([K|V], or [raw features|V] in raw-score mode) into the stage and one per starting target brings Q|QX (or Q') together
+//     with its position (four extra columns of the projection, see packing.PackedCell._pos_rows); edge lengths, wrap codes and the target list are written to the stage by the producer lanes.  Everything of a
 //     tile completes on ONE mbarrier (expect_tx); NS stages, full/empty barrier pair per stage.
 //   * NC consumer warps: target i (index in the compacted list) belongs to warp i mod NC in EVERY tile, so a row that straddles a
 //     tile boundary (always inside one unit, hence inside one CTA) stays with its warp and the online-softmax state (running
@@ -45,8 +45,7 @@ constexpr int CH = 3;                 // edges per softmax chunk (joints have ex
 
 struct TiledParams {
     const float* P_src; int ld_src, k_off;
-    const float* P_dst; int ld_dst, q_off;
-    const float* pos_dst; int ld_pd;
+    const float* P_dst; int ld_dst, q_off;          // target block at q_off: Q | QX (or Q') | position
     const int* rowptr; const int* col; const float* ea; const int* wrap;
     const int* nz; const int* nzptr; const int4* tiles; const int* cta_ptr;
     const float* Wv3;
@@ -256,8 +255,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             if (mine < ne) bulk_g2s(base + (uint32_t)mine * K::ES, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, K::ES, bar);
             if (has_hdr) {
                 const uint32_t hd = base + K::HDR + (uint32_t)h * K::HB;
-                bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn * p.ld_dst + p.q_off, K::QB, bar);
-                bulk_g2s(hd + K::QB, p.pos_dst + (size_t)m_cur.tn * p.ld_pd, 16u, bar);
+                bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn * p.ld_dst + p.q_off, K::HB, bar);     // Q | QX (Q') and the position behind it
             }
             d_cur = d_nxt; d_nxt = d_n2; m_cur = m_nxt;
             if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -345,7 +343,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                         for (int r = 0; r < NQ; ++r) q[r] = ldg4p(qrow + gsel * C + 4 * (sub + 8 * r));
                         qx = ldg4(qrow + GC + 4 * gsel);
                     }
-                    pi = ldg4(p.pos_dst + (size_t)node * p.ld_pd);
+                    pi = ldg4(qrow + K::QB / 4);
                 }
                 if (RAW) { unpack2(q[0].lo, qx.x, qx.y); float dummy; unpack2(q[0].hi, qx.z, dummy); }   // Q'[0:3] = Wk3^T q
                 const u64 px = pack2(pi.x, pi.x), py = pack2(pi.y, pi.y), pz = pack2(pi.z, pi.z);
@@ -512,7 +510,6 @@ extern "C" int gg_gather_ctas(void) {
 
 extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t k_off,
                                     const float* P_dst, int32_t ld_dst, int32_t q_off,
-                                    const float* pos_dst, int32_t ld_pos_dst,
                                     const int32_t* rowptr, const int32_t* col, const float* eattr_csr, const int32_t* wrap_csr,
                                     const int32_t* nz, const int32_t* nzptr, const int32_t* tiles, const int32_t* cta_ptr,
                                     int32_t n_ctas, int32_t ecap, int64_t n_edges,
@@ -522,16 +519,15 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
     const int my_ecap = host_ecap(G, C, raw_k != 0);
     if (my_ecap == 0 || ecap != my_ecap) return GG_EINVAL;
     if (n_dst == 0) return 0;
-    if (!P_src || !P_dst || !pos_dst || !rowptr || !Wv3 || !agg || !ea) return GG_EINVAL;
+    if (!P_src || !P_dst || !rowptr || !Wv3 || !agg || !ea) return GG_EINVAL;
     if (!cta_ptr || n_ctas < 1) return GG_EINVAL;
     if (n_edges > 0 && (!col || !eattr_csr || !wrap_csr || !nz || !nzptr || !tiles || !gg_aligned16(tiles))) return GG_EINVAL;
-    if ((ld_src | k_off | ld_dst | q_off | ld_agg | ld_pos_dst) & 3) return GG_EALIGN;
-    if (!gg_aligned16(P_src) || !gg_aligned16(P_dst) || !gg_aligned16(pos_dst) || !gg_aligned16(agg) || !gg_aligned16(Wv3)) return GG_EALIGN;
+    if ((ld_src | k_off | ld_dst | q_off | ld_agg) & 3) return GG_EALIGN;
+    if (!gg_aligned16(P_src) || !gg_aligned16(P_dst) || !gg_aligned16(agg) || !gg_aligned16(Wv3)) return GG_EALIGN;
     if (!gg_device_is_sm100()) return GG_EARCH;
     TiledParams p;
     p.P_src = P_src; p.ld_src = ld_src; p.k_off = k_off;
     p.P_dst = P_dst; p.ld_dst = ld_dst; p.q_off = q_off;
-    p.pos_dst = pos_dst; p.ld_pd = ld_pos_dst;
     p.rowptr = rowptr; p.col = col; p.ea = eattr_csr; p.wrap = wrap_csr;
     p.nz = nz; p.nzptr = nzptr; p.tiles = reinterpret_cast<const int4*>(tiles); p.cta_ptr = cta_ptr;
     p.Wv3 = Wv3;

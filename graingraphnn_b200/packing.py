@@ -60,6 +60,15 @@ class PackedCell:
 
     RAW_K = 16          # floats of the raw-feature block / of Q' per gate in raw-score mode
 
+    def _pos_rows(self, e, off, k1p, k2, rows_w, rows_b):
+        """Four identity columns (x, y, z, 0) of the TARGET's features right behind its Q | QX (or Q') block, so that the tiled
+        gather stages a target's query and position (periodGATconv.py:209) with ONE bulk copy."""
+        self.posoff[e] = off
+        eye = torch.zeros(4, k1p + k2, dtype=torch.float64)
+        eye[0, 0] = eye[1, 1] = eye[2, 2] = 1.0
+        rows_w.append(eye.to(rows_w[-1].device)); rows_b.append(torch.zeros(4, dtype=torch.float64, device=rows_b[-1].device))
+        return off + 4
+
     def __init__(self, edge_types, gates, in_dims, C, conv_of, gate_bias=None, weighted=True, device=None, raw_scores=False):
         self.edge_types, self.gates, self.C, self.G = list(edge_types), list(gates), C, len(gates)
         self.weighted = bool(weighted)
@@ -74,7 +83,7 @@ class PackedCell:
         GC = G * C
         self.k1p = {t: pad4(k[0]) for t, k in self.in_dims.items()}
         self.kin = {t: self.k1p[t] + self.in_dims[t][1] for t in self.in_dims}
-        self.koff, self.voff, self.qoff, self.qxoff, self.ncols = {}, {}, {}, {}, {}
+        self.koff, self.voff, self.qoff, self.qxoff, self.posoff, self.ncols = {}, {}, {}, {}, {}, {}
         self.Wcat, self.bcat, self.Wskip, self.btot = {}, {}, {}, {}
         self.Wv3, self.W2, self.We, self.b2 = {}, {}, {}, {}
         self.into = {t: [e for e in self.edge_types if e[2] == t] for t in self.node_types}
@@ -120,6 +129,7 @@ class PackedCell:
                         m[:, self.raw_k - 1] = cw.we.detach().double().reshape(C)
                         rows_w.append(m.t() @ wq); rows_b.append(m.t() @ bq)
                     off += self.raw_k * G
+                    off = self._pos_rows(e, off, k1p, k2, rows_w, rows_b)
                     continue
                 self.qoff[e] = off
                 for g in self.gates:
@@ -133,6 +143,7 @@ class PackedCell:
                     m = torch.cat([cw.wk.detach().double()[:, :3], cw.we.detach().double().reshape(C, 1)], dim=1)  # [C,4]
                     rows_w.append(m.t() @ wq); rows_b.append(m.t() @ bq)
                 off += 4 * G
+                off = self._pos_rows(e, off, k1p, k2, rows_w, rows_b)
             if off == 0:                            # a node type that is neither source nor target of anything
                 rows_w.append(torch.zeros(4, k1p + k2, dtype=torch.float64)); rows_b.append(torch.zeros(4, dtype=torch.float64))
                 off = 4

@@ -132,7 +132,8 @@ int gg_csr_items(const int32_t* rowptr, int32_t n_dst, int32_t dcap, int32_t* it
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Warp-specialised form of (b) (gather_tiled.cu; sm_100, weighted, G <= 4): same arithmetic and outputs as gg_pgat_gather on
- * the same layout (K|V adjacent at k_off, or raw16|V in raw-score mode; Q|QX adjacent at q_off, or Q'), driven by the TILE
+ * the same layout (K|V adjacent at k_off, or raw16|V in raw-score mode; Q|QX adjacent at q_off, or Q' — in both cases
+ * directly followed by the target's position x, y, z, 0 as four more columns of P_dst), driven by the TILE
  * index instead of the item list: the CSR edge array is cut into tiles of ecap = gg_gather_tile_ecap(G, C, raw_k) consecutive
  * in-edges (0 = this shape is not supported), producer warps stage each tile with cp.async.bulk, consumer warps compute.
  *   gg_csr_compact: nz[NZ] = targets with in-edges (ascending), nzptr[NZ + 1] = where their rows start (nzptr[NZ] = E),
@@ -155,7 +156,6 @@ int gg_csr_tiles(const int32_t* nzptr, const int32_t* nz_count, int64_t n_edges,
                  int32_t* tiles, int32_t* cta_ptr, int32_t* scratch, void* stream);
 int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t k_off,
                          const float* P_dst, int32_t ld_dst, int32_t q_off,
-                         const float* pos_dst, int32_t ld_pos_dst,
                          const int32_t* rowptr, const int32_t* col, const float* eattr_csr, const int32_t* wrap_csr,
                          const int32_t* nz, const int32_t* nzptr, const int32_t* tiles, const int32_t* cta_ptr,
                          int32_t n_ctas, int32_t ecap, int64_t n_edges,
