@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(LIBDIR, os.path.basename(s)[:-3] + '.o')
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (['-DGG_TILED_PROFILE'] if os.environ.get('GG_TILED_PROFILE') else []) + ['-c', '-o', o, s]
+            cmd = [nvcc] + NVCC_FLAGS + (['-DGG_TILED_PROFILE'] if os.environ.get('GG_TILED_PROFILE') else []) + [f'-D{d}' for d in os.environ.get('GG_DEFINES', '').split()] + ['-c', '-o', o, s]
             if verbose:
                 print(' '.join(cmd))
             subprocess.run(cmd, check=True)
