@@ -130,6 +130,31 @@ __global__ void feature_update_kernel(float* __restrict__ xj, int ldj, int nj, c
     }
 }
 
+// Ensemble form (block-diagonal batch of independent rollouts, each with its own span): per-node z increments; the clamp of
+// test.py:405-407 is applied per node, which is the same thing as per graph because all nodes of a graph carry one z.
+__global__ void feature_update_batched_kernel(float* __restrict__ xj, int ldj, int nj, const float* __restrict__ yj,
+                                              float* __restrict__ xg, int ldg, int ng, const float* __restrict__ yg,
+                                              const float* __restrict__ dzj, const float* __restrict__ dzg, float z_max, int last_g) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nj) {
+        float* r = xj + (int64_t)i * ldj;
+        const float dx = yj[2 * i], dy = yj[2 * i + 1];
+        r[0] += dx / 5.0f; r[1] += dy / 5.0f;
+        const float z = r[2] + dzj[i];
+        r[2] = z > z_max ? z_max : z;
+        r[6] = dx; r[7] = dy;
+    } else if (i < nj + ng) {
+        i -= nj;
+        float* r = xg + (int64_t)i * ldg;
+        const float ds = yg[2 * i], dv = yg[2 * i + 1];
+        r[3] += ds / 20.0f;
+        r[4] = dv;
+        r[last_g] = ds;
+        const float z = r[2] + dzg[i];
+        r[2] = z > z_max ? z_max : z;
+    }
+}
+
 __global__ void z_probe_kernel(const float* __restrict__ xg, float z_max, int* __restrict__ flag) {
     *flag = (xg[2] > z_max) ? 1 : 0;
 }
@@ -223,6 +248,18 @@ extern "C" int gg_feature_update(float* x_joint, int32_t ld_j, int32_t n_joint, 
     z_probe_kernel<<<1, 1, 0, st>>>(x_grain, z_max, scratch);
     GG_LAUNCH_OK();
     z_clamp_kernel<<<(n + 255) / 256, 256, 0, st>>>(x_joint, ld_j, n_joint, x_grain, ld_g, n_grain, z_max, scratch);
+    GG_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int gg_feature_update_batched(float* x_joint, int32_t ld_j, int32_t n_joint, const float* y_joint,
+                                         float* x_grain, int32_t ld_g, int32_t n_grain, int32_t n_grain_feat, const float* y_grain,
+                                         const float* dz_joint, const float* dz_grain, float z_max, void* stream) {
+    if (n_joint < 0 || n_grain < 1 || ld_j < 8 || n_grain_feat < 6 || ld_g < n_grain_feat) return GG_EINVAL;
+    if (!x_joint || !x_grain || !y_joint || !y_grain || !dz_joint || !dz_grain) return GG_EINVAL;
+    const int n = n_joint + n_grain;
+    feature_update_batched_kernel<<<(n + 255) / 256, 256, 0, GG_STREAM(stream)>>>(x_joint, ld_j, n_joint, y_joint, x_grain, ld_g, n_grain,
+                                                                                  y_grain, dz_joint, dz_grain, z_max, n_grain_feat - 1);
     GG_LAUNCH_OK();
     return 0;
 }

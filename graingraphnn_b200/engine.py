@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from .cell import run_cell
 from .graph import build_csr, edge_length, edge_wrap
-from .heads import edge_head, feature_update, node_head
+from .heads import edge_head, feature_update, feature_update_batched, node_head
 from .models import GrainNN_classifier, GrainNN_regressor
 from .packing import pad4
 
@@ -156,11 +156,36 @@ class RolloutEngine:
                              area_in=self.xbuf['grain'][:, 3], area_scale=20.0, n_rows=ng)
         ev, ed = edge_head(sC['hd']['joint'], self.edge_index[ET_JJ], self.edge_attr[ET_JJ],
                            Cm.lin1.weight, Cm.lin1.bias, Cm.lin2.weight, Cm.lin2.bias)
-        feature_update(self.x['joint'], self.x['grain'], yj, yg, span / (self.train_frames + 1),
-                       self.train_frames / (self.train_frames + 1), self._scratch, n_joint=nj, n_grain=ng)
+        if isinstance(span, (tuple, list)):                  # ensemble: one span per graph of the block-diagonal batch
+            dzj, dzg = self._dz_vectors(tuple(span))
+            feature_update_batched(self.x['joint'], self.x['grain'], yj, yg, dzj, dzg,
+                                   self.train_frames / (self.train_frames + 1), n_joint=nj, n_grain=ng)
+        else:
+            feature_update(self.x['joint'], self.x['grain'], yj, yg, span / (self.train_frames + 1),
+                           self.train_frames / (self.train_frames + 1), self._scratch, n_joint=nj, n_grain=ng)
         yield [self.xbuf]                                    # moved coordinates of the halo -> edge lengths, next step
         self.rebuild_edge_attr()
         self.pred = {'joint': yj, 'grain': yg, 'grain_area': area, 'edge_event': ev, 'edge': ed}
+
+    graph_ptr = None         # {node type: [0, n_0, n_0 + n_1, ...]} of a block-diagonal batch (ensemble.EnsembleEngine)
+
+    def _dz_vectors(self, spans):
+        """Per-node z increment span_of_graph / (train_frames + 1) for a block-diagonal batch (cached per span tuple)."""
+        if self.graph_ptr is None:
+            raise ValueError('a per-graph span needs a batched graph (EnsembleEngine.set_graphs)')
+        cache = self.__dict__.setdefault('_dz_cache', {})
+        hit = cache.get(spans)
+        if hit is None:
+            out = []
+            for t in ('joint', 'grain'):
+                ptr_t = self.graph_ptr[t]
+                if len(ptr_t) - 1 != len(spans):
+                    raise ValueError(f'{len(spans)} spans for {len(ptr_t) - 1} graphs')
+                counts = torch.tensor([ptr_t[i + 1] - ptr_t[i] for i in range(len(spans))])
+                dz = torch.tensor([float(sp) / (self.train_frames + 1) for sp in spans], dtype=torch.float32)
+                out.append(torch.repeat_interleave(dz, counts).to(self.device))
+            hit = cache[spans] = tuple(out)
+        return hit
 
     def _step_impl(self, span):
         for _ in self._step_gen(span):
@@ -170,6 +195,8 @@ class RolloutEngine:
     @torch.no_grad()
     def step(self, span=6):
         """One rollout step on the resident graph. Returns the prediction dict (device tensors)."""
+        if isinstance(span, list):
+            span = tuple(span)
         if self._graph is not None and self._graph[0] == span:
             self._graph[1].replay()
             return self.pred

@@ -47,3 +47,13 @@ def feature_update(x_joint, x_grain, y_joint, y_grain, dz, z_max, scratch=None, 
                                            ptr(y_joint), ptr(x_grain), x_grain.stride(0),
                                            x_grain.shape[0] if n_grain is None else n_grain, x_grain.shape[1], ptr(y_grain),
                                            float(dz), float(z_max), ptr(scratch), _stream()), 'gg_feature_update')
+
+
+def feature_update_batched(x_joint, x_grain, y_joint, y_grain, dz_joint, dz_grain, z_max, n_joint=None, n_grain=None):
+    """Ensemble form of feature_update: per-node z increments (span of the node's graph / 121), per-node clamp."""
+    assert x_joint.stride(1) == 1 and x_grain.stride(1) == 1
+    with torch.cuda.device(x_joint.device):
+        check(_lib.lib().gg_feature_update_batched(ptr(x_joint), x_joint.stride(0), x_joint.shape[0] if n_joint is None else n_joint,
+                                                   ptr(y_joint), ptr(x_grain), x_grain.stride(0),
+                                                   x_grain.shape[0] if n_grain is None else n_grain, x_grain.shape[1], ptr(y_grain),
+                                                   ptr(dz_joint), ptr(dz_grain), float(z_max), _stream()), 'gg_feature_update_batched')

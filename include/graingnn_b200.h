@@ -249,6 +249,12 @@ int gg_edge_head(const float* h, int32_t ldh, int32_t C, const int64_t* edge_ind
 int gg_feature_update(float* x_joint, int32_t ld_j, int32_t n_joint, const float* y_joint,
                       float* x_grain, int32_t ld_g, int32_t n_grain, int32_t n_grain_feat, const float* y_grain,
                       float dz, float z_max, int32_t* scratch, void* stream);
+/* Ensemble form (BASELINE config 5: a block-diagonal batch of independent rollouts, each with its own span): dz_joint /
+ * dz_grain hold span_of_graph / 121 per node; z = min(z + dz, z_max) per node (all nodes of a graph carry one z, so this
+ * is test.py:405-407 per graph). */
+int gg_feature_update_batched(float* x_joint, int32_t ld_j, int32_t n_joint, const float* y_joint,
+                              float* x_grain, int32_t ld_g, int32_t n_grain, int32_t n_grain_feat, const float* y_grain,
+                              const float* dz_joint, const float* dz_grain, float z_max, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (e) halo pack / unpack for the slab-partitioned domain: out[i, :] = src[idx[i], :] and the inverse.

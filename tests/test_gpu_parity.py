@@ -397,3 +397,31 @@ def test_full_size_properties_100k_grains():
     # node outputs: same up to summation order inside a row; edge outputs: permuted the same way
     assert rel_err(p2['joint'], p1['joint']) < 1e-5 and rel_err(p2['grain_area'], p1['grain_area']) < 1e-5
     assert rel_err(p2['edge_event'], p1['edge_event'][perms[ET[2]].to(dev())]) < 1e-5
+
+
+def test_ensemble_of_rollouts_with_per_graph_span_matches_oracle_per_member():
+    """BASELINE config 5: a block-diagonal batch of independent rollouts (different sizes, different spans) steps every
+    member exactly as the oracle steps it alone; two steps, the second one through the clamp of z (test.py:405-407)."""
+    from graingraphnn_b200.ensemble import EnsembleEngine
+    sd_r, sd_c = orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
+    members, spans = [], (6, 12, 120)
+    for i, name in enumerate(('c1', 'c2', 'c1')):
+        x, ei, ea = load_graph(name)
+        x = {t: v.clone() for t, v in x.items()}
+        g = torch.Generator().manual_seed(100 + i)
+        x['joint'][:, :2] = (x['joint'][:, :2] + 0.01 * torch.rand(x['joint'].shape[0], 2, generator=g)) % 1.0
+        members.append((x, ei, None))
+    eng = EnsembleEngine.from_state_dicts(sd_r, sd_c, device=dev())
+    eng.set_graphs([(to_dev(x), to_dev(ei), None) for x, ei, _ in members])
+    ref_x = [{t: v.clone() for t, v in m[0].items()} for m in members]
+    ref_ea = [orc.edge_attr_rebuild(m[0], m[1]) for m in members]
+    for step in range(2):
+        pred = eng.split(eng.step(list(spans)))
+        for i, (m, sp) in enumerate(zip(members, spans)):
+            ref, ref_ea[i] = orc.nn_step(sd_r, sd_c, ref_x[i], m[1], ref_ea[i], sp)
+            for k in ('joint', 'grain', 'grain_area', 'edge_event'):
+                assert rel_err(pred[i][k], ref[k]) < TOL, (step, i, k)
+            got = eng.member_features(i)
+            for t in ('joint', 'grain'):
+                assert rel_err(got[t], ref_x[i][t]) < TOL, (step, i, t)
+    assert abs(float(eng.member_features(2)['grain'][0, 2]) - 120 / 121) < 1e-6      # span 120 twice: clamped

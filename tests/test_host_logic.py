@@ -172,3 +172,22 @@ def test_sage_cells_have_the_reference_state_dict_layout():
     assert gc.conv_i.conv(ET[0]).lin_l.weight.shape == (96, 11) and gc.conv_i.conv(ET[0]).lin_r.weight.shape == (96, 8)
     with pytest.raises(RuntimeError):
         cell({'grain': torch.zeros(3, 11), 'joint': torch.zeros(4, 8)}, {})      # CPU tensors: no fallback
+
+
+def test_collate_offsets_edges_like_the_reference_loader():
+    """Block-diagonal batch (BASELINE config 5): node features stacked, edge indices offset per graph (data_loader.py:113-162)."""
+    from graingraphnn_b200.ensemble import collate
+    x1, ei1, ea1 = load_graph('c1')
+    x2, ei2, ea2 = load_graph('c2')
+    x, ei, ea, ptr = collate([(x1, ei1, ea1), (x2, ei2, ea2), (x1, ei1, ea1)])
+    ng1, nj1, ng2, nj2 = x1['grain'].shape[0], x1['joint'].shape[0], x2['grain'].shape[0], x2['joint'].shape[0]
+    assert ptr['grain'] == [0, ng1, ng1 + ng2, 2 * ng1 + ng2] and ptr['joint'] == [0, nj1, nj1 + nj2, 2 * nj1 + nj2]
+    for e in ET:
+        E1, E2 = ei1[e].shape[1], ei2[e].shape[1]
+        assert ptr[e] == [0, E1, E1 + E2, 2 * E1 + E2]
+        off = torch.tensor([[ptr[e[0]][1]], [ptr[e[2]][1]]])
+        assert torch.equal(ei[e][:, E1:E1 + E2], ei2[e] + off)
+        off = torch.tensor([[ptr[e[0]][2]], [ptr[e[2]][2]]])
+        assert torch.equal(ei[e][:, E1 + E2:], ei1[e] + off)
+        assert torch.equal(ea[e][E1:E1 + E2].reshape(-1), ea2[e].reshape(-1))
+    assert torch.equal(x['grain'][ng1:ng1 + ng2], x2['grain'])
