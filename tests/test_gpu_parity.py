@@ -425,3 +425,27 @@ def test_ensemble_of_rollouts_with_per_graph_span_matches_oracle_per_member():
             for t in ('joint', 'grain'):
                 assert rel_err(got[t], ref_x[i][t]) < TOL, (step, i, t)
     assert abs(float(eng.member_features(2)['grain'][0, 2]) - 120 / 121) < 1e-6      # span 120 twice: clamped
+
+
+def test_engine_topology_change_between_steps_matches_oracle():
+    """Dynamic topology (models.py:840-841 rebinds new edge_index tensors after an elimination): step, drop every edge that
+    touches two grains (their rows stay, with in-degree 0: dead nodes keep flowing through the NN), set_topology, step again."""
+    from graingraphnn_b200.engine import RolloutEngine
+    x, ei, ea = load_graph('c1')
+    sd_r, sd_c = orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
+    eng = RolloutEngine.from_state_dicts(sd_r, sd_c, dev())
+    eng.set_graph(to_dev(x), to_dev(ei), to_dev(ea))
+    xo = {k: v.clone() for k, v in x.items()}
+    pred = eng.step(6)
+    ref, ea1 = orc.nn_step(sd_r, sd_c, xo, ei, ea, 6)
+    assert rel_err(pred['edge_event'], ref['edge_event']) < TOL
+    dead = torch.tensor([5, 77])
+    ei2 = {ET[0]: ei[ET[0]][:, ~torch.isin(ei[ET[0]][0], dead)], ET[1]: ei[ET[1]][:, ~torch.isin(ei[ET[1]][1], dead)],
+           ET[2]: ei[ET[2]][:, 12:]}                      # also drop a few joint-joint edges: in-degree 2 rows
+    eng.set_topology(to_dev(ei2))
+    pred = eng.step(6)
+    ref, _ = orc.nn_step(sd_r, sd_c, xo, ei2, orc.edge_attr_rebuild(xo, ei2), 6)
+    for k in ('joint', 'grain', 'grain_area', 'edge_event'):
+        assert torch.isfinite(pred[k]).all() and rel_err(pred[k], ref[k]) < TOL, k
+    assert rel_err(eng.x['grain'], xo['grain']) < TOL and rel_err(eng.x['joint'], xo['joint']) < TOL
+    assert pred['edge_event'].shape[0] == ei2[ET[2]].shape[1]
