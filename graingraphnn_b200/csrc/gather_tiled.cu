@@ -147,18 +147,13 @@ constexpr uint32_t cfg_stage_bytes(int G, int C, bool raw, int ecap, int hcap) {
     return ((uint32_t)ecap * cfg_es(G, C, raw) + (uint32_t)hcap * (cfg_qb(G, C, raw) + 16u) + 2u * e8 + 16u + 127u) & ~127u;
 }
 constexpr int cfg_hcap(int ecap) { return ecap / 3 + 2; }
-// Tiles of 36 edges (12 joint targets = one per consumer warp, 6 grain targets) in as many stages as fit 227 KB (at most 6);
-// where not even two such stages fit, the largest multiple of 6 edges that gives three stages, else two.  what = 0: ECAP, 1: stages
+// The largest tile (multiple of 6 edges: joints have 3 in-edges, grains ~6) that fits 227 KB with three stages, else with two
+// (measured on the bench graph, encoder form: 54 edges x 3 stages 179 / 152 / 179 us per launch, 36 x 4: 192 / 164 / 192 us).
+// what = 0: ECAP, 1: stages
 constexpr int cfg_pick(int G, int C, bool raw, int what) {
-    const long long budget = 227 * 1024 - 256;
-    const long long b36 = cfg_stage_bytes(G, C, raw, 36, cfg_hcap(36));
-    if (2 * b36 <= budget) {
-        const int ns = (int)(budget / b36);
-        return what == 0 ? 36 : (ns > 6 ? 6 : ns);
-    }
     for (int ns = 3; ns >= 2; --ns)
-        for (int ecap = 30; ecap >= 12; ecap -= 6)
-            if ((long long)ns * cfg_stage_bytes(G, C, raw, ecap, cfg_hcap(ecap)) <= budget) return what == 0 ? ecap : ns;
+        for (int ecap = 60; ecap >= 12; ecap -= 6)
+            if ((long long)ns * cfg_stage_bytes(G, C, raw, ecap, cfg_hcap(ecap)) <= 227 * 1024 - 256) return what == 0 ? ecap : ns;
     return 0;
 }
 template <int NV, int G_, bool RAW>
