@@ -54,6 +54,18 @@ def raw_gather_available():
     return hasattr(L, 'gg_tc_supported') and L.gg_tc_supported() == 1
 
 
+def raw_hidden_available(G, C):
+    """True when cells WITH hidden state may be packed for raw scores (source row = [input | V]): only the warp-specialised
+    gather implements that form.  GG_RAWH=0 keeps the K | V form (A/B measurements)."""
+    mode = os.environ.get('GG_GATHER', '').lower()
+    if mode.startswith('l') or mode.startswith('i') or os.environ.get('GG_RAWH', '1') == '0':
+        return False
+    L = _lib.lib()
+    if not (hasattr(L, 'gg_tc_supported') and L.gg_tc_supported() == 1):
+        return False
+    return int(L.gg_gather_tile_ecap(G, C, 32 + C)) > 0
+
+
 def tiled_ecap(pk, e):
     """Tile size of the warp-specialised gather for edge type e of this pack, 0 when that kernel does not apply (unweighted
     sum variant, G > 4, operand blocks not adjacent, not an sm_100 device, GG_GATHER=ldg|items)."""

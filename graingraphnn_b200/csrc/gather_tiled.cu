@@ -140,9 +140,10 @@ __device__ __forceinline__ float wrapv(int code) { return code == 0 ? 0.f : (cod
 // Tile geometry and shared-memory layout of one stage (byte offsets; every block 16-byte aligned), fixed at compile time per
 // (width, gates, mode) so that every address in the consumer loop is a constant offset.
 //   rows [ECAP x ES] | headers [HCAP x HB] | target descriptors [ECAP x 8] | edge metadata [ECAP x 8] | info [16]
-constexpr uint32_t cfg_es(int G, int C, bool raw) { return raw ? 64u + (uint32_t)G * C * 4u : 2u * (uint32_t)G * C * 4u; }   // [raw16 | V] or [K | V]
-constexpr uint32_t cfg_qb(int G, int C, bool raw) { return raw ? 64u * G : (uint32_t)G * C * 4u + 16u * G; }                 // Q' (16 per gate) or Q | QX
-constexpr uint32_t cfg_stage_bytes(int G, int C, bool raw, int ecap, int hcap) {
+// rawk: floats of the raw block in front of V (0: K | V form; 16: encoder; 32 + C: cells with hidden state)
+constexpr uint32_t cfg_es(int G, int C, int rawk) { return rawk ? 4u * rawk + (uint32_t)G * C * 4u : 2u * (uint32_t)G * C * 4u; }   // [raw | V] or [K | V]
+constexpr uint32_t cfg_qb(int G, int C, int rawk) { return rawk ? 4u * rawk * G : (uint32_t)G * C * 4u + 16u * G; }            // Q' (rawk per gate) or Q | QX
+constexpr uint32_t cfg_stage_bytes(int G, int C, int raw, int ecap, int hcap) {
     const uint32_t e8 = (((uint32_t)ecap * 8u) + 15u) & ~15u;
     return ((uint32_t)ecap * cfg_es(G, C, raw) + (uint32_t)hcap * (cfg_qb(G, C, raw) + 16u) + 2u * e8 + 16u + 127u) & ~127u;
 }
@@ -150,15 +151,17 @@ constexpr int cfg_hcap(int ecap) { return ecap / 3 + 2; }
 // The largest tile (multiple of 6 edges: joints have 3 in-edges, grains ~6) that fits 227 KB with three stages, else with two
 // (measured on the bench graph, encoder form: 54 edges x 3 stages 179 / 152 / 179 us per launch, 36 x 4: 192 / 164 / 192 us).
 // what = 0: ECAP, 1: stages
-constexpr int cfg_pick(int G, int C, bool raw, int what) {
+constexpr int cfg_pick(int G, int C, int raw, int what) {
     for (int ns = 3; ns >= 2; --ns)
         for (int ecap = 60; ecap >= 12; ecap -= 6)
             if ((long long)ns * cfg_stage_bytes(G, C, raw, ecap, cfg_hcap(ecap)) <= 227 * 1024 - 256) return what == 0 ? ecap : ns;
     return 0;
 }
-template <int NV, int G_, bool RAW>
+// MODE: 0 = K | V rows, 1 = raw scores without hidden state (16-float raw block), 2 = raw scores on [X padded to 32 | h]
+__host__ __device__ constexpr int mode_rawk(int mode, int C) { return mode == 0 ? 0 : (mode == 1 ? 16 : 32 + C); }
+template <int NV, int G_, int MODE>
 struct TCfg {
-    static constexpr int C = 32 * NV, G = G_, GC = G * C;
+    static constexpr int C = 32 * NV, G = G_, GC = G * C, RAW = mode_rawk(MODE, 32 * NV);
     static constexpr int ECAP = cfg_pick(G, C, RAW, 0), NS = cfg_pick(G, C, RAW, 1), HCAP = cfg_hcap(ECAP);
     static constexpr uint32_t ES = cfg_es(G, C, RAW), QB = cfg_qb(G, C, RAW), HB = QB + 16u;
     static constexpr uint32_t HDR = (uint32_t)ECAP * ES;
@@ -171,14 +174,16 @@ struct TCfg {
     static_assert(BYTES == ((INFO + 16u + 127u) & ~127u), "layout");
 };
 // shapes with a compiled kernel: the encoder (3 live gates, raw scores), the decoder (4 gates), single convolutions (1 gate)
-constexpr bool cfg_supported(int G, bool raw) { return raw ? G == 3 : (G == 4 || G == 1); }
+constexpr bool cfg_supported(int G, int mode) { return mode == 1 ? G == 3 : (mode == 2 ? G == 4 : (G == 4 || G == 1)); }
 
-template <int NV, int G, bool RAW>
+template <int NV, int G, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 pgat_gather_tiled_kernel(const TiledParams p) {
-    using K = TCfg<NV, G, RAW>;
+    using K = TCfg<NV, G, MODE>;
+    constexpr bool RAW = MODE != 0, RAWH = MODE == 2;        // raw scores; ... on the full cell input (with hidden state)
+    constexpr int RAWK = K::RAW;
     constexpr int C = 32 * NV, GC = G * C;
-    constexpr int NQ = RAW ? 4 : NV;                         // float4 registers of the target's query
+    constexpr int NQ = MODE == 1 ? 4 : (RAWH ? NV + 1 : NV); // float4 registers of the target's query (raw: this lane's share of Q')
     constexpr float LOG2E = 1.4426950408889634f;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -269,7 +274,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     const bool active = grp < G;
     const int gsel = active ? grp : 0;                       // idle 8-lane groups (G < 4) shadow gate 0 and store nothing
     const uint32_t lane_off = 4u * (gsel * C + 4 * sub);     // byte offset of this lane's first float4 inside a staged row
-    const uint32_t v_off = RAW ? 64u : (uint32_t)GC * 4u;    // V row behind the raw features / the K row
+    const uint32_t v_off = RAW ? 4u * RAWK : (uint32_t)GC * 4u;   // V row behind the raw block / the K row
     const float sc2 = p.inv_sqrt_c * LOG2E;                  // scores are kept in log2 units: exp(x) = ex2(x log2 e)
     const int me = sub % 3;                                  // raw-score mode: the edge of a chunk this lane scores (lanes 0..2 of a group publish)
     const int src0 = lane & 24;                              // lane `sub == 0` of this gate group
@@ -319,7 +324,11 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 float4 pi;
                 if (hs != 255) {
                     const uint32_t hd = base + K::HDR + (uint32_t)hs * K::HB;
-                    if (RAW) {
+                    if (RAWH) {                               // this lane's share of Q'_gate: float4 slots sub, sub + 8, ...
+#pragma unroll
+                        for (int r = 0; r < NQ; ++r) q[r] = lds4p(hd + gsel * (4 * RAWK) + 16 * (sub + 8 * r));
+                        qx = lds4(hd + gsel * (4 * RAWK));    // Q'[0:3] = Wk3^T q
+                    } else if (RAW) {
 #pragma unroll
                         for (int r = 0; r < NQ; ++r) q[r] = lds4p(hd + gsel * 64 + 16 * r);
                     } else {
@@ -330,7 +339,11 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                     pi = lds4(hd + K::QB);
                 } else {                                      // more starting targets than header slots (runs of in-degree < 3): plain loads
                     const float* qrow = p.P_dst + (size_t)node * p.ld_dst + p.q_off;
-                    if (RAW) {
+                    if (RAWH) {
+#pragma unroll
+                        for (int r = 0; r < NQ; ++r) q[r] = ldg4p(qrow + gsel * RAWK + 4 * (sub + 8 * r));
+                        qx = ldg4(qrow + gsel * RAWK);
+                    } else if (RAW) {
 #pragma unroll
                         for (int r = 0; r < NQ; ++r) q[r] = ldg4p(qrow + gsel * 16 + 4 * r);
                     } else {
@@ -340,7 +353,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                     }
                     pi = ldg4(qrow + K::QB / 4);
                 }
-                if (RAW) { unpack2(q[0].lo, qx.x, qx.y); float dummy; unpack2(q[0].hi, qx.z, dummy); }   // Q'[0:3] = Wk3^T q
+                if (MODE == 1) { unpack2(q[0].lo, qx.x, qx.y); float dummy; unpack2(q[0].hi, qx.z, dummy); }   // Q'[0:3] = Wk3^T q
                 const u64 px = pack2(pi.x, pi.x), py = pack2(pi.y, pi.y), pz = pack2(pi.z, pi.z);
 #pragma unroll
                 for (int r = 0; r < NV; ++r) {                // vp = Wv3 p_i:  V_j + Wv3 (w_e - p_i) > 0  <=>  V_j + Wv3 w_e > vp
@@ -358,7 +371,26 @@ pgat_gather_tiled_kernel(const TiledParams p) {
 #pragma unroll
                 for (int e = 0; e < CH; ++e) { int ai; lds2(base + K::EM + 8u * sl[e], ai, wc[e]); ae[e] = __int_as_float(ai); }
                 const int wc_any = wc[0] | wc[1] | wc[2];
-                if (RAW) {
+                if (RAWH) {
+                    // x_j . Q'_i over the 32 + C input slots: lane `sub` of a gate group owns the float4 slots sub, sub + 8, ...;
+                    // the four gate groups read the same addresses (broadcast).  Slot 31 (We . q) meets the edge length.
+#pragma unroll
+                    for (int e = 0; e < CH; ++e) {
+                        const uint32_t xrow = base + (uint32_t)sl[e] * K::ES + 16u * sub;
+                        u64 da = 0ull, db = 0ull;
+#pragma unroll
+                        for (int r = 0; r < NQ; ++r) {
+                            P4 xx = lds4p(xrow + 128 * r);
+                            if (r == 0 && sub == 7) { float x30, x31; unpack2(xx.hi, x30, x31); xx.hi = pack2(x30, ae[e]); }
+                            da = ffma2(q[r].lo, xx.lo, da); db = ffma2(q[r].hi, xx.hi, db);
+                        }
+                        float dd = group_sum8(hsum2(da, db));
+                        if (wc[e]) {
+                            dd = fmaf(qx.x, wrapv(wc[e] & 3), dd); dd = fmaf(qx.y, wrapv((wc[e] >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((wc[e] >> 4) & 3), dd);
+                        }
+                        sc[e] = dd * sc2;
+                    }
+                } else if (RAW) {
                     // each lane scores ONE edge of the chunk (edge `me`) for its gate; lanes 0..2 of the group publish
                     const float my_ae = me == 0 ? ae[0] : (me == 1 ? ae[1] : ae[2]);
                     const uint32_t row = base + (uint32_t)(me == 0 ? sl[0] : (me == 1 ? sl[1] : sl[2])) * K::ES;
@@ -479,15 +511,17 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     }
 }
 
-int host_ecap(int G, int C, bool raw) {
-    if (G < 1 || G > 4 || C % 32 || C < 32 || C > 128 || !cfg_supported(G, raw)) return 0;
-    return cfg_pick(G, C, raw, 0);
+int host_mode(int C, int raw_k) { return raw_k == 0 ? 0 : (raw_k == 16 ? 1 : (raw_k == 32 + C ? 2 : -1)); }
+int host_ecap(int G, int C, int raw_k) {
+    const int mode = host_mode(C, raw_k);
+    if (mode < 0 || G < 1 || G > 4 || C % 32 || C < 32 || C > 128 || !cfg_supported(G, mode)) return 0;
+    return cfg_pick(G, C, raw_k, 0);
 }
 
 }  // namespace
 
 extern "C" int gg_gather_tile_ecap(int32_t G, int32_t C, int32_t raw_k) {
-    return host_ecap(G, C, raw_k != 0);
+    return host_ecap(G, C, raw_k);
 }
 
 // number of persistent CTAs the tile lists are laid out for: one per SM (GG_GATHER_SMS caps it for experiments)
@@ -510,8 +544,8 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
                                     int32_t n_ctas, int32_t ecap, int64_t n_edges,
                                     int32_t raw_k, const float* Wv3, int32_t n_dst, int32_t G, int32_t C,
                                     float* agg, int32_t ld_agg, float* ea, void* stream) {
-    if (n_dst < 0 || n_edges < 0 || n_edges > 0x7fffffffLL || (raw_k != 0 && raw_k != 16)) return GG_EINVAL;
-    const int my_ecap = host_ecap(G, C, raw_k != 0);
+    if (n_dst < 0 || n_edges < 0 || n_edges > 0x7fffffffLL) return GG_EINVAL;
+    const int my_ecap = host_ecap(G, C, raw_k);
     if (my_ecap == 0 || ecap != my_ecap) return GG_EINVAL;
     if (n_dst == 0) return 0;
     if (!P_src || !P_dst || !rowptr || !Wv3 || !agg || !ea) return GG_EINVAL;
@@ -532,7 +566,7 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
     const unsigned grid = (unsigned)n_ctas;                  // the tile list is ordered for exactly this many CTAs
     cudaStream_t st = GG_STREAM(stream);
     cudaError_t err = cudaSuccess;
-#define GG_TILED(NV, GV, RAWV)                                                                                                      \
+#define GG_TILED(NV, GV, RAWV)                                                                                                     \
     do {                                                                                                                            \
         using KC = TCfg<NV, GV, RAWV>;                                                                                              \
         const size_t smem = (size_t)KC::NS * KC::BYTES + 16 * KC::NS;                                                               \
@@ -547,9 +581,10 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
         case 3: GG_TILED(3, GV, RAWV); break;        \
         default: GG_TILED(4, GV, RAWV); break;       \
     }
-    if (raw_k) { GG_TILED_NV(3, true) }
-    else if (G == 4) { GG_TILED_NV(4, false) }
-    else { GG_TILED_NV(1, false) }
+    if (raw_k == 16) { GG_TILED_NV(3, 1) }
+    else if (raw_k) { GG_TILED_NV(4, 2) }
+    else if (G == 4) { GG_TILED_NV(4, 0) }
+    else { GG_TILED_NV(1, 0) }
 #undef GG_TILED_NV
 #undef GG_TILED
     GG_LAUNCH_OK();

@@ -249,8 +249,8 @@ class RolloutEngine:
         gather, classic (decoder): per edge type and cell  4*G*C*(2 N_src + 2 N_dst) + 4*4*G*N_dst + 12 N_dst + 8 (N_dst+1) + 12 E
           (K, V once per source; Q, QX once and agg written once per target; target position; rowptr-equivalent item
           offsets; col + edge length + wrap code per edge)
-        gather, raw-score (encoder): 4*(G*C + 16)*N_src + 4*(G*C + 16 G)*N_dst + 12 N_dst + 8 (N_dst+1) + 12 E
-          (raw features + V per source; Q' (16 per gate) and agg per target)
+        gather, raw-score: 4*(G*C + R)*N_src + 4*(G*C + R G)*N_dst + 12 N_dst + 8 (N_dst+1) + 12 E, R = 16 (encoder) or 32 + C (decoder)
+          (raw input + V per source; Q' (R per gate) and agg per target)
         node_proj: 2 * N_t * K_t * ncols_t flop per node type and cell (K = F (+C with hidden state), unpadded)
         gate_update: 2 * N_t * G*C * (C * n_in_types + K_t) flop per node type and cell"""
         n = {t: self.xbuf[t].shape[0] for t in self.node_types}
@@ -264,7 +264,7 @@ class RolloutEngine:
                     ns, nd, E = n[e[0]], n[e[2]], int(self.edge_index[e].shape[1])
                     common = 12.0 * nd + 8.0 * (nd + 1) + 12.0 * E
                     if pk.raw_k:
-                        out['gg_pgat_gather'] += 4.0 * (G * C + 16) * ns + 4.0 * (G * C + 16 * G) * nd + common
+                        out['gg_pgat_gather'] += 4.0 * (G * C + pk.raw_k) * ns + 4.0 * (G * C + pk.raw_k * G) * nd + common
                     else:
                         out['gg_pgat_gather'] += 4.0 * G * C * (2 * ns + 2 * nd) + 16.0 * G * nd + common
                 for t in self.node_types:

@@ -15,7 +15,7 @@ from torch import nn
 from torch.nn import Parameter
 
 from . import _lib
-from .cell import _as_f32c, pad_features, raw_gather_available, require_cuda, run_cell
+from .cell import _as_f32c, pad_features, raw_gather_available, raw_hidden_available, require_cuda, run_cell
 from .graph import GLOBAL_CSR_CACHE, permute_to_csr
 from .nn import HeteroConv, glorot_
 from .packing import ConvWeights, PackedCell, version_key
@@ -79,7 +79,8 @@ class _PGCBase(nn.Module):
         gather path will take it (sm_100 device, <= 4 gates, <= 15 padded features per node type)."""
         edge_types = tuple(self.metadata[1]) if edge_types is None else tuple(edge_types)
         if raw is None:
-            raw = (not with_h) and len(gates) <= 4 and str(device).startswith('cuda') and raw_gather_available() \
+            raw = len(gates) <= 4 and str(device).startswith('cuda') and \
+                (raw_hidden_available(len(gates), self.out_channels) if with_h else raw_gather_available()) \
                 and all((f + 3) // 4 * 4 <= PackedCell.RAW_K - 1 for f in self.in_channels_dict.values())
         cws = self._weights(gates)
         tensors = [t for cw in cws.values() for t in cw.tensors()]
@@ -92,7 +93,7 @@ class _PGCBase(nn.Module):
             in_dims = {t: (f, C) for t, f in self.in_channels_dict.items()}
             pk = PackedCell(edge_types, gates, in_dims, C, lambda g, e: cws[(g, e)],
                             gate_bias=lambda g, t: getattr(self, f'b_{g}')[t],
-                            weighted=self.conv_class.weighted, device=device, raw_scores=bool(raw))
+                            weighted=self.conv_class.weighted, device=device, raw_scores=bool(raw), raw_hidden=bool(raw) and with_h)
             if not with_h and not raw:   # h == 0: only the feature columns of every weight matter (K = K1p)
                 for t in pk.node_types:
                     k1p = pk.k1p[t]

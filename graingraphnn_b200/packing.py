@@ -8,7 +8,10 @@ All re-associations are linear and exact in real arithmetic (SURVEY.md §7 "Alge
   * all gates of a cell share one projection GEMM; lin_skip of the edge types that end in the same node type are summed.
   * "raw scores" (cells without hidden state, i.e. the encoder, models.py:237-238): q_i . (Wk x_j) = x_j . (Wk^T q_i), so the
     key projection disappears altogether: the target carries Q'_i = [Wk[:, :F]^T q_i (F <= 15 source features) | We . q_i]
-    (16 floats per gate instead of C + 4) and the source row only its raw features next to V.
+    (16 floats per gate instead of C + 4) and the source row only its raw features next to V.  With hidden state (decoder)
+    the same identity holds on the full input [X padded to 32 | h]: the staged source row shrinks from K | V (2 G C floats) to
+    [input (32 + C) | V (G C)] and Q' grows to 32 + C floats per gate (slot 31 = We . q) — fewer bytes per edge through the
+    L2 -> shared-memory path that bounds the decoder gather.
 Packing runs once per weight version (on whatever device the parameters live on) in float64, then rounds to fp32.
 """
 import torch
@@ -69,14 +72,20 @@ class PackedCell:
         rows_w.append(eye.to(rows_w[-1].device)); rows_b.append(torch.zeros(4, dtype=torch.float64, device=rows_b[-1].device))
         return off + 4
 
-    def __init__(self, edge_types, gates, in_dims, C, conv_of, gate_bias=None, weighted=True, device=None, raw_scores=False):
+    def __init__(self, edge_types, gates, in_dims, C, conv_of, gate_bias=None, weighted=True, device=None, raw_scores=False,
+                 raw_hidden=False):
         self.edge_types, self.gates, self.C, self.G = list(edge_types), list(gates), C, len(gates)
         self.weighted = bool(weighted)
-        self.raw_k = self.RAW_K if raw_scores else 0
-        if raw_scores:      # h == 0: only the feature columns of every weight act; the hidden columns are dropped here
+        self.raw_k, self.we_slot = 0, None
+        if raw_scores and not raw_hidden:   # h == 0: only the feature columns of every weight act; the hidden columns are dropped here
+            self.raw_k, self.we_slot = self.RAW_K, self.RAW_K - 1
             in_dims = {t: (k[0], 0) for t, k in in_dims.items()}
             assert all(pad4(k[0]) <= self.RAW_K - 1 for k in in_dims.values()), 'raw-score mode needs <= 15 (padded) features'
             self._full_k2 = C
+        elif raw_scores:                    # raw scores on [X padded to 32 | h]: the staged source row is the cell input itself
+            k2s = {k[1] for k in in_dims.values()}
+            assert k2s == {C} and all(pad4(k[0]) <= 31 for k in in_dims.values()), 'raw scores with hidden state: K2 == C, <= 31 features'
+            self.raw_k, self.we_slot = 32 + C, 31
         self.in_dims = dict(in_dims)
         self.node_types = list(self.in_dims)
         G = self.G
@@ -95,11 +104,13 @@ class PackedCell:
             for e in self.edge_types:              # source roles: K and V gate blocks
                 if e[0] != t:
                     continue
-                if self.raw_k:                     # raw-score mode: [raw features (16) | V gate block], one bulk copy per edge
+                if self.raw_k:                     # raw-score mode: [raw input (16, or 32 + C with hidden state) | V gate block], one bulk copy per edge
                     self.koff[e] = off
                     dev0 = conv_of(self.gates[0], e).wv.device
                     eye = torch.zeros(self.raw_k, k1p + k2, dtype=torch.float64, device=dev0)
                     eye[:k1p, :k1p] = torch.eye(k1p, dtype=torch.float64, device=dev0)
+                    if k2:                         # hidden state in slots 32 .. 32 + C
+                        eye[32:32 + k2, k1p:] = torch.eye(k2, dtype=torch.float64, device=dev0)
                     rows_w.append(eye); rows_b.append(torch.zeros(self.raw_k, dtype=torch.float64, device=dev0))
                     off += self.raw_k
                     self.voff[e] = off
@@ -118,15 +129,17 @@ class PackedCell:
             for e in self.edge_types:              # target roles: Q gate block, directly followed by its QX block
                 if e[2] != t:                      # ([Wk[:, :3]^T q (3), We . q (1)] per gate) so one bulk copy stages both
                     continue
-                if self.raw_k:                     # Q'[g] = [Wk[:, :F_src]^T q (padded to 15) | We . q]: 16 floats per gate
+                if self.raw_k:                     # Q'[g] = Wk^T q laid out like the staged source row, We . q in the spare slot
                     self.qoff[e] = self.qxoff[e] = off
-                    fs = self.in_dims[e[0]][0]
+                    fs, hs = self.in_dims[e[0]]
                     for g in self.gates:
                         cw = conv_of(g, e)
                         wq, bq = _cols(cw.wq, k1, k1p, k2), _vec(cw.bq, C, cw.wq.device)
                         m = torch.zeros(C, self.raw_k, dtype=torch.float64, device=wq.device)
                         m[:, :fs] = cw.wk.detach().double()[:, :fs]
-                        m[:, self.raw_k - 1] = cw.we.detach().double().reshape(C)
+                        if hs:
+                            m[:, 32:32 + hs] = cw.wk.detach().double()[:, fs:fs + hs]
+                        m[:, self.we_slot] = cw.we.detach().double().reshape(C)
                         rows_w.append(m.t() @ wq); rows_b.append(m.t() @ bq)
                     off += self.raw_k * G
                     off = self._pos_rows(e, off, k1p, k2, rows_w, rows_b)

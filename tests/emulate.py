@@ -30,7 +30,7 @@ def emu_gather(pk, e, P_src, P_dst, pos_src, pos_dst, rowptr, col, ea_csr):
         V = P_src[src, pk.voff[e] + g * C: pk.voff[e] + (g + 1) * C]
         if rk:      # raw-score mode: the source row carries its raw features, the target Q' = [Wk^T q | We . q] (16 per gate)
             xj = P_src[src, pk.koff[e]: pk.koff[e] + rk].clone()
-            xj[:, rk - 1] = ea_csr
+            xj[:, pk.we_slot] = ea_csr
             Qp = P_dst[dst, pk.qoff[e] + rk * g: pk.qoff[e] + rk * (g + 1)]
             raw_s = (Qp * xj).sum(1) + (Qp[:, :3] * w).sum(1)
         else:

@@ -83,10 +83,12 @@ def _csr(ei, x):
     return csr
 
 
-@pytest.mark.parametrize('cls,gates,mode', [(HeteroPGCLSTM, ('i', 'f', 'c', 'o'), _lib.GG_GATE_LSTM),
-                                            (HeteroPGC, ('i',), _lib.GG_GATE_RELU)])
-def test_packed_cell_algebra_matches_oracle(cls, gates, mode):
-    """fp64 emulation of the three kernels on the packed (fp32-rounded) weights == oracle cell to ~1e-7."""
+@pytest.mark.parametrize('cls,gates,mode,raw', [(HeteroPGCLSTM, ('i', 'f', 'c', 'o'), _lib.GG_GATE_LSTM, False),
+                                                (HeteroPGCLSTM, ('i', 'f', 'c', 'o'), _lib.GG_GATE_LSTM, True),
+                                                (HeteroPGC, ('i',), _lib.GG_GATE_RELU, False)])
+def test_packed_cell_algebra_matches_oracle(cls, gates, mode, raw):
+    """fp64 emulation of the three kernels on the packed (fp32-rounded) weights == oracle cell to ~1e-7; raw: the raw-score
+    layout with hidden state (source row [X padded to 32 | h | V], Q' of 32 + C floats per gate, We . q in slot 31)."""
     x, ei, ea = load_graph('c1', torch.float64)
     sd = orc.synth_state_dict('regressor', 1)
     cell = cls({'grain': 11, 'joint': 8}, 96, (['grain', 'joint'], list(ET)))
@@ -98,7 +100,8 @@ def test_packed_cell_algebra_matches_oracle(cls, gates, mode):
     h0, c0 = orc.pgclstm_cell(sd64, 'gclstm_encoder.cell_list.0', x, ei, ea)
     csr = _csr(ei, x)
     eac = {e: ea[e].reshape(-1)[csr[e][2]] for e in ET}
-    pk = cell.packed(gates, True, 'cpu')
+    pk = cell.packed(gates, True, 'cpu', raw=raw)
+    assert pk.raw_k == (128 if raw else 0) and (not raw or (pk.we_slot == 31 and pk.ncols['joint'] == 2 * (128 + 384) + 2 * (4 * 128 + 4)))
     xpad = {t: pad_features(x[t].float(), pk.k1p[t]).double() for t in x}
     hh, cc = emu_cell(pk, xpad, h0, c0, {e: csr[e][:2] for e in ET}, eac, mode)
     if cls is HeteroPGCLSTM:
