@@ -80,6 +80,16 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
         }
     } while (!done);
 }
+// Producer-side wait: the try_wait carries a suspend-time hint, so a waiting producer warp sleeps in hardware until the phase
+// completes instead of polling — its polls otherwise take ~10 % of the issue slots the consumer warps of the same schedulers need.
+__device__ __forceinline__ void mbar_wait_sleepy_(uint32_t bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
+        if (!done && ++spins > 100000u) __trap();            // 100000 x 100 us: a lost arrival must surface as an error
+    } while (!done);
+}
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
     float4 r;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
@@ -208,7 +218,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
         // spreads the warp-serial issue of the bulk copies (~50 clk each) over NP warps.  Tile descriptors are read two tiles
         // ahead and the per-edge / per-target metadata one tile ahead, so the chain tiles -> col -> row address is never waited for.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");          // registers go to the consumer warpgroups
-        struct Meta { int col, wrap, tn, ta, tb, t0; float ea; };
+        struct Meta { int col, wrap, tn, ta, tb, t0, colA, colB; float ea; };
         const int mine = warp + NP * lane;                           // the slot and the target this lane serves in every tile
         auto load_desc = [&](int t) -> int4 {                        // {first edge, edges, first target, last target}
             return t < n_tiles ? __ldg(&p.tiles[f0 + t]) : make_int4(0, 0, 0, -1);
@@ -217,6 +227,8 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             Meta m;
             const int e0 = d.x, ne = d.y, cnt = d.w - d.z + 1;
             m.col = 0; m.wrap = 0; m.ea = 0.f; m.tn = 0; m.ta = 0; m.tb = 0; m.t0 = 0;
+            m.colA = lane < ne ? __ldg(&p.col[e0 + lane]) : -1 - lane;               // every slot's source, for the duplicate search
+            m.colB = (ECAP > 32 && 32 + lane < ne) ? __ldg(&p.col[e0 + 32 + lane]) : -33 - lane;
             if (mine < ne) { m.col = __ldg(&p.col[e0 + mine]); m.ea = __ldg(&p.ea[e0 + mine]); m.wrap = __ldg(&p.wrap[e0 + mine]); }
             if (mine < cnt) { m.tn = __ldg(&p.nz[d.z + mine]); m.ta = __ldg(&p.nzptr[d.z + mine]); m.tb = __ldg(&p.nzptr[d.z + mine + 1]); }
             if (cnt > 0) m.t0 = __ldg(&p.nzptr[d.z]);
@@ -240,11 +252,19 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             const int h = mine - (1 - fs);
             const bool has_hdr = mine < cnt && starts && h < HCAP;           // else: continuing row, or more starts than header slots
             const int n_hdr = __popc(__ballot_sync(0xffffffffu, has_hdr));
-            const int n_rows = ne > warp ? (ne - warp + NP - 1) / NP : 0;
+            // Neighbouring targets share sources (grain -> joint: ~48 % of a tile's edges repeat a source of the same tile, the other
+            // types 20-25 %): within each group of 32 slots a source row is staged ONCE, at the slot of its first edge, and every
+            // edge carries the slot its row lives in (bits 8.. of the wrap word).  This form is bound by L2 -> shared-memory bytes.
+            const int leadA = __ffs(__match_any_sync(0xffffffffu, m_cur.colA)) - 1;
+            const int leadB = ECAP > 32 ? 32 + __ffs(__match_any_sync(0xffffffffu, m_cur.colB)) - 1 : 0;
+            const int la = __shfl_sync(0xffffffffu, leadA, mine & 31), lb = __shfl_sync(0xffffffffu, leadB, mine & 31);
+            const int row_slot = (ECAP > 32 && mine >= 32) ? lb : la;         // where the row of edge `mine` is staged
+            const bool copies_row = mine < ne && row_slot == mine;
+            const int n_rows = __popc(__ballot_sync(0xffffffffu, copies_row));
             GG_PROF_ADD(prof_busy);
-            mbar_wait_(empty_bar(stage), phase ^ 1u);
+            mbar_wait_sleepy_(empty_bar(stage), phase ^ 1u);
             GG_PROF_ADD(prof_wait);
-            if (mine < ne) sts2(base + K::EM + 8u * mine, __float_as_int(m_cur.ea), m_cur.wrap);
+            if (mine < ne) sts2(base + K::EM + 8u * mine, __float_as_int(m_cur.ea), m_cur.wrap | (row_slot << 8));
             if (mine < cnt)
                 sts2(base + K::TD + 8u * mine, m_cur.tn,
                      (max(m_cur.ta, e0) - e0) | ((min(m_cur.tb, e1) - e0) << 8) | (starts << 16) | (ends << 17) | ((has_hdr ? h : 255) << 24));
@@ -252,7 +272,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             __syncwarp();
             if (lane == 0) mbar_expect_tx_(bar, (uint32_t)n_rows * K::ES + (uint32_t)n_hdr * K::HB);
             __syncwarp();
-            if (mine < ne) bulk_g2s(base + (uint32_t)mine * K::ES, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, K::ES, bar);
+            if (copies_row) bulk_g2s(base + (uint32_t)mine * K::ES, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, K::ES, bar);
             if (has_hdr) {
                 const uint32_t hd = base + K::HDR + (uint32_t)h * K::HB;
                 bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn * p.ld_dst + p.q_off, K::HB, bar);     // Q | QX (Q') and the position behind it
@@ -369,14 +389,20 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 float ae[CH], sc[CH];
                 int wc[CH];
 #pragma unroll
-                for (int e = 0; e < CH; ++e) { int ai; lds2(base + K::EM + 8u * sl[e], ai, wc[e]); ae[e] = __int_as_float(ai); }
+                int rs[CH];                                   // slot the edge's source row is staged in (shared by duplicates)
+#pragma unroll
+                for (int e = 0; e < CH; ++e) {
+                    int ai, ww;
+                    lds2(base + K::EM + 8u * sl[e], ai, ww);
+                    ae[e] = __int_as_float(ai); wc[e] = ww & 0xff; rs[e] = ww >> 8;
+                }
                 const int wc_any = wc[0] | wc[1] | wc[2];
                 if (RAWH) {
                     // x_j . Q'_i over the 32 + C input slots: lane `sub` of a gate group owns the float4 slots sub, sub + 8, ...;
                     // the four gate groups read the same addresses (broadcast).  Slot 31 (We . q) meets the edge length.
 #pragma unroll
                     for (int e = 0; e < CH; ++e) {
-                        const uint32_t xrow = base + (uint32_t)sl[e] * K::ES + 16u * sub;
+                        const uint32_t xrow = base + (uint32_t)rs[e] * K::ES + 16u * sub;
                         u64 da = 0ull, db = 0ull;
 #pragma unroll
                         for (int r = 0; r < NQ; ++r) {
@@ -393,7 +419,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 } else if (RAW) {
                     // each lane scores ONE edge of the chunk (edge `me`) for its gate; lanes 0..2 of the group publish
                     const float my_ae = me == 0 ? ae[0] : (me == 1 ? ae[1] : ae[2]);
-                    const uint32_t row = base + (uint32_t)(me == 0 ? sl[0] : (me == 1 ? sl[1] : sl[2])) * K::ES;
+                    const uint32_t row = base + (uint32_t)(me == 0 ? rs[0] : (me == 1 ? rs[1] : rs[2])) * K::ES;
                     const P4 x0 = lds4p(row), x1 = lds4p(row + 16), x2 = lds4p(row + 32);
                     P4 x3 = lds4p(row + 48);
                     { float x14, x15; unpack2(x3.hi, x14, x15); x3.hi = pack2(x14, my_ae); }    // Q'[15] = We . q multiplies the edge length
@@ -412,7 +438,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 } else {
 #pragma unroll
                     for (int e = 0; e < CH; ++e) {
-                        const uint32_t krow = base + (uint32_t)sl[e] * K::ES + lane_off;
+                        const uint32_t krow = base + (uint32_t)rs[e] * K::ES + lane_off;
                         u64 da = 0ull, db = 0ull;
 #pragma unroll
                         for (int r = 0; r < NV; ++r) {
@@ -448,7 +474,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                         const u64 pe2 = pack2(pe, pe);
                         l_run += pe;
                         ea_acc = fmaf(pe, ae[e], ea_acc);
-                        const uint32_t vrow = base + (uint32_t)sl[e] * K::ES + v_off + lane_off;
+                        const uint32_t vrow = base + (uint32_t)rs[e] * K::ES + v_off + lane_off;
                         P4 v[NV];
 #pragma unroll
                         for (int r = 0; r < NV; ++r) v[r] = lds4p(vrow + 128 * r);
