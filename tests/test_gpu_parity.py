@@ -326,9 +326,12 @@ def test_regressor_and_classifier_forward_match_reference_golden(name, gemm, mon
     assert torch.equal(y['grain_area'].cpu() < 1e-4, g['r_grain_area'] < 1e-4)
 
 
-def test_engine_three_rollout_steps_match_reference_golden():
-    """RolloutEngine (resident state + fused step) over 3 steps vs reference Rmodel.update + edge-attr rebuild."""
+@pytest.mark.parametrize('rawh', ['1', '0'])
+def test_engine_three_rollout_steps_match_reference_golden(rawh, monkeypatch):
+    """RolloutEngine (resident state + fused step) over 3 steps vs reference Rmodel.update + edge-attr rebuild; decoder gather
+    in the raw-score form ([input | V] rows, default) and in the K | V form (GG_RAWH=0)."""
     from graingraphnn_b200.engine import RolloutEngine
+    monkeypatch.setenv('GG_RAWH', rawh)
     x, ei, ea = load_graph('c1')
     g = load_golden('c1')
     eng = RolloutEngine.from_state_dicts(orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2), dev())
