@@ -76,8 +76,8 @@ def tiled_ecap(pk, e):
         return 0
     if not pk.raw_k and pk.qxoff[e] != pk.qoff[e] + pk.G * pk.C:
         return 0
-    if pk.posoff.get(e) != (pk.qoff[e] + pk.raw_k * pk.G if pk.raw_k else pk.qxoff[e] + 4 * pk.G):
-        return 0                                   # the target's position must sit right behind its Q | QX (Q') block
+    if pk.posoff.get(e) != (pk.qoff[e] + pk.we_slot - 3 if pk.raw_k else pk.qxoff[e] + 4 * pk.G):
+        return 0                                   # the target's position: right behind Q | QX, or in the spare slots of the first Q'
     L = _lib.lib()
     if not (hasattr(L, 'gg_tc_supported') and L.gg_tc_supported() == 1):
         return 0

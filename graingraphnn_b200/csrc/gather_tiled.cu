@@ -153,9 +153,11 @@ __device__ __forceinline__ float wrapv(int code) { return code == 0 ? 0.f : (cod
 // rawk: floats of the raw block in front of V (0: K | V form; 16: encoder; 32 + C: cells with hidden state)
 constexpr uint32_t cfg_es(int G, int C, int rawk) { return rawk ? 4u * rawk + (uint32_t)G * C * 4u : 2u * (uint32_t)G * C * 4u; }   // [raw | V] or [K | V]
 constexpr uint32_t cfg_qb(int G, int C, int rawk) { return rawk ? 4u * rawk * G : (uint32_t)G * C * 4u + 16u * G; }            // Q' (rawk per gate) or Q | QX
+// target block: Q | QX | position (x, y, z, -), or Q' alone — there the position rides in three spare slots of the first gate's Q'
+constexpr uint32_t cfg_hb(int G, int C, int rawk) { return cfg_qb(G, C, rawk) + (rawk ? 0u : 16u); }
 constexpr uint32_t cfg_stage_bytes(int G, int C, int raw, int ecap, int hcap) {
     const uint32_t e8 = (((uint32_t)ecap * 8u) + 15u) & ~15u;
-    return ((uint32_t)ecap * cfg_es(G, C, raw) + (uint32_t)hcap * (cfg_qb(G, C, raw) + 16u) + 2u * e8 + 16u + 127u) & ~127u;
+    return ((uint32_t)ecap * cfg_es(G, C, raw) + (uint32_t)hcap * cfg_hb(G, C, raw) + 2u * e8 + 16u + 127u) & ~127u;
 }
 constexpr int cfg_hcap(int ecap) { return ecap / 3 + 2; }
 // The largest tile (multiple of 6 edges: joints have 3 in-edges, grains ~6) that fits 227 KB with three stages, else with two
@@ -173,7 +175,8 @@ template <int NV, int G_, int MODE>
 struct TCfg {
     static constexpr int C = 32 * NV, G = G_, GC = G * C, RAW = mode_rawk(MODE, 32 * NV);
     static constexpr int ECAP = cfg_pick(G, C, RAW, 0), NS = cfg_pick(G, C, RAW, 1), HCAP = cfg_hcap(ECAP);
-    static constexpr uint32_t ES = cfg_es(G, C, RAW), QB = cfg_qb(G, C, RAW), HB = QB + 16u;
+    static constexpr uint32_t ES = cfg_es(G, C, RAW), QB = cfg_qb(G, C, RAW), HB = cfg_hb(G, C, RAW);
+    static constexpr uint32_t POS = RAW == 0 ? QB : (RAW == 16 ? 48u : 112u);   // byte offset of x, y, z inside the target block
     static constexpr uint32_t HDR = (uint32_t)ECAP * ES;
     static constexpr uint32_t TD = HDR + (uint32_t)HCAP * HB;            // {node, lo | hi << 8 | starts << 16 | ends << 17 | header slot << 24}
     static constexpr uint32_t E8 = (((uint32_t)ECAP * 8u) + 15u) & ~15u;
@@ -356,7 +359,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                         for (int r = 0; r < NQ; ++r) q[r] = lds4p(hd + lane_off + 128 * r);
                         qx = lds4(hd + (uint32_t)GC * 4u + 16u * gsel);
                     }
-                    pi = lds4(hd + K::QB);
+                    pi = lds4(hd + K::POS);
                 } else {                                      // more starting targets than header slots (runs of in-degree < 3): plain loads
                     const float* qrow = p.P_dst + (size_t)node * p.ld_dst + p.q_off;
                     if (RAWH) {
@@ -371,7 +374,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                         for (int r = 0; r < NQ; ++r) q[r] = ldg4p(qrow + gsel * C + 4 * (sub + 8 * r));
                         qx = ldg4(qrow + GC + 4 * gsel);
                     }
-                    pi = ldg4(qrow + K::QB / 4);
+                    pi = ldg4(qrow + K::POS / 4);
                 }
                 if (MODE == 1) { unpack2(q[0].lo, qx.x, qx.y); float dummy; unpack2(q[0].hi, qx.z, dummy); }   // Q'[0:3] = Wk3^T q
                 const u64 px = pack2(pi.x, pi.x), py = pack2(pi.y, pi.y), pz = pack2(pi.z, pi.z);

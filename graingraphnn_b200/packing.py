@@ -140,9 +140,15 @@ class PackedCell:
                         if hs:
                             m[:, 32:32 + hs] = cw.wk.detach().double()[:, fs:fs + hs]
                         m[:, self.we_slot] = cw.we.detach().double().reshape(C)
-                        rows_w.append(m.t() @ wq); rows_b.append(m.t() @ bq)
+                        rw, rb = m.t() @ wq, m.t() @ bq
+                        if g == self.gates[0]:     # the target's x, y, z ride in three spare slots of the first gate's Q': the source
+                            p0 = self.we_slot - 3  # input is zero there (feature padding), so the score does not see them
+                            assert pad4(fs) <= p0 and not rw[p0:p0 + 3].any() and not rb[p0:p0 + 3].any()
+                            for i in range(3):
+                                rw[p0 + i, i] = 1.0
+                            self.posoff[e] = off + p0
+                        rows_w.append(rw); rows_b.append(rb)
                     off += self.raw_k * G
-                    off = self._pos_rows(e, off, k1p, k2, rows_w, rows_b)
                     continue
                 self.qoff[e] = off
                 for g in self.gates:

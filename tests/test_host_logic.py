@@ -101,7 +101,7 @@ def test_packed_cell_algebra_matches_oracle(cls, gates, mode, raw):
     csr = _csr(ei, x)
     eac = {e: ea[e].reshape(-1)[csr[e][2]] for e in ET}
     pk = cell.packed(gates, True, 'cpu', raw=raw)
-    assert pk.raw_k == (128 if raw else 0) and (not raw or (pk.we_slot == 31 and pk.ncols['joint'] == 2 * (128 + 384) + 2 * (4 * 128 + 4)))
+    assert pk.raw_k == (128 if raw else 0) and (not raw or (pk.we_slot == 31 and pk.ncols['joint'] == 2 * (128 + 384) + 2 * 4 * 128 and pk.ncols['grain'] == 1024))
     xpad = {t: pad_features(x[t].float(), pk.k1p[t]).double() for t in x}
     hh, cc = emu_cell(pk, xpad, h0, c0, {e: csr[e][:2] for e in ET}, eac, mode)
     if cls is HeteroPGCLSTM:
@@ -123,11 +123,11 @@ def test_packed_encoder_drops_forget_gate_and_hidden_columns(raw):
     pk = cell.packed(('i', 'c', 'o'), False, 'cpu', raw=raw)
     assert pk.G == 3 and pk.Wcat['grain'].shape[1] == 12 and pk.Wcat['joint'].shape[1] == 8
     if raw:
-        assert pk.raw_k == 16 and pk.ncols['joint'] == 2 * (16 + 3 * 96) + 2 * (3 * 16 + 4) and pk.ncols['grain'] == 16 + 3 * 96 + 3 * 16 + 4
+        assert pk.raw_k == 16 and pk.ncols['joint'] == 2 * (16 + 3 * 96) + 2 * 3 * 16 and pk.ncols['grain'] == 16 + 3 * 96 + 3 * 16
         assert all(pk.voff[e] == pk.koff[e] + 16 for e in ET)
     else:
         assert pk.raw_k == 0 and pk.ncols['joint'] == 6 * 3 * 96 + 2 * (3 * 4 + 4) and pk.ncols['grain'] == 3 * 3 * 96 + 3 * 4 + 4
-    assert all(pk.posoff[e] == (pk.qoff[e] + 3 * 16 if raw else pk.qxoff[e] + 3 * 4) for e in ET)     # position behind Q | QX (Q')
+    assert all(pk.posoff[e] == (pk.qoff[e] + 12 if raw else pk.qxoff[e] + 3 * 4) for e in ET)     # position: slots 12..14 of the first Q', or behind Q | QX
     csr = _csr(ei, x)
     eac = {e: ea[e].reshape(-1)[csr[e][2]] for e in ET}
     xpad = {t: pad_features(x[t].float(), pk.k1p[t]).double() for t in x}
