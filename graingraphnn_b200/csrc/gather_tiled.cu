@@ -13,10 +13,14 @@
 //     with in-edges (nz, nzptr); gg_csr_tiles emits the tile list {first edge, edges, first target, last target} ordered by
 //     CTA: unit k belongs to CTA k mod n_ctas (neighbouring units, which share source rows, are in flight together on
 //     different SMs and meet in L2), and cta_ptr[b] .. cta_ptr[b + 1] are the tiles of CTA b in processing order.
-//   * Persistent CTA per SM.  NP producer warps: per tile, one cp.async.bulk per edge brings the source row
-//     ([K|V], or [raw features|V] in raw-score mode) into the stage and one per starting target brings Q|QX (or Q') together
-//     with its position (four extra columns of the projection, see packing.PackedCell._pos_rows); edge lengths, wrap codes and the target list are written to the stage by the producer lanes.  Everything of a
-//     tile completes on ONE mbarrier (expect_tx); NS stages, full/empty barrier pair per stage.
+//   * Persistent CTA per SM.  NP producer warps: per tile, one cp.async.bulk per DISTINCT source row brings it into the stage
+//     (neighbouring targets share sources; __match_any_sync finds the repeats inside a tile and every edge records the slot its
+//     row is staged in) and one per starting target brings its block (Q|QX|position, or Q' with the position in three spare
+//     slots); edge lengths, wrap codes, row slots and the target descriptors are written to the stage by the producer lanes.
+//     Everything of a tile completes on ONE mbarrier (expect_tx); NS stages, full/empty barrier pair per stage.
+//   * Three row forms (template MODE): 0 = [K | V] with Q | QX targets; 1 = raw scores without hidden state (encoder):
+//     [16 raw features | V], Q' of 16 floats per gate; 2 = raw scores on the whole cell input (decoder): [X padded to 32 | h | V],
+//     Q' of 32 + C floats per gate.  q.(Wk x) = x.(Wk^T q): the raw forms need no key rows, 2 KB instead of 3 KB per decoder edge.
 //   * NC consumer warps: target i (index in the compacted list) belongs to warp i mod NC in EVERY tile, so a row that straddles a
 //     tile boundary (always inside one unit, hence inside one CTA) stays with its warp and the online-softmax state (running
 //     max, denominator, accumulators) simply stays in registers across tiles.  8 lanes per gate, 128-bit shared-memory loads, no atomics, edges of a row accumulate in CSR order.

@@ -132,8 +132,10 @@ int gg_csr_items(const int32_t* rowptr, int32_t n_dst, int32_t dcap, int32_t* it
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Warp-specialised form of (b) (gather_tiled.cu; sm_100, weighted, G <= 4): same arithmetic and outputs as gg_pgat_gather on
- * the same layout (K|V adjacent at k_off, or raw16|V in raw-score mode; Q|QX adjacent at q_off, or Q' — in both cases
- * directly followed by the target's position x, y, z, 0 as four more columns of P_dst), driven by the TILE
+ * these layouts: raw_k = 0: P_src row holds K|V adjacent at k_off, P_dst row Q|QX|x,y,z,0 adjacent at q_off; raw_k = 16
+ * (cells without hidden state) or 32 + C (with hidden state): P_src row holds [raw input (raw_k floats) | V] at k_off and
+ * P_dst row Q' (raw_k floats per gate: Wk^T q laid out like the raw input, We . q in slot 15 / 31, and the target's x, y, z in
+ * the three slots in front of it of the FIRST gate — the source input is zero there) at q_off.  Driven by the TILE
  * index instead of the item list: the CSR edge array is cut into tiles of ecap = gg_gather_tile_ecap(G, C, raw_k) consecutive
  * in-edges (0 = this shape is not supported), producer warps stage each tile with cp.async.bulk, consumer warps compute.
  *   gg_csr_compact: nz[NZ] = targets with in-edges (ascending), nzptr[NZ + 1] = where their rows start (nzptr[NZ] = E),
