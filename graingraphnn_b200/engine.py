@@ -263,8 +263,8 @@ class RolloutEngine:
                 for e in self.edge_types:
                     ns, nd, E = n[e[0]], n[e[2]], int(self.edge_index[e].shape[1])
                     common = 12.0 * nd + 8.0 * (nd + 1) + 12.0 * E
-                    if pk.raw_k:
-                        out['gg_pgat_gather'] += 4.0 * (G * C + pk.raw_k) * ns + 4.0 * (G * C + pk.raw_k * G) * nd + common
+                    if pk.raw_k:                  # the target's position rides inside Q' (no separate 12 bytes per target)
+                        out['gg_pgat_gather'] += 4.0 * (G * C + pk.raw_k) * ns + 4.0 * (G * C + pk.raw_k * G) * nd + common - 12.0 * nd
                     else:
                         out['gg_pgat_gather'] += 4.0 * G * C * (2 * ns + 2 * nd) + 16.0 * G * nd + common
                 for t in self.node_types:
