@@ -88,10 +88,14 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
 // completes instead of polling — its polls otherwise take ~10 % of the issue slots the consumer warps of the same schedulers need.
 __device__ __forceinline__ void mbar_wait_sleepy_(uint32_t bar, uint32_t parity) {
     uint32_t done, spins = 0;
+    long long t0 = 0;
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
-        if (!done && ++spins > 100000u) __trap();            // 100000 x 100 us: a lost arrival must surface as an error
+        if (!done && (++spins & 0xffu) == 0) {               // a lost arrival must surface as an error, not as a hung GPU
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 8000000000LL) __trap();
+        }
     } while (!done);
 }
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
