@@ -303,6 +303,7 @@ def main():
     work = {'gg_pgat_gather': ('hbm', alg['gg_pgat_gather'], 'GB/s', pk['hbm_gbs']),
             'gg_node_proj': ('tensor', alg['gg_node_proj'], 'TFLOP/s', pk['bf16_sustained']),
             'gg_node_proj_tc': ('tensor', alg['gg_node_proj'], 'TFLOP/s', pk['bf16_sustained']),
+            'gg_node_proj_fused': ('tensor', alg['gg_node_proj'], 'TFLOP/s', pk['bf16_sustained']),
             'gg_gate_update': ('tensor', alg['gg_gate_update'], 'TFLOP/s', pk['bf16_sustained'])}
     if top in work:
         bound, amount, unit, peak = work[top]

@@ -126,6 +126,11 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                     from .packing import tc_weight_layout
                     pk.tcW[t] = tc_weight_layout(pk, t)
                 whi, wlo = pk.tcW[t]
+                if os.environ.get('GG_PROJ', 'fused') != 'split' and hasattr(L, 'gg_node_proj_fused') and k2 % 32 == 0:
+                    check(L.gg_node_proj_fused(ptr(x), x.stride(0), pk.k1p[t], ptr(ht), 0 if ht is None else ht.stride(0), k2,
+                                               ptr(whi), ptr(wlo), pk.ncols[t], ptr(pk.bcat[t]), ptr(P[t]), pk.ncols[t], n, 0, st),
+                          'gg_node_proj_fused')
+                    continue
                 ahi, alo = buf(('Ahi', t), (n, kp)), buf(('Alo', t), (n, kp))
                 check(L.gg_split_tf32(ptr(x), x.stride(0), pk.k1p[t], ptr(ht), 0 if ht is None else ht.stride(0), k2,
                                       n, ptr(ahi), ptr(alo), kp, 32, st), 'gg_split_tf32')

@@ -264,6 +264,208 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------ projection, fused split
+// gg_node_proj_fused: the same GEMM without the split pass and without A_hi / A_lo in HBM.  TMA lands the fp32 chunk of
+// [X (zero-extended to 32 columns by the TMA box) | h] in the first half of an A slot; the tensor core reads a TF32 operand's
+// upper 19 bits only, so that half IS A_hi (= trunc_tf32(a)).  Four converter warps (thread = row) write
+// a - trunc_tf32(a) (exact in fp32) into the second half of the slot, in the same 128-byte-swizzled layout.  Term order
+// (A_hi, W_hi), (A_hi, W_lo), (A_lo, W_hi): the converters work while the first two groups are issued.  Per chunk and tile
+// 16 + 64 KB come through TMA instead of 32 + 64 KB, and gg_split_tf32 (one read of [X | h], two writes of 32 + C floats per
+// node) is gone.
+constexpr int kFusedThreads = 384;       // warps 0-3 TMA / MMA / TMEM / idle, 4-7 epilogue, 8-11 converters
+constexpr int kFRingA = 2;               // A slots of [fp32 chunk | lo chunk] (2 x 16 KB)
+constexpr int kFRingB = 4;               // W tiles (32 KB): W_hi and W_lo of two chunks
+constexpr int FUSED_SMEM_BYTES = kFRingA * 2 * A_BYTES + kFRingB * B_BYTES + kOutBufs * OUT_BYTES + 1024 + 256;
+static_assert(FUSED_SMEM_BYTES <= 227 * 1024, "fused projection shared memory");
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+                       const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, int M, int N, int chunks, int k_first_steps) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ringA = smem_base, ringB = smem_base + kFRingA * 2 * A_BYTES;
+    const uint32_t out_base = ringB + kFRingB * B_BYTES;
+    const uint32_t bar_base = out_base + kOutBufs * OUT_BYTES;
+    auto fullA = [&](int s) { return bar_base + 8u * s; };
+    auto convA = [&](int s) { return bar_base + 8u * (kFRingA + s); };
+    auto emptyA = [&](int s) { return bar_base + 8u * (2 * kFRingA + s); };
+    auto fullB = [&](int s) { return bar_base + 8u * (3 * kFRingA + s); };
+    auto emptyB = [&](int s) { return bar_base + 8u * (3 * kFRingA + kFRingB + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * kFRingA + 2 * kFRingB + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * kFRingA + 2 * kFRingB + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kFRingA + 2 * kFRingB + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
+    const int n_tiles = m_blocks * n_blocks;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kFRingA; ++s) { mbar_init(fullA(s), 1); mbar_init(convA(s), 4); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < kFRingB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer: per chunk the fp32 A tile, then W_hi, then W_lo =====
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            auto load_b = [&](const CUtensorMap* map, int k0, int n0) {
+                mbar_wait(emptyB(sb), pb ^ 1u);
+                mbar_expect_tx(fullB(sb), B_BYTES);
+                tma_load_2d(ringB + sb * B_BYTES, map, fullB(sb), k0, n0);
+                if (++sb == kFRingB) { sb = 0; pb ^= 1u; }
+            };
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int m0 = (t / n_blocks) * BM, n0 = (t % n_blocks) * BN;
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait(emptyA(sa), pa ^ 1u);
+                    mbar_expect_tx(fullA(sa), A_BYTES);
+                    if (c == 0) tma_load_2d(ringA + sa * 2 * A_BYTES, &tmX, fullA(sa), 0, m0);
+                    else tma_load_2d(ringA + sa * 2 * A_BYTES, &tmH, fullA(sa), (c - 1) * BK, m0);
+                    if (++sa == kFRingA) { sa = 0; pa ^= 1u; }
+                    load_b(&tmW_hi, c * BK, n0);
+                    load_b(&tmW_lo, c * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int n0 = (t % n_blocks) * BN;
+                int ncols = N - n0; ncols = ncols > BN ? BN : ncols; ncols = (ncols + 15) & ~15;
+                const uint32_t idesc = make_idesc(BM, ncols);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int c = 0; c < chunks; ++c) {
+                    const int ks = c == 0 ? k_first_steps : BK / 8;      // MMAs of the zero padding behind the features are not issued
+                    auto group = [&](uint32_t a_addr, uint32_t b_addr, bool first) {
+                        const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(b_addr);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k)
+                            if (k < ks) umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                    };
+                    const int a_s = sa; const uint32_t a_par = pa;
+                    if (++sa == kFRingA) { sa = 0; pa ^= 1u; }
+                    const uint32_t a_hi = ringA + a_s * 2 * A_BYTES, a_lo = a_hi + A_BYTES;
+                    // (A_hi, W_hi)
+                    mbar_wait(fullA(a_s), a_par);
+                    const int b_hi = sb; mbar_wait(fullB(sb), pb); if (++sb == kFRingB) { sb = 0; pb ^= 1u; }
+                    tc_fence_after();
+                    group(a_hi, ringB + b_hi * B_BYTES, c == 0);
+                    // (A_hi, W_lo)
+                    const int b_lo = sb; mbar_wait(fullB(sb), pb); if (++sb == kFRingB) { sb = 0; pb ^= 1u; }
+                    tc_fence_after();
+                    group(a_hi, ringB + b_lo * B_BYTES, false);
+                    umma_commit(emptyB(b_lo));
+                    // (A_lo, W_hi): the converters have written the lo half by now
+                    mbar_wait(convA(a_s), a_par);
+                    tc_fence_after();
+                    group(a_lo, ringB + b_hi * B_BYTES, false);
+                    umma_commit(emptyA(a_s));
+                    umma_commit(emptyB(b_hi));
+                }
+                umma_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== converters: lo = a - trunc_tf32(a), row r of the chunk, same swizzled layout, second half of the slot =====
+        const int r = threadIdx.x - 256;
+        int sa = 0; uint32_t pa = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(fullA(sa), pa);
+                const uint32_t row = ringA + sa * 2 * A_BYTES + (uint32_t)r * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                    // 16-byte chunk j of the row sits at (j ^ (r % 8)) * 16: same place in both halves
+                    uint32_t a0, a1, a2, a3;
+                    const uint32_t off = (uint32_t)((j ^ (r & 7)) << 4);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(row + off));
+                    // the residual has 13 significant bits; rounding it to TF32 here (rna) keeps the hardware's truncation from biasing it
+                    auto lo_of = [](uint32_t a) -> uint32_t {
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(__uint_as_float(a) - __uint_as_float(a & 0xFFFFE000u)));
+                        return u;
+                    };
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + A_BYTES + off), "r"(lo_of(a0)), "r"(lo_of(a1)), "r"(lo_of(a2)), "r"(lo_of(a3)) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(convA(sa));
+                if (++sa == kFRingA) { sa = 0; pa ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> (+bias) -> swizzled smem staging -> TMA store (as in node_proj_tc_kernel) =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        int obuf = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int m0 = (t / n_blocks) * BM, n0 = (t % n_blocks) * BN;
+            int ncols = N - n0; ncols = ncols > BN ? BN : ncols;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            for (int c0 = 0; c0 < ncols; c0 += OUT_CHUNK) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kOutBufs - 1) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t srow = out_base + obuf * OUT_BYTES + (uint32_t)r * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    if (bias && c0 + 4 * j < ncols) {
+                        const float4 b = ldg4(bias + n0 + c0 + 4 * j);
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    const uint32_t dst = srow + (uint32_t)((j ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 128) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmOut), "r"(out_base + obuf * OUT_BYTES), "r"(n0 + c0), "r"(m0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (++obuf == kOutBufs) obuf = 0;
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ gate GEMM + LSTM
 // gg_gate_update_tc: per 128-node tile and gate g, D_g[128, C] (TMEM columns [g*C, (g+1)*C)) accumulates
 //   sum over K chunks of  A_chunk (agg of every incoming edge type, then X, then h)  x  Wall[g*C + n, k]   (3xTF32),
@@ -712,6 +914,41 @@ extern "C" int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp,
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < n_sms ? tiles : n_sms;
     node_proj_tc_kernel<<<grid, kThreads, SMEM_BYTES, GG_STREAM(stream)>>>(mA_hi, mA_lo, mW_hi, mW_lo, mOut, bias, M, N, Kp, (k_first + 7) / 8);
+    GG_LAUNCH_OK();
+    return 0;
+}
+
+// Projection with the TF32 split fused in: out[M, N] = [X (K1 <= 32 columns, zero-extended to 32) | H (K2 columns)] W^T + bias,
+// W_hi / W_lo [N, 32 + K2] as for gg_node_proj_tc.  No A_hi / A_lo arrays, no gg_split_tf32 pass.
+extern "C" int gg_node_proj_fused(const float* X, int32_t ldx, int32_t K1, const float* H, int32_t ldh, int32_t K2,
+                                  const float* W_hi, const float* W_lo, int32_t N, const float* bias, float* out, int32_t ldo,
+                                  int32_t M, int32_t n_sms, void* stream) {
+    if (M < 0 || N < 0 || K1 < 4 || K1 > BK || (K1 & 3) || K2 < 0 || (K2 % BK)) return GG_EINVAL;
+    if (M == 0 || N == 0) return 0;
+    if (!X || !W_hi || !W_lo || !out || (K2 > 0 && !H)) return GG_EINVAL;
+    if ((N & 3) || (ldo & 3) || !gg_aligned16(out) || (bias && !gg_aligned16(bias))) return GG_EALIGN;
+    const int Kp = BK + K2;
+    CUtensorMap mX, mH, mW_hi, mW_lo, mOut;
+    int rc;
+    if ((rc = make_map(&mX, X, M, K1, ldx, BM))) return rc;
+    if (K2 > 0) { if ((rc = make_map(&mH, H, M, K2, ldh, BM))) return rc; } else mH = mX;
+    if ((rc = make_map(&mW_hi, W_hi, N, Kp, Kp, BN))) return rc;
+    if ((rc = make_map(&mW_lo, W_lo, N, Kp, Kp, BN))) return rc;
+    if ((rc = make_map(&mOut, out, M, N, ldo, BM))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(node_proj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    if (n_sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < n_sms ? tiles : n_sms;
+    node_proj_fused_kernel<<<grid, kFusedThreads, FUSED_SMEM_BYTES, GG_STREAM(stream)>>>(mX, mH, mW_hi, mW_lo, mOut, bias, M, N, Kp / BK, (K1 + 7) / 8);
     GG_LAUNCH_OK();
     return 0;
 }

@@ -87,6 +87,14 @@ int gg_split_tf32(const float* X, int32_t ldx, int32_t K1, const float* H /* nul
 int gg_node_proj_tc(const float* A_hi, const float* A_lo, int32_t Kp, int32_t k_first, const float* W_hi, const float* W_lo,
                     int32_t N, const float* bias /* nullable */, float* out, int32_t ldo, int32_t M, int32_t n_sms,
                     void* stream);
+/* The same projection with the TF32 split fused into the kernel (no gg_split_tf32 pass, no A_hi / A_lo in HBM): the fp32 chunk of
+ * [X zero-extended to 32 columns | H] is the hi operand as it stands (the tensor core reads the upper 19 bits), converter warps
+ * write a - trunc_tf32(a) next to it.  X [M, K1] (4 <= K1 <= 32, K1 % 4 == 0, row stride ldx), H [M, K2] (K2 % 32 == 0, may be
+ * NULL with K2 == 0); W_hi / W_lo [N, 32 + K2].  Replaces lin_key / lin_value / lin_query on the gathered rows
+ * (periodGATconv.py:216-218) like gg_node_proj. */
+int gg_node_proj_fused(const float* X, int32_t ldx, int32_t K1, const float* H /* nullable */, int32_t ldh, int32_t K2,
+                       const float* W_hi, const float* W_lo, int32_t N, const float* bias /* nullable */, float* out, int32_t ldo,
+                       int32_t M, int32_t n_sms, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (b) fused periodic-attention gather.  One launch = one edge type, all G gates of one cell.

@@ -53,7 +53,7 @@ def bench_gate(sms, M=249120, G=4, C=96, n_in=2, has_h=True):
               f'({stages * kb * 1024 / us / 1e3 / n / 1.965:5.1f} B/clk/SM)  {2 * M * G * C * ktot * 3 / us / 1e6:7.1f} TF/s tf32 issued')
 
 
-def bench_proj(sms, M=249120, N=2336, K2=96):
+def bench_proj(sms, M=249120, N=2048, K2=96):
     L, d = _lib.lib(), torch.device('cuda')
     st = torch.cuda.current_stream().cuda_stream
     kp = 32 + K2
@@ -63,6 +63,9 @@ def bench_proj(sms, M=249120, N=2336, K2=96):
     for n in sms:
         us = timeit(lambda: check(L.gg_node_proj_tc(ptr(ahi), ptr(alo), kp, 8, ptr(whi), ptr(wlo), N, ptr(bias), ptr(out), N, M, n, st), 'gg_node_proj_tc'))
         print(f'proj M={M} N={N} Kp={kp} sms={n:3d}: {us:8.1f} us   out {M * N * 4 / us / 1e6:5.2f} TB/s   {2 * M * N * kp * 3 / us / 1e6:7.1f} TF/s tf32 issued')
+        x, h = torch.rand(M, 8, device=d), (torch.randn(M, K2, device=d) if K2 else None)
+        us = timeit(lambda: check(L.gg_node_proj_fused(ptr(x), 8, 8, ptr(h), K2, K2, ptr(whi), ptr(wlo), N, ptr(bias), ptr(out), N, M, n, st), 'gg_node_proj_fused'))
+        print(f'proj (fused split) sms={n:3d}: {us:8.1f} us   out {M * N * 4 / us / 1e6:5.2f} TB/s')
 
 
 if __name__ == '__main__':
@@ -77,4 +80,4 @@ if __name__ == '__main__':
         bench_gate(sms[:1], M=124560, n_in=1)
     if a.what in ('proj', 'all'):
         bench_proj(sms)
-        bench_proj(sms[:1], N=1752, K2=0)
+        bench_proj(sms[:1], N=704, K2=0)

@@ -168,6 +168,12 @@ def test_tcgen05_node_proj_matches_fp32(M, N, K2):
         torch.cuda.synchronize()
         assert torch.isfinite(out).all()
         assert rel_err(out, ref) < 2e-6, rel_err(out, ref)
+    # the projection with the split fused in (no A_hi / A_lo arrays): same operands, same bar
+    out.fill_(float('nan'))
+    check(L.gg_node_proj_fused(ptr(xd), K1, K1, ptr(hd), K2, K2, ptr(whi), ptr(wlo), N, ptr(bd), ptr(out), N, M, 0, st), 'gg_node_proj_fused')
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 2e-6, rel_err(out, ref)
     # the fp32 CUDA-core kernel on the same (unsplit) operands
     Wd = torch.cat([W[:, :K1], W[:, 32:]], 1).contiguous().to(d)
     out2 = torch.empty(M, N, device=d)
