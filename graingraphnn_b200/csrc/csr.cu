@@ -15,6 +15,10 @@
 namespace {
 
 constexpr int kScanTile = 2048;  // elements per scan block (256 threads x 8)
+#ifndef GG_UNIT_TILES
+#define GG_UNIT_TILES 8
+#endif
+constexpr int kUnitTiles = GG_UNIT_TILES;   // tiles per unit of the tiled gather (units go round-robin over the CTAs)
 
 __global__ void csr_histogram(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
                               int n_src, int n_dst, int* __restrict__ count, int* __restrict__ status) {
@@ -289,13 +293,13 @@ extern "C" int gg_csr_compact(const int32_t* rowptr, int32_t n_dst, int32_t* nz,
 
 extern "C" int64_t gg_csr_tiles_capacity(int64_t n_edges, int32_t ecap, int32_t n_ctas) {
     if (n_edges < 0 || ecap < 1 || n_ctas < 1) return 0;
-    const int64_t B = 8LL * ecap, n_units = (n_edges + B - 1) / B;
+    const int64_t B = (int64_t)kUnitTiles * ecap, n_units = (n_edges + B - 1) / B;
     return n_units + n_edges / ecap + 1;              // every unit ends in at most one partial tile
 }
 
 extern "C" size_t gg_csr_tiles_scratch_ints(int64_t n_edges, int32_t ecap, int32_t n_ctas) {
     if (n_edges < 0 || ecap < 1 || n_ctas < 1) return 0;
-    const int64_t B = 8LL * ecap, n_units = (n_edges + B - 1) / B, Uc = (n_units + n_ctas - 1) / n_ctas;
+    const int64_t B = (int64_t)kUnitTiles * ecap, n_units = (n_edges + B - 1) / B, Uc = (n_units + n_ctas - 1) / n_ctas;
     const int64_t n = (int64_t)n_ctas * Uc + 1;
     return (size_t)(2 * n + (n + kScanTile - 1) / kScanTile + 64);
 }
@@ -305,7 +309,7 @@ extern "C" int gg_csr_tiles(const int32_t* nzptr, const int32_t* nz_count, int64
     if (n_edges < 0 || n_edges > 0x7fffffffLL || ecap < 1 || n_ctas < 1 || !nzptr || !nz_count || !cta_ptr || !scratch) return GG_EINVAL;
     if (n_edges > 0 && (!tiles || !gg_aligned16(tiles))) return GG_EINVAL;
     cudaStream_t st = GG_STREAM(stream);
-    const int B = 8 * ecap;
+    const int B = kUnitTiles * ecap;
     const int n_units = (int)((n_edges + B - 1) / B);
     const int Uc = (n_units + n_ctas - 1) / n_ctas;
     const int n = n_ctas * Uc + 1;
