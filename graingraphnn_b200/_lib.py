@@ -40,6 +40,7 @@ _PROTOS = {
     'gg_csr_tiles': (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P]),
     'gg_pgat_gather_tiled': (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P, _I, _I, _I, _P, _I, _P, _P]),
     'gg_edge_wrap': (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _P]),
+    'gg_edge_refresh': (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
     'gg_gate_update': (_I, [POINTER(AggInput), _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'gg_node_head': (_I, [_P, _I, _I, _P, _P, _I, POINTER(c_int32), _P, _I, _P, _I, _F, _P, _I, _P]),
     'gg_edge_head': (_I, [_P, _I, _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -89,7 +90,7 @@ def exported_symbols():
 
 
 # kernels launched by one successful call of each entry point (for bench.py's gpu_launches accounting)
-KERNELS_PER_CALL = {'gg_csr_build': 6, 'gg_csr_items': 5, 'gg_csr_compact': 5, 'gg_csr_tiles': 5, 'gg_pgat_gather_tiled': 1, 'gg_edge_wrap': 1, 'gg_permute_f32': 1, 'gg_edge_length': 2, 'gg_node_proj': 1, 'gg_pgat_gather': 1,
+KERNELS_PER_CALL = {'gg_csr_build': 6, 'gg_csr_items': 5, 'gg_csr_compact': 5, 'gg_csr_tiles': 5, 'gg_pgat_gather_tiled': 1, 'gg_edge_wrap': 1, 'gg_edge_refresh': 1, 'gg_permute_f32': 1, 'gg_edge_length': 2, 'gg_node_proj': 1, 'gg_pgat_gather': 1,
                     'gg_gate_update': 1, 'gg_node_head': 1, 'gg_edge_head': 1, 'gg_feature_update': 3, 'gg_feature_update_batched': 1,
                     'gg_gather_rows': 1, 'gg_scatter_rows': 1, 'gg_segment_mean': 1, 'gg_node_proj_tc': 1, 'gg_node_proj_fused': 1, 'gg_split_tf32': 1, 'gg_gate_update_tc': 1}
 LAUNCHES = [0]

@@ -347,7 +347,40 @@ __global__ void edge_wrap_kernel(const float* __restrict__ ps, int ld_ps, const 
         wrap[k] = wrap_code2(__ldg(pj) - x) | (wrap_code2(__ldg(pj + 1) - y) << 2) | (wrap_code2(__ldg(pj + 2) - z) << 4);
     }
 }
+// One pass per edge type and step over the CSR rows: wrap code (periodGATconv.py:209-210) and wrapped 2-D length
+// (test.py:562-575, same arithmetic as edge_length_kernel: bit-identical) of every in-edge, written in CSR order and - through
+// perm - in the reference's original edge order.  Replaces edge_wrap + edge_length + permute (3 launches) in the rollout step.
+__global__ void edge_refresh_kernel(const float* __restrict__ ps, int ld_ps, const float* __restrict__ pd, int ld_pd,
+                                    const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int n_dst,
+                                    int* __restrict__ wrap, float* __restrict__ ea_csr, float* __restrict__ ea_orig) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_dst) return;
+    const float x = __ldg(pd + (size_t)i * ld_pd), y = __ldg(pd + (size_t)i * ld_pd + 1), z = __ldg(pd + (size_t)i * ld_pd + 2);
+    const int b = __ldg(&rowptr[i]), e = __ldg(&rowptr[i + 1]);
+    for (int k = b; k < e; ++k) {
+        const float* pj = ps + (size_t)__ldg(&col[k]) * ld_ps;
+        float dx = __ldg(pj) - x, dy = __ldg(pj + 1) - y;
+        wrap[k] = wrap_code2(dx) | (wrap_code2(dy) << 2) | (wrap_code2(__ldg(pj + 2) - z) << 4);
+        dx = (float)((dx < -0.5f) - (dx > 0.5f)) + dx;
+        dy = (float)((dy < -0.5f) - (dy > 0.5f)) + dy;
+        const float len = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));   // no FMA contraction: matches torch
+        ea_csr[k] = len;
+        ea_orig[__ldg(&perm[k])] = len;
+    }
+}
 }  // namespace
+
+extern "C" int gg_edge_refresh(const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
+                               const int32_t* rowptr, const int32_t* col, const int32_t* perm, int32_t n_dst,
+                               int32_t* wrap_csr, float* eattr_csr, float* eattr, void* stream) {
+    if (n_dst < 0 || ld_pos_src < 3 || ld_pos_dst < 3) return GG_EINVAL;
+    if (n_dst == 0) return 0;
+    if (!pos_src || !pos_dst || !rowptr || !col || !perm || !wrap_csr || !eattr_csr || !eattr) return GG_EINVAL;
+    edge_refresh_kernel<<<(n_dst + 255) / 256, 256, 0, GG_STREAM(stream)>>>(pos_src, ld_pos_src, pos_dst, ld_pos_dst, rowptr, col, perm,
+                                                                          n_dst, wrap_csr, eattr_csr, eattr);
+    GG_LAUNCH_OK();
+    return 0;
+}
 
 extern "C" int gg_edge_wrap(const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
                             const int32_t* rowptr, const int32_t* col, int32_t n_dst, int32_t* wrap_csr, void* stream) {

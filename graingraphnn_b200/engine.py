@@ -15,6 +15,9 @@ from .heads import edge_head, feature_update, feature_update_batched, node_head
 from .models import GrainNN_classifier, GrainNN_regressor
 from .packing import pad4
 
+import os
+_EDGE_REFRESH = os.environ.get('GG_EDGE_REFRESH', '0') == '1'
+
 ET_GJ, ET_JG, ET_JJ = ('grain', 'push', 'joint'), ('joint', 'pull', 'grain'), ('joint', 'connect', 'joint')
 DEFAULT_EDGE_TYPES = (ET_GJ, ET_JG, ET_JJ)
 
@@ -101,15 +104,26 @@ class RolloutEngine:
             edge_wrap(self.csr[e], self.xbuf[e[0]], self.xbuf[e[2]], self.wrap[e])
 
     def rebuild_edge_attr(self):
-        """test.py:562-575 for every edge type, written in original and CSR order (+ the wrap codes of the new coordinates)."""
-        self.rebuild_edge_wrap()
+        """test.py:562-575 for every edge type, written in original and CSR order, together with the wrap codes of the new
+        coordinates (periodGATconv.py:209-210).  GG_EDGE_REFRESH=1: one pass over the CSR rows per edge type (gg_edge_refresh)
+        instead of gg_edge_wrap + gg_edge_length (3 launches per edge type)."""
         L = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
+        fused = _EDGE_REFRESH
+        if not fused:
+            self.rebuild_edge_wrap()
         for e in self.edge_types:
             xs, xd = self.xbuf[e[0]], self.xbuf[e[2]]
+            g = self.csr[e]
+            if fused:
+                if g.n_edges:
+                    _lib.check(L.gg_edge_refresh(_lib.ptr(xs), xs.stride(0), _lib.ptr(xd), xd.stride(0), _lib.ptr(g.rowptr), _lib.ptr(g.col),
+                                                 _lib.ptr(g.perm), g.n_dst, _lib.ptr(self.wrap[e]), _lib.ptr(self.ea_csr[e]),
+                                                 _lib.ptr(self.edge_attr[e]), st), 'gg_edge_refresh')
+                continue
             ei = self.edge_index[e]
             _lib.check(L.gg_edge_length(_lib.ptr(xs), xs.stride(0), _lib.ptr(xd), xd.stride(0), _lib.ptr(ei), ei.shape[1],
-                                        _lib.ptr(self.csr[e].perm), _lib.ptr(self.edge_attr[e]), _lib.ptr(self.ea_csr[e]), st),
+                                        _lib.ptr(g.perm), _lib.ptr(self.edge_attr[e]), _lib.ptr(self.ea_csr[e]), st),
                        'gg_edge_length')
 
     # ---------------------------------------------------------------------------------------------------- step

@@ -177,6 +177,13 @@ int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t k_off,
 int gg_edge_wrap(const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
                  const int32_t* rowptr, const int32_t* col, int32_t n_dst, int32_t* wrap_csr, void* stream);
 
+/* gg_edge_wrap and gg_edge_length in ONE pass over the CSR rows of an edge type (the rollout step's per-step rebuild,
+ * test.py:562-575 + periodGATconv.py:209-210): wrap_csr and eattr_csr in CSR order, eattr[perm[k]] in original edge order.
+ * Lengths are bit-identical to gg_edge_length. */
+int gg_edge_refresh(const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,
+                    const int32_t* rowptr, const int32_t* col, const int32_t* perm, int32_t n_dst,
+                    int32_t* wrap_csr, float* eattr_csr, float* eattr, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (c) post-aggregation gate GEMM fused with the LSTM update.  Per node m of one node type, gate g:
  *        pre_g = sum_t [ W2_{t,g} agg_t[m,g] + We_{t,g} ea_t[m,g] + b2_{t,g} * cnt_t(m) ]      (lin_l2, lin_edge;
