@@ -40,3 +40,21 @@ def test_error_strings_and_argument_checks_without_gpu():
     assert L.gg_gather_dcap() == 3 and L.gg_csr_items(None, -1, 3, None, None, None, 0, None) == -1
     assert L.gg_edge_wrap(None, 0, None, 0, None, None, 5, None, None) == -1
     assert L.gg_node_proj(None, 0, 0, None, 0, 0, None, 0, None, None, 0, 0, 0, None) == 0   # empty problem is a no-op
+
+
+def test_tiled_gather_geometry_and_argument_checks_without_gpu():
+    """Tile sizes of the warp-specialised gather per (gates, width, row form) and host-side validation of its entry points."""
+    L = _lib.lib()
+    assert L.gg_gather_tile_ecap(3, 96, 16) == 54          # encoder: [16 raw | V] rows, three stages of 54 edges
+    assert L.gg_gather_tile_ecap(4, 96, 128) == 24         # decoder: [input (32 + C) | V] rows
+    assert L.gg_gather_tile_ecap(4, 96, 0) == 18           # decoder, K | V rows
+    assert L.gg_gather_tile_ecap(1, 96, 0) > 0 and L.gg_gather_tile_ecap(2, 96, 0) == 0 and L.gg_gather_tile_ecap(4, 96, 64) == 0
+    assert L.gg_csr_tiles_capacity(1000, 24, 148) >= (1000 + 23) // 24
+    assert L.gg_csr_tiles_scratch_ints(1000, 24, 148) > 0
+    assert L.gg_csr_tiles(None, None, -1, 24, 148, None, None, None, None) == -1
+    assert L.gg_csr_compact(None, -1, None, None, None, None, None, 0, None) == -1
+    # wrong tile size for the shape -> invalid argument, before any CUDA call
+    assert L.gg_pgat_gather_tiled(None, 0, 0, None, 0, 0, None, None, None, None, None, None, None, None, 148, 99, 10, 16, None,
+                                  5, 3, 96, None, 0, None, None) == -1
+    assert L.gg_node_proj_fused(None, 8, 3, None, 0, 0, None, None, 32, None, None, 32, 10, 0, None) == -1   # K1 % 4 != 0
+    assert L.gg_edge_refresh(None, 0, None, 0, None, None, None, 5, None, None, None, None) == -1
