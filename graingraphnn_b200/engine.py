@@ -16,7 +16,7 @@ from .models import GrainNN_classifier, GrainNN_regressor
 from .packing import pad4
 
 import os
-_EDGE_REFRESH = os.environ.get('GG_EDGE_REFRESH', '0') == '1'
+_EDGE_REFRESH = os.environ.get('GG_EDGE_REFRESH', '1') == '1'
 
 ET_GJ, ET_JG, ET_JJ = ('grain', 'push', 'joint'), ('joint', 'pull', 'grain'), ('joint', 'connect', 'joint')
 DEFAULT_EDGE_TYPES = (ET_GJ, ET_JG, ET_JJ)
@@ -105,8 +105,8 @@ class RolloutEngine:
 
     def rebuild_edge_attr(self):
         """test.py:562-575 for every edge type, written in original and CSR order, together with the wrap codes of the new
-        coordinates (periodGATconv.py:209-210).  GG_EDGE_REFRESH=1: one pass over the CSR rows per edge type (gg_edge_refresh)
-        instead of gg_edge_wrap + gg_edge_length (3 launches per edge type)."""
+        coordinates (periodGATconv.py:209-210).  One pass over the CSR rows per edge type (gg_edge_refresh); GG_EDGE_REFRESH=0:
+        gg_edge_wrap + gg_edge_length (3 launches per edge type)."""
         L = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
         fused = _EDGE_REFRESH

@@ -94,6 +94,29 @@ def test_edge_length_bit_exact(name):
         assert torch.equal(out_csr.cpu(), out.cpu().reshape(-1)[g.perm.cpu().long()])
 
 
+def test_edge_refresh_equals_edge_length_and_edge_wrap_bit_for_bit():
+    """gg_edge_refresh (one pass over the CSR rows) == gg_edge_length + gg_permute + gg_edge_wrap, bit for bit."""
+    from graingraphnn_b200 import _lib
+    from graingraphnn_b200._lib import check, ptr
+    from graingraphnn_b200.cell import pad_features
+    from graingraphnn_b200.graph import build_csr, edge_length, edge_wrap
+    x, ei, _ = load_graph('c2')
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    xp = {t: pad_features(v.to(dev()), (v.shape[1] + 3) // 4 * 4) for t, v in x.items()}
+    for e in ET:
+        eid = ei[e].to(dev())
+        g = build_csr(eid, x[e[0]].shape[0], x[e[2]].shape[0])
+        ea, ea_csr = edge_length(xp[e[0]], xp[e[2]], eid, g)
+        wr = edge_wrap(g, xp[e[0]], xp[e[2]])
+        E = eid.shape[1]
+        ea2, ea_csr2 = torch.full((E, 1), -1.0, device=dev()), torch.full((E,), -1.0, device=dev())
+        wr2 = torch.full((E,), -1, dtype=torch.int32, device=dev())
+        check(L.gg_edge_refresh(ptr(xp[e[0]]), xp[e[0]].stride(0), ptr(xp[e[2]]), xp[e[2]].stride(0), ptr(g.rowptr), ptr(g.col),
+                                ptr(g.perm), g.n_dst, ptr(wr2), ptr(ea_csr2), ptr(ea2), st), 'gg_edge_refresh')
+        assert torch.equal(ea2, ea) and torch.equal(ea_csr2, ea_csr) and torch.equal(wr2, wr[:E])
+
+
 # ------------------------------------------------------------------------------------------------ (b)+(c) single conv
 @pytest.mark.parametrize('tag', ['gat', 'sum'])
 @pytest.mark.parametrize('et', [ET[0], ET[2]])
