@@ -16,7 +16,7 @@ namespace {
 
 constexpr int kScanTile = 2048;  // elements per scan block (256 threads x 8)
 #ifndef GG_UNIT_TILES
-#define GG_UNIT_TILES 8
+#define GG_UNIT_TILES 4
 #endif
 constexpr int kUnitTiles = GG_UNIT_TILES;   // tiles per unit of the tiled gather (units go round-robin over the CTAs)
 

@@ -7,7 +7,7 @@
 // Here the irregular part lives in dedicated producer warps and the consumers execute straight-line arithmetic out of shared
 // memory:
 //
-//   * Targets are grouped into UNITS by the CSR position of their first in-edge (unit k: first edge in [k B, (k+1) B), B = 8 ECAP)
+//   * Targets are grouped into UNITS by the CSR position of their first in-edge (unit k: first edge in [k B, (k+1) B), B = 4 ECAP; measured 2 / 4 / 8 tiles per unit: 4 is best)
 //     and the edges of a unit are cut into TILES of ECAP consecutive in-edges (the last one shorter) — independent of where
 //     target rows begin and end, so any in-degree works with a fixed shared-memory slot count.  gg_csr_compact lists the targets
 //     with in-edges (nz, nzptr); gg_csr_tiles emits the tile list {first edge, edges, first target, last target} ordered by

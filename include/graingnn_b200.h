@@ -149,7 +149,7 @@ int gg_csr_items(const int32_t* rowptr, int32_t n_dst, int32_t dcap, int32_t* it
  *   gg_csr_compact: nz[NZ] = targets with in-edges (ascending), nzptr[NZ + 1] = where their rows start (nzptr[NZ] = E),
  *                   nz_count[0] = NZ;  nz / nzptr sized n_dst / n_dst + 1, scratch int32[n_dst + 1],
  *                   workspace gg_csr_workspace_bytes(0, n_dst).
- *   gg_csr_tiles:   targets are grouped into units by the CSR position of their first in-edge (unit k: [8 ecap k, 8 ecap (k+1)))
+ *   gg_csr_tiles:   targets are grouped into units by the CSR position of their first in-edge (unit k: [4 ecap k, 4 ecap (k+1)))
  *                   and each unit's edges are cut into tiles of <= ecap edges; tiles[f] = {first CSR edge, edges, index in nz of
  *                   the target owning the first edge, ... the last edge} (int32 x 4, 16-byte aligned), ordered by CTA (unit k
  *                   belongs to CTA k mod n_ctas), cta_ptr[n_ctas + 1] = where each CTA's tiles start.  tiles holds
