@@ -92,6 +92,8 @@ def edge_wrap(csr, x_src, x_dst, out=None):
     """Per-edge periodic wrap codes (periodGATconv.py:209-210) in CSR order from the CURRENT positions (columns 0..2)."""
     if out is None:
         out = torch.empty(max(csr.n_edges, 1), dtype=torch.int32, device=x_dst.device)
+    if csr.n_edges == 0:                       # an edge type that lost all its edges: nothing to classify
+        return out
     with torch.cuda.device(x_dst.device):
         check(_lib.lib().gg_edge_wrap(ptr(x_src), x_src.stride(0), ptr(x_dst), x_dst.stride(0), ptr(csr.rowptr), ptr(csr.col),
                                       csr.n_dst, ptr(out), _stream()), 'gg_edge_wrap')

@@ -157,6 +157,19 @@ def test_period_conv_other_widths_and_ragged_graph(C):
     assert rel_err(out[17].cpu(), skip[17]) < 1e-5 and torch.isfinite(out).all()
 
 
+def test_period_conv_without_edges_returns_the_skip_term():
+    """An edge type that lost all its edges (E = 0): PyG's scatter-add leaves zeros, the output is lin_skip alone."""
+    from graingraphnn_b200.periodGATconv import PeriodConv
+    torch.manual_seed(3)
+    xs, xd = torch.rand(40, 10), torch.rand(25, 7)
+    conv = PeriodConv(in_channels=(10, 7), out_channels=96)
+    sd = {k: v.clone() for k, v in conv.state_dict().items()}
+    ei = torch.zeros(2, 0, dtype=torch.int64)
+    out = conv.to(dev())((xs.to(dev()), xd.to(dev())), ei.to(dev()), torch.zeros(0, 1, device=dev()))
+    skip = xd @ sd['lin_skip.weight'].t() + sd['lin_skip.bias']
+    assert out.shape == (25, 96) and rel_err(out, skip) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ (c) tensor-core GEMM
 @pytest.mark.parametrize('M,N,K2', [(300, 2336, 96), (1000, 1168, 96), (129, 1752, 0), (5000, 256, 64), (128, 32, 32)])
 def test_tcgen05_node_proj_matches_fp32(M, N, K2):
