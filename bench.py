@@ -155,8 +155,11 @@ def kernel_breakdown(eng, peak):
                 return rc
             return wrapped
 
+    from graingraphnn_b200 import engine as _engine
     real = _lib._LIB
     _lib._LIB = Timed(real)
+    two = _engine._TWO_STREAMS
+    _engine._TWO_STREAMS = False            # one stream: the events must bracket one kernel at a time
     try:
         saved = eng._graph
         eng._graph = None
@@ -166,6 +169,7 @@ def kernel_breakdown(eng, peak):
         eng._graph = saved
     finally:
         _lib._LIB = real
+        _engine._TWO_STREAMS = two
     return {k: {'calls': len(v), 'ms_total': sum(a.elapsed_time(b) for a, b in v), 'ms_each': [round(a.elapsed_time(b), 4) for a, b in v]}
             for k, v in times.items()}
 
@@ -336,7 +340,8 @@ def main():
                    'step': 'nn-step: regressor+classifier fwd (enc+dec HeteroPGCLSTM), heads, feature update, edge-length rebuild; fixed topology',
                    'weights': 'seeded stand-ins with the reference state_dict layout (regressor0.pt/classifier1.pt absent)',
                    'l2': 'per-step working set (projections, GBs) exceeds the 126 MB L2; no explicit flush',
-                   'cuda_graph': bool(use_graph), 'gemm': os.environ.get('GG_GEMM', 'auto')},
+                   'cuda_graph': bool(use_graph), 'gemm': os.environ.get('GG_GEMM', 'auto'),
+                   'streams': 'regressor and classifier cells on two streams (two graph branches); per-kernel times from a one-stream step'},
         'clocks': clocks,
         'e2e': {'value': edges_total * args.steps / (ms_e2e / 1e3), 'unit': 'edges/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},

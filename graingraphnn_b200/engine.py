@@ -17,6 +17,7 @@ from .packing import pad4
 
 import os
 _EDGE_REFRESH = os.environ.get('GG_EDGE_REFRESH', '1') == '1'
+_TWO_STREAMS = os.environ.get('GG_STREAMS', '2') == '2'
 
 ET_GJ, ET_JG, ET_JJ = ('grain', 'push', 'joint'), ('joint', 'pull', 'grain'), ('joint', 'connect', 'joint')
 DEFAULT_EDGE_TYPES = (ET_GJ, ET_JG, ET_JJ)
@@ -38,6 +39,8 @@ class RolloutEngine:
         self.train_frames = 120
         self._graph = None
         self._work = {}
+        self._work2 = {}          # second workspace set (GG_STREAMS=2: the classifier's cells run on their own stream)
+        self._side = None
         self.x, self.xbuf, self.edge_index, self.edge_attr, self.ea_csr, self.csr, self.wrap = {}, {}, {}, {}, {}, {}, {}
         self.pred = {}
         self._scratch = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -153,14 +156,33 @@ class RolloutEngine:
         if self._state is None:
             self._state = {}
         R, Cm = self.R, self.Cm
-        packs, w, nr = self._pack(), self._work, self.n_rows
+        packs, nr = self._pack(), self.n_rows
         sR, sC = self._states('R'), self._states('C')
+        models = (('R', sR), ('C', sC))
+
+        def both(fn):
+            """The regressor's and the classifier's cells are independent until the heads.  They are issued on two
+            streams (GG_STREAMS=1: one) (two branches of the captured graph): every kernel is one persistent CTA per SM, so nothing overlaps except
+            the tail of one model's kernel with the head of the other's.  Each model then needs its own workspaces."""
+            if not _TWO_STREAMS:
+                for name, st in models:
+                    fn(name, st, self._work)
+                return
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)
+            fn('R', sR, self._work)
+            with torch.cuda.stream(self._side):
+                fn('C', sC, self._work2)
+            main.wait_stream(self._side)
+
         # encoders of both models read only X (h0 = c0 = 0, models.py:237-238)
-        for name, st in (('R', sR), ('C', sC)):
-            run_cell(packs[name][0], self.xbuf, None, None, self.csr, self.ea_csr, _lib.GG_GATE_LSTM0, st['he'], st['ce'], w, nr, self.wrap)
+        both(lambda name, st, w: run_cell(packs[name][0], self.xbuf, None, None, self.csr, self.ea_csr, _lib.GG_GATE_LSTM0,
+                                          st['he'], st['ce'], w, nr, self.wrap))
         yield [sR['he'], sC['he']]
-        for name, st in (('R', sR), ('C', sC)):
-            run_cell(packs[name][1], self.xbuf, st['he'], st['ce'], self.csr, self.ea_csr, _lib.GG_GATE_LSTM, st['hd'], st['cd'], w, nr, self.wrap)
+        both(lambda name, st, w: run_cell(packs[name][1], self.xbuf, st['he'], st['ce'], self.csr, self.ea_csr, _lib.GG_GATE_LSTM,
+                                          st['hd'], st['cd'], w, nr, self.wrap))
         yield [{'joint': sC['hd']['joint']}]                 # models.py:602 gathers h[src] of the joint-joint edges
         nj = None if nr is None else nr['joint']
         ng = None if nr is None else nr['grain']
