@@ -84,6 +84,7 @@ class RolloutEngine:
 
     def set_topology(self, edge_index_dict, edge_attr_dict=None):
         self._graph = None
+        self._region = None
         for e in self.edge_types:
             ei = edge_index_dict[e].to(self.device).contiguous()
             self.edge_index[e] = ei
@@ -100,6 +101,29 @@ class RolloutEngine:
                 _lib.check(L.gg_permute_f32(_lib.ptr(self.edge_attr[e]), _lib.ptr(self.csr[e].perm), _lib.ptr(self.ea_csr[e]),
                                             self.ea_csr[e].numel(), torch.cuda.current_stream().cuda_stream), 'gg_permute_f32')
             self.rebuild_edge_wrap()
+
+    # ------------------------------------------------------------------------------------- geometry feedback (f2)
+    _geom = None
+    _region = None
+    centers = None
+
+    def enable_geometry_feedback(self, joint_offset=None, domain_factor=1):
+        """From now on every step moves the grain coordinates to the centres of their joints before the edge lengths are
+        rebuilt, as the reference's loop does on the host (traj.GNN_update -> graph.update, graph_datastruct.py:672-708, then
+        test.py:556-559).  joint_offset [Nj,2] / domain_factor: the patch scaling of test.py:29-44 (global = (x + offset) / factor).
+        self.centers holds the float64 centres of the last step (NaN rows: grains with <= 1 joint)."""
+        if self.n_rows is not None:
+            raise NotImplementedError('geometry feedback on a slab-partitioned domain (the dict order of the joints is global)')
+        self._geom = (None if joint_offset is None else joint_offset.to(self.device, torch.float32).contiguous(), domain_factor)
+        self._graph = None
+
+    def region_feedback(self):
+        from .geometry import RegionIndex, region_center
+        if self._region is None:
+            self._region = RegionIndex(self.edge_index[ET_GJ], self.xbuf['grain'].shape[0], self.xbuf['joint'].shape[0])
+            self.centers = torch.empty(self._region.n_grain, 2, dtype=torch.float64, device=self.device)
+        off, factor = self._geom
+        region_center(self.xbuf['joint'], self._region, self.xbuf['grain'], off, factor, self.centers)
 
     def rebuild_edge_wrap(self):
         """Per-edge periodic wrap codes (periodGATconv.py:209-210) of the CURRENT coordinates, shared by all 48 convs of a step."""
@@ -199,6 +223,8 @@ class RolloutEngine:
         else:
             feature_update(self.x['joint'], self.x['grain'], yj, yg, span / (self.train_frames + 1),
                            self.train_frames / (self.train_frames + 1), self._scratch, n_joint=nj, n_grain=ng)
+        if self._geom is not None:                           # row f2: grain centres follow their joints (test.py:471-476, :556-559)
+            self.region_feedback()
         yield [self.xbuf]                                    # moved coordinates of the halo -> edge lengths, next step
         self.rebuild_edge_attr()
         self.pred = {'joint': yj, 'grain': yg, 'grain_area': area, 'edge_event': ev, 'edge': ed}

@@ -274,6 +274,30 @@ int gg_feature_update_batched(float* x_joint, int32_t ld_j, int32_t n_joint, con
                               const float* dz_joint, const float* dz_grain, float z_max, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (f2) geometry feedback: grain centres from the joint positions, periodic boundary.  Replaces the host loop of
+ *      graph.update (graph_datastruct.py:672-708) that graph_trajectory.GNN_update (graph_trajectory.py:1010-1098) runs
+ *      after every NN step, and the write-back of test.py:556-559.  Bit-exact against the reference's numpy arithmetic:
+ *      per grain, its joints in the order of the reference's joint2vertex dict, each unwrapped against the PREVIOUS
+ *      moved joint (periodic_move :55-72; the first vertex stays float32, later ones become float64), the whole grain
+ *      shifted by +1 along an axis where a vertex is <= -1e-12, centre = np.mean (numpy's pairwise float64 sum).
+ *  gg_joint_rank: rank[j] = index of the first grain->joint edge whose target is j (dict order of
+ *      graph_trajectory.py:1062-1080); gj_dst = row 1 of the grain->joint edge_index.
+ *  gg_region_key: key[k] = rank[col[k]] for the CSR of the grain->joint edges taken BY GRAIN (gg_csr_build on the edge
+ *      list with its two rows swapped: rowptr over grains, col = joints).
+ *  gg_region_center: one thread per grain.  x_joint rows hold (x, y) in columns 0..1 (ld_j even, 8-byte aligned);
+ *      domain_factor > 1: global = (x + joint_offset[j]) / domain_factor in fp32 (test.py:472-474), joint_offset [Nj,2];
+ *      centers (nullable): float64 [n_grain, 2], NaN for grains with <= 1 joint (skipped by :684, features untouched);
+ *      x_grain (nullable): columns 0..1 <- fp32(centre), `(c * domain_factor) % 1` on scaled patches (test.py:558-559).
+ *      Preconditions (the reference's own, graph_trajectory.py:1066-1067): (grain, joint) pairs are unique, and no two
+ *      joints touch the same three grains (the reference's dict drops one of such a pair).
+ * ---------------------------------------------------------------------------------------------- */
+int gg_joint_rank(const int64_t* gj_dst, int64_t n_edges, int32_t n_joint, int32_t* rank, void* stream);
+int gg_region_key(const int32_t* col, const int32_t* rank, int64_t n_edges, int32_t* key, void* stream);
+int gg_region_center(const float* x_joint, int32_t ld_j, const float* joint_offset /* nullable */, float domain_factor,
+                     const int32_t* rowptr, const int32_t* col, const int32_t* key, int32_t n_grain,
+                     double* centers /* nullable */, float* x_grain /* nullable */, int32_t ld_g, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (e) halo pack / unpack for the slab-partitioned domain: out[i, :] = src[idx[i], :] and the inverse.
  *     width must be a multiple of 4 floats and rows 16-byte aligned.
  * ---------------------------------------------------------------------------------------------- */

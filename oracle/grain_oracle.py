@@ -209,6 +209,62 @@ def nn_step(sd_r, sd_c, x_dict, edge_index_dict, edge_attr_dict, span=6):
     return pred, edge_attr_rebuild(x_dict, edge_index_dict)
 
 
+def region_center(x_joint, gj_edge_index, n_grain, joint_offset=None, domain_factor=1):
+    """Grain centres from the joint positions — SURVEY.md §8 row f2, the geometry feedback of a rollout step.
+
+    Restates, for the periodic boundary, test.py:471-476 (patch -> global joint coordinates in fp32),
+    graph_trajectory.py:1036-1039 (vertices = fp32 joint rows), :1062-1075 (vertex2joint / joint2vertex: joints in the
+    order of their first appearance as a target of the grain->joint edges; grains are 1-based regions; a later joint with
+    the same grain triple takes the place of the earlier one, as the reference's dict does) and
+    graph_datastruct.py:672-708 (per region: chain of periodic_move :55-72 against the PREVIOUS moved vertex, shift by
+    +1 along an axis where any vertex is <= -eps, np.mean).  The numpy scalar types of the reference are kept: the first
+    vertex stays float32 (and its +1 shift rounds in float32), later vertices become float64 through `x += int64`.
+    Returns centers float64 [n_grain, 2] with NaN rows for grains the reference skips (<= 1 vertex)."""
+    eps = 1e-12                                                            # graph_datastruct.py:36
+    xj = x_joint.detach().cpu() if isinstance(x_joint, torch.Tensor) else torch.as_tensor(np.asarray(x_joint))
+    X = xj[:, :2].clone().float()
+    if domain_factor > 1:                                                  # test.py:472-474
+        X = (X + torch.as_tensor(np.asarray(joint_offset), dtype=torch.float32)) / domain_factor
+    X_j = X.numpy()
+    gj = gj_edge_index.cpu().numpy() if isinstance(gj_edge_index, torch.Tensor) else np.asarray(gj_edge_index)
+    vertex2joint = {}
+    for grain, joint in gj.T:                                              # graph_trajectory.py:1062-1064
+        vertex2joint.setdefault(int(joint), set()).add(int(grain) + 1)
+    joint2vertex = dict((tuple(sorted(v)), k) for k, v in vertex2joint.items())    # :1080
+    region_coors = {}
+    for k, v in joint2vertex.items():                                      # graph_datastruct.py:672-678
+        for region in set(k):
+            region_coors.setdefault(region, []).append(X_j[v])
+    centers = np.full((n_grain, 2), np.nan)
+    for region, verts in region_coors.items():                             # :682-708
+        if len(verts) <= 1:
+            continue
+        for i in range(1, len(verts)):
+            x, y = verts[i]
+            xc, yc = verts[i - 1]
+            rel_x, rel_y = x - xc, y - yc
+            x += -1 * (rel_x > 0.5) + 1 * (rel_x < -0.5)                  # np.float32 += np.int64 -> np.float64
+            y += -1 * (rel_y > 0.5) + 1 * (rel_y < -0.5)
+            verts[i] = [x, y]
+        inbound = [True, True]
+        for vert in verts:
+            inbound = [i and (j > -eps) for i, j in zip(inbound, vert)]
+        moved = [[i + 1 * (not j) for i, j in zip(vert, inbound)] for vert in verts]
+        x, y = zip(*moved)
+        centers[region - 1] = [np.mean(x), np.mean(y)]
+    return centers
+
+
+def grain_xy_writeback(x_grain, centers, domain_factor=1):
+    """test.py:556-559: grain (x, y) <- fp32(region centre), `(.. * domain_factor) % 1` on scaled patches.  In place."""
+    for g in range(centers.shape[0]):
+        if not np.isnan(centers[g, 0]):
+            x_grain[g, :2] = torch.FloatTensor(centers[g])
+            if domain_factor > 1:
+                x_grain[g, :2] = (x_grain[g, :2] * domain_factor) % 1
+    return x_grain
+
+
 def csr_by_dst(edge_index, n_dst):
     """Stable dst-sorted CSR (the index structure kernel (a) must reproduce bit-exactly).
     rowptr[n_dst+1], col[E] = src in (dst, original-edge-id) order, perm[E] = original edge id."""

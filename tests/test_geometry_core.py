@@ -1,0 +1,128 @@
+"""CPU: geometry feedback.  The golden vectors are the output of the reference's OWN
+graph_trajectory.GNN_update / graph.update (oracle/make_golden_geometry.py); checked against them are (1) the oracle
+restatement and (2) the per-grain arithmetic of the CUDA kernel, compiled for the host from the same header
+(graingraphnn_b200/csrc/geometry_core.h) — bit-exact, float64 centres and fp32 write-back alike."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import grain_oracle as orc
+from util import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = [('c1', 1), ('c2', 3), ('syn', 1)]
+
+
+def load_case(name):
+    G = np.load(os.path.join(GOLDEN, 'geometry_golden.npz'))
+    if name == 'syn':
+        gj, xg0, off = G['syn_ei_gj'], G['syn_x_grain'], None
+    else:
+        z = np.load(os.path.join(GOLDEN, f'{name}_graph.npz'))
+        gj, xg0, off = z['ei_gj'], z['x_grain'], G[f'{name}_offset']
+    return dict(gj=gj.astype(np.int64), xg0=xg0, off=off, xj=G[f'{name}_x_joint'], center=G[f'{name}_center'],
+                xg_out=G[f'{name}_x_grain_out'])
+
+
+@pytest.mark.parametrize('name,factor', CASES)
+def test_oracle_region_center_equals_reference_gnn_update(name, factor):
+    c = load_case(name)
+    got = orc.region_center(torch.from_numpy(c['xj']), c['gj'], c['xg0'].shape[0], c['off'], factor)
+    assert np.array_equal(got, c['center'], equal_nan=True)
+    xg = orc.grain_xy_writeback(torch.from_numpy(c['xg0'].copy()), got, factor)
+    assert np.array_equal(xg.numpy(), c['xg_out'])
+    skipped = np.isnan(c['center'][:, 0])
+    assert np.array_equal(c['xg_out'][skipped], c['xg0'][skipped])           # <= 1 joint: features untouched
+
+
+def region_index_numpy(gj, n_grain, n_joint):
+    """What gg_csr_build (rows swapped) + gg_joint_rank + gg_region_key produce, in numpy."""
+    rank = np.full(n_joint, 2 ** 31 - 1, np.int32)
+    np.minimum.at(rank, gj[1], np.arange(gj.shape[1], dtype=np.int32))
+    perm = np.argsort(gj[0], kind='stable')
+    col = gj[1][perm].astype(np.int32)
+    rowptr = np.zeros(n_grain + 1, np.int32)
+    rowptr[1:] = np.cumsum(np.bincount(gj[0], minlength=n_grain))
+    return rowptr, col, rank[col].astype(np.int32), rank
+
+
+@pytest.fixture(scope='module')
+def host_lib(tmp_path_factory):
+    gxx = shutil.which('g++')
+    if gxx is None:
+        pytest.skip('g++ not available')
+    out = str(tmp_path_factory.mktemp('geom') / 'libgeom_host.so')
+    subprocess.run([gxx, '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-o', out,
+                    os.path.join(ROOT, 'tests', 'geometry_host.cpp')], check=True)
+    return ctypes.CDLL(out)
+
+
+@pytest.mark.parametrize('name,factor', CASES)
+def test_kernel_arithmetic_on_the_host_equals_reference(host_lib, name, factor):
+    c = load_case(name)
+    ng, nj = c['xg0'].shape[0], c['xj'].shape[0]
+    rowptr, col, key, _ = region_index_numpy(c['gj'], ng, nj)
+    xj = np.ascontiguousarray(c['xj'])
+    off = np.ascontiguousarray(c['off']) if c['off'] is not None else np.zeros((nj, 2), np.float32)
+    centers, xg = np.zeros((ng, 2)), c['xg0'].copy()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)                          # noqa: E731
+    host_lib.region_center_host(P(xj), xj.shape[1], P(off), ctypes.c_float(factor), P(rowptr), P(col), P(key), ng,
+                                P(centers), P(xg), xg.shape[1])
+    assert np.array_equal(centers, c['center'], equal_nan=True)
+    assert np.array_equal(xg, c['xg_out'])
+
+
+def test_golden_covers_the_branches():
+    """The fixtures exercise: seam-straddling grains (shift by +1), grains of >= 9 joints (numpy's 8-lane sum),
+    skipped grains, shuffled edge order (dict order != joint id order), scaled patches."""
+    syn, c2 = load_case('syn'), load_case('c2')
+    deg = np.bincount(syn['gj'][0], minlength=syn['xg0'].shape[0])
+    assert deg.max() >= 17 and (deg == 0).any() and (deg == 1).any() and (deg == 2).any()
+    assert np.isnan(syn['center'][deg <= 1]).all() and not np.isnan(syn['center'][deg >= 2]).any()
+    assert not np.all(np.diff(syn['gj'][1]) >= 0)
+    assert np.nanmax(syn['center']) > 1.0                                   # a grain shifted across the seam
+    assert c2['off'].max() >= 2.0 and not np.all(np.diff(c2['gj'][1]) >= 0)
+
+
+def test_entry_points_validate_arguments_without_gpu():
+    from graingraphnn_b200 import _lib
+    L = _lib.lib()
+    assert L.gg_joint_rank(None, -1, 0, None, None) == -1
+    assert L.gg_joint_rank(None, 0, 0, None, None) == 0
+    assert L.gg_region_key(None, None, 5, None, None) == -1
+    assert L.gg_region_center(None, 8, None, 1.0, None, None, None, 5, None, None, 0, None) == -1
+    buf = (ctypes.c_float * 16)()
+    rp = (ctypes.c_int32 * 2)()
+    # odd row stride / scaled patches without offsets -> invalid argument before any CUDA call; empty problem is a no-op
+    assert L.gg_region_center(buf, 7, None, 1.0, rp, None, None, 1, None, None, 0, None) == -1
+    assert L.gg_region_center(buf, 8, None, 3.0, rp, None, None, 1, None, None, 0, None) == -1
+    assert L.gg_region_center(buf, 8, None, 1.0, rp, None, None, 0, None, None, 0, None) == 0
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/graph_trajectory.py'), reason='reference tree not present')
+def test_oracle_equals_live_reference_on_fresh_random_incidence():
+    """Only in the build container: the reference's GNN_update, imported live, on an incidence no fixture holds."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import make_golden_geometry as mg
+    rng = np.random.default_rng(123)
+    n_g, n_j = 30, 150
+    tri, seen = [], set()
+    while len(tri) < n_j:
+        t = tuple(sorted(rng.choice(n_g, 3, replace=False).tolist()))
+        if t not in seen:
+            seen.add(t)
+            tri.append(t)
+    gj = np.stack([np.array(tri).reshape(-1), np.repeat(np.arange(n_j), 3)])
+    gj = gj[:, rng.permutation(gj.shape[1])]
+    jj = np.stack([np.arange(n_j), (np.arange(n_j) + 1) % n_j])
+    xj = torch.zeros(n_j, 8)
+    xj[:, :2] = torch.from_numpy(((rng.random((n_j, 2)) * 0.3 + 0.85) % 1.0).astype(np.float32))   # straddles the seam
+    ref = mg.reference_centers(xj.clone(), torch.rand(n_g, 11), gj, jj)
+    got = orc.region_center(xj, gj, n_g)
+    assert np.array_equal(got, ref, equal_nan=True)

@@ -494,3 +494,98 @@ def test_engine_topology_change_between_steps_matches_oracle():
         assert torch.isfinite(pred[k]).all() and rel_err(pred[k], ref[k]) < TOL, k
     assert rel_err(eng.x['grain'], xo['grain']) < TOL and rel_err(eng.x['joint'], xo['joint']) < TOL
     assert pred['edge_event'].shape[0] == ei2[ET[2]].shape[1]
+
+
+# ------------------------------------------------------------------------------------------ geometry feedback (row f2)
+@pytest.mark.parametrize('name,factor', [('c1', 1), ('c2', 3), ('syn', 1)])
+def test_region_center_bit_exact_vs_reference_gnn_update(name, factor):
+    """gg_joint_rank + gg_region_key + gg_region_center against the output of the reference's own GNN_update / graph.update
+    (tests/golden/geometry_golden.npz): index arrays, float64 centres and the fp32 write-back, all bit-exact."""
+    from graingraphnn_b200.geometry import RegionIndex, region_center
+    from test_geometry_core import load_case, region_index_numpy
+    c = load_case(name)
+    ng, nj = c['xg0'].shape[0], c['xj'].shape[0]
+    idx = RegionIndex(torch.from_numpy(c['gj']).to(dev()), ng, nj)
+    rowptr, col, key, rank = region_index_numpy(c['gj'], ng, nj)
+    assert np.array_equal(idx.rowptr.cpu().numpy(), rowptr) and np.array_equal(idx.col.cpu().numpy(), col)
+    assert np.array_equal(idx.rank.cpu().numpy()[:nj], rank) and np.array_equal(idx.key.cpu().numpy()[:len(key)], key)
+    xj = torch.from_numpy(c['xj']).to(dev())
+    xg = torch.from_numpy(c['xg0'].copy()).to(dev())
+    off = None if c['off'] is None else torch.from_numpy(c['off']).to(dev())
+    centers = region_center(xj, idx, xg, off, factor)
+    assert np.array_equal(centers.cpu().numpy(), c['center'], equal_nan=True)
+    assert np.array_equal(xg.cpu().numpy(), c['xg_out'])
+    assert torch.equal(xj.cpu(), torch.from_numpy(c['xj']))                  # the joint rows are read only
+    # centres only (no write-back), and write-back only (no centres)
+    c2 = region_center(xj, idx, None, off, factor)
+    assert torch.equal(torch.nan_to_num(c2, nan=-7.0), torch.nan_to_num(centers, nan=-7.0))
+    xg2 = torch.from_numpy(c['xg0'].copy()).to(dev())
+    assert region_center(xj, idx, xg2, off, factor, want_centers=False) is None and torch.equal(xg2, xg)
+
+
+def test_engine_steps_with_geometry_feedback_match_oracle():
+    """Rollout steps in the reference's order (test.py:382-407, :471-476, :556-575): NN step, feature update, grain centres
+    from the moved joints, write-back, edge lengths from the new coordinates — eager and replayed from a CUDA graph."""
+    from graingraphnn_b200.engine import RolloutEngine
+    x, ei, ea = load_graph('c1')
+    sd_r, sd_c = orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
+    xo = {k: v.clone() for k, v in x.items()}
+    eao = {k: v.clone() for k, v in ea.items()}
+    ref = []
+    for step in range(3):
+        pred = orc.regressor_forward(sd_r, xo, ei, eao)
+        pred.update(orc.classifier_forward(sd_c, xo, ei, eao))
+        orc.regressor_update(xo, pred, 6)
+        cen = orc.region_center(xo['joint'], ei[ET[0]], xo['grain'].shape[0])
+        orc.grain_xy_writeback(xo['grain'], cen)
+        eao = orc.edge_attr_rebuild(xo, ei)
+        ref.append((pred['edge_event'].clone(), xo['grain'].clone(), xo['joint'].clone(), cen.copy(), eao[ET[1]].clone()))
+    for use_graph in (False, True):
+        eng = RolloutEngine.from_state_dicts(sd_r, sd_c, dev())
+        eng.set_graph(to_dev(x), to_dev(ei), to_dev(ea))
+        eng.enable_geometry_feedback()
+        first = 0
+        if use_graph:
+            eng.capture(span=6, warmup=1)
+            first = 1                                   # the warm-up step was step 0
+        for step in range(first, 3):
+            pred = eng.step(6)
+            ev, xg, xj, cen, ea_jg = ref[step]
+            assert rel_err(pred['edge_event'], ev) < TOL
+            assert rel_err(eng.x['grain'], xg) < TOL and rel_err(eng.x['joint'], xj) < TOL
+            assert np.nanmax(np.abs(eng.centers.cpu().numpy() - cen)) < 1e-5
+            assert rel_err(eng.edge_attr[ET[1]], ea_jg) < TOL
+        # the centres written are exactly the centres of the joints the engine holds
+        cen_exact = orc.region_center(eng.x['joint'].cpu(), ei[ET[0]], 118)
+        assert np.array_equal(eng.centers.cpu().numpy(), cen_exact, equal_nan=True)
+        assert torch.equal(eng.x['grain'][:, :2].cpu(), torch.from_numpy(cen_exact).float())
+
+
+def test_region_center_full_size_properties_100k_grains():
+    """~10^5 grains: against an independent vectorised fp64 formulation on the device (every joint unwrapped against the
+    grain's first joint; equal to the chain unwrap for grains narrower than half the domain), compared on the circle."""
+    from graingraphnn_b200.synth import honeycomb_graph
+    from graingraphnn_b200.geometry import RegionIndex, region_center
+    x, ei = honeycomb_graph(320, 320, seed=0)
+    xj, xg = x['joint'].to(dev()), x['grain'].to(dev())
+    gj = ei[ET[0]].to(dev())
+    ng, nj = xg.shape[0], xj.shape[0]
+    idx = RegionIndex(gj, ng, nj)
+    xg_out = xg.clone()
+    centers = region_center(xj, idx, xg_out)
+    deg = (idx.rowptr[1:] - idx.rowptr[:-1]).long()
+    assert int(deg.min()) >= 2 and not torch.isnan(centers).any()
+    grain_of = torch.repeat_interleave(torch.arange(ng, device=dev()), deg)
+    key = idx.key[:gj.shape[1]].long()
+    first_key = torch.full((ng,), 2 ** 31 - 1, device=dev(), dtype=torch.long).scatter_reduce(0, grain_of, key, 'amin')
+    first_joint = gj[1][first_key]                                           # key = edge position of the first appearance
+    p = xj[idx.col.long(), :2].double()
+    p0 = xj[first_joint, :2].double()[grain_of]
+    d = p - p0
+    d = d - torch.round(d)
+    mean = torch.zeros(ng, 2, dtype=torch.float64, device=dev()).index_add_(0, grain_of, d) / deg[:, None] + xj[first_joint, :2].double()
+    diff = centers - mean
+    diff = diff - torch.round(diff)
+    assert float(diff.abs().max()) < 1e-12
+    assert torch.equal(xg_out[:, :2], centers.float()) and torch.equal(xg_out[:, 2:], xg[:, 2:])
+    assert float(centers.min()) > -1e-12 and float(centers.max()) < 2.0
