@@ -586,6 +586,8 @@ def test_region_center_full_size_properties_100k_grains():
     mean = torch.zeros(ng, 2, dtype=torch.float64, device=dev()).index_add_(0, grain_of, d) / deg[:, None] + xj[first_joint, :2].double()
     diff = centers - mean
     diff = diff - torch.round(diff)
-    assert float(diff.abs().max()) < 1e-12
+    # not 1e-12: the reference keeps the FIRST vertex of a region in float32, so its +1 seam shift rounds at fp32 precision
+    # (graph_datastruct.py:701-703 on an np.float32 scalar) and moves the mean by <= 2^-24 — reproduced, not corrected
+    assert float(diff.abs().max()) < 6e-8
     assert torch.equal(xg_out[:, :2], centers.float()) and torch.equal(xg_out[:, 2:], xg[:, 2:])
     assert float(centers.min()) > -1e-12 and float(centers.max()) < 2.0
