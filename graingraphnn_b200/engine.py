@@ -112,15 +112,18 @@ class RolloutEngine:
         rebuilt, as the reference's loop does on the host (traj.GNN_update -> graph.update, graph_datastruct.py:672-708, then
         test.py:556-559).  joint_offset [Nj,2] / domain_factor: the patch scaling of test.py:29-44 (global = (x + offset) / factor).
         self.centers holds the float64 centres of the last step (NaN rows: grains with <= 1 joint)."""
-        if self.n_rows is not None:
-            raise NotImplementedError('geometry feedback on a slab-partitioned domain (the dict order of the joints is global)')
         self._geom = (None if joint_offset is None else joint_offset.to(self.device, torch.float32).contiguous(), domain_factor)
         self._graph = None
+        self._region = None
+
+    def _region_index(self):
+        from .geometry import RegionIndex
+        return RegionIndex(self.edge_index[ET_GJ], self.xbuf['grain'].shape[0], self.xbuf['joint'].shape[0])
 
     def region_feedback(self):
-        from .geometry import RegionIndex, region_center
+        from .geometry import region_center
         if self._region is None:
-            self._region = RegionIndex(self.edge_index[ET_GJ], self.xbuf['grain'].shape[0], self.xbuf['joint'].shape[0])
+            self._region = self._region_index()
             self.centers = torch.empty(self._region.n_grain, 2, dtype=torch.float64, device=self.device)
         off, factor = self._geom
         region_center(self.xbuf['joint'], self._region, self.xbuf['grain'], off, factor, self.centers)
@@ -223,9 +226,10 @@ class RolloutEngine:
         else:
             feature_update(self.x['joint'], self.x['grain'], yj, yg, span / (self.train_frames + 1),
                            self.train_frames / (self.train_frames + 1), self._scratch, n_joint=nj, n_grain=ng)
-        if self._geom is not None:                           # row f2: grain centres follow their joints (test.py:471-476, :556-559)
-            self.region_feedback()
         yield [self.xbuf]                                    # moved coordinates of the halo -> edge lengths, next step
+        if self._geom is not None:                           # row f2: grain centres follow their joints (test.py:471-476, :556-559)
+            self.region_feedback()                           # owned grains, from owned + halo joints
+            yield [{'grain': self.xbuf['grain']}]            # centres of the halo grains
         self.rebuild_edge_attr()
         self.pred = {'joint': yj, 'grain': yg, 'grain_area': area, 'edge_event': ev, 'edge': ed}
 

@@ -25,7 +25,10 @@ class RegionIndex:
 
     __slots__ = ('rowptr', 'col', 'key', 'rank', 'n_grain', 'n_joint', 'n_edges')
 
-    def __init__(self, gj_edge_index, n_grain, n_joint):
+    def __init__(self, gj_edge_index, n_grain, n_joint, edge_key=None):
+        """edge_key (optional, int32 [E]): the dict position of each edge's joint, given by the caller — a slab of a
+        partitioned domain passes the GLOBAL positions, so every rank walks a grain's joints in the same order as the
+        undivided graph (partition.region_edges)."""
         if not gj_edge_index.is_cuda:
             raise RuntimeError('graingraphnn_b200 runs on CUDA tensors only (no CPU fallback)')
         ei = gj_edge_index.contiguous()
@@ -34,11 +37,15 @@ class RegionIndex:
         L = _lib.lib()
         by_grain = build_csr(torch.stack([ei[1], ei[0]]), n_joint, n_grain)    # rows = grains, col = joints, edge order kept
         self.rowptr, self.col = by_grain.rowptr, by_grain.col
-        self.rank = torch.empty(max(n_joint, 1), dtype=torch.int32, device=dev)
-        self.key = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
-            check(L.gg_joint_rank(ptr(ei[1].contiguous()), E, n_joint, ptr(self.rank), _stream()), 'gg_joint_rank')
-            check(L.gg_region_key(ptr(self.col), ptr(self.rank), E, ptr(self.key), _stream()), 'gg_region_key')
+        if edge_key is not None:
+            self.rank = None
+            self.key = edge_key.to(dev, torch.int32)[by_grain.perm.long()].contiguous() if E else torch.empty(1, dtype=torch.int32, device=dev)
+        else:
+            self.rank = torch.empty(max(n_joint, 1), dtype=torch.int32, device=dev)
+            self.key = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                check(L.gg_joint_rank(ptr(ei[1].contiguous()), E, n_joint, ptr(self.rank), _stream()), 'gg_joint_rank')
+                check(L.gg_region_key(ptr(self.col), ptr(self.rank), E, ptr(self.key), _stream()), 'gg_region_key')
         self.n_grain, self.n_joint, self.n_edges = n_grain, n_joint, E
 
 

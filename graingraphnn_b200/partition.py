@@ -125,6 +125,26 @@ def build_plan(n_nodes, edge_index, owner, rank, world):
     return plan
 
 
+def region_edges(plan, edge_index_dict, owner):
+    """Geometry feedback on a slab (engine.region_feedback): the grain->joint edges of the grains this rank owns, in local
+    numbering, and for each the GLOBAL place of its joint in the reference's joint2vertex dict (first appearance as a target
+    of the undivided grain->joint edge list, graph_trajectory.py:1062-1080) — so a grain's joints are walked in the same
+    order on every partition.  The joints of an owned grain are local rows (own or halo) because the joint->grain edges
+    into owned grains are this rank's; raises if the two edge types are not each other's reverse."""
+    gj = edge_index_dict[('grain', 'push', 'joint')]
+    gj = gj.numpy() if isinstance(gj, torch.Tensor) else np.asarray(gj)
+    n_joint = owner['joint'].shape[0]
+    first = np.full(n_joint, np.iinfo(np.int32).max, dtype=np.int64)
+    np.minimum.at(first, gj[1], np.arange(gj.shape[1], dtype=np.int64))
+    m = owner['grain'][gj[0]] == plan.rank
+    g = plan._g2l['grain'][gj[0][m]]
+    j = plan._g2l['joint'][gj[1][m]]
+    if (j < 0).any():
+        raise ValueError('a joint of an owned grain is neither owned nor halo: the joint->grain edges are not the reverse of '
+                         'the grain->joint edges')
+    return np.stack([g, j]).astype(np.int64), first[gj[1][m]].astype(np.int32)
+
+
 def local_features(plan, x_dict):
     """Rows of the global feature tensors in this rank's local numbering (owned, then halo)."""
     out = {}
@@ -241,9 +261,25 @@ class PartitionedEngine(RolloutEngine):
         self.plan = build_plan(n_nodes, edge_index_dict, owner, rank, world)
         self.halo = HaloExchange(self.plan, self.device, transport, group)
         self.n_rows = dict(self.plan.n_own)           # kernels that WRITE per-node results stop at the owned rows
+        self._region_edges = region_edges(self.plan, edge_index_dict, owner)
         xl = local_features(self.plan, x_dict)
         ei = {e: torch.from_numpy(v) for e, v in self.plan.edge_index.items()}
         self.set_graph({t: v.to(self.device) for t, v in xl.items()}, {e: v.to(self.device) for e, v in ei.items()})
+
+    _region_edges = None
+
+    def _region_index(self):
+        from .geometry import RegionIndex
+        edges, key = self._region_edges
+        return RegionIndex(torch.from_numpy(edges).to(self.device), self.plan.n_own['grain'], self.plan.n_local['joint'],
+                           edge_key=torch.from_numpy(key))
+
+    def enable_geometry_feedback(self, joint_offset=None, domain_factor=1):
+        """joint_offset: GLOBAL [Nj, 2] (as passed to the single-GPU engine); rows are taken in this rank's local numbering."""
+        if joint_offset is not None:
+            ids = torch.from_numpy(np.concatenate([self.plan.own['joint'], self.plan.halo['joint']]))
+            joint_offset = joint_offset.cpu().index_select(0, ids)
+        super().enable_geometry_feedback(joint_offset, domain_factor)
 
     def alloc_rows(self, node_type, width):
         if self.halo is None:
@@ -296,6 +332,7 @@ class LocalSlabGroup:
             e.plan = build_plan({t: int(v.shape[0]) for t, v in x_dict.items()}, edge_index_dict, owner, r, world)
             e.halo = None
             e.n_rows = dict(e.plan.n_own)
+            e._region_edges = region_edges(e.plan, edge_index_dict, owner)
             xl = local_features(e.plan, x_dict)
             e.set_graph({t: v.to(e.device) for t, v in xl.items()},
                         {k: torch.from_numpy(v).to(e.device) for k, v in e.plan.edge_index.items()})

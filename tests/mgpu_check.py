@@ -31,11 +31,16 @@ def main():
     sd_r, sd_c = orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
     eng = PartitionedEngine.from_state_dicts(sd_r, sd_c, device=dev)
     eng.set_global_graph(x, ei, glob, rank, world)
+    feedback = os.environ.get('GG_FEEDBACK', '0') == '1'      # row f2: grain centres follow the joints (fourth exchange)
+    if feedback:
+        eng.enable_geometry_feedback()
     steps = 3
     outs = []
     for _ in range(steps):
         eng.step(6)
-        outs.append({k: (gid, v.cpu()) for k, (gid, v) in eng.owned_predictions().items()})
+        o = {k: (gid, v.cpu()) for k, (gid, v) in eng.owned_predictions().items()}
+        o['x_grain'] = (eng.plan.own['grain'], eng.x['grain'][:eng.plan.n_own['grain']].cpu())
+        outs.append(o)
     torch.cuda.synchronize()
     gathered = [None] * world
     dist.all_gather_object(gathered, outs)
@@ -43,9 +48,12 @@ def main():
     if rank == 0:
         single = RolloutEngine.from_state_dicts(sd_r, sd_c, dev)
         single.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
+        if feedback:
+            single.enable_geometry_feedback()
         for s in range(steps):
             ref = {k: v.cpu() for k, v in single.step(6).items()}
-            for k in ('joint', 'grain', 'grain_area', 'edge_event'):
+            ref['x_grain'] = single.x['grain'].cpu()
+            for k in ('joint', 'grain', 'grain_area', 'edge_event', 'x_grain'):
                 got = torch.full_like(ref[k], float('nan'))
                 for r in range(world):
                     gid, val = gathered[r][s][k]
@@ -58,8 +66,8 @@ def main():
                     same = err < 1e-5
                     print(f'step {s} {k}: not bit-identical, max rel err {err:.3e} ({"within" if same else "OUTSIDE"} 1e-5)', flush=True)
                 ok &= same
-        print(f'MGPU {"OK" if ok else "FAIL"} world={world} transport={eng.halo.transport} '
-              f'halo_bytes_per_exchange={eng.halo.bytes_sent_per_exchange[:3]} counts={eng.counts()}', flush=True)
+        print(f'MGPU {"OK" if ok else "FAIL"} world={world} transport={eng.halo.transport} feedback={int(feedback)} '
+              f'halo_bytes_per_exchange={eng.halo.bytes_sent_per_exchange[:4]} counts={eng.counts()}', flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

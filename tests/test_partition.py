@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 import grain_oracle as orc
 from util import ET, rel_err
 
-from graingraphnn_b200.partition import HaloExchange, build_plan, local_features, owners_by_x
+from graingraphnn_b200.partition import HaloExchange, build_plan, local_features, owners_by_x, region_edges
 from graingraphnn_b200.synth import honeycomb_graph, lattice_dims
 
 
@@ -130,6 +130,47 @@ def test_local_features_follow_local_numbering():
         assert torch.equal(xl[t], x[t][torch.from_numpy(ids)])
 
 
+@pytest.mark.parametrize('world', [2, 3])
+def test_region_edges_give_every_owned_grain_its_joints_in_the_global_dict_order(world):
+    """Geometry feedback on slabs (row f2): each rank holds, for the grains it owns, all their joints as local rows, keyed by
+    the joint's first appearance in the UNDIVIDED grain->joint edge list (centres against the single-GPU engine: GPU test below)."""
+    x, ei, glob = domain(8, 2)
+    pl, owner = plans(x, ei, glob, world)
+    gj = ei[ET[0]].numpy()
+    first = np.full(x['joint'].shape[0], 2 ** 31 - 1, dtype=np.int64)
+    np.minimum.at(first, gj[1], np.arange(gj.shape[1]))
+    seen = 0
+    for p in pl:
+        edges, key = region_edges(p, ei, owner)
+        l2g = {t: np.concatenate([p.own[t], p.halo[t]]) for t in x}
+        assert (edges[0] < p.n_own['grain']).all() and (edges[1] < p.n_local['joint']).all()
+        gg, jg = l2g['grain'][edges[0]], l2g['joint'][edges[1]]
+        m = owner['grain'][gj[0]] == p.rank
+        assert np.array_equal(gg, gj[0][m]) and np.array_equal(jg, gj[1][m])
+        assert np.array_equal(key, first[jg])
+        seen += edges.shape[1]
+        # a grain's joints sorted by key come out in the order of the undivided graph's dict
+        for g_loc in (0, p.n_own['grain'] // 2, p.n_own['grain'] - 1):
+            sel = np.nonzero(edges[0] == g_loc)[0]
+            mine = jg[sel][np.argsort(key[sel], kind='stable')]
+            glob_sel = np.nonzero(gj[0] == p.own['grain'][g_loc])[0]
+            assert np.array_equal(mine, gj[1][glob_sel][np.argsort(first[gj[1][glob_sel]], kind='stable')])
+    assert seen == gj.shape[1]
+
+
+def test_region_edges_reject_a_joint_that_is_not_local():
+    x, ei, glob = domain(8, 2)
+    pl, owner = plans(x, ei, glob, 2)
+    bad = {e: v.clone() for e, v in ei.items()}
+    far = int(np.argmin(np.abs(np.asarray(glob['joint'])[:, 0] - 0.75)))            # a joint deep inside slab 1 ...
+    g0 = int(np.argmin(np.abs(np.asarray(glob['grain'])[:, 0] - 0.25)))              # ... hung on a grain deep inside slab 0
+    assert owner['joint'][far] == 1 and owner['grain'][g0] == 0
+    bad[ET[0]] = torch.cat([bad[ET[0]], torch.tensor([[g0], [far]])], 1)
+    with pytest.raises(ValueError):
+        region_edges(pl[0], bad, owner)
+
+
+
 # ------------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize('world', [2, 4])
@@ -161,8 +202,42 @@ def test_partitioned_rollout_equals_single_gpu(world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('world', [2, 3])
+def test_partitioned_rollout_with_geometry_feedback_equals_single_gpu(world):
+    """Row f2 on slabs: owned grains take the centres of their (owned + halo) joints, halo grains receive theirs through a
+    fourth exchange; features, centres and predictions equal the single-GPU engine bit for bit over 3 steps."""
+    from graingraphnn_b200.engine import RolloutEngine
+    from graingraphnn_b200.partition import LocalSlabGroup
+    dev = torch.device('cuda:0')
+    x, ei, glob = domain(8, 2, seed=5)
+    sd_r, sd_c = orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
+    single = RolloutEngine.from_state_dicts(sd_r, sd_c, dev)
+    single.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
+    single.enable_geometry_feedback()
+    group = LocalSlabGroup.build(sd_r, sd_c, x, ei, glob, world, dev)
+    for e in group.engines:
+        e.enable_geometry_feedback()
+    for _ in range(3):
+        ref = single.step(6)
+        group.step(6)
+        for e in group.engines:
+            pl = e.plan
+            for k, (gid, val) in e.owned_predictions().items():
+                assert torch.equal(val, ref[k][torch.from_numpy(gid).to(dev)]), k
+            for t in ('grain', 'joint'):        # owned AND halo rows: the halo grains carry the centres their owners computed
+                ids = torch.from_numpy(np.concatenate([pl.own[t], pl.halo[t]])).to(dev)
+                assert torch.equal(e.x[t], single.x[t][ids]), t
+            own_g = torch.from_numpy(pl.own['grain']).to(dev)
+            assert torch.equal(torch.nan_to_num(e.centers, nan=-7.0), torch.nan_to_num(single.centers[own_g], nan=-7.0))
+            for et in ET:
+                gid = torch.from_numpy(pl.edge_gid[et]).to(dev)
+                assert torch.equal(e.edge_attr[et], single.edge_attr[et][gid])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('feedback', ['0', '1'])
 @pytest.mark.parametrize('transport', ['nccl', 'p2p'])
-def test_multi_gpu_partition(transport):
+def test_multi_gpu_partition(transport, feedback):
     """Real ranks, real halo exchange (needs >= 2 GPUs; skipped on the single-GPU box)."""
     import subprocess
     import sys
@@ -170,7 +245,7 @@ def test_multi_gpu_partition(transport):
     if n < 2:
         pytest.skip('needs >= 2 GPUs')
     n = 2 if n < 4 else 4
-    env = dict(os.environ, GG_HALO=transport)
+    env = dict(os.environ, GG_HALO=transport, GG_FEEDBACK=feedback)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n}', '--master-addr', '127.0.0.1',
            '--master-port', str(_free_port()), os.path.join(os.path.dirname(os.path.abspath(__file__)), 'mgpu_check.py')]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
