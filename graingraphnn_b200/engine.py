@@ -102,6 +102,27 @@ class RolloutEngine:
                                             self.ea_csr[e].numel(), torch.cuda.current_stream().cuda_stream), 'gg_permute_f32')
             self.rebuild_edge_wrap()
 
+    # ------------------------------------------------------------------------------------- event candidates (f1, first stage)
+    _events = None
+    _event_mask = None
+
+    def enable_event_selection(self, mask_grain=None, edge_threshold=0.6, area_threshold=1e-4, cap=4096):
+        """Every step also leaves the candidates of the host topology update on the device — the edges with
+        sigmoid(edge_event) > edge_threshold and src < dst (models.py:627-629) and the live grains with predicted area below
+        area_threshold (test.py:414) — so that `fetch_events()` copies a few (id, value) pairs instead of the full arrays.
+        mask_grain: [Ng] or [Ng,1] fp32, > 0 for live grains (data['mask']['grain'])."""
+        from .events import EventSelector
+        self._events = EventSelector(self.device, edge_threshold, area_threshold, cap, cap)
+        self._event_mask = None if mask_grain is None else mask_grain.to(self.device, torch.float32).reshape(mask_grain.shape[0], -1)[:, 0].contiguous()
+        self._graph = None
+
+    def fetch_events(self):
+        """Host lists of the last step: {'L1' (ascending edge ids, models.py:629), 'L1_logit', 'grain_event' (sorted by area,
+        test.py:416), ...}; ids are rows / edges of the graph this engine holds."""
+        if self._events is None:
+            raise RuntimeError('enable_event_selection() first')
+        return self._events.fetch()
+
     # ------------------------------------------------------------------------------------- geometry feedback (f2)
     _geom = None
     _region = None
@@ -219,6 +240,10 @@ class RolloutEngine:
                              area_in=self.xbuf['grain'][:, 3], area_scale=20.0, n_rows=ng)
         ev, ed = edge_head(sC['hd']['joint'], self.edge_index[ET_JJ], self.edge_attr[ET_JJ],
                            Cm.lin1.weight, Cm.lin1.bias, Cm.lin2.weight, Cm.lin2.bias)
+        if self._events is not None:                         # row f1, first stage: only the event candidates leave the device
+            self._events.select_edge_events(ev, self.edge_index[ET_JJ])
+            self._events.select_grain_events(area if ng is None else area[:ng],
+                                             None if self._event_mask is None else self._event_mask[:area.shape[0] if ng is None else ng])
         if isinstance(span, (tuple, list)):                  # ensemble: one span per graph of the block-diagonal batch
             dzj, dzg = self._dz_vectors(tuple(span))
             feature_update_batched(self.x['joint'], self.x['grain'], yj, yg, dzj, dzg,

@@ -298,6 +298,24 @@ int gg_region_center(const float* x_joint, int32_t ld_j, const float* joint_offs
                      double* centers /* nullable */, float* x_grain /* nullable */, int32_t ld_g, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (f1, first stage) event candidates.  Replaces the host scans of the full prediction arrays,
+ *      L1 = ((sigmoid(edge_event) > threshold) & (src < dst)).nonzero()            models.py:627-629
+ *      grain_event = ((mask_grain > 0) & (grain_area < threshold)).nonzero()       test.py:414
+ *  by one streaming pass that leaves only the candidates on the device:
+ *      mode 0 keeps values[i*ld] >= threshold, mode 1 keeps values[i*ld] < threshold;
+ *      src/dst (both or neither; int64 [n]): additionally src[i] < dst[i];  mask (nullable, fp32, stride ld_mask): mask > 0.
+ *  For mode 0 the caller passes the smallest fp32 logit whose sigmoid exceeds the probability threshold (found on the
+ *  host with the reference's sigmoid), so the decision equals the reference's bit for bit.
+ *  count (device int32[1]) receives the number of candidates — it may exceed cap, in which case only cap of them were
+ *  stored and the caller repeats with larger buffers; ids / vals [cap] hold them in NO particular order (the caller sorts
+ *  the few survivors: by id for `nonzero` order, then as test.py:416 / models.py:730-731 prescribe).
+ * ---------------------------------------------------------------------------------------------- */
+int gg_select_events(const float* values, int64_t n, int32_t ld, float threshold, int32_t mode,
+                     const int64_t* src /* nullable */, const int64_t* dst /* nullable */,
+                     const float* mask /* nullable */, int32_t ld_mask,
+                     int32_t cap, int32_t* count, int32_t* ids, float* vals, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (e) halo pack / unpack for the slab-partitioned domain: out[i, :] = src[idx[i], :] and the inverse.
  *     width must be a multiple of 4 floats and rows 16-byte aligned.
  * ---------------------------------------------------------------------------------------------- */

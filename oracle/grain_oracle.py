@@ -265,6 +265,18 @@ def grain_xy_writeback(x_grain, centers, domain_factor=1):
     return x_grain
 
 
+def event_candidates(y_dict, jj_edge_index, mask_grain=None, edge_threshold=0.6, area_threshold=1e-4):
+    """Event candidates exactly as the reference's host code selects them: models.py:627-629 (edges that may switch) and
+    test.py:414-416 (grains that vanish, sorted by predicted area)."""
+    src, dst = jj_edge_index[0], jj_edge_index[1]
+    prob = torch.sigmoid(y_dict['edge_event'])
+    L1 = ((prob > edge_threshold) & (src < dst)).nonzero().view(-1)
+    alive = torch.ones_like(y_dict['grain_area'], dtype=torch.bool) if mask_grain is None else (mask_grain.reshape(len(mask_grain), -1)[:, 0] > 0)
+    grain_event = (alive & (y_dict['grain_area'] < area_threshold)).nonzero().view(-1)
+    grain_event = grain_event[torch.argsort(y_dict['grain_area'][grain_event])]
+    return L1, grain_event
+
+
 def csr_by_dst(edge_index, n_dst):
     """Stable dst-sorted CSR (the index structure kernel (a) must reproduce bit-exactly).
     rowptr[n_dst+1], col[E] = src in (dst, original-edge-id) order, perm[E] = original edge id."""

@@ -57,6 +57,26 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     out = {'grains': ng, 'joints': nj, 'edges_gj': E, 'region_center_us_cold_l2': t_kernel * 1e3, 'region_center_us_warm_l2': t_warm * 1e3,
            'algorithmic_bytes': alg, 'achieved_GBps_cold': alg / (t_kernel * 1e-3) / 1e9, 'peaks_file': peaks}
+    # event candidates (row f1, first stage): one pass over the jj edge logits + one over the grain areas
+    from graingraphnn_b200.events import EventSelector
+    from graingraphnn_b200.engine import ET_JJ
+    jj = ei[ET_JJ].to(dev)
+    logits = torch.randn(jj.shape[1], device=dev) * 1.5 - 4.0
+    area = torch.rand(ng, device=dev) * 0.02
+    sel = EventSelector(dev)
+
+    def select():
+        sel.select_edge_events(logits, jj)
+        sel.select_grain_events(area)
+    for _ in range(3):
+        select()
+    t_sel = events(select, 20, flush)
+    ev = sel.fetch()
+    out['select_events_us_cold_l2'] = t_sel * 1e3
+    out['select_events_algorithmic_bytes'] = 4 * jj.shape[1] + 4 * ng
+    out['select_events_GBps'] = out['select_events_algorithmic_bytes'] / (t_sel * 1e-3) / 1e9
+    out['select_events_candidates'] = [len(ev['L1']), len(ev['grain_event'])]
+    out['select_events_d2h_bytes_vs_full'] = [sel.d2h_bytes, 4 * (jj.shape[1] + 3 * ng + 2 * nj)]
     # the step with and without the feedback, replayed from a CUDA graph
     sd_r, sd_c = bench.synth_weights()
     for fb in (False, True):
@@ -64,6 +84,7 @@ def main():
         eng.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
         if fb:
             eng.enable_geometry_feedback()
+            eng.enable_event_selection()
         eng.capture(span=6, warmup=3)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
