@@ -326,6 +326,32 @@ def main():
     if os.environ.get('GG_BENCH_VERBOSE'):
         roof['per_call_ms'] = {k: v['ms_each'] for k, v in bd.items()}
 
+    # ---- the same step with the rows SURVEY §8f adds switched on (not part of `value`): grain centres from the moved
+    #      joints (gg_region_center, row f2) and the event candidates of the host topology update (gg_select_events, row f1)
+    widened = None
+    if world == 1:
+        try:
+            eng.enable_geometry_feedback()
+            eng.enable_event_selection()
+            if use_graph:
+                eng.capture(SPAN, warmup=2)
+            else:
+                eng.step(SPAN)
+            torch.cuda.synchronize()
+            e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e4.record()
+            for _ in range(args.steps):
+                eng.step(SPAN)
+            e5.record()
+            torch.cuda.synchronize()
+            ev = eng.fetch_events()
+            widened = {'ms_per_step': e4.elapsed_time(e5) / args.steps, 'launches_per_step': eng.launches_per_step,
+                       'adds': 'gg_region_center (grain centres, test.py:476 + :556-559) and gg_select_events (models.py:627-629, test.py:414)',
+                       'event_candidates_last_step': [int(ev['L1'].numel()), int(ev['grain_event'].numel())],
+                       'event_d2h_bytes': 8 + 8 * int(ev['L1'].numel() + ev['grain_event'].numel())}
+        except Exception as exc:                                   # never lose the headline line to the extra measurement
+            widened = {'error': repr(exc)[:200]}
+
     cpu = None if args.no_cpu_baseline else cpu_reference_run(5, 1)
     steps_per_s = args.steps / (ms / 1e3)
     line = {
@@ -347,6 +373,7 @@ def main():
                 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'roofline': roof,
+        'step_with_geometry_feedback_and_event_selection': widened,
         'cpu_baseline': None if cpu is None else {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
     }
     print(json.dumps(line))
