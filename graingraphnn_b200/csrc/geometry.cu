@@ -43,6 +43,24 @@ struct FetchJoint {
     }
 };
 
+// Once per topology: the joints of every grain in dict order (selection by repeated minimum over the keys, ~6 per grain).
+__global__ void region_sort_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                   const int32_t* __restrict__ key, int32_t n_grain, int32_t* __restrict__ col_sorted) {
+    int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_grain) return;
+    int32_t beg = rowptr[g], end = rowptr[g + 1], last = -1;
+    for (int32_t i = beg; i < end; ++i) {
+        int32_t best = 0x7fffffff, at = beg;
+        for (int32_t k = beg; k < end; ++k) {
+            int32_t v = key[k];
+            if (v > last && v < best) { best = v; at = k; }
+        }
+        last = best;
+        col_sorted[i] = col[at];
+    }
+}
+
+template <bool ORDERED>
 __global__ void __launch_bounds__(128)
 region_center_kernel(const float* __restrict__ xj, int32_t ld_j, const float* __restrict__ off, float factor,
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ key,
@@ -50,9 +68,16 @@ region_center_kernel(const float* __restrict__ xj, int32_t ld_j, const float* __
     int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_grain) return;
     int32_t beg = rowptr[g], end = rowptr[g + 1];
-    GGRegionWalk<FetchJoint> w{key + beg, end - beg, FetchJoint{xj, ld_j, off, factor, col + beg}, -1};
     double cx, cy;
-    if (gg_region_center_one(w, &cx, &cy)) {
+    bool ok;
+    if (ORDERED) {
+        GGOrderedWalk<FetchJoint> w{end - beg, FetchJoint{xj, ld_j, off, factor, col + beg}, 0};
+        ok = gg_region_center_one(w, &cx, &cy);
+    } else {
+        GGRegionWalk<FetchJoint> w{key + beg, end - beg, FetchJoint{xj, ld_j, off, factor, col + beg}, -1};
+        ok = gg_region_center_one(w, &cx, &cy);
+    }
+    if (ok) {
         if (centers) { centers[2 * (size_t)g] = cx; centers[2 * (size_t)g + 1] = cy; }
         if (x_grain) {
             x_grain[(size_t)g * ld_g]     = gg_patch_coord((float)cx, factor);
@@ -93,9 +118,22 @@ extern "C" int gg_region_center(const float* x_joint, int32_t ld_j, const float*
         return GG_EALIGN;
     if (domain_factor > 1.0f && !joint_offset) return GG_EINVAL;
     if (n_grain == 0) return 0;
-    region_center_kernel<<<(n_grain + 127) / 128, 128, 0, GG_STREAM(stream)>>>(
-        x_joint, ld_j, domain_factor > 1.0f ? joint_offset : nullptr, domain_factor, rowptr, col, key, n_grain,
-        centers, x_grain, ld_g);
+    const float* off = domain_factor > 1.0f ? joint_offset : nullptr;
+    if (key)
+        region_center_kernel<false><<<(n_grain + 127) / 128, 128, 0, GG_STREAM(stream)>>>(
+            x_joint, ld_j, off, domain_factor, rowptr, col, key, n_grain, centers, x_grain, ld_g);
+    else
+        region_center_kernel<true><<<(n_grain + 127) / 128, 128, 0, GG_STREAM(stream)>>>(
+            x_joint, ld_j, off, domain_factor, rowptr, col, nullptr, n_grain, centers, x_grain, ld_g);
+    GG_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int gg_region_sort(const int32_t* rowptr, const int32_t* col, const int32_t* key, int32_t n_grain,
+                              int32_t* col_sorted, void* stream) {
+    if (n_grain < 0 || (n_grain > 0 && (!rowptr || !col_sorted))) return GG_EINVAL;
+    if (n_grain == 0) return 0;
+    region_sort_kernel<<<(n_grain + 127) / 128, 128, 0, GG_STREAM(stream)>>>(rowptr, col, key, n_grain, col_sorted);
     GG_LAUNCH_OK();
     return 0;
 }

@@ -64,6 +64,17 @@ struct GGRegionWalk {
     }
 };
 
+// The same walk over a joint list that is ALREADY in dict order (gg_region_sort ran once for the topology): the per-step
+// kernel then reads each joint id once per pass, no keys.
+template <class Fetch>
+struct GGOrderedWalk {
+    int32_t n;
+    Fetch fetch;
+    int32_t at;
+    GG_HD void rewind() { at = 0; }
+    GG_HD void next(float* x, float* y) { fetch(at++, x, y); }
+};
+
 // One axis of the chain unwrap; state = previous moved vertex.
 struct GGChain {
     float first;
@@ -121,8 +132,8 @@ struct GGNumpySum {
 };
 
 // Centre of one region.  Returns false (centre untouched) for regions of <= 1 vertex (graph_datastruct.py:684).
-template <class Fetch>
-GG_HD bool gg_region_center_one(GGRegionWalk<Fetch>& w, double* cx, double* cy) {
+template <class Walk>
+GG_HD bool gg_region_center_one(Walk& w, double* cx, double* cy) {
     const int32_t n = w.n;
     if (n <= 1) return false;
     const float feps = -1e-12f;                    // `j > -eps` on a float32 scalar compares in float32 (NEP 50)

@@ -23,7 +23,7 @@ class RegionIndex:
     """rowptr[n_grain+1], col[E] (joint ids), key[E] (place of the joint in the reference's joint2vertex dict) — int32.
     Built from the ('grain','push','joint') edge_index ([2,E] int64, CUDA); rebuilt whenever the topology changes."""
 
-    __slots__ = ('rowptr', 'col', 'key', 'rank', 'n_grain', 'n_joint', 'n_edges')
+    __slots__ = ('rowptr', 'col', 'key', 'rank', 'col_sorted', 'n_grain', 'n_joint', 'n_edges')
 
     def __init__(self, gj_edge_index, n_grain, n_joint, edge_key=None):
         """edge_key (optional, int32 [E]): the dict position of each edge's joint, given by the caller — a slab of a
@@ -46,15 +46,20 @@ class RegionIndex:
             with torch.cuda.device(dev):
                 check(L.gg_joint_rank(ptr(ei[1].contiguous()), E, n_joint, ptr(self.rank), _stream()), 'gg_joint_rank')
                 check(L.gg_region_key(ptr(self.col), ptr(self.rank), E, ptr(self.key), _stream()), 'gg_region_key')
+        # the joints of every grain in dict order: the per-step kernel walks them without keys
+        self.col_sorted = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(L.gg_region_sort(ptr(self.rowptr), ptr(self.col), ptr(self.key), n_grain, ptr(self.col_sorted), _stream()), 'gg_region_sort')
         self.n_grain, self.n_joint, self.n_edges = n_grain, n_joint, E
 
 
-def region_center(x_joint, index, x_grain=None, joint_offset=None, domain_factor=1, centers=None, want_centers=True):
+def region_center(x_joint, index, x_grain=None, joint_offset=None, domain_factor=1, centers=None, want_centers=True, presorted=True):
     """Centres of all grains from the CURRENT joint rows (columns 0..1 of `x_joint`, fp32, even row stride).
 
     x_grain (optional): its columns 0..1 receive fp32(centre) — `(centre * domain_factor) % 1` on scaled patches
     (test.py:556-559); grains with <= 1 joint keep their coordinates (graph_datastruct.py:684).
     joint_offset [Nj,2] fp32 and domain_factor: global = (patch + offset) / factor (test.py:472-474).
+    presorted=False walks the unsorted joint list by key (same results; kept as the cross-check of gg_region_sort).
     Returns float64 [n_grain, 2] centres (NaN rows for skipped grains), or None with want_centers=False."""
     if not x_joint.is_cuda:
         raise RuntimeError('graingraphnn_b200 runs on CUDA tensors only (no CPU fallback)')
@@ -74,7 +79,8 @@ def region_center(x_joint, index, x_grain=None, joint_offset=None, domain_factor
         raise ValueError('x_grain must be fp32 [>= n_grain, >= 2] with unit column stride')
     with torch.cuda.device(x_joint.device):
         check(_lib.lib().gg_region_center(ptr(x_joint), x_joint.stride(0), ptr(joint_offset), float(domain_factor),
-                                          ptr(index.rowptr), ptr(index.col), ptr(index.key), index.n_grain,
+                                          ptr(index.rowptr), ptr(index.col_sorted if presorted else index.col),
+                                          None if presorted else ptr(index.key), index.n_grain,
                                           ptr(centers), ptr(x_grain), x_grain.stride(0) if x_grain is not None else 0,
                                           _stream()), 'gg_region_center')
     return centers

@@ -284,7 +284,10 @@ int gg_feature_update_batched(float* x_joint, int32_t ld_j, int32_t n_joint, con
  *      graph_trajectory.py:1062-1080); gj_dst = row 1 of the grain->joint edge_index.
  *  gg_region_key: key[k] = rank[col[k]] for the CSR of the grain->joint edges taken BY GRAIN (gg_csr_build on the edge
  *      list with its two rows swapped: rowptr over grains, col = joints).
- *  gg_region_center: one thread per grain.  x_joint rows hold (x, y) in columns 0..1 (ld_j even, 8-byte aligned);
+ *  gg_region_sort: col_sorted = the joints of every grain in dict order (increasing key) — once per topology, so that the
+ *      per-step kernel walks each grain's joints without keys.
+ *  gg_region_center: one thread per grain.  key == NULL: `col` is already in dict order (gg_region_sort); otherwise the
+ *      joints are visited in increasing key order by repeated minimum search.  x_joint rows hold (x, y) in columns 0..1 (ld_j even, 8-byte aligned);
  *      domain_factor > 1: global = (x + joint_offset[j]) / domain_factor in fp32 (test.py:472-474), joint_offset [Nj,2];
  *      centers (nullable): float64 [n_grain, 2], NaN for grains with <= 1 joint (skipped by :684, features untouched);
  *      x_grain (nullable): columns 0..1 <- fp32(centre), `(c * domain_factor) % 1` on scaled patches (test.py:558-559).
@@ -293,8 +296,10 @@ int gg_feature_update_batched(float* x_joint, int32_t ld_j, int32_t n_joint, con
  * ---------------------------------------------------------------------------------------------- */
 int gg_joint_rank(const int64_t* gj_dst, int64_t n_edges, int32_t n_joint, int32_t* rank, void* stream);
 int gg_region_key(const int32_t* col, const int32_t* rank, int64_t n_edges, int32_t* key, void* stream);
+int gg_region_sort(const int32_t* rowptr, const int32_t* col, const int32_t* key, int32_t n_grain,
+                   int32_t* col_sorted, void* stream);
 int gg_region_center(const float* x_joint, int32_t ld_j, const float* joint_offset /* nullable */, float domain_factor,
-                     const int32_t* rowptr, const int32_t* col, const int32_t* key, int32_t n_grain,
+                     const int32_t* rowptr, const int32_t* col, const int32_t* key /* nullable */, int32_t n_grain,
                      double* centers /* nullable */, float* x_grain /* nullable */, int32_t ld_g, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

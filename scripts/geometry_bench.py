@@ -53,9 +53,10 @@ def main():
     # algorithmic bytes per launch: per edge key + col (8 B) and a joint (x, y) (8 B, every joint row is needed once per
     # incident grain but lives in a 32-B sector with its unused columns: 32 B per joint of DRAM traffic at best);
     # per grain rowptr (4 B), centre out (16 B), (x, y) write-back (8 B)
-    alg = E * 8 + nj * 8 + ng * (4 + 16 + 8)
+    t_bykey = events(lambda: region_center(xj, idx, xg, centers=centers, presorted=False), 20, flush)
+    alg = E * 4 + nj * 8 + ng * (4 + 16 + 8)            # joint ids in dict order (gg_region_sort, once per topology): no keys
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
-    out = {'grains': ng, 'joints': nj, 'edges_gj': E, 'region_center_us_cold_l2': t_kernel * 1e3, 'region_center_us_warm_l2': t_warm * 1e3,
+    out = {'grains': ng, 'joints': nj, 'edges_gj': E, 'region_center_us_cold_l2': t_kernel * 1e3, 'region_center_us_warm_l2': t_warm * 1e3, 'region_center_by_key_us_cold_l2': t_bykey * 1e3,
            'algorithmic_bytes': alg, 'achieved_GBps_cold': alg / (t_kernel * 1e-3) / 1e9, 'peaks_file': peaks}
     # event candidates (row f1, first stage): one pass over the jj edge logits + one over the grain areas
     from graingraphnn_b200.events import EventSelector

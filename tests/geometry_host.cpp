@@ -19,9 +19,16 @@ extern "C" void region_center_host(const float* xj, int ld, const float* off, fl
                                    const int32_t* col, const int32_t* key, int n_grain, double* centers, float* xg, int ld_g) {
     for (int g = 0; g < n_grain; ++g) {
         int beg = rowptr[g], end = rowptr[g + 1];
-        GGRegionWalk<FetchHost> w{key + beg, end - beg, FetchHost{xj, ld, factor > 1.f ? off : nullptr, factor, col + beg}, -1};
         double cx, cy;
-        if (gg_region_center_one(w, &cx, &cy)) {
+        bool ok;
+        if (key) {
+            GGRegionWalk<FetchHost> w{key + beg, end - beg, FetchHost{xj, ld, factor > 1.f ? off : nullptr, factor, col + beg}, -1};
+            ok = gg_region_center_one(w, &cx, &cy);
+        } else {                                  // col already in dict order
+            GGOrderedWalk<FetchHost> w{end - beg, FetchHost{xj, ld, factor > 1.f ? off : nullptr, factor, col + beg}, 0};
+            ok = gg_region_center_one(w, &cx, &cy);
+        }
+        if (ok) {
             centers[2 * g] = cx; centers[2 * g + 1] = cy;
             xg[(size_t)g * ld_g] = gg_patch_coord((float)cx, factor);
             xg[(size_t)g * ld_g + 1] = gg_patch_coord((float)cy, factor);

@@ -62,16 +62,21 @@ def host_lib(tmp_path_factory):
     return ctypes.CDLL(out)
 
 
+@pytest.mark.parametrize('presorted', [False, True])
 @pytest.mark.parametrize('name,factor', CASES)
-def test_kernel_arithmetic_on_the_host_equals_reference(host_lib, name, factor):
+def test_kernel_arithmetic_on_the_host_equals_reference(host_lib, name, factor, presorted):
     c = load_case(name)
     ng, nj = c['xg0'].shape[0], c['xj'].shape[0]
     rowptr, col, key, _ = region_index_numpy(c['gj'], ng, nj)
+    if presorted:                                                             # what gg_region_sort leaves: dict order per grain
+        grain_of = np.repeat(np.arange(ng), np.diff(rowptr))
+        col = col[np.lexsort((key, grain_of))].astype(np.int32)
+        key = None
     xj = np.ascontiguousarray(c['xj'])
     off = np.ascontiguousarray(c['off']) if c['off'] is not None else np.zeros((nj, 2), np.float32)
     centers, xg = np.zeros((ng, 2)), c['xg0'].copy()
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)                          # noqa: E731
-    host_lib.region_center_host(P(xj), xj.shape[1], P(off), ctypes.c_float(factor), P(rowptr), P(col), P(key), ng,
+    host_lib.region_center_host(P(xj), xj.shape[1], P(off), ctypes.c_float(factor), P(rowptr), P(col), P(key) if key is not None else None, ng,
                                 P(centers), P(xg), xg.shape[1])
     assert np.array_equal(centers, c['center'], equal_nan=True)
     assert np.array_equal(xg, c['xg_out'])
@@ -95,6 +100,7 @@ def test_entry_points_validate_arguments_without_gpu():
     assert L.gg_joint_rank(None, -1, 0, None, None) == -1
     assert L.gg_joint_rank(None, 0, 0, None, None) == 0
     assert L.gg_region_key(None, None, 5, None, None) == -1
+    assert L.gg_region_sort(None, None, None, 5, None, None) == -1 and L.gg_region_sort(None, None, None, 0, None, None) == 0
     assert L.gg_region_center(None, 8, None, 1.0, None, None, None, 5, None, None, 0, None) == -1
     buf = (ctypes.c_float * 16)()
     rp = (ctypes.c_int32 * 2)()

@@ -516,6 +516,10 @@ def test_region_center_bit_exact_vs_reference_gnn_update(name, factor):
     assert np.array_equal(centers.cpu().numpy(), c['center'], equal_nan=True)
     assert np.array_equal(xg.cpu().numpy(), c['xg_out'])
     assert torch.equal(xj.cpu(), torch.from_numpy(c['xj']))                  # the joint rows are read only
+    grain_of = np.repeat(np.arange(ng), np.diff(rowptr))
+    assert np.array_equal(idx.col_sorted.cpu().numpy()[:len(col)], col[np.lexsort((key, grain_of))])      # gg_region_sort
+    c_key = region_center(xj, idx, None, off, factor, presorted=False)                                    # walk by key
+    assert torch.equal(torch.nan_to_num(c_key, nan=-7.0), torch.nan_to_num(centers, nan=-7.0))
     # centres only (no write-back), and write-back only (no centres)
     c2 = region_center(xj, idx, None, off, factor)
     assert torch.equal(torch.nan_to_num(c2, nan=-7.0), torch.nan_to_num(centers, nan=-7.0))
