@@ -281,6 +281,22 @@ class PartitionedEngine(RolloutEngine):
             joint_offset = joint_offset.cpu().index_select(0, ids)
         super().enable_geometry_feedback(joint_offset, domain_factor)
 
+    def enable_event_selection(self, mask_grain=None, edge_threshold=0.6, area_threshold=1e-4, cap=4096):
+        """mask_grain: GLOBAL [Ng] or [Ng,1]; the owned rows are taken."""
+        if mask_grain is not None:
+            mask_grain = mask_grain.cpu().reshape(mask_grain.shape[0], -1)[:, 0][torch.from_numpy(self.plan.own['grain'])]
+        super().enable_event_selection(mask_grain, edge_threshold, area_threshold, cap)
+
+    def fetch_events(self):
+        """Candidates among the joint-joint edges and grains this rank owns, as GLOBAL ids (each edge / grain is owned by
+        exactly one rank: the union over ranks, sorted the same way, is the undivided graph's list)."""
+        ev = super().fetch_events()
+        gid = torch.from_numpy(self.plan.edge_gid[('joint', 'connect', 'joint')])
+        own = torch.from_numpy(self.plan.own['grain'])
+        ev['L1'] = gid[ev['L1']]
+        ev['grain_event'], ev['grain_event_ids'] = own[ev['grain_event']], own[ev['grain_event_ids']]
+        return ev
+
     def alloc_rows(self, node_type, width):
         if self.halo is None:
             return super().alloc_rows(node_type, width)

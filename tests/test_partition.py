@@ -235,6 +235,36 @@ def test_partitioned_rollout_with_geometry_feedback_equals_single_gpu(world):
 
 
 @pytest.mark.gpu
+def test_partitioned_event_candidates_union_equals_single_gpu():
+    """Row f1, first stage, on slabs: the union of the ranks' candidates (global ids) is the undivided graph's list."""
+    from graingraphnn_b200.engine import RolloutEngine
+    from graingraphnn_b200.partition import LocalSlabGroup
+    dev = torch.device('cuda:0')
+    x, ei, glob = domain(8, 2, seed=5)
+    x['grain'][:, 3] *= 0.02                                  # some areas end up below the 1e-4 threshold
+    mask = torch.ones(x['grain'].shape[0], 1)
+    mask[::11] = 0
+    sd_r, sd_c = orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
+    single = RolloutEngine.from_state_dicts(sd_r, sd_c, dev)
+    single.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
+    single.enable_event_selection(mask)
+    group = LocalSlabGroup.build(sd_r, sd_c, x, ei, glob, 3, dev)
+    for e in group.engines:
+        e.enable_event_selection(mask)
+    for _ in range(2):
+        single.step(6)
+        group.step(6)
+        ref = single.fetch_events()
+        got = [e.fetch_events() for e in group.engines]
+        assert torch.equal(torch.sort(torch.cat([g['L1'] for g in got])).values, ref['L1'])
+        ids = torch.cat([g['grain_event_ids'] for g in got])
+        area = torch.cat([g['grain_event_area'] for g in got])
+        order = torch.argsort(ids)
+        assert torch.equal(ids[order], ref['grain_event_ids']) and torch.equal(area[order], ref['grain_event_area'])
+        assert len(ref['L1']) > 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('feedback', ['0', '1'])
 @pytest.mark.parametrize('transport', ['nccl', 'p2p'])
 def test_multi_gpu_partition(transport, feedback):
