@@ -105,6 +105,7 @@ class RolloutEngine:
     # ------------------------------------------------------------------------------------- event candidates (f1, first stage)
     _events = None
     _event_mask = None
+    _event_edges = None      # [2, E] endpoints the `src < dst` test reads, when they differ from edge_index (slabs: global ids)
 
     def enable_event_selection(self, mask_grain=None, edge_threshold=0.6, area_threshold=1e-4, cap=4096):
         """Every step also leaves the candidates of the host topology update on the device — the edges with
@@ -241,7 +242,7 @@ class RolloutEngine:
         ev, ed = edge_head(sC['hd']['joint'], self.edge_index[ET_JJ], self.edge_attr[ET_JJ],
                            Cm.lin1.weight, Cm.lin1.bias, Cm.lin2.weight, Cm.lin2.bias)
         if self._events is not None:                         # row f1, first stage: only the event candidates leave the device
-            self._events.select_edge_events(ev, self.edge_index[ET_JJ])
+            self._events.select_edge_events(ev, self.edge_index[ET_JJ] if self._event_edges is None else self._event_edges)
             self._events.select_grain_events(area if ng is None else area[:ng],
                                              None if self._event_mask is None else self._event_mask[:area.shape[0] if ng is None else ng])
         if isinstance(span, (tuple, list)):                  # ensemble: one span per graph of the block-diagonal batch

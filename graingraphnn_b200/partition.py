@@ -122,6 +122,9 @@ def build_plan(n_nodes, edge_index, owner, rank, world):
         assert (src >= 0).all() and (dst >= 0).all() and (dst < plan.n_own[e[2]]).all()
         plan.edge_index[e] = np.stack([src, dst])
         plan.edge_gid[e] = gids
+        if e[0] == e[2]:       # same-type edges: the GLOBAL endpoints decide `src < dst` (models.py:629), local numbering does not
+            plan.edge_global = getattr(plan, 'edge_global', {})
+            plan.edge_global[e] = np.stack([idx[0][gids], idx[1][gids]]).astype(np.int64)
     return plan
 
 
@@ -262,6 +265,7 @@ class PartitionedEngine(RolloutEngine):
         self.halo = HaloExchange(self.plan, self.device, transport, group)
         self.n_rows = dict(self.plan.n_own)           # kernels that WRITE per-node results stop at the owned rows
         self._region_edges = region_edges(self.plan, edge_index_dict, owner)
+        self._events = self._event_edges = None       # bound to the previous plan's numbering: enable_event_selection() again
         xl = local_features(self.plan, x_dict)
         ei = {e: torch.from_numpy(v) for e, v in self.plan.edge_index.items()}
         self.set_graph({t: v.to(self.device) for t, v in xl.items()}, {e: v.to(self.device) for e, v in ei.items()})
@@ -286,6 +290,7 @@ class PartitionedEngine(RolloutEngine):
         if mask_grain is not None:
             mask_grain = mask_grain.cpu().reshape(mask_grain.shape[0], -1)[:, 0][torch.from_numpy(self.plan.own['grain'])]
         super().enable_event_selection(mask_grain, edge_threshold, area_threshold, cap)
+        self._event_edges = torch.from_numpy(self.plan.edge_global[('joint', 'connect', 'joint')]).to(self.device)
 
     def fetch_events(self):
         """Candidates among the joint-joint edges and grains this rank owns, as GLOBAL ids (each edge / grain is owned by

@@ -48,6 +48,8 @@ def test_plan_covers_every_node_and_edge_exactly_once(world):
             assert np.array_equal(l2g[e[2]][dst], ei[e][1].numpy()[p.edge_gid[e]])
             assert (dst < p.n_own[e[2]]).all()                                    # targets are owned
             assert np.all(np.diff(p.edge_gid[e]) > 0)                             # original relative order kept
+            if e[0] == e[2]:                                                      # global endpoints for the `src < dst` test
+                assert np.array_equal(p.edge_global[e], ei[e].numpy()[:, p.edge_gid[e]])
 
 
 @pytest.mark.parametrize('world', [2, 4])
