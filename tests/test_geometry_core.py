@@ -110,14 +110,7 @@ def test_entry_points_validate_arguments_without_gpu():
     assert L.gg_region_center(buf, 8, None, 1.0, rp, None, None, 0, None, None, 0, None) == 0
 
 
-@pytest.mark.skipif(not os.path.exists('/root/reference/graph_trajectory.py'), reason='reference tree not present')
-def test_oracle_equals_live_reference_on_fresh_random_incidence():
-    """Only in the build container: the reference's GNN_update, imported live, on an incidence no fixture holds."""
-    import sys
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import make_golden_geometry as mg
-    rng = np.random.default_rng(123)
-    n_g, n_j = 30, 150
+def _random_incidence(rng, n_g, n_j, spread):
     tri, seen = [], set()
     while len(tri) < n_j:
         t = tuple(sorted(rng.choice(n_g, 3, replace=False).tolist()))
@@ -126,9 +119,38 @@ def test_oracle_equals_live_reference_on_fresh_random_incidence():
             tri.append(t)
     gj = np.stack([np.array(tri).reshape(-1), np.repeat(np.arange(n_j), 3)])
     gj = gj[:, rng.permutation(gj.shape[1])]
+    xj = np.zeros((n_j, 8), np.float32)
+    corner = rng.random(2) if spread < 0.45 else np.array([0.8, 0.8])
+    xj[:, :2] = ((rng.random((n_j, 2)) * spread + corner) % 1.0).astype(np.float32)        # may straddle the seam
+    return gj, xj
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/graph_trajectory.py'), reason='reference tree not present')
+@pytest.mark.parametrize('seed', range(12))
+def test_oracle_and_kernel_arithmetic_equal_the_live_reference_on_random_incidences(host_lib, seed):
+    """Only in the build container: the reference's GNN_update, imported live, on incidences no fixture holds (6 to 24 joints
+    per grain on average, clusters anywhere in the periodic cell) — against the oracle and the host build of the kernel arithmetic."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import make_golden_geometry as mg
+    rng = np.random.default_rng(1000 + seed)
+    n_g = int(rng.integers(8, 40))
+    n_j = int(rng.integers(n_g * 2, n_g * 8))
+    gj, xj = _random_incidence(rng, n_g, n_j, spread=float(rng.choice([0.05, 0.2, 0.3])))
     jj = np.stack([np.arange(n_j), (np.arange(n_j) + 1) % n_j])
-    xj = torch.zeros(n_j, 8)
-    xj[:, :2] = torch.from_numpy(((rng.random((n_j, 2)) * 0.3 + 0.85) % 1.0).astype(np.float32))   # straddles the seam
-    ref = mg.reference_centers(xj.clone(), torch.rand(n_g, 11), gj, jj)
-    got = orc.region_center(xj, gj, n_g)
-    assert np.array_equal(got, ref, equal_nan=True)
+    xg0 = rng.random((n_g, 11)).astype(np.float32)
+    ref = mg.reference_centers(torch.from_numpy(xj.copy()), torch.from_numpy(xg0.copy()), gj, jj)
+    assert np.array_equal(orc.region_center(torch.from_numpy(xj), gj, n_g), ref, equal_nan=True)
+    rowptr, col, key, _ = region_index_numpy(gj, n_g, n_j)
+    off = np.zeros((n_j, 2), np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)                          # noqa: E731
+    for presorted in (False, True):
+        c_, k_ = col, key
+        if presorted:
+            grain_of = np.repeat(np.arange(n_g), np.diff(rowptr))
+            c_, k_ = col[np.lexsort((key, grain_of))].astype(np.int32), None
+        centers, xg = np.zeros((n_g, 2)), xg0.copy()
+        host_lib.region_center_host(P(xj), 8, P(off), ctypes.c_float(1.0), P(rowptr), P(c_), P(k_) if k_ is not None else None, n_g,
+                                    P(centers), P(xg), 11)
+        assert np.array_equal(centers, ref, equal_nan=True)
+        assert np.array_equal(xg, mg.writeback(torch.from_numpy(xg0.copy()), ref, 1).numpy())
