@@ -138,7 +138,8 @@ def region_edges(plan, edge_index_dict, owner):
     gj = gj.numpy() if isinstance(gj, torch.Tensor) else np.asarray(gj)
     n_joint = owner['joint'].shape[0]
     first = np.full(n_joint, np.iinfo(np.int32).max, dtype=np.int64)
-    np.minimum.at(first, gj[1], np.arange(gj.shape[1], dtype=np.int64))
+    uj, pos = np.unique(gj[1], return_index=True)                      # index of the first occurrence of every target
+    first[uj] = pos
     m = owner['grain'][gj[0]] == plan.rank
     g = plan._g2l['grain'][gj[0][m]]
     j = plan._g2l['joint'][gj[1][m]]
@@ -264,16 +265,20 @@ class PartitionedEngine(RolloutEngine):
         self.plan = build_plan(n_nodes, edge_index_dict, owner, rank, world)
         self.halo = HaloExchange(self.plan, self.device, transport, group)
         self.n_rows = dict(self.plan.n_own)           # kernels that WRITE per-node results stop at the owned rows
-        self._region_edges = region_edges(self.plan, edge_index_dict, owner)
+        self._region_src = (edge_index_dict, owner)   # region_edges() runs when the geometry feedback is first used
+        self._region_edges = None
         self._events = self._event_edges = None       # bound to the previous plan's numbering: enable_event_selection() again
         xl = local_features(self.plan, x_dict)
         ei = {e: torch.from_numpy(v) for e, v in self.plan.edge_index.items()}
         self.set_graph({t: v.to(self.device) for t, v in xl.items()}, {e: v.to(self.device) for e, v in ei.items()})
 
     _region_edges = None
+    _region_src = None
 
     def _region_index(self):
         from .geometry import RegionIndex
+        if self._region_edges is None:
+            self._region_edges = region_edges(self.plan, *self._region_src)
         edges, key = self._region_edges
         return RegionIndex(torch.from_numpy(edges).to(self.device), self.plan.n_own['grain'], self.plan.n_local['joint'],
                            edge_key=torch.from_numpy(key))
@@ -353,7 +358,7 @@ class LocalSlabGroup:
             e.plan = build_plan({t: int(v.shape[0]) for t, v in x_dict.items()}, edge_index_dict, owner, r, world)
             e.halo = None
             e.n_rows = dict(e.plan.n_own)
-            e._region_edges = region_edges(e.plan, edge_index_dict, owner)
+            e._region_src = (edge_index_dict, owner)
             xl = local_features(e.plan, x_dict)
             e.set_graph({t: v.to(e.device) for t, v in xl.items()},
                         {k: torch.from_numpy(v).to(e.device) for k, v in e.plan.edge_index.items()})
