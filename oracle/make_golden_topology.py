@@ -33,7 +33,7 @@ ET = mgold.ET
 GJ, JG, JJ = ET
 
 
-def craft(rng, x, ei, n_switch, n_vanish):
+def craft(rng, x, ei, n_switch, n_vanish, max_sides=5):
     nj, ng, E = x['joint'].shape[0], x['grain'].shape[0], ei[JJ].shape[1]
     y = {'joint': torch.from_numpy((rng.standard_normal((nj, 2)) * 0.02).astype(np.float32)),
          'grain': torch.from_numpy(np.stack([rng.standard_normal(ng) * 0.02, np.abs(rng.standard_normal(ng)) * 0.01], 1).astype(np.float32))}
@@ -44,7 +44,7 @@ def craft(rng, x, ei, n_switch, n_vanish):
     y['edge_event'] = logits
     area = x['grain'][:, 3] + torch.tanh(y['grain'][:, 0]) / 20                  # models.py:445
     deg = torch.bincount(ei[JG][1], minlength=ng)
-    small = torch.nonzero(deg <= 5).view(-1).numpy()
+    small = torch.nonzero(deg <= max_sides).view(-1).numpy()
     vanish = rng.choice(small, min(n_vanish, len(small)), replace=False)
     area[torch.from_numpy(vanish)] = torch.from_numpy((rng.random(len(vanish)) * 9e-5).astype(np.float32))
     y['grain_area'] = area
@@ -69,17 +69,21 @@ def run_reference(R, C, x, ei, ea, y):
 
 def main():
     gold, log = {}, {}
-    for name, factor, n_switch, n_vanish, want in (('c1', 1, 3, 1, 3), ('c2', 3, 12, 4, 3)):
+    plans = {'c1': (1, [(3, 1, 5, 3), (10, 3, 6, 2)]),                  # (switching edges, vanishing grains, max sides, cases)
+             'c2': (3, [(12, 4, 5, 3), (60, 10, 7, 3)])}
+    for name, (factor, configs) in plans.items():
         g, x, ei, ea = mgold.load_graph({'c1': '/root/reference/graphs/40_40/seed10020_G1.904_R0.558_span6.pkl',
                                          'c2': '/root/reference/graphs/120_120/seed0_G10.0_R2.0_span6.pkl'}[name], factor)
         R, C = mgold.build_models(g)
         R.threshold, C.threshold = 1e-4, 0.6                                     # test.py:186-187
         done, tried, seed = 0, 0, 0
-        while done < want and tried < 60:
+        for n_switch, n_vanish, max_sides, want in configs:
+          target = done + want
+          while done < target and tried < 200:
             rng = np.random.default_rng(5000 + seed)
             seed += 1
             tried += 1
-            y = craft(rng, x, ei, n_switch, n_vanish)
+            y = craft(rng, x, ei, n_switch, n_vanish, max_sides)
             try:
                 xo, eio, mask, yo, pairs, first_events, gs = run_reference(R, C, x, ei, ea, y)
             except (KeyError, AssertionError, ValueError, RuntimeError, IndexError) as exc:
@@ -100,6 +104,7 @@ def main():
             gold[f'{k}_active_joints'] = gs['active_joints'].numpy()
             for et, short in mgold.SHORT.items():
                 gold[f'{k}_ei_{short}_out'] = eio[et].numpy().astype(np.int32)
+            print(k, 'events in/out', len(first_events), len(yo['grain_event']), 'switches', len(pairs))
             done += 1
         gold[f'{name}_cases'] = np.array(done)
         print(name, 'cases', done, 'tried', tried, 'reference raised on', log.get(name, []))

@@ -12,12 +12,14 @@ import torch
 import grain_oracle as orc
 from util import ET, GOLDEN, load_graph
 
-CASES = [(n, i) for n in ('c1', 'c2') for i in range(3)]
+CASES = [('c1', i) for i in range(5)] + [('c2', i) for i in range(6)]      # gold['c1_cases'], gold['c2_cases']
 
 
 @pytest.fixture(scope='module')
 def gold():
-    return np.load(os.path.join(GOLDEN, 'topology_golden.npz'))
+    g = np.load(os.path.join(GOLDEN, 'topology_golden.npz'))
+    assert int(g['c1_cases']) == 5 and int(g['c2_cases']) == 6
+    return g
 
 
 def case(gold, name, i):
@@ -34,7 +36,7 @@ def test_event_candidates_equal_what_the_reference_update_consumed(gold, name, i
     assert np.array_equal(grain_event.numpy(), c['grain_event_in'])                  # test.py:414-416
     # every switching pair the reference reports (models.py:742) stems from a candidate edge that survived the eliminations
     assert 0 < len(c['switching_list']) <= len(L1)
-    assert len(L1) == {'c1': 3, 'c2': 12}[name]
+    assert len(L1) == {('c1', False): 3, ('c1', True): 10, ('c2', False): 12, ('c2', True): 60}[(name, i >= 3)]
     # eliminated grains: the predicted ones, plus any the update forced (models.py:757-759)
     assert np.array_equal(c['grain_event_out'][:len(c['grain_event_in'])], c['grain_event_in'])
 
@@ -63,7 +65,7 @@ def test_updated_topology_keeps_the_invariants_of_a_periodic_trivalent_tiling(go
     assert np.isfinite(c['x_joint_out']).all() and np.isfinite(c['x_grain_out']).all()
 
 
-@pytest.mark.parametrize('name,i', [('c1', 0), ('c2', 0), ('c2', 2)])
+@pytest.mark.parametrize('name,i', [('c1', 0), ('c1', 4), ('c2', 0), ('c2', 5)])
 def test_geometry_feedback_oracle_on_the_updated_topology(gold, name, i):
     """Row f2 after a topology change: centres of the surviving grains from the surviving joints; vanished grains have none."""
     c = case(gold, name, i)
@@ -78,3 +80,70 @@ def test_geometry_feedback_oracle_on_the_updated_topology(gold, name, i):
         ref = mg.reference_centers(torch.from_numpy(c['x_joint_out'].copy()), torch.from_numpy(c['x_grain_out'].copy()),
                                    c['ei_gj_out'].astype(np.int64), c['ei_jj_out'].astype(np.int64))
         assert np.array_equal(cen, ref, equal_nan=True)
+
+
+@pytest.mark.parametrize('name,i', CASES)
+def test_topology_oracle_equals_the_reference_update(gold, name, i):
+    """oracle/topology_oracle.py (restatement of models.py:614-1053) against the reference's own outputs: edge arrays position
+    for position, moved joints bit for bit, masks, forced eliminations, the switching list."""
+    import topology_oracle as topo
+    c = case(gold, name, i)
+    x, ei, _ = load_graph(name)
+    y = {'joint': torch.from_numpy(c['y_joint'].copy()), 'grain': torch.from_numpy(c['y_grain'].copy()),
+         'edge_event': torch.from_numpy(c['y_edge_event']), 'grain_area': torch.from_numpy(c['y_grain_area'])}
+    orc.regressor_update(x, y, span=0)                   # models.py:503-516 (test.py:400); the z step (test.py:405-407) follows the update
+    _, y['grain_event'] = orc.event_candidates(y, ei[ET[2]])
+    mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+    xo, eio, pairs = topo.topology_update(x, ei, y, mask, torch.from_numpy(c['active_grains']), torch.from_numpy(c['active_joints']))
+    for et, short in (((ET[2]), 'jj'), (ET[1], 'jg'), (ET[0], 'gj')):
+        assert np.array_equal(eio[et].numpy(), c[f'ei_{short}_out']), short
+    assert np.array_equal(pairs.numpy(), c['switching_list'])
+    assert np.array_equal(y['grain_event'].numpy(), c['grain_event_out'])
+    for t in ('joint', 'grain'):
+        assert np.array_equal(xo[t].numpy(), c[f'x_{t}_out']), t
+        assert np.array_equal(mask[t].numpy(), c[f'mask_{t}_out']), t
+        assert np.array_equal(y[t].numpy(), c[f'y_{t}_out']), t
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/models.py'), reason='reference tree not present')
+@pytest.mark.parametrize('name,n_switch,n_vanish,max_sides', [('c1', 25, 5, 7), ('c2', 150, 25, 8), ('c2', 300, 5, 5)])
+def test_topology_oracle_equals_the_live_reference_on_denser_event_sets(name, n_switch, n_vanish, max_sides):
+    """Only in the build container: the reference's update, imported live on the PyG stub, on event sets denser than the
+    fixtures hold (adjacent switching edges, grains of up to 8 sides); where the reference raises on an inconsistent event,
+    the oracle must raise the same exception type."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), '..', 'oracle'))
+    import make_golden_topology as mt
+    import topology_oracle as topo
+    g, x, ei, ea = mt.mgold.load_graph({'c1': '/root/reference/graphs/40_40/seed10020_G1.904_R0.558_span6.pkl',
+                                        'c2': '/root/reference/graphs/120_120/seed0_G10.0_R2.0_span6.pkl'}[name], {'c1': 1, 'c2': 3}[name])
+    R, C = mt.mgold.build_models(g)
+    R.threshold, C.threshold = 1e-4, 0.6
+    compared = raised = 0
+    for seed in range(4):
+        y = mt.craft(np.random.default_rng(9000 + seed), x, ei, n_switch, n_vanish, max_sides)
+        ref = ref_exc = None
+        try:
+            ref = mt.run_reference(R, C, x, ei, ea, y)
+        except (KeyError, AssertionError, ValueError, RuntimeError, IndexError) as exc:
+            ref_exc = type(exc)
+        xo = {k: v.clone() for k, v in x.items()}
+        yo = {k: v.clone() for k, v in y.items()}
+        orc.regressor_update(xo, yo, span=0)
+        _, yo['grain_event'] = orc.event_candidates(yo, ei[ET[2]])
+        mask = {'grain': torch.ones(xo['grain'].shape[0], 1), 'joint': torch.ones(xo['joint'].shape[0], 1)}
+        active = ((yo['grain'][:, 0] > -10).nonzero().view(-1), (yo['joint'][:, 0] > -10).nonzero().view(-1))   # models.py:505-506
+        if ref_exc is not None:
+            with pytest.raises(ref_exc):
+                topo.topology_update(xo, ei, yo, mask, *active)
+            raised += 1
+            continue
+        _, eio, pairs = topo.topology_update(xo, ei, yo, mask, *active)
+        rx, rei, rmask, ry, rpairs, _, _ = ref
+        for et in ET:
+            assert torch.equal(eio[et], rei[et]), et
+        assert torch.equal(pairs, rpairs) and torch.equal(yo['grain_event'], ry['grain_event'])
+        for t in ('joint', 'grain'):
+            assert torch.equal(xo[t], rx[t]) and torch.equal(mask[t], rmask[t]) and torch.equal(yo[t], ry[t]), t
+        compared += 1
+    assert compared + raised == 4 and compared >= 1
