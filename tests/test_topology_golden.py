@@ -147,3 +147,87 @@ def test_topology_oracle_equals_the_live_reference_on_denser_event_sets(name, n_
             assert torch.equal(xo[t], rx[t]) and torch.equal(mask[t], rmask[t]) and torch.equal(yo[t], ry[t]), t
         compared += 1
     assert compared + raised == 4 and compared >= 1
+
+
+def _run(fn, name, c):
+    x, ei, _ = load_graph(name)
+    y = {'joint': torch.from_numpy(c['y_joint'].copy()), 'grain': torch.from_numpy(c['y_grain'].copy()),
+         'edge_event': torch.from_numpy(c['y_edge_event']), 'grain_area': torch.from_numpy(c['y_grain_area'])}
+    orc.regressor_update(x, y, span=0)
+    _, y['grain_event'] = orc.event_candidates(y, ei[ET[2]])
+    mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+    xo, eio, pairs = fn(x, ei, y, mask, torch.from_numpy(c['active_grains']), torch.from_numpy(c['active_joints']))
+    return xo, eio, pairs, y, mask
+
+
+@pytest.mark.parametrize('name,i', CASES)
+def test_indexed_host_update_equals_the_reference_update(gold, name, i):
+    """graingraphnn_b200.topology (position lists instead of O(E) scans) against the reference's own outputs."""
+    from graingraphnn_b200 import topology
+    c = case(gold, name, i)
+    xo, eio, pairs, y, mask = _run(topology.topology_update, name, c)
+    for et, short in ((ET[2], 'jj'), (ET[1], 'jg'), (ET[0], 'gj')):
+        assert np.array_equal(eio[et].numpy(), c[f'ei_{short}_out']), short
+    assert np.array_equal(pairs.numpy(), c['switching_list'])
+    assert np.array_equal(y['grain_event'].numpy(), c['grain_event_out'])
+    for t in ('joint', 'grain'):
+        assert np.array_equal(xo[t].numpy(), c[f'x_{t}_out']), t
+        assert np.array_equal(mask[t].numpy(), c[f'mask_{t}_out']), t
+        assert np.array_equal(y[t].numpy(), c[f'y_{t}_out']), t
+
+
+def _craft(rng, x, ei, n_switch, n_vanish, max_sides):
+    """Crafted predictions like oracle/make_golden_topology.craft (kept here so the test needs no reference tree)."""
+    nj, ng, E = x['joint'].shape[0], x['grain'].shape[0], ei[ET[2]].shape[1]
+    y = {'joint': torch.from_numpy((rng.standard_normal((nj, 2)) * 0.02).astype(np.float32)),
+         'grain': torch.from_numpy(np.stack([rng.standard_normal(ng) * 0.02, np.abs(rng.standard_normal(ng)) * 0.01], 1).astype(np.float32))}
+    logits = torch.full((E,), -4.0) + torch.from_numpy(rng.standard_normal(E).astype(np.float32)) * 0.3
+    fwd = torch.nonzero(ei[ET[2]][0] < ei[ET[2]][1]).view(-1).numpy()
+    pick = rng.choice(fwd, n_switch, replace=False)
+    logits[torch.from_numpy(pick)] = torch.from_numpy((2.0 + rng.random(n_switch) * 2).astype(np.float32))
+    y['edge_event'] = logits
+    area = x['grain'][:, 3] + torch.tanh(y['grain'][:, 0]) / 20
+    deg = torch.bincount(ei[ET[1]][1], minlength=ng)
+    small = torch.nonzero(deg <= max_sides).view(-1).numpy()
+    vanish = rng.choice(small, min(n_vanish, len(small)), replace=False)
+    area[torch.from_numpy(vanish)] = torch.from_numpy((rng.random(len(vanish)) * 9e-5).astype(np.float32))
+    y['grain_area'] = area
+    return y
+
+
+@pytest.mark.parametrize('name,n_switch,n_vanish,max_sides', [('c1', 25, 5, 7), ('c1', 60, 12, 8), ('c2', 150, 25, 8), ('c2', 400, 60, 8)])
+def test_indexed_host_update_equals_the_oracle_on_denser_event_sets(name, n_switch, n_vanish, max_sides):
+    """Adjacent switching edges, grains of up to 8 sides, forced eliminations: the position-list update and the O(E)-scan
+    oracle (itself pinned by the reference's outputs) agree array for array, and raise the same exception type on event sets
+    the reference's algorithm cannot digest."""
+    import topology_oracle as topo
+    from graingraphnn_b200 import topology
+    x0, ei, _ = load_graph(name)
+    agreed = raised = 0
+    for seed in range(5):
+        y0 = _craft(np.random.default_rng(7000 + seed), x0, ei, n_switch, n_vanish, max_sides)
+        res = []
+        for fn in (topo.topology_update, topology.topology_update):
+            x = {k: v.clone() for k, v in x0.items()}
+            y = {k: v.clone() for k, v in y0.items()}
+            orc.regressor_update(x, y, span=0)
+            _, y['grain_event'] = orc.event_candidates(y, ei[ET[2]])
+            mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+            active = ((y['grain'][:, 0] > -10).nonzero().view(-1), (y['joint'][:, 0] > -10).nonzero().view(-1))
+            try:
+                _, eio, pairs = fn(x, ei, y, mask, *active)
+                res.append((x, eio, pairs, y, mask))
+            except (KeyError, AssertionError, ValueError, RuntimeError, IndexError) as exc:
+                res.append(type(exc))
+        a, b = res
+        if isinstance(a, type) or isinstance(b, type):
+            assert a is b, (a, b)
+            raised += 1
+            continue
+        for et in ET:
+            assert torch.equal(a[1][et], b[1][et]), et
+        assert torch.equal(a[2], b[2]) and torch.equal(a[3]['grain_event'], b[3]['grain_event'])
+        for t in ('joint', 'grain'):
+            assert torch.equal(a[0][t], b[0][t]) and torch.equal(a[4][t], b[4][t]) and torch.equal(a[3][t], b[3][t]), t
+        agreed += 1
+    assert agreed >= 1 and agreed + raised == 5
