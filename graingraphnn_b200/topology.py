@@ -148,6 +148,7 @@ class _Surgery:
         pp, pq, x, y = self.pp, self.pq, self.x['joint'], self.y['joint']
         forced = []
         edges = [int(e) for e in edges]
+        edges_arr = np.asarray(edges, dtype=np.int64)
         touched = sorted({pp.get(r, e) for e in edges for r in (0, 1)})
         before = {}
         for p in touched:
@@ -185,7 +186,7 @@ class _Surgery:
             mid = 0.5 * (x1 + _wrap_to(x2, x1))
             x[p1, :2], x[p2, :2] = mid, _wrap_to(mid, x2)
             swap = _inside(x[p2, :2], x[p1, :2], x[a1, :2], x[a2, :2])
-            ahead = {pp.get(r, f) for f in edges[k:] for r in (0, 1)}
+            ahead = set(pp.a[:, edges_arr[k:]].ravel().tolist())      # endpoints of the events still to come, as they are NOW
             if a2 in ahead and b2 not in ahead:
                 swap = False
             if b2 in ahead and a2 not in ahead:
