@@ -75,6 +75,29 @@ def test_no_cpu_fallback():
         conv(x['joint'], ei[ET[2]], ea[ET[2]])
 
 
+def test_no_cpu_fallback_in_the_widened_rows():
+    """Geometry feedback and event selection refuse CPU tensors; the host topology update is host code by design and never
+    imports the oracle."""
+    import inspect
+    from graingraphnn_b200 import events, geometry, topology
+    x, ei, _ = load_graph('c1')
+    with pytest.raises(RuntimeError, match='no CPU'):
+        geometry.RegionIndex(ei[ET[0]], 118, 236)
+
+    class _Idx:                      # region_center checks its tensors before it touches the index
+        n_grain, n_joint = 118, 236
+    with pytest.raises(RuntimeError, match='no CPU'):
+        geometry.region_center(x['joint'], _Idx())
+    sel = object.__new__(events.EventSelector)
+    sel._buf = {'edge': (None, None, None, 0, None)}
+    sel.device = torch.device('cpu')
+    with pytest.raises(RuntimeError, match='no CPU'):
+        sel._select('edge', torch.zeros(4), 0.0, 0)
+    for mod in (events, geometry, topology):
+        src = inspect.getsource(mod)
+        assert 'grain_oracle' not in src and 'topology_oracle' not in src and 'import oracle' not in src
+
+
 def _csr(ei, x):
     csr = {}
     for e in ET:
