@@ -20,13 +20,18 @@ JJ, JG, GJ = ('joint', 'connect', 'joint'), ('joint', 'pull', 'grain'), ('grain'
 JOINT_SCALE = 5          # models.py:546
 
 
+_F0, _F1, _HALF = np.float32(0.0), np.float32(1.0), np.float32(0.5)
+
+
 def _wrap_to(p, pc):
-    rel = p - pc                                           # periodic_move, models.py:1097-1100
-    return p - 1 * (rel > 0.5) + 1 * (rel < -0.5)
+    """periodic_move (models.py:1097-1100) on float32 numpy rows: p - 1*(rel > .5) + 1*(rel < -.5), every step in float32
+    (torch promotes float32 - int64 to float32; numpy would go to float64, hence the explicit casts)."""
+    rel = p - pc
+    return (p - (rel > _HALF).astype(np.float32)) + (rel < -_HALF).astype(np.float32)
 
 
 def _inside(t, v1, v2, v3):
-    def sign(a, b, c):                                     # point_in_triangle, models.py:1055-1072
+    def sign(a, b, c):                                     # point_in_triangle, models.py:1055-1072 (float32 scalars)
         return (a[0] - c[0]) * (b[1] - c[1]) - (b[0] - c[0]) * (a[1] - c[1])
     a, b, c = _wrap_to(v1, t), _wrap_to(v2, t), _wrap_to(v3, t)
     d = (sign(t, a, b), sign(t, b, c), sign(t, c, a))
@@ -42,16 +47,20 @@ class _Rows:
     def __init__(self, edges, n0, n1):
         self.a = edges.numpy().astype(np.int64).copy()
         self.n = (n0, n1)
-        # positions grouped by value, vectorised (one stable argsort per row); a value's Python list is made on first use and
-        # kept current from then on, so a step touches O(events) lists, not O(N)
-        self.order, self.starts, self.lists = [], [], ({}, {})
-        for r in (0, 1):
-            order = np.argsort(self.a[r], kind='stable')
-            self.order.append(order)
-            self.starts.append(np.searchsorted(self.a[r][order], np.arange(self.n[r] + 1)))
+        # positions grouped by value: one stable argsort per row, made when the row is first queried (from the array as it is
+        # THEN — edits before that need no bookkeeping); a value's Python list is made on first use and kept current from
+        # then on, so a step touches O(events) lists, not O(N)
+        self.order, self.starts, self.lists = [None, None], [None, None], ({}, {})
+
+    def _index(self, r):
+        order = np.argsort(self.a[r], kind='stable')
+        self.order[r] = order
+        self.starts[r] = np.searchsorted(self.a[r][order], np.arange(self.n[r] + 1))
 
     def at(self, r, v):
         v = int(v)
+        if self.order[r] is None:
+            self._index(r)
         hit = self.lists[r].get(v)
         if hit is None:
             hit = self.lists[r][v] = self.order[r][self.starts[r][v]:self.starts[r][v + 1]].tolist() if v < self.n[r] else []
@@ -69,10 +78,11 @@ class _Rows:
         old, v = int(self.a[r, pos]), int(v)
         if old == v:
             return
-        if old >= 0:
-            self.at(r, old).remove(pos)
-        if v >= 0:
-            bisect.insort(self.at(r, v), pos)
+        if self.order[r] is not None:                       # row not indexed yet: the index will read the edited array
+            if old >= 0:
+                self.at(r, old).remove(pos)
+            if v >= 0:
+                bisect.insort(self.at(r, v), pos)
         self.a[r, pos] = v
 
     def kill(self, pos):
@@ -145,14 +155,17 @@ class _Surgery:
         return cand
 
     def switch(self, edges, elim_grain):                    # models.py:899-1053
-        pp, pq, x, y = self.pp, self.pq, self.x['joint'], self.y['joint']
+        # joint rows as float32 numpy views of the torch tensors (same memory): IEEE single arithmetic like torch's, without
+        # the per-op overhead of 0-d tensors
+        pp, pq, x, y = self.pp, self.pq, self.x['joint'].numpy(), self.y['joint'].numpy()
+        assert x.dtype == np.float32 and y.dtype == np.float32
         forced = []
         edges = [int(e) for e in edges]
         edges_arr = np.asarray(edges, dtype=np.int64)
         touched = sorted({pp.get(r, e) for e in edges for r in (0, 1)})
         before = {}
         for p in touched:
-            x[p, :2] -= y[p] / JOINT_SCALE
+            x[p, :2] -= y[p] / np.float32(JOINT_SCALE)
             before[p] = x[p, :2]                            # a view: it follows later moves (as in the reference)
         for k, e in enumerate(edges):
             p1, p2 = pp.get(0, e), pp.get(1, e)
@@ -183,7 +196,7 @@ class _Surgery:
             if b1 == b2 and shrink_b != elim_grain:
                 forced.append(shrink_b)
             x1, x2 = x[p1, :2], x[p2, :2]                   # both ends collapse onto the midpoint (models.py:989-996)
-            mid = 0.5 * (x1 + _wrap_to(x2, x1))
+            mid = _HALF * (x1 + _wrap_to(x2, x1))
             x[p1, :2], x[p2, :2] = mid, _wrap_to(mid, x2)
             swap = _inside(x[p2, :2], x[p1, :2], x[a1, :2], x[a2, :2])
             ahead = set(pp.a[:, edges_arr[k:]].ravel().tolist())      # endpoints of the events still to come, as they are NOW
@@ -209,7 +222,7 @@ class _Surgery:
             for i in self.pp_between(b1, p1):
                 pp.set(1, i, p2)
         for p in touched:
-            y[p] = JOINT_SCALE * (x[p, :2] - before[p])
+            y[p] = np.float32(JOINT_SCALE) * (x[p, :2] - before[p])
             x[p, 6:8] = y[p]
         return forced
 
