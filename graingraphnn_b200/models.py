@@ -136,3 +136,30 @@ class GrainNN_classifier(nn.Module):
         ev, ed = edge_head(h_dict['joint'], edge_index_dict[jj], edge_attr[jj],
                            self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias)           # :595-609
         return {'edge_event': ev, 'edge': ed}
+
+    @torch.no_grad()
+    def update(self, x_dict, edge_index_dict, edge_attr, y_dict, mask, geometry_scaling, nucleation_prob=0.0):
+        """Topology update of a rollout step with the reference's signature and results (models.py:614-845; called at
+        test.py:426): grain elimination, neighbour switching, cleanup.  Host code, like the reference's — tensors on a CUDA
+        device are brought to the host and the results put back — but every lookup is answered from position lists instead
+        of an O(E) scan (topology.py).  `self.threshold` is set by the caller (test.py:187).  Returns
+        (x_dict, edge_index_dict, switching_list); `edge_index_dict`, `x_dict['joint']`, `y_dict` and `mask` are updated in
+        place as the reference does.  The optional nucleation branch (:771-835) is not implemented."""
+        from .topology import topology_update
+        if nucleation_prob > 1e-6:
+            raise NotImplementedError('nucleation (models.py:771-835) is outside the rollout hot path')
+        dev = x_dict['joint'].device
+        host = lambda d: {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}   # noqa: E731
+        xh, yh, mh, eh = host(x_dict), host(y_dict), host(mask), host(edge_index_dict)
+        _, new_ei, pairs = topology_update(xh, eh, yh, mh, geometry_scaling['active_grains'].cpu(),
+                                           geometry_scaling['active_joints'].cpu(), threshold=self.threshold)
+        for t in ('joint', 'grain'):
+            if x_dict[t].device.type != 'cpu':                 # on the host the tensors were edited in place already
+                x_dict[t].copy_(xh[t])
+                mask[t].copy_(mh[t])
+                y_dict[t].copy_(yh[t])
+        y_dict['grain_event'] = yh['grain_event'].to(y_dict['grain_event'].device)
+        for e, v in new_ei.items():
+            edge_index_dict[e] = v.to(dev)
+        return x_dict, edge_index_dict, pairs.to(dev)
+

@@ -231,3 +231,33 @@ def test_indexed_host_update_equals_the_oracle_on_denser_event_sets(name, n_swit
             assert torch.equal(a[0][t], b[0][t]) and torch.equal(a[4][t], b[4][t]) and torch.equal(a[3][t], b[3][t]), t
         agreed += 1
     assert agreed >= 1 and agreed + raised == 5
+
+
+@pytest.mark.parametrize('name,i', [('c1', 3), ('c2', 0), ('c2', 4)])
+def test_classifier_update_has_the_reference_signature_and_results(gold, name, i):
+    """models.GrainNN_classifier.update(x_dict, edge_index_dict, edge_attr, y_dict, mask, geometry_scaling, nucleation_prob)
+    — the call of test.py:426 — on host tensors: the reference's outputs, in-place updates included."""
+    from graingraphnn_b200.engine import _Hyper
+    from graingraphnn_b200.models import GrainNN_classifier
+    c = case(gold, name, i)
+    x, ei, ea = load_graph(name)
+    C = GrainNN_classifier(_Hyper({'grain': list(range(11)), 'joint': list(range(8))}, {'grain': [0, 1], 'joint': [0, 1]}, 96,
+                                  (['grain', 'joint', 'mask'], list(ET)), 'cpu'))
+    C.threshold = 0.6                                                          # test.py:187
+    y = {'joint': torch.from_numpy(c['y_joint'].copy()), 'grain': torch.from_numpy(c['y_grain'].copy()),
+         'edge_event': torch.from_numpy(c['y_edge_event']), 'grain_area': torch.from_numpy(c['y_grain_area'])}
+    orc.regressor_update(x, y, span=0)
+    _, y['grain_event'] = orc.event_candidates(y, ei[ET[2]])
+    mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+    gs = {'domain_offset': 0, 'domain_factor': 1, 'active_grains': torch.from_numpy(c['active_grains']),
+          'active_joints': torch.from_numpy(c['active_joints'])}
+    xo, eio, pairs = C.update(x, ei, ea, y, mask, gs, 0.0)
+    assert xo is x and eio is ei
+    for et, short in ((ET[2], 'jj'), (ET[1], 'jg'), (ET[0], 'gj')):
+        assert np.array_equal(ei[et].numpy(), c[f'ei_{short}_out']), short
+    assert np.array_equal(pairs.numpy(), c['switching_list']) and np.array_equal(y['grain_event'].numpy(), c['grain_event_out'])
+    for t in ('joint', 'grain'):
+        assert np.array_equal(x[t].numpy(), c[f'x_{t}_out']) and np.array_equal(mask[t].numpy(), c[f'mask_{t}_out'])
+        assert np.array_equal(y[t].numpy(), c[f'y_{t}_out'])
+    with pytest.raises(NotImplementedError):
+        C.update(x, ei, ea, y, mask, gs, 0.01)
