@@ -67,6 +67,45 @@ def run_reference(R, C, x, ei, ea, y):
     return x, ei, mask, y, pairs, first_events, gs
 
 
+def forced_case(gold):
+    """The one committed vector on which the reference's FORCED eliminations fire (models.py:967-973, :757-759): round 3 of a
+    chain of updates on the C2 graph (tests/test_topology_golden.py::test_six_consecutive_updates_equal_the_live_reference,
+    chain 0) — state before the round (features, edges, masks), the crafted predictions, the reference's state after it."""
+    sys.path.insert(0, os.path.join(HERE, '..', 'tests'))
+    from test_topology_golden import _craft_on
+    g, x, ei, ea = mgold.load_graph('/root/reference/graphs/120_120/seed0_G10.0_R2.0_span6.pkl', 3)
+    R, C = mgold.build_models(g)
+    R.threshold, C.threshold = 1e-4, 0.6
+    rng = np.random.default_rng(500)
+    mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+    for rnd in range(4):
+        y = _craft_on(rng, x, ei, mask, 80, 25, 6)
+        rx, rei, ry, rm = ({k: v.clone() for k, v in d.items()} for d in (x, ei, y, mask))
+        gs = {'domain_offset': 0, 'domain_factor': 1}
+        with contextlib.redirect_stdout(io.StringIO()):
+            R.update(rx, ry, gs)
+            ry['grain_event'] = ((rm['grain'][:, 0] > 0) & (ry['grain_area'] < R.threshold)).nonzero().view(-1)
+            ry['grain_event'] = ry['grain_event'][torch.argsort(ry['grain_area'][ry['grain_event']])]
+            first = ry['grain_event'].clone()
+            rx, rei, pairs = C.update(rx, rei, ea, ry, rm, gs, 0.0)
+        if rnd == 3:
+            k = 'c2_forced'
+            for t in ('joint', 'grain'):
+                gold[f'{k}_x_{t}_in'], gold[f'{k}_mask_{t}_in'] = x[t].numpy(), mask[t].numpy()
+                gold[f'{k}_y_{t}'], gold[f'{k}_x_{t}_out'] = y[t].numpy(), rx[t].numpy()
+                gold[f'{k}_mask_{t}_out'], gold[f'{k}_y_{t}_out'] = rm[t].numpy(), ry[t].numpy()
+            gold[f'{k}_y_edge_event'], gold[f'{k}_y_grain_area'] = y['edge_event'].numpy(), y['grain_area'].numpy()
+            gold[f'{k}_grain_event_in'], gold[f'{k}_grain_event_out'] = first.numpy(), ry['grain_event'].numpy()
+            gold[f'{k}_switching_list'] = pairs.numpy()
+            gold[f'{k}_active_grains'], gold[f'{k}_active_joints'] = gs['active_grains'].numpy(), gs['active_joints'].numpy()
+            for et, short in mgold.SHORT.items():
+                gold[f'{k}_ei_{short}_in'] = ei[et].numpy().astype(np.int32)
+                gold[f'{k}_ei_{short}_out'] = rei[et].numpy().astype(np.int32)
+            print('forced case: events in/out', len(first), len(ry['grain_event']), 'switches', len(pairs))
+            assert len(ry['grain_event']) > len(first)
+        x, ei, mask = rx, rei, rm
+
+
 def main():
     gold, log = {}, {}
     plans = {'c1': (1, [(3, 1, 5, 3), (10, 3, 6, 2)]),                  # (switching edges, vanishing grains, max sides, cases)
@@ -108,6 +147,7 @@ def main():
             done += 1
         gold[f'{name}_cases'] = np.array(done)
         print(name, 'cases', done, 'tried', tried, 'reference raised on', log.get(name, []))
+    forced_case(gold)
     np.savez_compressed(os.path.join(OUT, 'topology_golden.npz'), **gold)
     print({k: v.shape for k, v in gold.items() if k.endswith('_0_ei_jj_out') or k.endswith('switching_list') or 'grain_event' in k})
 

@@ -261,3 +261,94 @@ def test_classifier_update_has_the_reference_signature_and_results(gold, name, i
         assert np.array_equal(y[t].numpy(), c[f'y_{t}_out'])
     with pytest.raises(NotImplementedError):
         C.update(x, ei, ea, y, mask, gs, 0.01)
+
+
+def _craft_on(rng, x, ei, mask, n_switch, n_vanish, max_sides):
+    """Crafted events on an EVOLVING topology: only live grains vanish, every other area stays well above the threshold."""
+    nj, ng, E = x['joint'].shape[0], x['grain'].shape[0], ei[ET[2]].shape[1]
+    y = {'joint': torch.from_numpy((rng.standard_normal((nj, 2)) * 0.01).astype(np.float32)),
+         'grain': torch.from_numpy(np.stack([rng.standard_normal(ng) * 0.02, np.abs(rng.standard_normal(ng)) * 0.01], 1).astype(np.float32))}
+    logits = torch.full((E,), -4.0)
+    fwd = torch.nonzero(ei[ET[2]][0] < ei[ET[2]][1]).view(-1).numpy()
+    pick = rng.choice(fwd, min(n_switch, len(fwd)), replace=False)
+    logits[torch.from_numpy(pick)] = torch.from_numpy((2.0 + rng.random(len(pick)) * 2).astype(np.float32))
+    y['edge_event'] = logits
+    area = (x['grain'][:, 3] + torch.tanh(y['grain'][:, 0]) / 20).clamp(min=1e-3)
+    deg = torch.bincount(ei[ET[1]][1], minlength=ng)
+    small = torch.nonzero((deg <= max_sides) & (deg > 0) & (mask['grain'][:, 0] > 0)).view(-1).numpy()
+    van = rng.choice(small, min(n_vanish, len(small)), replace=False)
+    area[torch.from_numpy(van)] = torch.from_numpy((rng.random(len(van)) * 9e-5).astype(np.float32))
+    y['grain_area'] = area
+    return y
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/models.py'), reason='reference tree not present')
+@pytest.mark.parametrize('name,chain,n_switch,n_vanish,forced_expected', [('c1', 0, 8, 3, 0), ('c2', 0, 80, 25, 2), ('c2', 3, 80, 25, 1)])
+def test_six_consecutive_updates_equal_the_live_reference(name, chain, n_switch, n_vanish, forced_expected):
+    """Only in the build container: six updates in a row on an evolving topology (triangles appear, masks carry over) —
+    the only vectors on which the reference's forced eliminations (models.py:967-973, :757-759) fire.  Each round the
+    product (`topology.py`) and the oracle start from the reference's state and must reproduce its next state exactly."""
+    import contextlib
+    import io
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), '..', 'oracle'))
+    import make_golden_topology as mt
+    import topology_oracle as topo
+    from graingraphnn_b200 import topology
+    g, x, ei, ea = mt.mgold.load_graph({'c1': '/root/reference/graphs/40_40/seed10020_G1.904_R0.558_span6.pkl',
+                                        'c2': '/root/reference/graphs/120_120/seed0_G10.0_R2.0_span6.pkl'}[name], {'c1': 1, 'c2': 3}[name])
+    R, C = mt.mgold.build_models(g)
+    R.threshold, C.threshold = 1e-4, 0.6
+    rng = np.random.default_rng(500 + chain)
+    mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+    forced = 0
+    for rnd in range(6):
+        y = _craft_on(rng, x, ei, mask, n_switch, n_vanish, 6)
+        rx, rei, ry, rm = ({k: v.clone() for k, v in d.items()} for d in (x, ei, y, mask))
+        gs = {'domain_offset': 0, 'domain_factor': 1}
+        with contextlib.redirect_stdout(io.StringIO()):
+            R.update(rx, ry, gs)                                                                   # test.py:400
+            ry['grain_event'] = ((rm['grain'][:, 0] > 0) & (ry['grain_area'] < R.threshold)).nonzero().view(-1)
+            ry['grain_event'] = ry['grain_event'][torch.argsort(ry['grain_area'][ry['grain_event']])]
+            n_in = len(ry['grain_event'])
+            rx, rei, rpairs = C.update(rx, rei, ea, ry, rm, gs, 0.0)                               # test.py:426
+        for fn in (topology.topology_update, topo.topology_update):
+            ox, oy, om = ({k: v.clone() for k, v in d.items()} for d in (x, y, mask))
+            orc.regressor_update(ox, oy, span=0)
+            _, oy['grain_event'] = orc.event_candidates(oy, ei[ET[2]], om['grain'])
+            _, oei, op = fn(ox, ei, oy, om, gs['active_grains'], gs['active_joints'])
+            for et in ET:
+                assert torch.equal(oei[et], rei[et]), (rnd, et)
+            assert torch.equal(op, rpairs) and torch.equal(oy['grain_event'], ry['grain_event']), rnd
+            for t in ('joint', 'grain'):
+                assert torch.equal(ox[t], rx[t]) and torch.equal(om[t], rm[t]) and torch.equal(oy[t], ry[t]), (rnd, t)
+        forced += len(ry['grain_event']) - n_in
+        x, ei, mask = rx, rei, rm
+    assert forced == forced_expected
+
+
+@pytest.mark.parametrize('impl', ['product', 'oracle'])
+def test_forced_eliminations_equal_the_reference(gold, impl):
+    """The committed vector on which the reference's forced eliminations fire (two grains beyond the predicted ones): state
+    after three earlier updates on C2, masks carried over."""
+    import topology_oracle as topo
+    from graingraphnn_b200 import topology
+    k = 'c2_forced_'
+    c = {f[len(k):]: gold[f] for f in gold.files if f.startswith(k)}
+    x = {t: torch.from_numpy(c[f'x_{t}_in'].copy()) for t in ('joint', 'grain')}
+    mask = {t: torch.from_numpy(c[f'mask_{t}_in'].copy()) for t in ('joint', 'grain')}
+    ei = {et: torch.from_numpy(c[f'ei_{short}_in'].astype(np.int64)) for et, short in ((ET[0], 'gj'), (ET[1], 'jg'), (ET[2], 'jj'))}
+    y = {'joint': torch.from_numpy(c['y_joint'].copy()), 'grain': torch.from_numpy(c['y_grain'].copy()),
+         'edge_event': torch.from_numpy(c['y_edge_event']), 'grain_area': torch.from_numpy(c['y_grain_area'])}
+    orc.regressor_update(x, y, span=0)
+    _, y['grain_event'] = orc.event_candidates(y, ei[ET[2]], mask['grain'])
+    assert np.array_equal(y['grain_event'].numpy(), c['grain_event_in'])
+    fn = topology.topology_update if impl == 'product' else topo.topology_update
+    _, eio, pairs = fn(x, ei, y, mask, torch.from_numpy(c['active_grains']), torch.from_numpy(c['active_joints']))
+    assert len(c['grain_event_out']) == len(c['grain_event_in']) + 2
+    assert np.array_equal(y['grain_event'].numpy(), c['grain_event_out']) and np.array_equal(pairs.numpy(), c['switching_list'])
+    for et, short in ((ET[2], 'jj'), (ET[1], 'jg'), (ET[0], 'gj')):
+        assert np.array_equal(eio[et].numpy(), c[f'ei_{short}_out']), short
+    for t in ('joint', 'grain'):
+        assert np.array_equal(x[t].numpy(), c[f'x_{t}_out']) and np.array_equal(mask[t].numpy(), c[f'mask_{t}_out'])
+        assert np.array_equal(y[t].numpy(), c[f'y_{t}_out'])
