@@ -352,3 +352,24 @@ def test_forced_eliminations_equal_the_reference(gold, impl):
     for t in ('joint', 'grain'):
         assert np.array_equal(x[t].numpy(), c[f'x_{t}_out']) and np.array_equal(mask[t].numpy(), c[f'mask_{t}_out'])
         assert np.array_equal(y[t].numpy(), c[f'y_{t}_out'])
+
+
+def test_update_from_device_selected_candidates_equals_internal_selection(gold):
+    """`L1` handed in (what EventSelector.fetch() returns: ascending edge ids) instead of being selected from the full
+    edge_event array inside the update: same result."""
+    from graingraphnn_b200 import topology
+    c = case(gold, 'c2', 4)
+    outs = []
+    for hand_in in (False, True):
+        x, ei, _ = load_graph('c2')
+        y = {'joint': torch.from_numpy(c['y_joint'].copy()), 'grain': torch.from_numpy(c['y_grain'].copy()),
+             'edge_event': torch.from_numpy(c['y_edge_event']), 'grain_area': torch.from_numpy(c['y_grain_area'])}
+        orc.regressor_update(x, y, span=0)
+        L1, y['grain_event'] = orc.event_candidates(y, ei[ET[2]])
+        mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+        _, eio, pairs = topology.topology_update(x, ei, y, mask, torch.from_numpy(c['active_grains']),
+                                                 torch.from_numpy(c['active_joints']), L1=L1 if hand_in else None)
+        outs.append((eio, pairs, x))
+    assert all(torch.equal(outs[0][0][et], outs[1][0][et]) for et in ET) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2]['joint'], outs[1][2]['joint'])
+    assert np.array_equal(outs[1][0][ET[2]].numpy(), c['ei_jj_out'])
