@@ -144,19 +144,22 @@ class GrainNN_classifier(nn.Module):
         device are brought to the host and the results put back — but every lookup is answered from position lists instead
         of an O(E) scan (topology.py).  `self.threshold` is set by the caller (test.py:187).  Returns
         (x_dict, edge_index_dict, switching_list); `edge_index_dict`, `x_dict['joint']`, `y_dict` and `mask` are updated in
-        place as the reference does.  The optional nucleation branch (:771-835) is not implemented."""
+        place as the reference does; with nucleation (:771-835) `x_dict` / `mask` entries are re-bound to grown tensors."""
         from .topology import topology_update
-        if nucleation_prob > 1e-6:
-            raise NotImplementedError('nucleation (models.py:771-835) is outside the rollout hot path')
         dev = x_dict['joint'].device
         host = lambda d: {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}   # noqa: E731
         xh, yh, mh, eh = host(x_dict), host(y_dict), host(mask), host(edge_index_dict)
         _, new_ei, pairs = topology_update(xh, eh, yh, mh, geometry_scaling['active_grains'].cpu(),
-                                           geometry_scaling['active_joints'].cpu(), threshold=self.threshold)
+                                           geometry_scaling['active_joints'].cpu(), threshold=self.threshold,
+                                           nucleation_prob=float(nucleation_prob))
         for t in ('joint', 'grain'):
-            if x_dict[t].device.type != 'cpu':                 # on the host the tensors were edited in place already
+            if xh[t].shape != x_dict[t].shape:                 # nucleation grew the node set: re-bind, as the reference does
+                x_dict[t] = xh[t].to(x_dict[t].device)
+                mask[t] = mh[t].to(mask[t].device)
+            elif x_dict[t].device.type != 'cpu':               # on the host the tensors were edited in place already
                 x_dict[t].copy_(xh[t])
                 mask[t].copy_(mh[t])
+            if y_dict[t].device.type != 'cpu':
                 y_dict[t].copy_(yh[t])
         y_dict['grain_event'] = yh['grain_event'].to(y_dict['grain_event'].device)
         for e, v in new_ei.items():

@@ -1,7 +1,7 @@
 """Host-side topology update of a rollout step with O(1) lookups.
 
 Same decisions, same edge arrays (position for position), same moved joints as the reference's
-`GrainNN_classifier.update` (models.py:614-845, nucleation branch excluded), `switching_edge_index` (:899-1053),
+`GrainNN_classifier.update` (models.py:614-845, nucleation included), `switching_edge_index` (:899-1053),
 `delete_grain_index` (:864-896) and `cleanup` (:846-862) — but every `(E == p).nonzero()` scan of the reference
 (O(E) each, O(events x E) per step: the step-time floor at >= 10^5 grains) is answered from position lists kept per joint
 and per grain, so a step costs O(E) once for the index plus O(1) per lookup.  The host stays Python, as in the reference;
@@ -227,8 +227,74 @@ class _Surgery:
         return forced
 
 
-def topology_update(x_dict, edge_index_dict, y_dict, mask, active_grains, active_joints, threshold=0.6, L1=None):
-    """The reference's GrainNN_classifier.update (nucleation_prob = 0) on CPU tensors.  Mutates x_dict / y_dict / mask like
+def _unit_towards(p, pc):
+    """periodic_norm, models.py:1102-1108."""
+    rel = p - pc
+    rel = rel - 1 * (rel > 0.5) + 1 * (rel < -0.5)
+    return torch.nn.functional.normalize(rel, p=2.0, dim=0, eps=1e-6)
+
+
+def _nucleate(s, nucleation_prob):
+    """models.py:771-835: a new grain opens at every live junction drawn by `torch.rand` (same draws, in the same order, as the
+    reference: one vector over the junctions, then two angles per site).  The junction keeps its neighbour 0 and becomes one
+    corner of the new triangular grain; two new junctions take over neighbours 1 and 2.  x_dict / mask entries are re-bound to
+    grown tensors exactly as the reference re-binds them."""
+    x, mask, pp, pq = s.x, s.mask, s.pp, s.pq
+    draws = torch.rand(x['joint'].size(dim=0))
+    sites = ((draws < nucleation_prob) & (mask['joint'][:, 0] > 0)).nonzero().view(-1)
+    n_grain, n_joint = mask['grain'].size(dim=0), mask['joint'].size(dim=0)
+    for junction in sites:
+        j = int(junction)
+        mask['joint'] = torch.cat((mask['joint'], torch.tensor([1, 1]).view(-1, 1)))
+        mask['grain'] = torch.cat((mask['grain'], torch.tensor([1]).view(-1, 1)))
+        (sx, sy, sz), dz = x['joint'][j, :3], x['joint'][j, -1]
+        theta_x, theta_z = torch.rand(2) * torch.pi / 2
+        area = 0.004
+        reach = torch.sqrt(area * 4 / 3 / torch.sqrt(torch.tensor(3)))
+        grain_row = torch.tensor([sx, sy, sz, area, 0, torch.cos(theta_x), torch.sin(theta_x),
+                                  torch.cos(theta_z), torch.sin(theta_z), area, dz])
+        x['grain'] = torch.cat((x['grain'], grain_row.view(1, -1)), dim=0)
+        j1, j2 = n_joint, n_joint + 1
+        nb = [pp.get(1, e) for e in pp.at(0, j)]
+        nb0, nb1, nb2 = nb
+        opposite = [0, 0, 0]                                 # the grain of the junction that neighbour k does NOT touch
+        for g in [pq.get(1, e) for e in pq.at(0, j)]:
+            for k in range(3):
+                if not any(pq.get(1, e) == g for e in pq.at(0, nb[k])):
+                    opposite[k] = g
+        g0, g1, g2 = opposite
+        assert g0 != g1 and g1 != g2 and g0 != g2
+        centre = x['joint'][j, :2].clone()
+        row1, row2 = x['joint'][j].clone(), x['joint'][j].clone()
+        x['joint'][j, :2] = centre + _unit_towards(x['joint'][nb0, :2], centre) * reach
+        row1[:2] = centre + _unit_towards(x['joint'][nb1, :2], centre) * reach
+        row2[:2] = centre + _unit_towards(x['joint'][nb2, :2], centre) * reach
+        x['joint'][j, -2:] = 0
+        row1[-2:] = 0
+        row2[-2:] = 0
+        x['joint'] = torch.cat((x['joint'], row1.view(1, -1), row2.view(1, -1)), dim=0)
+        for e in list(pq.at(0, j)):
+            pq.kill(e)
+        for e in s.pp_between(nb1, j):
+            pp.set(1, e, j1)
+        for e in s.pp_between(nb2, j):
+            pp.set(1, e, j2)
+        for e in s.pp_between(j, nb1):
+            pp.set(0, e, j1)
+        for e in s.pp_between(j, nb2):
+            pp.set(0, e, j2)
+        for a, b in ((j, j1), (j, j2), (j1, j), (j1, j2), (j2, j), (j2, j1)):
+            pp.append(a, b)
+        for a, b in ((j, n_grain), (j1, n_grain), (j2, n_grain), (j1, g0), (j2, g0), (j, g1), (j2, g1), (j, g2), (j1, g2)):
+            pq.append(a, b)
+        n_grain += 1
+        n_joint += 2
+
+
+def topology_update(x_dict, edge_index_dict, y_dict, mask, active_grains, active_joints, threshold=0.6, L1=None,
+                    nucleation_prob=0.0):
+    """The reference's GrainNN_classifier.update on CPU tensors (nucleation_prob > 1e-6: new grains open at random junctions,
+    drawn from torch's global generator like the reference's; x_dict / mask entries are then re-bound to grown tensors).  Mutates x_dict / y_dict / mask like
     the reference and returns (x_dict, new edge_index_dict, switching_list).  y_dict['grain_event']: grain ids sorted by area
     (test.py:414-416).  L1 (optional): the candidate edges, ascending ids (EventSelector.fetch()['L1']); selected here from
     y_dict['edge_event'] when absent (models.py:627-629)."""
@@ -280,6 +346,8 @@ def topology_update(x_dict, edge_index_dict, y_dict, mask, active_grains, active
     unexpected.extend(s.delete_two_sided())
     if unexpected:
         y_dict['grain_event'] = torch.cat([y_dict['grain_event'], torch.tensor(unexpected)])
+    if nucleation_prob > 1e-6:                                                               # models.py:771-835
+        _nucleate(s, nucleation_prob)
     out = {JJ: s.pp.compact(), JG: s.pq.compact()}
     out[GJ] = torch.flip(out[JG], dims=[0])                                                  # models.py:841
     return x_dict, out, switching_list

@@ -106,6 +106,37 @@ def forced_case(gold):
         x, ei, mask = rx, rei, rm
 
 
+def nucleation_case(gold, prob=0.03, seed=1):
+    """The optional nucleation branch (models.py:771-835) on the C1 graph: torch.manual_seed(seed) right before the update,
+    so the draws (one vector over the junctions, two angles per site) are reproducible wherever the test runs."""
+    sys.path.insert(0, os.path.join(HERE, '..', 'tests'))
+    from test_topology_golden import _craft_on
+    g, x, ei, ea = mgold.load_graph('/root/reference/graphs/40_40/seed10020_G1.904_R0.558_span6.pkl', 1)
+    R, C = mgold.build_models(g)
+    R.threshold, C.threshold = 1e-4, 0.6
+    mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+    y = _craft_on(np.random.default_rng(seed), x, ei, mask, 10, 3, 6)
+    rx, rei, ry, rm = ({k: v.clone() for k, v in d.items()} for d in (x, ei, y, mask))
+    gs = {'domain_offset': 0, 'domain_factor': 1}
+    with contextlib.redirect_stdout(io.StringIO()):
+        R.update(rx, ry, gs)
+        ry['grain_event'] = ((rm['grain'][:, 0] > 0) & (ry['grain_area'] < R.threshold)).nonzero().view(-1)
+        ry['grain_event'] = ry['grain_event'][torch.argsort(ry['grain_area'][ry['grain_event']])]
+        torch.manual_seed(seed)
+        rx, rei, pairs = C.update(rx, rei, ea, ry, rm, gs, prob)
+    k = 'c1_nucl'
+    gold[f'{k}_prob'], gold[f'{k}_seed'] = np.array(prob), np.array(seed)
+    for t in ('joint', 'grain'):
+        gold[f'{k}_y_{t}'], gold[f'{k}_x_{t}_out'], gold[f'{k}_mask_{t}_out'] = y[t].numpy(), rx[t].numpy(), rm[t].numpy()
+    gold[f'{k}_y_edge_event'], gold[f'{k}_y_grain_area'] = y['edge_event'].numpy(), y['grain_area'].numpy()
+    gold[f'{k}_switching_list'] = pairs.numpy()
+    gold[f'{k}_active_grains'], gold[f'{k}_active_joints'] = gs['active_grains'].numpy(), gs['active_joints'].numpy()
+    for et, short in mgold.SHORT.items():
+        gold[f'{k}_ei_{short}_out'] = rei[et].numpy().astype(np.int32)
+    print('nucleation case: grains', x['grain'].shape[0], '->', rx['grain'].shape[0], 'joints', x['joint'].shape[0], '->', rx['joint'].shape[0])
+    assert rx['grain'].shape[0] > x['grain'].shape[0]
+
+
 def main():
     gold, log = {}, {}
     plans = {'c1': (1, [(3, 1, 5, 3), (10, 3, 6, 2)]),                  # (switching edges, vanishing grains, max sides, cases)
@@ -148,6 +179,7 @@ def main():
         gold[f'{name}_cases'] = np.array(done)
         print(name, 'cases', done, 'tried', tried, 'reference raised on', log.get(name, []))
     forced_case(gold)
+    nucleation_case(gold)
     np.savez_compressed(os.path.join(OUT, 'topology_golden.npz'), **gold)
     print({k: v.shape for k, v in gold.items() if k.endswith('_0_ei_jj_out') or k.endswith('switching_list') or 'grain_event' in k})
 

@@ -259,8 +259,6 @@ def test_classifier_update_has_the_reference_signature_and_results(gold, name, i
     for t in ('joint', 'grain'):
         assert np.array_equal(x[t].numpy(), c[f'x_{t}_out']) and np.array_equal(mask[t].numpy(), c[f'mask_{t}_out'])
         assert np.array_equal(y[t].numpy(), c[f'y_{t}_out'])
-    with pytest.raises(NotImplementedError):
-        C.update(x, ei, ea, y, mask, gs, 0.01)
 
 
 def _craft_on(rng, x, ei, mask, n_switch, n_vanish, max_sides):
@@ -373,3 +371,65 @@ def test_update_from_device_selected_candidates_equals_internal_selection(gold):
     assert all(torch.equal(outs[0][0][et], outs[1][0][et]) for et in ET) and torch.equal(outs[0][1], outs[1][1])
     assert torch.equal(outs[0][2]['joint'], outs[1][2]['joint'])
     assert np.array_equal(outs[1][0][ET[2]].numpy(), c['ei_jj_out'])
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/models.py'), reason='reference tree not present')
+@pytest.mark.parametrize('name,prob,seed', [('c1', 0.03, 1), ('c2', 0.01, 2), ('c2', 0.004, 3)])
+def test_nucleation_equals_the_live_reference(name, prob, seed):
+    """Only in the build container: the optional nucleation branch (models.py:771-835) with the same torch generator state —
+    new grains / junctions, re-bound feature and mask tensors, edge arrays position for position."""
+    import contextlib
+    import io
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), '..', 'oracle'))
+    import make_golden_topology as mt
+    from graingraphnn_b200 import topology
+    g, x, ei, ea = mt.mgold.load_graph({'c1': '/root/reference/graphs/40_40/seed10020_G1.904_R0.558_span6.pkl',
+                                        'c2': '/root/reference/graphs/120_120/seed0_G10.0_R2.0_span6.pkl'}[name], {'c1': 1, 'c2': 3}[name])
+    R, C = mt.mgold.build_models(g)
+    R.threshold, C.threshold = 1e-4, 0.6
+    mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+    y = _craft_on(np.random.default_rng(seed), x, ei, mask, 10, 3, 6)
+    rx, rei, ry, rm = ({k: v.clone() for k, v in d.items()} for d in (x, ei, y, mask))
+    gs = {'domain_offset': 0, 'domain_factor': 1}
+    with contextlib.redirect_stdout(io.StringIO()):
+        R.update(rx, ry, gs)
+        ry['grain_event'] = ((rm['grain'][:, 0] > 0) & (ry['grain_area'] < R.threshold)).nonzero().view(-1)
+        ry['grain_event'] = ry['grain_event'][torch.argsort(ry['grain_area'][ry['grain_event']])]
+        torch.manual_seed(seed)
+        rx, rei, rpairs = C.update(rx, rei, ea, ry, rm, gs, prob)
+    ox, oy, om = ({k: v.clone() for k, v in d.items()} for d in (x, y, mask))
+    orc.regressor_update(ox, oy, span=0)
+    _, oy['grain_event'] = orc.event_candidates(oy, ei[ET[2]], om['grain'])
+    torch.manual_seed(seed)
+    ox, oei, op = topology.topology_update(ox, ei, oy, om, gs['active_grains'], gs['active_joints'], nucleation_prob=prob)
+    assert rx['grain'].shape[0] > x['grain'].shape[0]                       # grains were born
+    assert rx['joint'].shape[0] - x['joint'].shape[0] == 2 * (rx['grain'].shape[0] - x['grain'].shape[0])
+    for et in ET:
+        assert torch.equal(oei[et], rei[et]), et
+    assert torch.equal(op, rpairs)
+    for t in ('joint', 'grain'):
+        assert torch.equal(ox[t], rx[t]) and torch.equal(om[t], rm[t]) and om[t].dtype == rm[t].dtype, t
+
+
+def test_nucleation_equals_the_reference_vector(gold):
+    """Committed vector of the nucleation branch (C1, torch.manual_seed before the update): new grains and junctions, grown
+    feature / mask tensors, edge arrays position for position."""
+    from graingraphnn_b200 import topology
+    k = 'c1_nucl_'
+    c = {f[len(k):]: gold[f] for f in gold.files if f.startswith(k)}
+    x, ei, _ = load_graph('c1')
+    y = {'joint': torch.from_numpy(c['y_joint'].copy()), 'grain': torch.from_numpy(c['y_grain'].copy()),
+         'edge_event': torch.from_numpy(c['y_edge_event']), 'grain_area': torch.from_numpy(c['y_grain_area'])}
+    orc.regressor_update(x, y, span=0)
+    mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+    _, y['grain_event'] = orc.event_candidates(y, ei[ET[2]], mask['grain'])
+    torch.manual_seed(int(c['seed']))
+    x, eio, pairs = topology.topology_update(x, ei, y, mask, torch.from_numpy(c['active_grains']), torch.from_numpy(c['active_joints']),
+                                             nucleation_prob=float(c['prob']))
+    assert x['grain'].shape[0] > 118 and x['joint'].shape[0] - 236 == 2 * (x['grain'].shape[0] - 118)
+    for et, short in ((ET[2], 'jj'), (ET[1], 'jg'), (ET[0], 'gj')):
+        assert np.array_equal(eio[et].numpy(), c[f'ei_{short}_out']), short
+    assert np.array_equal(pairs.numpy(), c['switching_list'])
+    for t in ('joint', 'grain'):
+        assert np.array_equal(x[t].numpy(), c[f'x_{t}_out']) and np.array_equal(mask[t].numpy(), c[f'mask_{t}_out'])
