@@ -73,6 +73,7 @@ class RolloutEngine:
         """Copy features into padded resident buffers, build the CSR of every edge type, take (or compute) edge lengths."""
         self._graph = None
         self._state = None
+        self._event_mask = None                       # belongs to the previous grain set (set_event_mask)
         for t in self.node_types:
             xt = x_dict[t].to(self.device, torch.float32)
             buf = self.alloc_rows_x(t, xt.shape[0], pad4(xt.shape[1]))
@@ -92,6 +93,18 @@ class RolloutEngine:
             self.edge_attr[e] = torch.empty(ei.shape[1], 1, dtype=torch.float32, device=self.device)
             self.ea_csr[e] = torch.empty(ei.shape[1], dtype=torch.float32, device=self.device)
             self.wrap[e] = torch.empty(max(ei.shape[1], 1), dtype=torch.int32, device=self.device)
+        # The tile index of every (edge type, tile size) the cells will ask for is built HERE, on the current stream: run_cell
+        # would otherwise build it lazily inside the first model's cell while the second model's cell, on the side stream,
+        # finds it in the Python-side cache and launches its gather with nothing ordering it behind the build kernels.
+        from .cell import tiled_ecap
+        for encdec in self._pack().values():
+            for pk in encdec:
+                for e in self.edge_types:
+                    ecap = tiled_ecap(pk, e)
+                    if ecap:
+                        self.csr[e].tiles(ecap)
+        if self._event_mask is not None and self._event_mask.shape[0] < self.xbuf['grain'].shape[0]:
+            self._event_mask = None                   # the grain set grew (nucleation): the old mask no longer covers it
         if edge_attr_dict is None:
             self.rebuild_edge_attr()
         else:
@@ -107,14 +120,42 @@ class RolloutEngine:
     _event_mask = None
     _event_edges = None      # [2, E] endpoints the `src < dst` test reads, when they differ from edge_index (slabs: global ids)
 
-    def enable_event_selection(self, mask_grain=None, edge_threshold=0.6, area_threshold=1e-4, cap=4096):
+    def enable_event_selection(self, mask_grain=None, edge_threshold=0.6, area_threshold=1e-4, cap=None):
         """Every step also leaves the candidates of the host topology update on the device — the edges with
         sigmoid(edge_event) > edge_threshold and src < dst (models.py:627-629) and the live grains with predicted area below
         area_threshold (test.py:414) — so that `fetch_events()` copies a few (id, value) pairs instead of the full arrays.
-        mask_grain: [Ng] or [Ng,1] fp32, > 0 for live grains (data['mask']['grain'])."""
+        mask_grain: [Ng] or [Ng,1] fp32, > 0 for live grains (data['mask']['grain']); the reference reads the live mask every
+        step (test.py:418), so call `set_event_mask()` after every topology update that changes it.
+        cap: candidate slots per list; None = the worst case of the resident graph (E_jj / 2 edges with src < dst, every
+        grain), so the buffers are never replaced under a captured step."""
         from .events import EventSelector
-        self._events = EventSelector(self.device, edge_threshold, area_threshold, cap, cap)
-        self._event_mask = None if mask_grain is None else mask_grain.to(self.device, torch.float32).reshape(mask_grain.shape[0], -1)[:, 0].contiguous()
+        if cap is None:
+            ne = int(self.edge_index[ET_JJ].shape[1]) if ET_JJ in self.edge_index else 0
+            ng = int(self.xbuf['grain'].shape[0]) if 'grain' in self.xbuf else 0
+            cap_e, cap_g = max(ne // 2 + 1, 4096), max(ng, 4096)
+        else:
+            cap_e = cap_g = cap
+        self._events = EventSelector(self.device, edge_threshold, area_threshold, cap_e, cap_g, on_grow=self._drop_graph)
+        RolloutEngine.set_event_mask(self, mask_grain)   # (a subclass's override takes global rows)
+        self._graph = None
+
+    def _drop_graph(self):
+        """A buffer the captured step writes was replaced: the graph holds stale pointers; later steps run eagerly until
+        capture() is called again."""
+        self._graph = None
+
+    def set_event_mask(self, mask_grain):
+        """The live-grain mask of the event selection (data['mask']['grain'], test.py:418): [N] or [N,1], > 0 = live.  It is
+        copied, so call this again whenever the host topology update changes it (eliminations clear entries, nucleation
+        appends grains).  A captured step is dropped: it reads the previous copy."""
+        if mask_grain is None:
+            self._event_mask = None
+        else:
+            m = mask_grain.to(self.device, torch.float32).reshape(mask_grain.shape[0], -1)[:, 0].contiguous()
+            ng = int(self.xbuf['grain'].shape[0]) if 'grain' in self.xbuf else m.shape[0]
+            if m.shape[0] < ng:
+                raise ValueError(f'mask_grain has {m.shape[0]} rows for {ng} grains (refresh it after nucleation)')
+            self._event_mask = m
         self._graph = None
 
     def fetch_events(self):
@@ -243,8 +284,10 @@ class RolloutEngine:
                            Cm.lin1.weight, Cm.lin1.bias, Cm.lin2.weight, Cm.lin2.bias)
         if self._events is not None:                         # row f1, first stage: only the event candidates leave the device
             self._events.select_edge_events(ev, self.edge_index[ET_JJ] if self._event_edges is None else self._event_edges)
-            self._events.select_grain_events(area if ng is None else area[:ng],
-                                             None if self._event_mask is None else self._event_mask[:area.shape[0] if ng is None else ng])
+            n_sel = area.shape[0] if ng is None else ng
+            if self._event_mask is not None and self._event_mask.shape[0] < n_sel:
+                raise RuntimeError(f'event mask covers {self._event_mask.shape[0]} of {n_sel} grains: call set_event_mask() after the topology update')
+            self._events.select_grain_events(area[:n_sel], None if self._event_mask is None else self._event_mask[:n_sel])
         if isinstance(span, (tuple, list)):                  # ensemble: one span per graph of the block-diagonal batch
             dzj, dzg = self._dz_vectors(tuple(span))
             feature_update_batched(self.x['joint'], self.x['grain'], yj, yg, dzj, dzg,

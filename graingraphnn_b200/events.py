@@ -59,8 +59,10 @@ class EventSelector:
     """Preallocated candidate buffers for one graph; `select_*` enqueue on the current stream (capturable), `fetch()`
     synchronises and returns the reference's host-side lists."""
 
-    def __init__(self, device, edge_threshold=0.6, area_threshold=1e-4, cap_edges=4096, cap_grains=4096):
+    def __init__(self, device, edge_threshold=0.6, area_threshold=1e-4, cap_edges=4096, cap_grains=4096, on_grow=None):
         self.device = torch.device(device)
+        self.on_grow = on_grow        # called when a candidate buffer is replaced: a captured step still writes the old one
+        self._retired = []            # replaced buffers stay allocated: a CUDA graph captured earlier may still write into them
         self.edge_threshold, self.area_threshold = edge_threshold, area_threshold
         self.logit_min, self.logit_band_hi = sigmoid_threshold_band(edge_threshold)
         self._buf = {}
@@ -100,7 +102,10 @@ class EventSelector:
         n = int(count.item())
         self.d2h_bytes += 4
         if n > cap:                                   # rare: grow and repeat the pass on the same inputs
+            self._retired.append(self._buf[name][:3])
             self._alloc(name, 2 * n)
+            if self.on_grow is not None:              # the owner drops its captured graph (it holds the old pointers)
+                self.on_grow()
             values, thr, mode, src, dst, mask = args
             self._select(name, values, thr, mode, src, dst, mask)
             return self._fetch(name)

@@ -91,8 +91,9 @@ class _PGCBase(nn.Module):
         if hit is None or hit[0] != key:
             C = self.out_channels
             in_dims = {t: (f, C) for t, f in self.in_channels_dict.items()}
-            pk = PackedCell(edge_types, gates, in_dims, C, lambda g, e: cws[(g, e)],
-                            gate_bias=lambda g, t: getattr(self, f'b_{g}')[t],
+            hws = {k: cw.host() for k, cw in cws.items()}             # pack on the host (fp64), upload the fp32 result
+            pk = PackedCell(edge_types, gates, in_dims, C, lambda g, e: hws[(g, e)],
+                            gate_bias=lambda g, t: getattr(self, f'b_{g}')[t].detach().cpu(),
                             weighted=self.conv_class.weighted, device=device, raw_scores=bool(raw), raw_hidden=bool(raw) and with_h)
             if not with_h and not raw:   # h == 0: only the feature columns of every weight matter (K = K1p)
                 for t in pk.node_types:

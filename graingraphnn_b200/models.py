@@ -2,8 +2,8 @@
 
 Host-side mirror of the reference's models.py for the hot path only: constructors, `forward(x_dict, edge_index_dict,
 edge_attr)` and the `state_dict` layout follow models.py:151-301, :351-467, :529-611, so `regressor0.pt` /
-`classifier1.pt` load unchanged.  The host topology logic (`GrainNN_classifier.update`, models.py:614-1053) is outside
-this path: the reference's own implementation consumes our outputs unchanged.
+`classifier1.pt` load unchanged.  `GrainNN_classifier.update` (the topology update, models.py:614-1053)
+keeps the reference's signature and results; its decisions are made by `topology.topology_update` (host, position lists).
 """
 import copy
 
@@ -108,6 +108,8 @@ class GrainNN_regressor(nn.Module):
 class GrainNN_classifier(nn.Module):
     """Edge-event classifier sharing the regressor's encoder/decoder architecture (models.py:529-611)."""
 
+    threshold = 0.6          # edge-event probability threshold of `update`; the reference's driver sets it (test.py:187-191)
+
     def __init__(self, hyper, regressor=None, history=False):
         super().__init__()
         if history:
@@ -142,9 +144,11 @@ class GrainNN_classifier(nn.Module):
         """Topology update of a rollout step with the reference's signature and results (models.py:614-845; called at
         test.py:426): grain elimination, neighbour switching, cleanup.  Host code, like the reference's — tensors on a CUDA
         device are brought to the host and the results put back — but every lookup is answered from position lists instead
-        of an O(E) scan (topology.py).  `self.threshold` is set by the caller (test.py:187).  Returns
-        (x_dict, edge_index_dict, switching_list); `edge_index_dict`, `x_dict['joint']`, `y_dict` and `mask` are updated in
-        place as the reference does; with nucleation (:771-835) `x_dict` / `mask` entries are re-bound to grown tensors."""
+        of an O(E) scan (topology.py).  `self.threshold` is set by the caller (test.py:187; class default 0.6).  Returns
+        (x_dict, edge_index_dict, switching_list); `x_dict['joint']`, `y_dict` and `mask` are updated in place as the
+        reference does and the entries of `edge_index_dict` are re-bound to the cleaned-up arrays (models.py:838-841); the
+        caller's edge TENSORS are left as they were (the reference also writes -1 into them on the way, :877-880 — nothing
+        reads them afterwards); with nucleation (:771-835) `x_dict` / `mask` entries are re-bound to grown tensors."""
         from .topology import topology_update
         dev = x_dict['joint'].device
         host = lambda d: {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}   # noqa: E731

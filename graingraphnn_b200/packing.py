@@ -38,6 +38,15 @@ class ConvWeights:
     def tensors(self):
         return [getattr(self, n) for n in self.__slots__ if getattr(self, n) is not None]
 
+    def host(self):
+        """The same weights as host tensors: packing is fp64 arithmetic on ~50 small matrices per cell, done on the CPU so
+        that no fp64 ATen / cuBLAS kernels run on the device (only the packed fp32 buffers are uploaded)."""
+        h = object.__new__(ConvWeights)
+        for n in self.__slots__:
+            v = getattr(self, n)
+            setattr(h, n, None if v is None else v.detach().cpu())
+        return h
+
 
 def _cols(w, k1, k1p, k2):
     """[out, k1+k2] -> [out, k1p+k2] with zero columns inserted after the first k1 (a wider w is cut to its first k1+k2

@@ -290,12 +290,22 @@ class PartitionedEngine(RolloutEngine):
             joint_offset = joint_offset.cpu().index_select(0, ids)
         super().enable_geometry_feedback(joint_offset, domain_factor)
 
-    def enable_event_selection(self, mask_grain=None, edge_threshold=0.6, area_threshold=1e-4, cap=4096):
+    def enable_event_selection(self, mask_grain=None, edge_threshold=0.6, area_threshold=1e-4, cap=None):
         """mask_grain: GLOBAL [Ng] or [Ng,1]; the owned rows are taken."""
-        if mask_grain is not None:
-            mask_grain = mask_grain.cpu().reshape(mask_grain.shape[0], -1)[:, 0][torch.from_numpy(self.plan.own['grain'])]
+        mask_grain = self._own_mask(mask_grain)
         super().enable_event_selection(mask_grain, edge_threshold, area_threshold, cap)
         self._event_edges = torch.from_numpy(self.plan.edge_global[('joint', 'connect', 'joint')]).to(self.device)
+
+    def _own_mask(self, mask_grain):
+        if mask_grain is None:
+            return None
+        m = mask_grain.cpu().reshape(mask_grain.shape[0], -1)[:, 0][torch.from_numpy(self.plan.own['grain'])]
+        pad = self.plan.n_local['grain'] - m.shape[0]            # halo rows are never selected; the mask covers the local rows
+        return torch.cat([m, m.new_zeros(pad)]) if pad > 0 else m
+
+    def set_event_mask(self, mask_grain, local=False):
+        """mask_grain: GLOBAL [Ng] or [Ng,1] (local=True: already this rank's rows)."""
+        super().set_event_mask(mask_grain if local else self._own_mask(mask_grain))
 
     def fetch_events(self):
         """Candidates among the joint-joint edges and grains this rank owns, as GLOBAL ids (each edge / grain is owned by

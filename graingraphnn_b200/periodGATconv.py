@@ -62,7 +62,8 @@ class PeriodConv(nn.Module):
         if self._packed is None or self._packed_key != key:
             et = ('n', 'e', 'n') if same else ('s', 'e', 'd')
             in_dims = {'n': (d_src, 0)} if same else {'s': (d_src, 0), 'd': (d_dst, 0)}
-            pk = PackedCell([et], ['x'], in_dims, self.out_channels, lambda g, e: cw,
+            hw = cw.host()
+            pk = PackedCell([et], ['x'], in_dims, self.out_channels, lambda g, e: hw,
                             weighted=self.weighted, device=device)
             if not self.root_weight:
                 for t in pk.Wskip:

@@ -55,7 +55,9 @@ class _Rows:
     def _index(self, r):
         order = np.argsort(self.a[r], kind='stable')
         self.order[r] = order
-        self.starts[r] = np.searchsorted(self.a[r][order], np.arange(self.n[r] + 1))
+        # sized from the values actually present: ids appended after construction (nucleation) are indexed like any other
+        top = max(self.n[r], int(self.a[r].max()) + 1 if self.a.shape[1] else 0)
+        self.starts[r] = np.searchsorted(self.a[r][order], np.arange(top + 1))
 
     def at(self, r, v):
         v = int(v)
@@ -63,7 +65,7 @@ class _Rows:
             self._index(r)
         hit = self.lists[r].get(v)
         if hit is None:
-            hit = self.lists[r][v] = self.order[r][self.starts[r][v]:self.starts[r][v + 1]].tolist() if v < self.n[r] else []
+            hit = self.lists[r][v] = self.order[r][self.starts[r][v]:self.starts[r][v + 1]].tolist() if v + 1 < len(self.starts[r]) else []
         return hit
 
     def counts(self, r):
