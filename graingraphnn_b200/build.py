@@ -13,7 +13,30 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 
 
 def lib_path():
-    return os.path.join(LIBDIR, LIBNAME)
+    """GG_LIB=<path> selects another build of the same library (A/B measurements of kernel variants, scripts/ab_gather.sh)."""
+    return os.environ.get('GG_LIB') or os.path.join(LIBDIR, LIBNAME)
+
+
+def build_variant(name, defines=(), replace=None, verbose=False):
+    """A second library lib/variants/<name>.so that differs from the main one by -D defines (applied to every source) or
+    by replaced source files ({'gather_tiled.cu': '/path/to/other.cu'}); objects go to lib/variants/<name>/."""
+    import tempfile
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    os.makedirs(os.path.join(LIBDIR, 'variants'), exist_ok=True)
+    vdir = tempfile.mkdtemp(prefix=f'gg_{name}_')        # objects stay out of the tree (the tree travels to the GPU box)
+    objs = []
+    for s in SOURCES:
+        src = (replace or {}).get(s, os.path.join(CSRC, s))
+        o = os.path.join(vdir, s[:-3] + '.o')
+        cmd = [nvcc] + NVCC_FLAGS + ['-I', CSRC] + [f'-D{d}' for d in defines] + ['-c', '-o', o, src]
+        if verbose:
+            print(' '.join(cmd))
+        subprocess.run(cmd, check=True, stderr=None if verbose else subprocess.DEVNULL)
+        objs.append(o)
+    out = os.path.join(LIBDIR, 'variants', name + '.so')
+    subprocess.run([nvcc, '-shared', '-o', out] + objs + ['-lcuda'], check=True)
+    shutil.rmtree(vdir, ignore_errors=True)
+    return out
 
 
 def _stale(target, deps):

@@ -32,12 +32,19 @@
 #include <stdlib.h>
 
 #ifdef GG_TILED_PROFILE
-__device__ unsigned long long g_tiled_prof[8];   // [0] consumer wait, [1] consumer busy, [2] producer wait, [3] producer issue, [4] consumer warps, [5] producer warps
+__device__ unsigned long long g_tiled_prof[8];   // [0] consumer wait, [1] consumer busy, [2] producer wait, [3] producer issue, [4] consumer warps, [5] producer warps, [6] clocks and [7] ns of consumer warp 0 of CTA 0 (SM clock of the launch)
+__device__ unsigned long long g_clk_ring[256];     // (clocks, ns) of the last 128 launches, in launch order
+__device__ unsigned int g_clk_n;
+__device__ __forceinline__ unsigned long long gg_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define GG_PROF_T0() long long prof_t = clock64()
 #define GG_PROF_ADD(var) do { const long long now_ = clock64(); var += now_ - prof_t; prof_t = now_; } while (0)
 #else
 #define GG_PROF_T0() do {} while (0)
 #define GG_PROF_ADD(var) do {} while (0)
+#endif
+
+#ifndef GG_ENC_ROW_PAD
+#define GG_ENC_ROW_PAD 16u
 #endif
 
 namespace {
@@ -46,6 +53,8 @@ constexpr int NP = 4;                 // producer warps (exactly one warpgroup: 
 constexpr int NC = 12;                // consumer warps
 constexpr int kThreads = 32 * (NP + NC);
 constexpr int CH = 3;                 // edges per softmax chunk (joints have exactly 3 in-edges)
+struct FastTag { static constexpr bool value = true; };
+struct SlowTag { static constexpr bool value = false; };
 
 struct TiledParams {
     const float* P_src; int ld_src, k_off;
@@ -120,6 +129,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float rcp_nr(float x) {            // 1 / x for x in [1e-16, 1e3]: approximate reciprocal + one Newton step (<= 1 ulp)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
 __device__ __forceinline__ void stg4_stream(float* p, const float4& v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -141,7 +155,8 @@ __device__ __forceinline__ u64 fmax2(u64 a, u64 b) {           // no packed max 
     unpack2(a, ax, ay); unpack2(b, bx, by);
     return pack2(fmaxf(ax, bx), fmaxf(ay, by));
 }
-__device__ __forceinline__ float hsum2(u64 a, u64 b) { float ax, ay, bx, by; unpack2(a, ax, ay); unpack2(b, bx, by); return (ax + ay) + (bx + by); }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float hsum2(u64 a, u64 b) { float x, y; unpack2(fadd2(a, b), x, y); return x + y; }
 __device__ __forceinline__ P4 lds4p(uint32_t addr) {
     P4 r;
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r.lo), "=l"(r.hi) : "r"(addr));
@@ -163,9 +178,14 @@ constexpr uint32_t cfg_es(int G, int C, int rawk) { return rawk ? 4u * rawk + (u
 constexpr uint32_t cfg_qb(int G, int C, int rawk) { return rawk ? 4u * rawk * G : (uint32_t)G * C * 4u + 16u * G; }            // Q' (rawk per gate) or Q | QX
 // target block: Q | QX | position (x, y, z, -), or Q' alone — there the position rides in three spare slots of the first gate's Q'
 constexpr uint32_t cfg_hb(int G, int C, int rawk) { return cfg_qb(G, C, rawk) + (rawk ? 0u : 16u); }
+// Stride of a staged row.  Encoder form (16 raw floats in front): every lane of a gate group scores ANOTHER edge of the chunk, so the
+// lanes of one 128-bit shared load read the same 16 bytes of three different rows; with the natural stride (304 words = 16 mod 32)
+// rows an even number of slots apart sit in the same banks (ncu round 1: 1.3 conflicts per shared load).  16 bytes of padding make
+// the stride 308 words = 20 mod 32: rows up to 7 slots apart land in 8 different bank quads.
+constexpr uint32_t cfg_ess(int G, int C, int rawk) { return cfg_es(G, C, rawk) + (rawk == 16 ? GG_ENC_ROW_PAD : 0u); }
 constexpr uint32_t cfg_stage_bytes(int G, int C, int raw, int ecap, int hcap) {
     const uint32_t e8 = (((uint32_t)ecap * 8u) + 15u) & ~15u;
-    return ((uint32_t)ecap * cfg_es(G, C, raw) + (uint32_t)hcap * cfg_hb(G, C, raw) + 2u * e8 + 16u + 127u) & ~127u;
+    return ((uint32_t)ecap * cfg_ess(G, C, raw) + (uint32_t)hcap * cfg_hb(G, C, raw) + 2u * e8 + 16u + 127u) & ~127u;
 }
 constexpr int cfg_hcap(int ecap) { return ecap / 3 + 2; }
 // The largest tile (multiple of 6 edges: joints have 3 in-edges, grains ~6) that fits 227 KB with three stages, else with two
@@ -183,9 +203,9 @@ template <int NV, int G_, int MODE>
 struct TCfg {
     static constexpr int C = 32 * NV, G = G_, GC = G * C, RAW = mode_rawk(MODE, 32 * NV);
     static constexpr int ECAP = cfg_pick(G, C, RAW, 0), NS = cfg_pick(G, C, RAW, 1), HCAP = cfg_hcap(ECAP);
-    static constexpr uint32_t ES = cfg_es(G, C, RAW), QB = cfg_qb(G, C, RAW), HB = cfg_hb(G, C, RAW);
+    static constexpr uint32_t ES = cfg_es(G, C, RAW), ESS = cfg_ess(G, C, RAW), QB = cfg_qb(G, C, RAW), HB = cfg_hb(G, C, RAW);
     static constexpr uint32_t POS = RAW == 0 ? QB : (RAW == 16 ? 48u : 112u);   // byte offset of x, y, z inside the target block
-    static constexpr uint32_t HDR = (uint32_t)ECAP * ES;
+    static constexpr uint32_t HDR = (uint32_t)ECAP * ESS;
     static constexpr uint32_t TD = HDR + (uint32_t)HCAP * HB;            // {node, lo | hi << 8 | starts << 16 | ends << 17 | header slot << 24}
     static constexpr uint32_t E8 = (((uint32_t)ECAP * 8u) + 15u) & ~15u;
     static constexpr uint32_t EM = TD + E8;                              // {edge length, wrap code}
@@ -210,7 +230,9 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int ECAP = K::ECAP, HCAP = K::HCAP, NS = K::NS;
     (void)ECAP;
-    const uint32_t smem0 = smem_addr(smem);
+    uint32_t smem0 = smem_addr(smem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(smem0));            // opaque: ptxas otherwise re-derives the shared window base (S2UR SR_CgaCtaId,
+                                                              // ~30 clk on the critical path) in front of every group of shared loads
     const uint32_t bar0 = smem0 + (uint32_t)NS * K::BYTES;    // full[NS] | empty[NS]
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (NS + s); };
@@ -275,7 +297,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             GG_PROF_ADD(prof_busy);
             mbar_wait_sleepy_(empty_bar(stage), phase ^ 1u);
             GG_PROF_ADD(prof_wait);
-            if (mine < ne) sts2(base + K::EM + 8u * mine, __float_as_int(m_cur.ea), m_cur.wrap | (row_slot << 8));
+            if (mine < ne) sts2(base + K::EM + 8u * mine, __float_as_int(m_cur.ea), m_cur.wrap | ((row_slot * (int)K::ESS) << 8));   // wrap code | byte offset of the staged row
             if (mine < cnt)
                 sts2(base + K::TD + 8u * mine, m_cur.tn,
                      (max(m_cur.ta, e0) - e0) | ((min(m_cur.tb, e1) - e0) << 8) | (starts << 16) | (ends << 17) | ((has_hdr ? h : 255) << 24));
@@ -283,7 +305,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             __syncwarp();
             if (lane == 0) mbar_expect_tx_(bar, (uint32_t)n_rows * K::ES + (uint32_t)n_hdr * K::HB);
             __syncwarp();
-            if (copies_row) bulk_g2s(base + (uint32_t)mine * K::ES, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, K::ES, bar);
+            if (copies_row) bulk_g2s(base + (uint32_t)mine * K::ESS, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, K::ES, bar);
             if (has_hdr) {
                 const uint32_t hd = base + K::HDR + (uint32_t)h * K::HB;
                 bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn * p.ld_dst + p.q_off, K::HB, bar);     // Q | QX (Q') and the position behind it
@@ -335,6 +357,10 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     long long prof_wait = 0, prof_busy = 0;
     (void)prof_wait; (void)prof_busy;
     GG_PROF_T0();
+#ifdef GG_TILED_PROFILE
+    const long long prof_c0 = clock64();
+    const unsigned long long prof_n0 = gg_globaltimer();
+#endif
     for (int t = 0; t < n_tiles; ++t) {
         const uint32_t base = smem0 + (uint32_t)stage * K::BYTES;
         GG_PROF_ADD(prof_busy);
@@ -394,35 +420,32 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 }
                 m_run = -CUDART_INF_F; l_run = 0.f; ea_acc = 0.f;
             }
-            for (int s0 = lo; s0 < hi; s0 += CH) {
-                const int n_e = hi - s0;                      // >= 1, warp-uniform; slots beyond the row are clamped to its last edge
-                const int sl[CH] = {s0, s0 + (n_e > 1 ? 1 : 0), s0 + (n_e > 2 ? 2 : (n_e > 1 ? 1 : 0))};
+            // One chunk of <= CH consecutive in-edges of the target.  FAST = the chunk is full and none of its edges crosses a patch
+            // boundary (decided warp-uniformly from the staged edge words): straight-line code, no clamped slots, no per-edge
+            // predicates, no wrap corrections — the compiler schedules the loads of all three edges ahead of the arithmetic.
+            auto chunk = [&](auto fast_tag, const int (&ai)[CH], const int (&ww)[CH], const int n_e) {
+                constexpr bool FAST = decltype(fast_tag)::value;
                 float ae[CH], sc[CH];
                 int wc[CH];
+                uint32_t ro[CH];                              // shared-memory address of the edge's source row (shared by duplicates)
 #pragma unroll
-                int rs[CH];                                   // slot the edge's source row is staged in (shared by duplicates)
-#pragma unroll
-                for (int e = 0; e < CH; ++e) {
-                    int ai, ww;
-                    lds2(base + K::EM + 8u * sl[e], ai, ww);
-                    ae[e] = __int_as_float(ai); wc[e] = ww & 0xff; rs[e] = ww >> 8;
-                }
-                const int wc_any = wc[0] | wc[1] | wc[2];
+                for (int e = 0; e < CH; ++e) { ae[e] = __int_as_float(ai[e]); wc[e] = FAST ? 0 : (ww[e] & 0xff); ro[e] = base + ((uint32_t)ww[e] >> 8); }
                 if (RAWH) {
                     // x_j . Q'_i over the 32 + C input slots: lane `sub` of a gate group owns the float4 slots sub, sub + 8, ...;
                     // the four gate groups read the same addresses (broadcast).  Slot 31 (We . q) meets the edge length.
 #pragma unroll
                     for (int e = 0; e < CH; ++e) {
-                        const uint32_t xrow = base + (uint32_t)rs[e] * K::ES + 16u * sub;
+                        const uint32_t xrow = ro[e] + 16u * sub;
                         u64 da = 0ull, db = 0ull;
 #pragma unroll
                         for (int r = 0; r < NQ; ++r) {
                             P4 xx = lds4p(xrow + 128 * r);
                             if (r == 0 && sub == 7) { float x30, x31; unpack2(xx.hi, x30, x31); xx.hi = pack2(x30, ae[e]); }
-                            da = ffma2(q[r].lo, xx.lo, da); db = ffma2(q[r].hi, xx.hi, db);
+                            if (r == 0) { da = fmul2(q[r].lo, xx.lo); db = fmul2(q[r].hi, xx.hi); }
+                            else { da = ffma2(q[r].lo, xx.lo, da); db = ffma2(q[r].hi, xx.hi, db); }
                         }
                         float dd = group_sum8(hsum2(da, db));
-                        if (wc[e]) {
+                        if (!FAST && wc[e]) {
                             dd = fmaf(qx.x, wrapv(wc[e] & 3), dd); dd = fmaf(qx.y, wrapv((wc[e] >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((wc[e] >> 4) & 3), dd);
                         }
                         sc[e] = dd * sc2;
@@ -430,7 +453,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 } else if (RAW) {
                     // each lane scores ONE edge of the chunk (edge `me`) for its gate; lanes 0..2 of the group publish
                     const float my_ae = me == 0 ? ae[0] : (me == 1 ? ae[1] : ae[2]);
-                    const uint32_t row = base + (uint32_t)(me == 0 ? rs[0] : (me == 1 ? rs[1] : rs[2])) * K::ES;
+                    const uint32_t row = me == 0 ? ro[0] : (me == 1 ? ro[1] : ro[2]);
                     const P4 x0 = lds4p(row), x1 = lds4p(row + 16), x2 = lds4p(row + 32);
                     P4 x3 = lds4p(row + 48);
                     { float x14, x15; unpack2(x3.hi, x14, x15); x3.hi = pack2(x14, my_ae); }    // Q'[15] = We . q multiplies the edge length
@@ -439,7 +462,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                     da = ffma2(q[2].lo, x2.lo, da); db = ffma2(q[2].hi, x2.hi, db);
                     da = ffma2(q[3].lo, x3.lo, da); db = ffma2(q[3].hi, x3.hi, db);
                     float dd = hsum2(da, db);
-                    if (wc_any) {                             // periodGATconv.py:209-211: the wrapped displacement enters the key
+                    if (!FAST && (wc[0] | wc[1] | wc[2])) {   // periodGATconv.py:209-211: the wrapped displacement enters the key
                         const int my_wc = me == 0 ? wc[0] : (me == 1 ? wc[1] : wc[2]);
                         dd = fmaf(qx.x, wrapv(my_wc & 3), dd); dd = fmaf(qx.y, wrapv((my_wc >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((my_wc >> 4) & 3), dd);
                     }
@@ -449,7 +472,7 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 } else {
 #pragma unroll
                     for (int e = 0; e < CH; ++e) {
-                        const uint32_t krow = base + (uint32_t)rs[e] * K::ES + lane_off;
+                        const uint32_t krow = ro[e] + lane_off;
                         u64 da = 0ull, db = 0ull;
 #pragma unroll
                         for (int r = 0; r < NV; ++r) {
@@ -458,14 +481,16 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                         }
                         float dd = group_sum8(hsum2(da, db));
                         dd = fmaf(qx.w, ae[e], dd);
-                        if (wc[e]) {
+                        if (!FAST && wc[e]) {
                             dd = fmaf(qx.x, wrapv(wc[e] & 3), dd); dd = fmaf(qx.y, wrapv((wc[e] >> 2) & 3), dd); dd = fmaf(qx.z, wrapv((wc[e] >> 4) & 3), dd);
                         }
                         sc[e] = dd * sc2;
                     }
                 }
-                if (n_e < 2) sc[1] = -CUDART_INF_F;
-                if (n_e < 3) sc[2] = -CUDART_INF_F;
+                if (!FAST) {
+                    if (n_e < 2) sc[1] = -CUDART_INF_F;
+                    if (n_e < 3) sc[2] = -CUDART_INF_F;
+                }
                 const float m_new = fmaxf(fmaxf(m_run, sc[0]), fmaxf(sc[1], sc[2]));
                 if (m_new > m_run) {                          // online softmax: rescale what earlier chunks accumulated
                     if (m_run != -CUDART_INF_F) {
@@ -480,16 +505,16 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                 // relu(v + Wv3 (w_e - p_i)) = max(V_j + Wv3 w_e, vp) - vp: accumulate pe * max(., vp); vp * sum(pe) is subtracted once
 #pragma unroll
                 for (int e = 0; e < CH; ++e) {
-                    if (e < n_e) {
+                    if (FAST || e < n_e) {
                         const float pe = ex2_approx(sc[e] - m_run);
                         const u64 pe2 = pack2(pe, pe);
                         l_run += pe;
                         ea_acc = fmaf(pe, ae[e], ea_acc);
-                        const uint32_t vrow = base + (uint32_t)rs[e] * K::ES + v_off + lane_off;
+                        const uint32_t vrow = ro[e] + v_off + lane_off;
                         P4 v[NV];
 #pragma unroll
                         for (int r = 0; r < NV; ++r) v[r] = lds4p(vrow + 128 * r);
-                        if (wc[e]) {                          // edge crosses a periodic / patch boundary (warp-uniform, rare)
+                        if (!FAST && wc[e]) {                 // edge crosses a periodic / patch boundary (warp-uniform)
                             const float fx = wrapv(wc[e] & 3), fy = wrapv((wc[e] >> 2) & 3), fz = wrapv((wc[e] >> 4) & 3);
                             const u64 tx = pack2(fx, fx), ty = pack2(fy, fy), tz = pack2(fz, fz);
 #pragma unroll
@@ -505,10 +530,25 @@ pgat_gather_tiled_kernel(const TiledParams p) {
                         }
                     }
                 }
+            };
+            for (int s0 = lo; s0 < hi; s0 += CH) {
+                const int n_e = hi - s0;                      // >= 1, warp-uniform
+                int ai[CH], ww[CH];
+                const uint32_t em = base + K::EM + 8u * s0;
+                if (n_e >= CH) {
+#pragma unroll
+                    for (int e = 0; e < CH; ++e) lds2(em + 8u * e, ai[e], ww[e]);
+                    if (((ww[0] | ww[1] | ww[2]) & 0xff) == 0) { chunk(FastTag{}, ai, ww, CH); continue; }
+                } else {                                      // slots beyond the row are clamped to its last edge
+                    lds2(em, ai[0], ww[0]);
+                    lds2(em + (n_e > 1 ? 8u : 0u), ai[1], ww[1]);
+                    ai[2] = ai[1]; ww[2] = ww[1];
+                }
+                chunk(SlowTag{}, ai, ww, n_e);
             }
             if (td & 0x20000) {
                 // ---- the target ends here: normalise and store (PyG softmax: exp(s - max) / (sum + 1e-16))
-                const float inv = 1.0f / (l_run + 1e-16f);
+                const float inv = rcp_nr(l_run + 1e-16f);
                 if (active) {
                     float* orow = p.agg + (size_t)node * p.ld_agg + grp * C + 4 * sub;
                     const u64 nl2 = pack2(-l_run, -l_run), inv2 = pack2(inv, inv);
@@ -527,6 +567,12 @@ pgat_gather_tiled_kernel(const TiledParams p) {
 #ifdef GG_TILED_PROFILE
     GG_PROF_ADD(prof_busy);
     if (lane == 0) { atomicAdd(&g_tiled_prof[0], (unsigned long long)prof_wait); atomicAdd(&g_tiled_prof[1], (unsigned long long)prof_busy); atomicAdd(&g_tiled_prof[4], 1ull); }
+    if (blockIdx.x == 0 && cw == 0 && lane == 0) {
+        const unsigned long long dc = (unsigned long long)(clock64() - prof_c0), dn = gg_globaltimer() - prof_n0;
+        g_tiled_prof[6] = dc; g_tiled_prof[7] = dn;
+        const unsigned int slot = atomicAdd(&g_clk_n, 1u) & 127u;
+        g_clk_ring[2 * slot] = dc; g_clk_ring[2 * slot + 1] = dn;
+    }
 #endif
     // ---- targets without in-edges: zero rows (PyG scatter-add leaves them 0)
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -626,6 +672,23 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
 #undef GG_TILED
     GG_LAUNCH_OK();
     return 0;
+}
+
+// Debug builds (-DGG_TILED_PROFILE): (SM clocks, ns) that consumer warp 0 of CTA 0 spent in each of the last <= 128 launches, in launch
+// order, WITHOUT disturbing the launch sequence (one synchronisation when it is read); returns the number of launches since the
+// last call and resets the counter.
+extern "C" int gg_gather_tiled_clocks(unsigned long long* out) {
+#ifdef GG_TILED_PROFILE
+    unsigned int n = 0, zero = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_clk_ring, sizeof(unsigned long long) * 256) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(&n, g_clk_n, sizeof(n)) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(g_clk_n, &zero, sizeof(zero));
+    return (int)n;
+#else
+    (void)out;
+    return -1;
+#endif
 }
 
 // Debug builds (-DGG_TILED_PROFILE): cycles the consumer / producer warps spent waiting and working since the last call, summed

@@ -38,7 +38,7 @@ def main():
         e1.record()
         assert L.gg_gather_tiled_profile(buf) == 0, 'library was not built with GG_TILED_PROFILE=1'
         v = list(buf)
-        rows.append((e0.elapsed_time(e1) * 1e3, v[0] / max(v[4], 1), v[1] / max(v[4], 1), v[2] / max(v[5], 1), v[3] / max(v[5], 1)))
+        rows.append((e0.elapsed_time(e1) * 1e3, v[0] / max(v[4], 1), v[1] / max(v[4], 1), v[2] / max(v[5], 1), v[3] / max(v[5], 1), v[6] * 1e3 / max(v[7], 1)))
         return rc
 
     class Proxy:
@@ -49,9 +49,9 @@ def main():
     eng.step(6)
     torch.cuda.synchronize()
     _lib._LIB = L
-    print('launch     us | consumer wait   busy (kcycles/warp) | producer wait   busy')
+    print('launch     us | consumer wait   busy (kcycles/warp) | producer wait   busy | SM MHz during the launch')
     for i, r in enumerate(rows):
-        print(f'{i:6d} {r[0]:7.1f} | {r[1] / 1e3:10.1f} {r[2] / 1e3:8.1f} | {r[3] / 1e3:10.1f} {r[4] / 1e3:8.1f}')
+        print(f'{i:6d} {r[0]:7.1f} | {r[1] / 1e3:10.1f} {r[2] / 1e3:8.1f} | {r[3] / 1e3:10.1f} {r[4] / 1e3:8.1f} | {r[5]:7.0f}')
 
 
 if __name__ == '__main__':
