@@ -1,11 +1,15 @@
 #!/usr/bin/env python
 """bench.py — GrainGNN rollout throughput (edges/s, steps/s) on B200, with roofline and CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--patches PXxPY]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--lxd L]
 
-Workload (weak scaling): a synthetic periodic hexagonal-lattice grain domain of 36 x 30 patches (40 um each) PER GPU,
-slabs side by side along x: N=1 -> 124,560 grains / 2.24 M directed edges (the ~10^5-grain single-B200 config),
-N=8 -> 288 x 30 patches = 996,480 grains / 17.9 M edges (the ~10^6-grain slab-partitioned config).
+Workload: the periodic hex-Voronoi grain domain `graph_trajectory.py --mode=generate` builds (graingraphnn_b200/generate.py
+— equal to the reference's output array for array at the sizes the reference reaches, tests/test_generate.py), G = 10,
+R = 2, seed 1, through the loader + patch scaling of the rollout driver (test.py:29-55).
+  N = 1: lxd = 1320 um (33 x 33 patches of 40 um, ~1.26 10^5 grains) — BASELINE config 3, single-B200 rollout;
+  N = 2 / 4 / 8: lxd = 1880 / 2640 / 3720 um (the same ~1.25 10^5 grains per GPU; N = 8 is BASELINE config 4, 93 x 93
+  patches, ~10^6 grains), x-slab partition with a halo exchange per message-passing hop (weak scaling);
+  strong scaling: the 10^6-grain domain of config 4 on the N GPUs of this run (`strong_scaling`, GG_BENCH_STRONG=0 skips it).
 One step = regressor + classifier forward (encoder + decoder cells) + heads + feature update + edge-length rebuild on a
 fixed topology (the "nn-step" of SURVEY.md §8d).  Prints ONE JSON line (rank 0).
 """
@@ -19,14 +23,20 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, 'oracle')):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-PATCHES_PER_GPU = (36, 30)
+WEAK_LXD = {1: 1320, 2: 1880, 4: 2640, 8: 3720}
+STRONG_LXD = 3720
+CPU_SAMPLE_LXD = 240
 SPAN = 6
+ET = [('grain', 'push', 'joint'), ('joint', 'pull', 'grain'), ('joint', 'connect', 'joint')]
+
+
+def weak_lxd(n):
+    return WEAK_LXD.get(n, int(round(1320 * n ** 0.5 / 40)) * 40)
 
 
 def peaks():
@@ -40,7 +50,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the timed region runs."""
     Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
@@ -49,10 +59,11 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
                                           '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            time.sleep(0.3)                       # the first sample must not miss a short timed region
         except Exception:
             self.proc = None
 
@@ -81,28 +92,56 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def make_domain(n_gpus, patches=None, seed=1):
-    from graingraphnn_b200.synth import honeycomb_graph, lattice_dims
-    px, py = patches if patches else (PATCHES_PER_GPU[0] * n_gpus, PATCHES_PER_GPU[1])
-    nx, ny = lattice_dims(px, py)
-    x, ei, glob = honeycomb_graph(nx, ny, seed=seed, patches=(px, py), return_global=True)
-    return x, ei, glob, (px, py)
+# ------------------------------------------------------------------------------------------------ workload
+def make_domain(lxd, seed=1, rank=0, world=1):
+    """(x, ei, ea, global positions, description) of the generate-mode domain, as the rollout driver hands it to the models.
+    Cached under $GG_BENCH_CACHE (default /tmp/gg_bench_cache): the N = 1, 2, 4, 8 runs of one box share the 10^6-grain domain;
+    with several ranks, rank 0 generates and the others read the file."""
+    cache = os.environ.get('GG_BENCH_CACHE', '/tmp/gg_bench_cache')
+    path = os.path.join(cache, f'generate_lxd{lxd}_seed{seed}_G10_R2.pt')
+
+    def build():
+        from graingraphnn_b200 import generate as G
+        hg = G.generate_graph(lxd=lxd, seed=seed, G=10.0, R=2.0, span=SPAN)
+        x, ei, ea, geom = G.model_inputs(hg, lxd)
+        d = {'x': x, 'ei': ei, 'ea': ea, 'glob': geom['global'], 'images': hg['tiling'].images, 'decimals': hg['tiling'].decimals}
+        try:
+            os.makedirs(cache, exist_ok=True)
+            torch.save(d, path + f'.tmp{os.getpid()}')
+            os.replace(path + f'.tmp{os.getpid()}', path)
+        except OSError:
+            pass
+        return d
+
+    if world > 1:
+        import torch.distributed as dist
+        if rank == 0 and not os.path.exists(path):
+            build()
+        dist.barrier()
+    d = torch.load(path) if os.path.exists(path) else build()
+    ng, nj = d['x']['grain'].shape[0], d['x']['joint'].shape[0]
+    ne = sum(int(v.shape[1]) for v in d['ei'].values())
+    desc = (f'periodic hex-Voronoi grain domain of graph_trajectory.py --mode=generate (graingraphnn_b200/generate.py, validated '
+            f'against the reference at lxd 40/120/240), lxd = {lxd} um = {lxd // 40} x {lxd // 40} patches, seed {seed}, G = 10, R = 2: '
+            f'{ng} grains / {nj} joints / {ne} directed edges, grain in-degree 3..9')
+    return d['x'], d['ei'], d['ea'], d['glob'], desc
 
 
 def synth_weights():
-    import grain_oracle as orc   # weights only (seeded stand-ins: the shipped .pt files are absent); not on the timed path
-    return orc.synth_state_dict('regressor', 1), orc.synth_state_dict('classifier', 2)
+    from graingraphnn_b200.weights import load_weights
+    return load_weights(os.environ.get('GG_REGRESSOR_PT'), os.environ.get('GG_CLASSIFIER_PT'))
 
 
-def cpu_reference_run(steps, warmup, sample_patches=(3, 3)):
-    """The reference-order CPU restatement (oracle) on a bounded sample: a 3 x 3 patch domain (~1,040 grains, the size of
-    the reference's 120x120 case), all host threads."""
+def cpu_reference_run(steps, warmup, lxd=CPU_SAMPLE_LXD):
+    """The reference-order CPU restatement (oracle/grain_oracle.py; PyG is not installable here) on a bounded sample of the
+    workload: the same generator, seed and physical parameters at lxd = 240 um (4,176 grains), all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import grain_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
-    x, ei, _, pp = make_domain(1, sample_patches, seed=1)
-    ea = orc.edge_attr_rebuild(x, ei)
-    sd_r, sd_c = synth_weights()
+    x, ei, ea, _, desc = make_domain(lxd)
+    sd_r, sd_c, _ = synth_weights()
     edges = sum(int(v.shape[1]) for v in ei.values())
+    x = {k: v.clone() for k, v in x.items()}
     with torch.no_grad():
         for _ in range(warmup):
             _, ea = orc.nn_step(sd_r, sd_c, x, ei, ea, SPAN)
@@ -111,7 +150,7 @@ def cpu_reference_run(steps, warmup, sample_patches=(3, 3)):
             _, ea = orc.nn_step(sd_r, sd_c, x, ei, ea, SPAN)
         dt = time.perf_counter() - t0
     return {'value': edges * steps / dt, 'unit': 'edges/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{steps} steps of a {pp[0]}x{pp[1]}-patch synthetic domain ({x["grain"].shape[0]} grains, {edges} edges), '
+            'sample': f'{steps} steps of the same generate-mode workload at lxd = {lxd} um ({x["grain"].shape[0]} grains, {edges} edges), '
                       f'oracle/grain_oracle.py in reference op order', 'ms_per_step': dt / steps * 1e3,
             'steps_per_s': steps / dt}
 
@@ -120,7 +159,7 @@ def ncu_traffic(n_grains, launches):
     """dram__bytes_read.sum + dram__bytes_write.sum per gather launch (mean over the launches of one step) from the committed
     `ncu --set full` capture of this very workload (profiles/gather_traffic.json, written by scripts/ncu_traffic.py); None when
     the capture is of another size."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'gather_traffic.json')
+    path = os.path.join(ROOT, 'profiles', 'gather_traffic.json')
     try:
         with open(path) as f:
             d = json.load(f)
@@ -131,11 +170,10 @@ def ncu_traffic(n_grains, launches):
     return None
 
 
-def kernel_breakdown(eng, peak):
+def kernel_breakdown(eng, halo_times=None):
     """Per-family device time of ONE eager step, CUDA events on the launching stream (torch's current stream)."""
-    from graingraphnn_b200 import _lib, cell, heads, graph
+    from graingraphnn_b200 import _lib
     times = {}
-    L = _lib.lib()
 
     class Timed:
         def __init__(self, inner):
@@ -160,6 +198,17 @@ def kernel_breakdown(eng, peak):
     _lib._LIB = Timed(real)
     two = _engine._TWO_STREAMS
     _engine._TWO_STREAMS = False            # one stream: the events must bracket one kernel at a time
+    real_exchange = None
+    if halo_times is not None and getattr(eng, 'halo', None) is not None:
+        real_exchange = eng.halo.exchange
+
+        def timed_exchange(items):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            real_exchange(items)
+            e1.record()
+            halo_times.append((e0, e1))
+        eng.halo.exchange = timed_exchange
     try:
         saved = eng._graph
         eng._graph = None
@@ -170,8 +219,82 @@ def kernel_breakdown(eng, peak):
     finally:
         _lib._LIB = real
         _engine._TWO_STREAMS = two
+        if real_exchange is not None:
+            eng.halo.exchange = real_exchange
     return {k: {'calls': len(v), 'ms_total': sum(a.elapsed_time(b) for a, b in v), 'ms_each': [round(a.elapsed_time(b), 4) for a, b in v]}
             for k, v in times.items()}
+
+
+def build_engine(x, ei, ea, glob, dev, rank, world):
+    sd_r, sd_c, _ = synth_weights()
+    if world > 1:
+        from graingraphnn_b200.partition import PartitionedEngine
+        eng = PartitionedEngine.from_state_dicts(sd_r, sd_c, device=dev)
+        eng.set_global_graph(x, ei, glob, rank, world)
+    else:
+        from graingraphnn_b200.engine import RolloutEngine
+        eng = RolloutEngine.from_state_dicts(sd_r, sd_c, device=dev)
+        eng.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()}, {k: v.to(dev) for k, v in ea.items()},
+                      global_pos=None if os.environ.get('GG_BENCH_ORDER', 'morton') != 'morton' else glob)
+    return eng
+
+
+def timed_steps(eng, steps, world, dev, barrier):
+    """K steps between barriers, CUDA events on the launching stream, max over ranks -> ms for the K steps."""
+    import torch.distributed as dist
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.step(SPAN)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def partition_parity(dev, rank, world, steps=3):
+    """Before anything is timed: the slab-partitioned engine on `world` real ranks (this run's transport) against rank 0's
+    undivided engine, on the reference-sized generate-mode domain (lxd = 240, 4,176 grains), `steps` rollout steps."""
+    import numpy as np
+    import torch.distributed as dist
+    from graingraphnn_b200.engine import RolloutEngine
+    x, ei, ea, glob, _ = make_domain(240, rank=rank, world=world)
+    eng = build_engine(x, ei, ea, glob, dev, rank, world)
+    outs = []
+    for _ in range(steps):
+        eng.step(SPAN)
+        o = {k: (gid, v.cpu()) for k, (gid, v) in eng.owned_predictions().items()}
+        o['x_joint'] = (eng.plan.own['joint'], eng.x['joint'][:eng.plan.n_own['joint']].cpu())
+        outs.append(o)
+    torch.cuda.synchronize()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, outs)
+    res = None
+    if rank == 0:
+        sd_r, sd_c, _ = synth_weights()
+        single = RolloutEngine.from_state_dicts(sd_r, sd_c, dev)
+        single.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
+        bit, worst = True, 0.0
+        for s in range(steps):
+            ref = {k: v.cpu() for k, v in single.step(SPAN).items()}
+            ref['x_joint'] = single.x['joint'].cpu()
+            for k in ('joint', 'grain', 'grain_area', 'edge_event', 'x_joint'):
+                got = torch.full_like(ref[k], float('nan'))
+                for r in range(world):
+                    gid, val = gathered[r][s][k]
+                    got[torch.from_numpy(np.asarray(gid))] = val
+                if not torch.equal(got, ref[k]):
+                    bit = False
+                    worst = max(worst, float((got - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-30)))
+        res = {'graph': 'generate-mode lxd 240 (4176 grains)', 'steps': steps, 'ranks': world, 'bit_identical': bit, 'max_rel': worst,
+               'ok': bool(bit or worst < 1e-5), 'transport': eng.halo.transport,
+               'note': 'a row whose in-edges straddle a gather tile is summed in other softmax chunks on a slab than on the undivided graph'}
+    del eng
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -180,15 +303,17 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--patches', default=None, help='PXxPY total domain in 40-um patches (default 36N x 30)')
+    ap.add_argument('--lxd', type=int, default=None, help='domain edge in um, a multiple of 40 (default: ~1.25e5 grains per GPU)')
     ap.add_argument('--no-graph', action='store_true', help='do not replay the step from a CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling measurement on the 10^6-grain domain')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    patches = tuple(int(v) for v in args.patches.lower().split('x')) if args.patches else None
+    lxd = args.lxd or weak_lxd(world if args.impl == 'ours' else max(args.gpus, 1))
+    step_desc = 'nn-step: regressor+classifier fwd (enc+dec HeteroPGCLSTM), heads, feature update, edge-length rebuild; fixed topology'
 
     if args.impl == 'reference':
         if rank != 0:
@@ -199,9 +324,9 @@ def main():
                           'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
                           'steps_per_sec': r['steps_per_s'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                           'dtype': 'f32', 'data': 'synthetic',
-                          'config': {'workload': 'GrainGNN nn-step (regressor+classifier fwd, heads, feature update, edge-length '
-                                                 'rebuild), reference-order CPU restatement; PyG is not installable here',
-                                     'sample': r['sample']},
+                          'config': {'workload': f'generate-mode periodic grain domain (lxd = {lxd} um in the GPU arm); reference-order CPU '
+                                                 f'restatement (PyG is not installable here) timed on a bounded sample of it',
+                                     'step': step_desc, 'sample': r['sample']},
                           'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                           'e2e': {'value': r['value'], 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return 0
@@ -216,28 +341,24 @@ def main():
     n_gpus = world
     pk = peaks()
 
-    x, ei, glob, pp = make_domain(n_gpus, patches)
-    sd_r, sd_c = synth_weights()
-    if world > 1:
-        from graingraphnn_b200.partition import PartitionedEngine
-        eng = PartitionedEngine.from_state_dicts(sd_r, sd_c, device=dev)
-        eng.set_global_graph(x, ei, glob, rank, world)
-    else:
-        from graingraphnn_b200.engine import RolloutEngine
-        eng = RolloutEngine.from_state_dicts(sd_r, sd_c, device=dev)
-        eng.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
-    ng_total, nj_total = x['grain'].shape[0], x['joint'].shape[0]
-    edges_total = sum(int(v.shape[1]) for v in ei.values())
-    cnt = eng.counts()
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = partition_parity(dev, rank, world) if world > 1 else None
+
+    x, ei, ea, glob, desc = make_domain(lxd, rank=rank, world=world)
+    eng = build_engine(x, ei, ea, glob, dev, rank, world)
+    ng_total, nj_total = x['grain'].shape[0], x['joint'].shape[0]
+    edges_total = sum(int(v.shape[1]) for v in ei.values())
+    weights_desc = synth_weights()[2]
+
     use_graph = not args.no_graph and world == 1
     for _ in range(args.warmup):
         eng.step(SPAN)
+    # per-family times of one eager step BEFORE the sustained load of the timed regions: SM clock at its maximum, no power cap yet
+    bd_cool = kernel_breakdown(eng) if world == 1 else None
     if use_graph:
         eng.capture(SPAN, warmup=1)
     barrier()
@@ -247,21 +368,10 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = _lib.LAUNCHES[0]
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        eng.step(SPAN)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed_steps(eng, args.steps, world, dev, barrier)
     launches = _lib.LAUNCHES[0] - l0
     if use_graph:
         launches = eng.launches_per_step * args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end: host buffers in, host predictions out, through the public engine API -------------------
@@ -288,27 +398,67 @@ def main():
         h2d, d2h = int(tt[0].item()), int(tt[1].item())
 
     # ---- per-family device time of one eager step (all ranks take part: the step contains the halo exchanges) ----
-    bd = kernel_breakdown(eng, pk)
+    halo_ev = []
+    bd = kernel_breakdown(eng, halo_ev)
+    halo = None
+    if world > 1:
+        c = eng.counts()
+        hms = torch.tensor([sum(a.elapsed_time(b) for a, b in halo_ev), float(sum(eng.halo.bytes_sent_per_exchange[-len(halo_ev):])) if halo_ev else 0.0,
+                            float(c['halo_grain'] + c['halo_joint'])], dtype=torch.float64, device=dev)
+        mx = hms.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hms)
+        halo = {'exchanges_per_step': len(halo_ev), 'bytes_per_step': int(hms[1].item()), 'ms_per_step': float(mx[0].item()),
+                'halo_rows_total': int(hms[2].item()), 'transport': eng.halo.transport,
+                'note': 'ms = pack kernels + transfers + waits of the slowest rank in one eager step (not overlapped with compute); bytes summed over ranks'}
     barrier()
+
+    # ---- strong scaling: the fixed 10^6-grain domain of BASELINE config 4 on this run's N GPUs ----------------
+    strong = None
+    alg = eng.algorithmic_work()
+    n_grain_local = eng.counts()['n_grain']
+    if not args.no_strong and os.environ.get('GG_BENCH_STRONG', '1') != '0':
+        if lxd == STRONG_LXD:
+            strong = {'lxd': lxd, 'grains': ng_total, 'n_gpus': n_gpus, 'ms_per_step': ms / args.steps, 'steps_per_sec': args.steps / (ms / 1e3),
+                      'steps': args.steps, 'same_run_as': 'value'}
+        else:
+            try:
+                del hx, hout
+                engs = None
+                sx, sei, sea, sglob, _ = make_domain(STRONG_LXD, rank=rank, world=world)
+                engs = build_engine(sx, sei, sea, sglob, dev, rank, world)
+                ksteps = max(3, min(args.steps, 8))
+                for _ in range(3):
+                    engs.step(SPAN)
+                if use_graph:
+                    engs.capture(SPAN, warmup=1)
+                sms = timed_steps(engs, ksteps, world, dev, barrier)
+                strong = {'lxd': STRONG_LXD, 'grains': int(sx['grain'].shape[0]), 'n_gpus': n_gpus, 'ms_per_step': sms / ksteps,
+                          'steps_per_sec': ksteps / (sms / 1e3), 'steps': ksteps, 'warmup': 3}
+                del engs
+                torch.cuda.empty_cache()
+            except Exception as exc:                                    # never lose the headline line to the extra measurement
+                strong = {'error': repr(exc)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (rank 0, live CUDA events) -----------------------------------------
-    if 'gg_pgat_gather_tiled' in bd:                       # both entry points are kernel family (b)
-        t = bd.pop('gg_pgat_gather_tiled')
-        g = bd.setdefault('gg_pgat_gather', {'calls': 0, 'ms_total': 0.0, 'ms_each': []})
-        g['calls'] += t['calls']; g['ms_total'] += t['ms_total']; g['ms_each'] += t['ms_each']
+    for name in ('gg_pgat_gather_tiled', 'gg_pgat_gather_tiled_multi'):      # all entry points of kernel family (b)
+        if name in bd:
+            t = bd.pop(name)
+            g = bd.setdefault('gg_pgat_gather', {'calls': 0, 'ms_total': 0.0, 'ms_each': []})
+            g['calls'] += t['calls']; g['ms_total'] += t['ms_total']; g['ms_each'] += t['ms_each']
     fam = {k: v['ms_total'] for k, v in bd.items()}
     total_fam = sum(fam.values())
     top = max(fam, key=fam.get)
-    alg = eng.algorithmic_work()
     work = {'gg_pgat_gather': ('hbm', alg['gg_pgat_gather'], 'GB/s', pk['hbm_gbs']),
             'gg_node_proj': ('tensor', alg['gg_node_proj'], 'TFLOP/s', pk['bf16_sustained']),
             'gg_node_proj_tc': ('tensor', alg['gg_node_proj'], 'TFLOP/s', pk['bf16_sustained']),
             'gg_node_proj_fused': ('tensor', alg['gg_node_proj'], 'TFLOP/s', pk['bf16_sustained']),
-            'gg_gate_update': ('tensor', alg['gg_gate_update'], 'TFLOP/s', pk['bf16_sustained'])}
+            'gg_gate_update': ('tensor', alg['gg_gate_update'], 'TFLOP/s', pk['bf16_sustained']),
+            'gg_gate_update_tc': ('tensor', alg['gg_gate_update'], 'TFLOP/s', pk['bf16_sustained'])}
     if top in work:
         bound, amount, unit, peak = work[top]
         dur_s = fam[top] / 1e3
@@ -319,7 +469,16 @@ def main():
         if top == 'gg_pgat_gather':
             # per-launch figures like `traffic`: algorithmic bytes and time of the average launch of the step
             roof['achieved_bytes_per_launch'] = amount / bd[top]['calls']
-            roof['traffic'] = ncu_traffic(ng_total, bd[top]['calls'])
+            roof['traffic'] = ncu_traffic(n_grain_local, bd[top]['calls'])
+            roof['launch'] = 'one launch per cell: its three edge types are segments of the same persistent kernel'
+            if bd_cool is not None:
+                cool = sum(v['ms_total'] for k, v in bd_cool.items() if k.startswith('gg_pgat_gather'))
+                roof['before_sustained_load'] = {
+                    'ms_per_step': cool, 'achieved': amount / (cool / 1e3) / 1e9, 'frac': amount / (cool / 1e3) / 1e9 / peak,
+                    'note': 'the same measurement on the same step right after the warm-up steps; `frac` above is taken after the timed '
+                            'regions, when the board sits at its 1 kW cap (sw_power_cap) and the SM clock has dropped: the gather is bound by '
+                            'the consumer warps\' instruction latency, so it follows the SM clock, a plain device copy does not '
+                            '(profiles/r2_hot_cold.txt)'}
     else:
         roof = {'kernel': top, 'bound': 'hbm', 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None, 'traffic': None}
     roof['breakdown_ms'] = {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}
@@ -354,18 +513,15 @@ def main():
 
     cpu = None if args.no_cpu_baseline else cpu_reference_run(5, 1)
     steps_per_s = args.steps / (ms / 1e3)
+    part = (f'; x-slab partition over {n_gpus} GPUs, {halo["transport"]} halo exchange per message-passing hop' if n_gpus > 1 else '; single B200 rollout')
     line = {
         'metric': 'rollout_edges_per_sec', 'value': edges_total * steps_per_s, 'unit': 'edges/s', 'n_gpus': n_gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'steps_per_sec': steps_per_s,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'synthetic periodic hex-lattice grain domain {pp[0]}x{pp[1]} patches (40 um), {ng_total} grains / '
-                               f'{nj_total} joints / {edges_total} directed edges, {PATCHES_PER_GPU[0]}x{PATCHES_PER_GPU[1]} patches per GPU, '
-                               f'x-slab partition + NCCL halo exchange' if n_gpus > 1 else
-                               f'synthetic periodic hex-lattice grain domain {pp[0]}x{pp[1]} patches (40 um), {ng_total} grains / '
-                               f'{nj_total} joints / {edges_total} directed edges, single B200 rollout',
-                   'step': 'nn-step: regressor+classifier fwd (enc+dec HeteroPGCLSTM), heads, feature update, edge-length rebuild; fixed topology',
-                   'weights': 'seeded stand-ins with the reference state_dict layout (regressor0.pt/classifier1.pt absent)',
+        'config': {'workload': desc + part, 'step': step_desc, 'weights': weights_desc,
                    'l2': 'per-step working set (projections, GBs) exceeds the 126 MB L2; no explicit flush',
+                   'rows': 'the engine keeps its node rows along a Morton curve of the global positions (RolloutEngine.set_graph(global_pos=...)); inputs, '
+                           'predictions and events keep the generator\'s numbering',
                    'cuda_graph': bool(use_graph), 'gemm': os.environ.get('GG_GEMM', 'auto'),
                    'streams': 'regressor and classifier cells on two streams (two graph branches); per-kernel times from a one-stream step'},
         'clocks': clocks,
@@ -376,6 +532,11 @@ def main():
         'step_with_geometry_feedback_and_event_selection': widened,
         'cpu_baseline': None if cpu is None else {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
     }
+    if n_gpus > 1:
+        line['partition_parity'] = parity
+        line['halo'] = halo
+    if strong is not None:
+        line['strong_scaling'] = strong
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,16 @@ class AggInput(Structure):
                 ('W2', c_void_p), ('We', c_void_p), ('b2', c_void_p), ('weighted', c_int32)]
 
 
+class GatherSegment(Structure):
+    """gg_gather_segment (include/graingnn_b200.h): one edge type of a multi-segment tiled gather launch."""
+    _fields_ = [('P_src', c_void_p), ('ld_src', c_int32), ('k_off', c_int32),
+                ('P_dst', c_void_p), ('ld_dst', c_int32), ('q_off', c_int32),
+                ('rowptr', c_void_p), ('col', c_void_p), ('eattr_csr', c_void_p), ('wrap_csr', c_void_p),
+                ('nz', c_void_p), ('nzptr', c_void_p), ('tiles', c_void_p), ('cta_ptr', c_void_p),
+                ('n_edges', c_int64), ('Wv3', c_void_p), ('n_dst', c_int32),
+                ('agg', c_void_p), ('ld_agg', c_int32), ('ea', c_void_p)]
+
+
 _P, _I, _L, _F, _S = c_void_p, c_int32, c_int64, c_float, c_size_t
 _PROTOS = {
     'gg_error_string': (c_char_p, [_I]),
@@ -39,6 +49,7 @@ _PROTOS = {
     'gg_csr_tiles_scratch_ints': (_S, [_L, _I, _I]),
     'gg_csr_tiles': (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P]),
     'gg_pgat_gather_tiled': (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P, _I, _I, _I, _P, _I, _P, _P]),
+    'gg_pgat_gather_tiled_multi': (_I, [POINTER(GatherSegment), _I, _I, _I, _I, _I, _I, _P]),
     'gg_edge_wrap': (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _P]),
     'gg_edge_refresh': (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
     'gg_gate_update': (_I, [POINTER(AggInput), _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
@@ -95,7 +106,7 @@ def exported_symbols():
 
 
 # kernels launched by one successful call of each entry point (for bench.py's gpu_launches accounting)
-KERNELS_PER_CALL = {'gg_csr_build': 6, 'gg_csr_items': 5, 'gg_csr_compact': 5, 'gg_csr_tiles': 5, 'gg_pgat_gather_tiled': 1, 'gg_edge_wrap': 1, 'gg_edge_refresh': 1, 'gg_permute_f32': 1, 'gg_edge_length': 2, 'gg_node_proj': 1, 'gg_pgat_gather': 1,
+KERNELS_PER_CALL = {'gg_csr_build': 6, 'gg_csr_items': 5, 'gg_csr_compact': 5, 'gg_csr_tiles': 5, 'gg_pgat_gather_tiled': 1, 'gg_pgat_gather_tiled_multi': 1, 'gg_edge_wrap': 1, 'gg_edge_refresh': 1, 'gg_permute_f32': 1, 'gg_edge_length': 2, 'gg_node_proj': 1, 'gg_pgat_gather': 1,
                     'gg_gate_update': 1, 'gg_node_head': 1, 'gg_edge_head': 1, 'gg_feature_update': 3, 'gg_feature_update_batched': 1,
                     'gg_gather_rows': 1, 'gg_scatter_rows': 1, 'gg_select_events': 1, 'gg_joint_rank': 2, 'gg_region_key': 1, 'gg_region_sort': 1, 'gg_region_center': 1, 'gg_segment_mean': 1, 'gg_node_proj_tc': 1, 'gg_node_proj_fused': 1, 'gg_split_tf32': 1, 'gg_gate_update_tc': 1}
 LAUNCHES = [0]

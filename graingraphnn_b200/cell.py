@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import AggInput, check, ptr
+from ._lib import AggInput, GatherSegment, check, ptr
 from .graph import _stream, edge_wrap
 
 
@@ -141,8 +141,10 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
                                  ptr(ht), 0 if ht is None else ht.stride(0), 0 if ht is None else ht.shape[1],
                                  ptr(pk.Wcat[t]), pk.kin[t], ptr(pk.bcat[t]),
                                  ptr(P[t]), pk.ncols[t], n, pk.ncols[t], st), 'gg_node_proj')
-        # (b) fused gather per edge type
+        # (b) fused gather: the edge types the warp-specialised kernel serves go into ONE launch per cell (GG_GATHER_MERGE=0: one
+        # launch per edge type), the others through the item-list kernel
         agg, ea = {}, {}
+        merged = []
         for e in pk.edge_types:
             s, _, d = e
             nd = xpad[d].shape[0]
@@ -154,17 +156,23 @@ def run_cell(pk, xpad, h, c, csr, ea_csr, mode, out_h=None, out_c=None, work=Non
             ecap = tiled_ecap(pk, e)
             if ecap:
                 tiles, cta_ptr, n_ctas = g.tiles(ecap)      # builds nz / nzptr on first use
-                check(L.gg_pgat_gather_tiled(ptr(P[s]), pk.ncols[s], pk.koff[e], ptr(P[d]), pk.ncols[d], pk.qoff[e],
-                                             ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(wr),
-                                             ptr(g.nz), ptr(g.nzptr), ptr(tiles), ptr(cta_ptr), n_ctas,
-                                             ecap, g.n_edges, pk.raw_k, ptr(pk.Wv3[e]), nd_out, G, C, ptr(agg[e]), GC, ptr(ea[e]), st),
-                      'gg_pgat_gather_tiled')
+                seg = GatherSegment(P[s].data_ptr(), pk.ncols[s], pk.koff[e], P[d].data_ptr(), pk.ncols[d], pk.qoff[e],
+                                    g.rowptr.data_ptr(), g.col.data_ptr() if g.n_edges else None, ea_csr[e].data_ptr() if g.n_edges else None,
+                                    wr.data_ptr(), g.nz.data_ptr(), g.nzptr.data_ptr(), tiles.data_ptr(), cta_ptr.data_ptr(),
+                                    g.n_edges, pk.Wv3[e].data_ptr(), nd_out, agg[e].data_ptr(), GC, ea[e].data_ptr())
+                merged.append((seg, n_ctas, ecap, wr))      # wr stays referenced until the launch that reads it is enqueued
                 continue
             check(L.gg_pgat_gather(ptr(P[s]), pk.ncols[s], pk.koff[e], pk.voff[e],
                                    ptr(P[d]), pk.ncols[d], pk.qoff[e], pk.qxoff[e],
                                    ptr(xpad[s]), xpad[s].stride(0), ptr(xpad[d]), xpad[d].stride(0),
                                    ptr(g.rowptr), ptr(g.col), ptr(ea_csr[e]), ptr(g.items), ptr(g.item_ptr), ptr(wr), pk.raw_k, ptr(pk.Wv3[e]),
                                    nd_out, G, C, 1 if pk.weighted else 0, ptr(agg[e]), GC, ptr(ea[e]), st), 'gg_pgat_gather')
+        if merged:
+            one = os.environ.get('GG_GATHER_MERGE', '1') == '0'
+            groups = [[m] for m in merged] if one else [merged[i:i + 3] for i in range(0, len(merged), 3)]
+            for grp in groups:
+                arr = (GatherSegment * len(grp))(*[m[0] for m in grp])
+                check(L.gg_pgat_gather_tiled_multi(arr, len(grp), grp[0][1], grp[0][2], pk.raw_k, G, C, st), 'gg_pgat_gather_tiled_multi')
         # (c') gate GEMM + LSTM update per node type
         out_h = {} if out_h is None else out_h
         out_c = {} if out_c is None else out_c

@@ -43,6 +43,9 @@ __device__ __forceinline__ unsigned long long gg_globaltimer() { unsigned long l
 #define GG_PROF_ADD(var) do {} while (0)
 #endif
 
+#ifndef GG_PRODUCER_SLEEP_NS
+#define GG_PRODUCER_SLEEP_NS 250u
+#endif
 #ifndef GG_ENC_ROW_PAD
 #define GG_ENC_ROW_PAD 16u
 #endif
@@ -56,7 +59,7 @@ constexpr int CH = 3;                 // edges per softmax chunk (joints have ex
 struct FastTag { static constexpr bool value = true; };
 struct SlowTag { static constexpr bool value = false; };
 
-struct TiledParams {
+struct TiledSeg {                                    // one edge type (all gates of the cell)
     const float* P_src; int ld_src, k_off;
     const float* P_dst; int ld_dst, q_off;          // target block at q_off: Q | QX (or Q') | position
     const int* rowptr; const int* col; const float* ea; const int* wrap;
@@ -64,6 +67,14 @@ struct TiledParams {
     const float* Wv3;
     int n_dst, n_edges;
     float* agg; int ld_agg; float* ea_out;
+};
+constexpr int kMaxSeg = 3;
+// One launch serves up to kMaxSeg edge types of a cell (same width, gates and row form, hence the same stage layout): every
+// persistent CTA walks its tiles of segment 0, then of segment 1, ... without draining the stage ring in between, so a cell
+// pays one launch ramp and one tail instead of three.
+struct TiledParams {
+    TiledSeg seg[kMaxSeg];
+    int n_seg;
     float inv_sqrt_c;
 };
 
@@ -93,17 +104,21 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
         }
     } while (!done);
 }
-// Producer-side wait: the try_wait carries a suspend-time hint, so a waiting producer warp sleeps in hardware until the phase
-// completes instead of polling — its polls otherwise take ~10 % of the issue slots the consumer warps of the same schedulers need.
+// Producer-side wait: a waiting producer warp must not poll — its polls take issue slots from the consumer warps of the same
+// scheduler (ncu round 2: the suspend-time hint of try_wait returns after ~50 ns, 32 polls per tile and warp, 12 % of all
+// instructions issued).  The producers run NS - 1 stages ahead, so they can afford to sleep between polls.
 __device__ __forceinline__ void mbar_wait_sleepy_(uint32_t bar, uint32_t parity) {
     uint32_t done, spins = 0;
     long long t0 = 0;
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
-        if (!done && (++spins & 0xffu) == 0) {               // a lost arrival must surface as an error, not as a hung GPU
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > 8000000000LL) __trap();
+        if (!done) {
+            asm volatile("nanosleep.u32 %0;" ::"r"(GG_PRODUCER_SLEEP_NS));
+            if ((++spins & 0xffu) == 0) {                    // a lost arrival must surface as an error, not as a hung GPU
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > 8000000000LL) __trap();
+            }
         }
     } while (!done);
 }
@@ -219,7 +234,7 @@ constexpr bool cfg_supported(int G, int mode) { return mode == 1 ? G == 3 : (mod
 
 template <int NV, int G, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-pgat_gather_tiled_kernel(const TiledParams p) {
+pgat_gather_tiled_kernel(const __grid_constant__ TiledParams P) {
     using K = TCfg<NV, G, MODE>;
     constexpr bool RAW = MODE != 0, RAWH = MODE == 2;        // raw scores; ... on the full cell input (with hidden state)
     constexpr int RAWK = K::RAW;
@@ -242,7 +257,6 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     }
     __syncthreads();
     const int grid = gridDim.x;
-    const int f0 = __ldg(&p.cta_ptr[blockIdx.x]), n_tiles = __ldg(&p.cta_ptr[blockIdx.x + 1]) - f0;   // this CTA's tiles
 
     if (warp < NP) {
         // =========================================================================================== producers
@@ -252,27 +266,32 @@ pgat_gather_tiled_kernel(const TiledParams p) {
         // ahead and the per-edge / per-target metadata one tile ahead, so the chain tiles -> col -> row address is never waited for.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");          // registers go to the consumer warpgroups
         struct Meta { int col, wrap, tn, ta, tb, t0, colA, colB; float ea; };
+        const TiledSeg* p = &P.seg[0];
+        int f0 = 0, n_tiles = 0;
         const int mine = warp + NP * lane;                           // the slot and the target this lane serves in every tile
         auto load_desc = [&](int t) -> int4 {                        // {first edge, edges, first target, last target}
-            return t < n_tiles ? __ldg(&p.tiles[f0 + t]) : make_int4(0, 0, 0, -1);
+            return t < n_tiles ? __ldg(&p->tiles[f0 + t]) : make_int4(0, 0, 0, -1);
         };
         auto load_meta = [&](const int4& d) -> Meta {
             Meta m;
             const int e0 = d.x, ne = d.y, cnt = d.w - d.z + 1;
             m.col = 0; m.wrap = 0; m.ea = 0.f; m.tn = 0; m.ta = 0; m.tb = 0; m.t0 = 0;
-            m.colA = lane < ne ? __ldg(&p.col[e0 + lane]) : -1 - lane;               // every slot's source, for the duplicate search
-            m.colB = (ECAP > 32 && 32 + lane < ne) ? __ldg(&p.col[e0 + 32 + lane]) : -33 - lane;
-            if (mine < ne) { m.col = __ldg(&p.col[e0 + mine]); m.ea = __ldg(&p.ea[e0 + mine]); m.wrap = __ldg(&p.wrap[e0 + mine]); }
-            if (mine < cnt) { m.tn = __ldg(&p.nz[d.z + mine]); m.ta = __ldg(&p.nzptr[d.z + mine]); m.tb = __ldg(&p.nzptr[d.z + mine + 1]); }
-            if (cnt > 0) m.t0 = __ldg(&p.nzptr[d.z]);
+            m.colA = lane < ne ? __ldg(&p->col[e0 + lane]) : -1 - lane;               // every slot's source, for the duplicate search
+            m.colB = (ECAP > 32 && 32 + lane < ne) ? __ldg(&p->col[e0 + 32 + lane]) : -33 - lane;
+            if (mine < ne) { m.col = __ldg(&p->col[e0 + mine]); m.ea = __ldg(&p->ea[e0 + mine]); m.wrap = __ldg(&p->wrap[e0 + mine]); }
+            if (mine < cnt) { m.tn = __ldg(&p->nz[d.z + mine]); m.ta = __ldg(&p->nzptr[d.z + mine]); m.tb = __ldg(&p->nzptr[d.z + mine + 1]); }
+            if (cnt > 0) m.t0 = __ldg(&p->nzptr[d.z]);
             return m;
         };
-        int4 d_cur = load_desc(0), d_nxt = load_desc(1);
-        Meta m_cur = load_meta(d_cur);
         int stage = 0; uint32_t phase = 0;
         long long prof_wait = 0, prof_busy = 0;
         (void)prof_wait; (void)prof_busy;
         GG_PROF_T0();
+        for (int sg = 0; sg < P.n_seg; ++sg) {
+        p = &P.seg[sg];
+        f0 = __ldg(&p->cta_ptr[blockIdx.x]); n_tiles = __ldg(&p->cta_ptr[blockIdx.x + 1]) - f0;   // this CTA's tiles of the segment
+        int4 d_cur = load_desc(0), d_nxt = load_desc(1);
+        Meta m_cur = load_meta(d_cur);
         for (int t = 0; t < n_tiles; ++t) {
             const int4 d_n2 = load_desc(t + 2);
             const Meta m_nxt = load_meta(d_nxt);
@@ -305,13 +324,14 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             __syncwarp();
             if (lane == 0) mbar_expect_tx_(bar, (uint32_t)n_rows * K::ES + (uint32_t)n_hdr * K::HB);
             __syncwarp();
-            if (copies_row) bulk_g2s(base + (uint32_t)mine * K::ESS, p.P_src + (size_t)m_cur.col * p.ld_src + p.k_off, K::ES, bar);
+            if (copies_row) bulk_g2s(base + (uint32_t)mine * K::ESS, p->P_src + (size_t)m_cur.col * p->ld_src + p->k_off, K::ES, bar);
             if (has_hdr) {
                 const uint32_t hd = base + K::HDR + (uint32_t)h * K::HB;
-                bulk_g2s(hd, p.P_dst + (size_t)m_cur.tn * p.ld_dst + p.q_off, K::HB, bar);     // Q | QX (Q') and the position behind it
+                bulk_g2s(hd, p->P_dst + (size_t)m_cur.tn * p->ld_dst + p->q_off, K::HB, bar);     // Q | QX (Q') and the position behind it
             }
             d_cur = d_nxt; d_nxt = d_n2; m_cur = m_nxt;
             if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
         }
 #ifdef GG_TILED_PROFILE
         GG_PROF_ADD(prof_busy);
@@ -328,21 +348,11 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     const int gsel = active ? grp : 0;                       // idle 8-lane groups (G < 4) shadow gate 0 and store nothing
     const uint32_t lane_off = 4u * (gsel * C + 4 * sub);     // byte offset of this lane's first float4 inside a staged row
     const uint32_t v_off = RAW ? 4u * RAWK : (uint32_t)GC * 4u;   // V row behind the raw block / the K row
-    const float sc2 = p.inv_sqrt_c * LOG2E;                  // scores are kept in log2 units: exp(x) = ex2(x log2 e)
+    const float sc2 = P.inv_sqrt_c * LOG2E;                  // scores are kept in log2 units: exp(x) = ex2(x log2 e)
     const int me = sub % 3;                                  // raw-score mode: the edge of a chunk this lane scores (lanes 0..2 of a group publish)
     const int src0 = lane & 24;                              // lane `sub == 0` of this gate group
 
-    // x, y, z columns of lin_value for this lane's channels (zero for idle groups): Wv3 is [G*C][4]; packed pairs
-    P4 wvx[NV], wvy[NV], wvz[NV];
-#pragma unroll
-    for (int r = 0; r < NV; ++r) {
-        float4 t4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) t4[i] = active ? ldg4(p.Wv3 + (size_t)(grp * C + 4 * (sub + 8 * r) + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        wvx[r].lo = pack2(t4[0].x, t4[1].x); wvx[r].hi = pack2(t4[2].x, t4[3].x);
-        wvy[r].lo = pack2(t4[0].y, t4[1].y); wvy[r].hi = pack2(t4[2].y, t4[3].y);
-        wvz[r].lo = pack2(t4[0].z, t4[1].z); wvz[r].hi = pack2(t4[2].z, t4[3].z);
-    }
+    P4 wvx[NV], wvy[NV], wvz[NV];                            // x, y, z columns of lin_value for this lane's channels (per segment)
 
     // per-target state (survives tile boundaries)
     P4 q[NQ], vp[NV], acc[NV];
@@ -361,6 +371,25 @@ pgat_gather_tiled_kernel(const TiledParams p) {
     const long long prof_c0 = clock64();
     const unsigned long long prof_n0 = gg_globaltimer();
 #endif
+    for (int sg = 0; sg < P.n_seg; ++sg) {
+    const TiledSeg& ps = P.seg[sg];
+    const int n_tiles = __ldg(&ps.cta_ptr[blockIdx.x + 1]) - __ldg(&ps.cta_ptr[blockIdx.x]);   // this CTA's tiles of the segment
+    // What the per-target code reads of the segment lives in registers: indexed constant-bank loads (c[0x0][R + off], ~30 clk)
+    // would otherwise sit on the critical path of every target (measured: +8 % on the launch).
+    struct { const float* P_dst; float* agg; float* ea_out; const int* rowptr; const float* Wv3; int n_dst, ld_dst, q_off, ld_agg; } p;
+    p.P_dst = ps.P_dst; p.agg = ps.agg; p.ea_out = ps.ea_out; p.rowptr = ps.rowptr; p.Wv3 = ps.Wv3;
+    p.n_dst = ps.n_dst; p.ld_dst = ps.ld_dst; p.q_off = ps.q_off; p.ld_agg = ps.ld_agg;
+    asm volatile("" : "+l"(p.P_dst), "+l"(p.agg), "+l"(p.ea_out), "+r"(p.n_dst), "+r"(p.ld_dst), "+r"(p.q_off), "+r"(p.ld_agg));
+    // x, y, z columns of lin_value for this lane's channels (zero for idle groups): Wv3 is [G*C][4]; packed pairs
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        float4 t4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t4[i] = active ? ldg4(p.Wv3 + (size_t)(grp * C + 4 * (sub + 8 * r) + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wvx[r].lo = pack2(t4[0].x, t4[1].x); wvx[r].hi = pack2(t4[2].x, t4[3].x);
+        wvy[r].lo = pack2(t4[0].y, t4[1].y); wvy[r].hi = pack2(t4[2].y, t4[3].y);
+        wvz[r].lo = pack2(t4[0].z, t4[1].z); wvz[r].hi = pack2(t4[2].z, t4[3].z);
+    }
     for (int t = 0; t < n_tiles; ++t) {
         const uint32_t base = smem0 + (uint32_t)stage * K::BYTES;
         GG_PROF_ADD(prof_busy);
@@ -564,16 +593,6 @@ pgat_gather_tiled_kernel(const TiledParams p) {
         if (++stage == NS) { stage = 0; phase ^= 1u; }
     }
 
-#ifdef GG_TILED_PROFILE
-    GG_PROF_ADD(prof_busy);
-    if (lane == 0) { atomicAdd(&g_tiled_prof[0], (unsigned long long)prof_wait); atomicAdd(&g_tiled_prof[1], (unsigned long long)prof_busy); atomicAdd(&g_tiled_prof[4], 1ull); }
-    if (blockIdx.x == 0 && cw == 0 && lane == 0) {
-        const unsigned long long dc = (unsigned long long)(clock64() - prof_c0), dn = gg_globaltimer() - prof_n0;
-        g_tiled_prof[6] = dc; g_tiled_prof[7] = dn;
-        const unsigned int slot = atomicAdd(&g_clk_n, 1u) & 127u;
-        g_clk_ring[2 * slot] = dc; g_clk_ring[2 * slot + 1] = dn;
-    }
-#endif
     // ---- targets without in-edges: zero rows (PyG scatter-add leaves them 0)
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t b0 = ((int64_t)blockIdx.x * NC + cw) * 32; b0 < p.n_dst; b0 += (int64_t)grid * NC * 32) {
@@ -592,6 +611,17 @@ pgat_gather_tiled_kernel(const TiledParams p) {
             }
         }
     }
+    }   // segments
+#ifdef GG_TILED_PROFILE
+    GG_PROF_ADD(prof_busy);
+    if (lane == 0) { atomicAdd(&g_tiled_prof[0], (unsigned long long)prof_wait); atomicAdd(&g_tiled_prof[1], (unsigned long long)prof_busy); atomicAdd(&g_tiled_prof[4], 1ull); }
+    if (blockIdx.x == 0 && cw == 0 && lane == 0) {
+        const unsigned long long dc = (unsigned long long)(clock64() - prof_c0), dn = gg_globaltimer() - prof_n0;
+        g_tiled_prof[6] = dc; g_tiled_prof[7] = dn;
+        const unsigned int slot = atomicAdd(&g_clk_n, 1u) & 127u;
+        g_clk_ring[2 * slot] = dc; g_clk_ring[2 * slot + 1] = dn;
+    }
+#endif
 }
 
 int host_mode(int C, int raw_k) { return raw_k == 0 ? 0 : (raw_k == 16 ? 1 : (raw_k == 32 + C ? 2 : -1)); }
@@ -620,33 +650,34 @@ extern "C" int gg_gather_ctas(void) {
     return n;
 }
 
-extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t k_off,
-                                    const float* P_dst, int32_t ld_dst, int32_t q_off,
-                                    const int32_t* rowptr, const int32_t* col, const float* eattr_csr, const int32_t* wrap_csr,
-                                    const int32_t* nz, const int32_t* nzptr, const int32_t* tiles, const int32_t* cta_ptr,
-                                    int32_t n_ctas, int32_t ecap, int64_t n_edges,
-                                    int32_t raw_k, const float* Wv3, int32_t n_dst, int32_t G, int32_t C,
-                                    float* agg, int32_t ld_agg, float* ea, void* stream) {
-    if (n_dst < 0 || n_edges < 0 || n_edges > 0x7fffffffLL) return GG_EINVAL;
+extern "C" int gg_pgat_gather_tiled_multi(const gg_gather_segment* segs, int32_t n_seg, int32_t n_ctas, int32_t ecap,
+                                          int32_t raw_k, int32_t G, int32_t C, void* stream) {
+    if (!segs || n_seg < 1 || n_seg > kMaxSeg) return GG_EINVAL;
     const int my_ecap = host_ecap(G, C, raw_k);
-    if (my_ecap == 0 || ecap != my_ecap) return GG_EINVAL;
-    if (n_dst == 0) return 0;
-    if (!P_src || !P_dst || !rowptr || !Wv3 || !agg || !ea) return GG_EINVAL;
-    if (!cta_ptr || n_ctas < 1) return GG_EINVAL;
-    if (n_edges > 0 && (!col || !eattr_csr || !wrap_csr || !nz || !nzptr || !tiles || !gg_aligned16(tiles))) return GG_EINVAL;
-    if ((ld_src | k_off | ld_dst | q_off | ld_agg) & 3) return GG_EALIGN;
-    if (!gg_aligned16(P_src) || !gg_aligned16(P_dst) || !gg_aligned16(agg) || !gg_aligned16(Wv3)) return GG_EALIGN;
-    if (!gg_device_is_sm100()) return GG_EARCH;
+    if (my_ecap == 0 || ecap != my_ecap || n_ctas < 1) return GG_EINVAL;
     TiledParams p;
-    p.P_src = P_src; p.ld_src = ld_src; p.k_off = k_off;
-    p.P_dst = P_dst; p.ld_dst = ld_dst; p.q_off = q_off;
-    p.rowptr = rowptr; p.col = col; p.ea = eattr_csr; p.wrap = wrap_csr;
-    p.nz = nz; p.nzptr = nzptr; p.tiles = reinterpret_cast<const int4*>(tiles); p.cta_ptr = cta_ptr;
-    p.Wv3 = Wv3;
-    p.n_dst = n_dst; p.n_edges = (int)n_edges;
-    p.agg = agg; p.ld_agg = ld_agg; p.ea_out = ea;
+    p.n_seg = 0;
     p.inv_sqrt_c = 1.0f / sqrtf((float)C);
-    const unsigned grid = (unsigned)n_ctas;                  // the tile list is ordered for exactly this many CTAs
+    for (int i = 0; i < n_seg; ++i) {
+        const gg_gather_segment& g = segs[i];
+        if (g.n_dst < 0 || g.n_edges < 0 || g.n_edges > 0x7fffffffLL) return GG_EINVAL;
+        if (g.n_dst == 0) continue;
+        if (!g.P_src || !g.P_dst || !g.rowptr || !g.Wv3 || !g.agg || !g.ea || !g.cta_ptr) return GG_EINVAL;
+        if (g.n_edges > 0 && (!g.col || !g.eattr_csr || !g.wrap_csr || !g.nz || !g.nzptr || !g.tiles || !gg_aligned16(g.tiles))) return GG_EINVAL;
+        if ((g.ld_src | g.k_off | g.ld_dst | g.q_off | g.ld_agg) & 3) return GG_EALIGN;
+        if (!gg_aligned16(g.P_src) || !gg_aligned16(g.P_dst) || !gg_aligned16(g.agg) || !gg_aligned16(g.Wv3)) return GG_EALIGN;
+        TiledSeg& t = p.seg[p.n_seg++];
+        t.P_src = g.P_src; t.ld_src = g.ld_src; t.k_off = g.k_off;
+        t.P_dst = g.P_dst; t.ld_dst = g.ld_dst; t.q_off = g.q_off;
+        t.rowptr = g.rowptr; t.col = g.col; t.ea = g.eattr_csr; t.wrap = g.wrap_csr;
+        t.nz = g.nz; t.nzptr = g.nzptr; t.tiles = reinterpret_cast<const int4*>(g.tiles); t.cta_ptr = g.cta_ptr;
+        t.Wv3 = g.Wv3;
+        t.n_dst = g.n_dst; t.n_edges = (int)g.n_edges;
+        t.agg = g.agg; t.ld_agg = g.ld_agg; t.ea_out = g.ea;
+    }
+    if (p.n_seg == 0) return 0;
+    if (!gg_device_is_sm100()) return GG_EARCH;
+    const unsigned grid = (unsigned)n_ctas;                  // the tile lists are ordered for exactly this many CTAs
     cudaStream_t st = GG_STREAM(stream);
     cudaError_t err = cudaSuccess;
 #define GG_TILED(NV, GV, RAWV)                                                                                                     \
@@ -672,6 +703,23 @@ extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t 
 #undef GG_TILED
     GG_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t k_off,
+                                    const float* P_dst, int32_t ld_dst, int32_t q_off,
+                                    const int32_t* rowptr, const int32_t* col, const float* eattr_csr, const int32_t* wrap_csr,
+                                    const int32_t* nz, const int32_t* nzptr, const int32_t* tiles, const int32_t* cta_ptr,
+                                    int32_t n_ctas, int32_t ecap, int64_t n_edges,
+                                    int32_t raw_k, const float* Wv3, int32_t n_dst, int32_t G, int32_t C,
+                                    float* agg, int32_t ld_agg, float* ea, void* stream) {
+    gg_gather_segment g;
+    g.P_src = P_src; g.ld_src = ld_src; g.k_off = k_off;
+    g.P_dst = P_dst; g.ld_dst = ld_dst; g.q_off = q_off;
+    g.rowptr = rowptr; g.col = col; g.eattr_csr = eattr_csr; g.wrap_csr = wrap_csr;
+    g.nz = nz; g.nzptr = nzptr; g.tiles = tiles; g.cta_ptr = cta_ptr;
+    g.n_edges = n_edges; g.Wv3 = Wv3; g.n_dst = n_dst;
+    g.agg = agg; g.ld_agg = ld_agg; g.ea = ea;
+    return gg_pgat_gather_tiled_multi(&g, 1, n_ctas, ecap, raw_k, G, C, stream);
 }
 
 // Debug builds (-DGG_TILED_PROFILE): (SM clocks, ns) that consumer warp 0 of CTA 0 spent in each of the last <= 128 launches, in launch

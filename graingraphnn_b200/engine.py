@@ -29,6 +29,16 @@ class _Hyper:
         self.metadata, self.device, self.out_win, self.window = metadata, device, 1, 1
 
 
+def morton_order(pos, bits=12):
+    """Row order along a Morton (Z) curve of pos[:, :2] in [0, 1)^2: int64 [N], order[i] = the node that takes row i."""
+    q = (pos[:, :2].to(torch.float32) * (1 << bits)).long().clamp_(0, (1 << bits) - 1)
+    code = torch.zeros(q.shape[0], dtype=torch.int64, device=pos.device)
+    for b in range(bits):
+        code |= ((q[:, 0] >> b) & 1) << (2 * b)
+        code |= ((q[:, 1] >> b) & 1) << (2 * b + 1)
+    return torch.sort(code, stable=True).indices
+
+
 class RolloutEngine:
     def __init__(self, regressor, classifier, device='cuda'):
         self.device = torch.device(device)
@@ -69,11 +79,32 @@ class RolloutEngine:
                                      dec.packed(('i', 'f', 'c', 'o'), True, self.device, self.edge_types))
         return self._packs
 
-    def set_graph(self, x_dict, edge_index_dict, edge_attr_dict=None):
-        """Copy features into padded resident buffers, build the CSR of every edge type, take (or compute) edge lengths."""
+    node_order = None        # {node type: int64 [N]}: engine row -> caller's node id (None: rows are in the caller's order)
+    _node_rank = None        # the inverse: caller's node id -> engine row
+
+    def set_graph(self, x_dict, edge_index_dict, edge_attr_dict=None, global_pos=None):
+        """Copy features into padded resident buffers, build the CSR of every edge type, take (or compute) edge lengths.
+
+        global_pos (optional): {node type: [N, >= 2]} position of every node in the WHOLE domain, each coordinate in [0, 1)
+        ((x_patch + domain_offset) / domain_factor, test.py:43-44, :474; the features themselves when the domain is one patch).
+        When given, the engine keeps its rows along a Morton curve of these positions: the reference numbers grains in seed-lattice
+        order and joints in first-seen order (graph_datastruct.py:118-160, :395-406), under which the targets of a gather tile share
+        no source rows and every edge stages its own 1-2 KB row; along the curve a tile is a compact patch of the tiling and
+        25-55 % of its edges find their source row already staged.  Everything the caller sees keeps the caller's numbering:
+        `step()` returns node predictions in the caller's order, edge predictions in the original edge order, `set_topology`,
+        `enable_geometry_feedback`, `enable_event_selection` / `fetch_events` take and return the caller's ids.  Only the resident
+        rows `self.x[t]` / `host_features()` / `load_features()` are in engine order: row i is the caller's node `node_order[t][i]`."""
         self._graph = None
         self._state = None
         self._event_mask = None                       # belongs to the previous grain set (set_event_mask)
+        self.node_order = self._node_rank = self._event_edges = None
+        if global_pos is not None:
+            self.node_order, self._node_rank = {}, {}
+            for t in self.node_types:
+                order = morton_order(global_pos[t].to(self.device))
+                self.node_order[t] = order
+                self._node_rank[t] = torch.empty_like(order).scatter_(0, order, torch.arange(order.shape[0], device=self.device))
+            x_dict = {t: x_dict[t].to(self.device).index_select(0, self.node_order[t]) for t in self.node_types}
         for t in self.node_types:
             xt = x_dict[t].to(self.device, torch.float32)
             buf = self.alloc_rows_x(t, xt.shape[0], pad4(xt.shape[1]))
@@ -84,10 +115,15 @@ class RolloutEngine:
         self.set_topology(edge_index_dict, edge_attr_dict)
 
     def set_topology(self, edge_index_dict, edge_attr_dict=None):
+        """edge_index_dict in the CALLER's node ids (and edge order: per-edge outputs follow it)."""
         self._graph = None
         self._region = None
         for e in self.edge_types:
             ei = edge_index_dict[e].to(self.device).contiguous()
+            if self._node_rank is not None:           # engine rows of the end points; the edge order is the caller's
+                if e == ET_JJ:
+                    self._event_edges = ei            # `src < dst` of the event selection reads the caller's ids (models.py:629)
+                ei = torch.stack([self._node_rank[e[0]][ei[0]], self._node_rank[e[2]][ei[1]]])
             self.edge_index[e] = ei
             self.csr[e] = build_csr(ei, self.xbuf[e[0]].shape[0], self.xbuf[e[2]].shape[0])
             self.edge_attr[e] = torch.empty(ei.shape[1], 1, dtype=torch.float32, device=self.device)
@@ -152,6 +188,8 @@ class RolloutEngine:
             self._event_mask = None
         else:
             m = mask_grain.to(self.device, torch.float32).reshape(mask_grain.shape[0], -1)[:, 0].contiguous()
+            if self.node_order is not None:
+                m = m.index_select(0, self.node_order['grain'])
             ng = int(self.xbuf['grain'].shape[0]) if 'grain' in self.xbuf else m.shape[0]
             if m.shape[0] < ng:
                 raise ValueError(f'mask_grain has {m.shape[0]} rows for {ng} grains (refresh it after nucleation)')
@@ -163,19 +201,30 @@ class RolloutEngine:
         test.py:416), ...}; ids are rows / edges of the graph this engine holds."""
         if self._events is None:
             raise RuntimeError('enable_event_selection() first')
-        return self._events.fetch()
+        ev = self._events.fetch()
+        if self.node_order is not None:               # grain rows -> the caller's grain ids
+            order = self.node_order['grain'].cpu()
+            ev['grain_event'], ev['grain_event_ids'] = order[ev['grain_event']], order[ev['grain_event_ids']]
+        return ev
 
     # ------------------------------------------------------------------------------------- geometry feedback (f2)
     _geom = None
+    _geom_in_step = True
     _region = None
     centers = None
 
-    def enable_geometry_feedback(self, joint_offset=None, domain_factor=1):
+    def enable_geometry_feedback(self, joint_offset=None, domain_factor=1, in_step=True):
         """From now on every step moves the grain coordinates to the centres of their joints before the edge lengths are
         rebuilt, as the reference's loop does on the host (traj.GNN_update -> graph.update, graph_datastruct.py:672-708, then
         test.py:556-559).  joint_offset [Nj,2] / domain_factor: the patch scaling of test.py:29-44 (global = (x + offset) / factor).
         self.centers holds the float64 centres of the last step (NaN rows: grains with <= 1 joint)."""
-        self._geom = (None if joint_offset is None else joint_offset.to(self.device, torch.float32).contiguous(), domain_factor)
+        if joint_offset is not None:
+            joint_offset = joint_offset.to(self.device, torch.float32)
+            if self.node_order is not None:
+                joint_offset = joint_offset.index_select(0, self.node_order['joint'])
+            joint_offset = joint_offset.contiguous()
+        self._geom = (joint_offset, domain_factor)
+        self._geom_in_step = bool(in_step)           # False: the caller runs region_feedback() itself, after its topology update (rollout.py)
         self._graph = None
         self._region = None
 
@@ -296,10 +345,14 @@ class RolloutEngine:
             feature_update(self.x['joint'], self.x['grain'], yj, yg, span / (self.train_frames + 1),
                            self.train_frames / (self.train_frames + 1), self._scratch, n_joint=nj, n_grain=ng)
         yield [self.xbuf]                                    # moved coordinates of the halo -> edge lengths, next step
-        if self._geom is not None:                           # row f2: grain centres follow their joints (test.py:471-476, :556-559)
+        if self._geom is not None and self._geom_in_step:    # row f2: grain centres follow their joints (test.py:471-476, :556-559)
             self.region_feedback()                           # owned grains, from owned + halo joints
             yield [{'grain': self.xbuf['grain']}]            # centres of the halo grains
         self.rebuild_edge_attr()
+        if self.node_order is not None:                      # node predictions in the caller's numbering (3 small gathers)
+            rj, rg = self._node_rank['joint'], self._node_rank['grain']
+            self._pred_rows = {'joint': yj, 'grain': yg, 'grain_area': area}
+            yj, yg, area = yj.index_select(0, rj), yg.index_select(0, rg), area.index_select(0, rg)
         self.pred = {'joint': yj, 'grain': yg, 'grain_area': area, 'edge_event': ev, 'edge': ed}
 
     graph_ptr = None         # {node type: [0, n_0, n_0 + n_1, ...]} of a block-diagonal batch (ensemble.EnsembleEngine)

@@ -61,8 +61,20 @@ def owners_by_x(global_x, world):
     return np.minimum((gx * world).astype(np.int64), world - 1).astype(np.int32)
 
 
-def build_plan(n_nodes, edge_index, owner, rank, world):
-    """n_nodes: {type: N}; edge_index: {(s, r, d): int64 [2, E] (numpy or torch)}; owner: {type: int32 [N]}."""
+def morton_key(pos, bits=12):
+    """Morton (Z-curve) key of pos[:, :2] in [0, 1)^2 (numpy int64) — the row order inside a slab, see RolloutEngine.set_graph."""
+    q = np.clip((np.asarray(pos, dtype=np.float64)[:, :2] * (1 << bits)).astype(np.int64), 0, (1 << bits) - 1)
+    code = np.zeros(q.shape[0], dtype=np.int64)
+    for b in range(bits):
+        code |= ((q[:, 0] >> b) & 1) << (2 * b)
+        code |= ((q[:, 1] >> b) & 1) << (2 * b + 1)
+    return code
+
+
+def build_plan(n_nodes, edge_index, owner, rank, world, order_key=None):
+    """n_nodes: {type: N}; edge_index: {(s, r, d): int64 [2, E] (numpy or torch)}; owner: {type: int32 [N]};
+    order_key (optional): {type: int64 [N]} — the owned rows of a slab are laid out by ascending key (ties: global id) instead of
+    ascending global id (a Morton key keeps the targets of a gather tile spatially compact)."""
     plan = SlabPlan(rank, world)
     ei = {e: (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for e, v in edge_index.items()}
     types = list(n_nodes)
@@ -84,6 +96,8 @@ def build_plan(n_nodes, edge_index, owner, rank, world):
         needer, gid = need[t]
         src_owner = owner[t][gid].astype(np.int64)
         plan.own[t] = np.nonzero(owner[t] == rank)[0]
+        if order_key is not None:
+            plan.own[t] = plan.own[t][np.argsort(order_key[t][plan.own[t]], kind='stable')]
         plan.n_own[t] = int(plan.own[t].shape[0])
         # our halo: rows we need, ordered by (owner rank, global id)
         mine = needer == rank
@@ -262,7 +276,8 @@ class PartitionedEngine(RolloutEngine):
         transport = transport or os.environ.get('GG_HALO', 'nccl')
         owner = {t: owners_by_x(np.asarray(global_pos[t])[:, 0], world) for t in x_dict}
         n_nodes = {t: int(v.shape[0]) for t, v in x_dict.items()}
-        self.plan = build_plan(n_nodes, edge_index_dict, owner, rank, world)
+        key = None if os.environ.get('GG_SLAB_ORDER', 'morton') != 'morton' else {t: morton_key(np.asarray(global_pos[t])) for t in x_dict}
+        self.plan = build_plan(n_nodes, edge_index_dict, owner, rank, world, key)
         self.halo = HaloExchange(self.plan, self.device, transport, group)
         self.n_rows = dict(self.plan.n_own)           # kernels that WRITE per-node results stop at the owned rows
         self._region_src = (edge_index_dict, owner)   # region_edges() runs when the geometry feedback is first used

@@ -110,3 +110,11 @@ def honeycomb_graph(nx, ny, seed=0, jitter=0.08, G=10.0, R=2.0, span=6, patches=
                 'patches': (Lx, Ly)}
         return x, ei, glob
     return x, ei
+
+
+def lattice_domain(patches=(36, 30), seed=1):
+    """(x, ei, global positions, patches) of the honeycomb stand-in covering `patches` 40-um patches — a quick regular test
+    domain for side scripts; benchmarks and parity tests use generate.generate_graph (the reference's generate mode)."""
+    nx, ny = lattice_dims(*patches)
+    x, ei, glob = honeycomb_graph(nx, ny, seed=seed, patches=patches, return_global=True)
+    return x, ei, glob, patches

@@ -172,6 +172,24 @@ int gg_pgat_gather_tiled(const float* P_src, int32_t ld_src, int32_t k_off,
                          int32_t raw_k, const float* Wv3, int32_t n_dst, int32_t G, int32_t C,
                          float* agg, int32_t ld_agg, float* ea, void* stream);
 
+/* The same kernel for up to 3 edge types of ONE cell in one launch (same C, G, raw_k, hence one stage layout): every persistent
+ * CTA walks its tiles of segment 0, then segment 1, ... without draining the stage ring in between — one launch ramp and one
+ * tail per cell instead of one per edge type (the 12 PeriodConv calls of a HeteroPGCLSTM cell, heteropgclstm.py:111-142, in a
+ * single launch).  Fields as the arguments of gg_pgat_gather_tiled; segments with n_dst == 0 are skipped. */
+typedef struct gg_gather_segment {
+    const float* P_src; int32_t ld_src, k_off;
+    const float* P_dst; int32_t ld_dst, q_off;
+    const int32_t* rowptr; const int32_t* col; const float* eattr_csr; const int32_t* wrap_csr;
+    const int32_t* nz; const int32_t* nzptr; const int32_t* tiles; const int32_t* cta_ptr;
+    int64_t n_edges;
+    const float* Wv3;
+    int32_t n_dst;
+    float* agg; int32_t ld_agg;
+    float* ea;
+} gg_gather_segment;
+int gg_pgat_gather_tiled_multi(const gg_gather_segment* segs, int32_t n_seg, int32_t n_ctas, int32_t ecap,
+                               int32_t raw_k, int32_t G, int32_t C, void* stream);
+
 /* Periodic wrap of every edge (periodGATconv.py:209-210), CSR order: r = p_src - p_dst per coordinate, code 1 where
  * r < -0.5 (+1), 2 where r > 0.5 (-1), else 0; wrap_csr[e] = cx | cy << 2 | cz << 4.  pos_* point at column 0 (x,y,z). */
 int gg_edge_wrap(const float* pos_src, int32_t ld_pos_src, const float* pos_dst, int32_t ld_pos_dst,

@@ -1,12 +1,14 @@
 #!/bin/bash
-# One gpurun call: A/B of library variants (graingraphnn_b200/lib/variants/*.so, GG_LIB) on the bench workload.
-#   VARIANTS="default r1 pad0" TESTS=1 NCU=default scripts/ab_gather.sh
+# One gpurun call: A/B of library variants (graingraphnn_b200/lib/variants/*.so, GG_LIB) and env switches on the bench workload.
+#   VARIANTS="default nosleep default:GG_GATHER_MERGE=0" TESTS=1 NCU=default scripts/ab_gather.sh
 mkdir -p gpurun_out
-if [ -n "$TESTS" ]; then timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log; fi
-for v in ${VARIANTS:-default}; do
+if [ -n "$TESTS" ]; then timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log; fi
+for spec in ${VARIANTS:-default}; do
+  v=${spec%%:*}; envs=""; [ "$spec" != "$v" ] && envs=${spec#*:}
+  tag=$(echo "$spec" | tr ':=' '__')
   lib=""; [ "$v" != default ] && lib="$PWD/graingraphnn_b200/lib/variants/$v.so"
-  GG_LIB=$lib GG_BENCH_VERBOSE=1 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline $BENCH_ARGS > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
-  python - "$v" <<'PY'
+  env GG_LIB=$lib GG_BENCH_VERBOSE=1 $envs timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-strong $BENCH_ARGS > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  python - "$tag" <<'PY'
 import json, sys
 v = sys.argv[1]
 try:
@@ -20,7 +22,7 @@ PY
 done
 if [ -n "$NCU" ]; then
   lib=""; [ "$NCU" != default ] && lib="$PWD/graingraphnn_b200/lib/variants/$NCU.so"
-  GG_LIB=$lib timeout 900 ncu --set full --clock-control none --import-source on -k regex:pgat_gather -s 36 -c 12 -o gpurun_out/prof_gather_$NCU -f \
-      python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_gather.log 2>&1
+  GG_LIB=$lib timeout 900 ncu --set full --clock-control none --import-source on -k regex:pgat_gather -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-4} -o gpurun_out/prof_gather_$NCU -f \
+      python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-strong > gpurun_out/ncu_gather.log 2>&1
   tail -3 gpurun_out/ncu_gather.log
 fi

@@ -20,10 +20,10 @@ from graingraphnn_b200.engine import RolloutEngine  # noqa: E402
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     dev = torch.device('cuda:0')
-    x, ei, _, pp = bench.make_domain(1, None, seed=1)
-    sd_r, sd_c = bench.synth_weights()
+    x, ei, ea, _, _ = bench.make_domain(bench.weak_lxd(1))
+    sd_r, sd_c, _ = bench.synth_weights()
     eng = RolloutEngine.from_state_dicts(sd_r, sd_c, device=dev)
-    eng.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
+    eng.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()}, {k: v.to(dev) for k, v in ea.items()})
     _engine._TWO_STREAMS = False
     for _ in range(3):
         eng.step(6)
@@ -31,7 +31,7 @@ def main():
     ring = (ctypes.c_ulonglong * 256)()
     L.gg_gather_tiled_clocks.restype = ctypes.c_int
     assert L.gg_gather_tiled_clocks(ring) >= 0, 'library was not built with GG_TILED_PROFILE'
-    real = L.gg_pgat_gather_tiled
+    real = L.gg_pgat_gather_tiled_multi_multi
     evs = []
 
     def wrapped(*a):
@@ -44,7 +44,7 @@ def main():
 
     class Proxy:
         def __getattr__(self, name):
-            return wrapped if name == 'gg_pgat_gather_tiled' else getattr(L, name)
+            return wrapped if name == 'gg_pgat_gather_tiled_multi' else getattr(L, name)
 
     _lib._LIB = Proxy()
     torch.cuda._sleep(40_000_000)
@@ -53,12 +53,13 @@ def main():
     torch.cuda.synchronize()
     _lib._LIB = L
     n = L.gg_gather_tiled_clocks(ring)
-    assert n == len(evs) == 12 * steps, (n, len(evs))
+    per = len(evs) // steps
+    assert n == len(evs) == per * steps, (n, len(evs))
     print('pos      us    MHz   (mean over %d back-to-back eager steps; positions 0-5 encoder R, C; 6-11 decoder R, C)' % steps)
     tot = 0.0
-    for pos in range(12):
-        us = [evs[s * 12 + pos][0].elapsed_time(evs[s * 12 + pos][1]) * 1e3 for s in range(steps)]
-        mhz = [ring[2 * ((s * 12 + pos) & 127)] * 1e3 / max(ring[2 * ((s * 12 + pos) & 127) + 1], 1) for s in range(steps)]
+    for pos in range(per):
+        us = [evs[s * per + pos][0].elapsed_time(evs[s * per + pos][1]) * 1e3 for s in range(steps)]
+        mhz = [ring[2 * ((s * per + pos) & 127)] * 1e3 / max(ring[2 * ((s * per + pos) & 127) + 1], 1) for s in range(steps)]
         tot += sum(us) / steps
         print(f'{pos:3d} {sum(us) / steps:7.1f} {sum(mhz) / steps:6.0f}   first step {us[0]:6.1f} us {mhz[0]:5.0f} MHz')
     print('gather per step: %.3f ms' % (tot / 1e3))

@@ -18,16 +18,16 @@ from graingraphnn_b200.engine import RolloutEngine  # noqa: E402
 
 def main():
     dev = torch.device('cuda:0')
-    x, ei, _, pp = bench.make_domain(1, None, seed=1)
-    sd_r, sd_c = bench.synth_weights()
+    x, ei, ea, _, _ = bench.make_domain(bench.weak_lxd(1))
+    sd_r, sd_c, _ = bench.synth_weights()
     eng = RolloutEngine.from_state_dicts(sd_r, sd_c, device=dev)
-    eng.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
+    eng.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()}, {k: v.to(dev) for k, v in ea.items()})
     for _ in range(2):
         eng.step(6)
     L = _lib.lib()
     L.gg_gather_tiled_profile.restype = ctypes.c_int
     buf = (ctypes.c_ulonglong * 8)()
-    real = L.gg_pgat_gather_tiled
+    real = L.gg_pgat_gather_tiled_multi_multi
     rows = []
 
     def wrapped(*a):
@@ -43,7 +43,7 @@ def main():
 
     class Proxy:
         def __getattr__(self, name):
-            return wrapped if name == 'gg_pgat_gather_tiled' else getattr(L, name)
+            return wrapped if name == 'gg_pgat_gather_tiled_multi' else getattr(L, name)
 
     _lib._LIB = Proxy()
     eng.step(6)

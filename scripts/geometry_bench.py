@@ -40,7 +40,8 @@ def main():
     args = ap.parse_args()
     patches = tuple(int(v) for v in args.patches.split('x'))
     dev = torch.device('cuda:0')
-    x, ei, glob, pp = bench.make_domain(1, patches)
+    from graingraphnn_b200.synth import lattice_domain
+    x, ei, glob, pp = lattice_domain(patches or (36, 30))
     ng, nj, E = x['grain'].shape[0], x['joint'].shape[0], ei[ET_GJ].shape[1]
     xj, xg = x['joint'].to(dev), x['grain'].to(dev)
     idx = RegionIndex(ei[ET_GJ].to(dev), ng, nj)
@@ -79,7 +80,7 @@ def main():
     out['select_events_candidates'] = [len(ev['L1']), len(ev['grain_event'])]
     out['select_events_d2h_bytes_vs_full'] = [sel.d2h_bytes, 4 * (jj.shape[1] + 3 * ng + 2 * nj)]
     # the step with and without the feedback, replayed from a CUDA graph
-    sd_r, sd_c = bench.synth_weights()
+    sd_r, sd_c, _ = bench.synth_weights()
     for fb in (False, True):
         eng = RolloutEngine.from_state_dicts(sd_r, sd_c, dev)
         eng.set_graph({k: v.to(dev) for k, v in x.items()}, {k: v.to(dev) for k, v in ei.items()})
@@ -101,7 +102,7 @@ def main():
         del eng
     # host port in the reference's order (per-grain Python loop + numpy), bounded sample
     import grain_oracle as orc
-    xs, eis, _, _ = bench.make_domain(1, (6, 6))
+    xs, eis, _, _ = lattice_domain((6, 6))
     t0 = time.perf_counter()
     orc.region_center(xs['joint'], eis[ET_GJ], xs['grain'].shape[0])
     dt = time.perf_counter() - t0

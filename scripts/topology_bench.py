@@ -43,7 +43,8 @@ def main():
     out = {'cores': os.cpu_count(), 'cases': []}
     import bench
     cases = [('c2 fixture', load_graph('c2')[:2], 150, 25, 8)]
-    xb, eib, _, pp = bench.make_domain(1, tuple(int(v) for v in args.patches.split('x')))
+    from graingraphnn_b200.synth import lattice_domain
+    xb, eib, _, pp = lattice_domain(tuple(int(v) for v in args.patches.split('x')))
     cases.append((f'synthetic {pp[0]}x{pp[1]} patches', (xb, eib), 300, 0, 6))
     for label, (x, ei), n_switch, n_vanish, sides in cases:
         for seed in range(20):

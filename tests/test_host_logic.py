@@ -1,13 +1,14 @@
 """CPU: host-side logic of the product — module API, state_dict layout, lazy materialisation, deepcopy, weight packing
 (checked by running a torch emulation of the kernels on the packed buffers against the oracle), and the no-CPU-fallback rule."""
 import copy
+import os
 
 import pytest
 import torch
 
 import grain_oracle as orc
 from emulate import emu_cell
-from util import ET, load_graph, rel_err
+from util import ET, GOLDEN, load_graph, rel_err
 
 from graingraphnn_b200 import _lib
 from graingraphnn_b200.cell import pad_features
@@ -24,10 +25,18 @@ def hyper():
 
 
 def test_state_dict_layout_equals_reference():
+    """Keys, order and shapes against the state_dict of the reference's OWN models (tests/golden/reference_state_dict_layout.json,
+    dumped by oracle/make_golden_layout.py from the unmodified models.py), the oracle's restatement and the bench helper."""
+    import json
+    from graingraphnn_b200.weights import state_dict_shapes
+    with open(os.path.join(GOLDEN, 'reference_state_dict_layout.json')) as f:
+        ref = json.load(f)
     R = GrainNN_regressor(hyper())
     C = GrainNN_classifier(hyper(), R)
     for m, kind, n in ((R, 'regressor', 1204612), (C, 'classifier', 1204806)):
         shapes = orc.param_shapes(kind)
+        assert [(k, tuple(s)) for k, s in ref[kind]['keys']] == list(shapes.items()) == list(state_dict_shapes(kind).items())
+        assert ref[kind]['n_params'] == n
         sd = m.state_dict()
         assert list(sd.keys()) == list(shapes.keys())
         assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
