@@ -137,3 +137,53 @@ extern "C" int gg_region_sort(const int32_t* rowptr, const int32_t* col, const i
     GG_LAUNCH_OK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// QoI bookkeeping of GNN_update (graph_trajectory.py:1041-1051, :1100-1103), on the device next to the features it reads.
+//   area_counts[g] = area_g * s^2 / area_sum,  area_sum = sum(area * mask) / (lxd / patch)^2        (live grains, else NaN)
+//   extraV[g]      = mask_g * extraV_g / 20 * s^3
+//   vertex_area[j] = mesh^2 * sum over the grains g of joint j of area_counts[g] / (number of joints of g)
+// area_sum comes from the caller (a float64 reduction over the grain rows); both kernels are one thread per row.
+namespace {
+__global__ void area_counts_kernel(const float* __restrict__ xg, int ld_g, const float* __restrict__ mask, int ld_m, int n_grain,
+                                   double s, double area_sum, double v_scale, double* __restrict__ area_counts, double* __restrict__ extra_v) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_grain) return;
+    const double m = mask ? (double)mask[(size_t)g * ld_m] : 1.0;
+    const double area = (double)xg[(size_t)g * ld_g + 3], ev = (double)xg[(size_t)g * ld_g + 4];
+    area_counts[g] = m > 0.0 ? area * (s * s) / area_sum : nan("");
+    extra_v[g] = m * ev / v_scale * (s * s * s);
+}
+__global__ void vertex_area_kernel(const int32_t* __restrict__ rowptr_j, const int32_t* __restrict__ col_g,
+                                   const int32_t* __restrict__ rowptr_g, const double* __restrict__ area_counts, double mesh2,
+                                   int n_joint, double* __restrict__ vertex_area) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_joint) return;
+    double acc = 0.0;
+    for (int e = rowptr_j[j]; e < rowptr_j[j + 1]; ++e) {
+        const int g = col_g[e];
+        const int deg = rowptr_g[g + 1] - rowptr_g[g];
+        const double a = area_counts[g];
+        if (deg > 0 && a == a) acc += a / (double)deg * mesh2;
+    }
+    vertex_area[j] = acc;
+}
+}  // namespace
+
+extern "C" int gg_area_bookkeeping(const float* x_grain, int32_t ld_g, const float* mask_grain, int32_t ld_m, int32_t n_grain,
+                                   double s, double area_sum, double v_scale, double* area_counts, double* extra_v,
+                                   const int32_t* rowptr_j, const int32_t* col_g, const int32_t* rowptr_g, int32_t n_joint,
+                                   double mesh2, double* vertex_area, void* stream) {
+    if (n_grain < 0 || n_joint < 0 || ld_g < 5 || !x_grain || !area_counts || !extra_v || !(area_sum == area_sum)) return GG_EINVAL;
+    if (n_grain > 0) {
+        area_counts_kernel<<<(n_grain + 255) / 256, 256, 0, GG_STREAM(stream)>>>(x_grain, ld_g, mask_grain, ld_m, n_grain, s, area_sum, v_scale,
+                                                                                area_counts, extra_v);
+        GG_LAUNCH_OK();
+    }
+    if (vertex_area && n_joint > 0) {
+        if (!rowptr_j || !col_g || !rowptr_g) return GG_EINVAL;
+        vertex_area_kernel<<<(n_joint + 255) / 256, 256, 0, GG_STREAM(stream)>>>(rowptr_j, col_g, rowptr_g, area_counts, mesh2, n_joint, vertex_area);
+        GG_LAUNCH_OK();
+    }
+    return 0;
+}

@@ -84,3 +84,29 @@ def region_center(x_joint, index, x_grain=None, joint_offset=None, domain_factor
                                           ptr(centers), ptr(x_grain), x_grain.stride(0) if x_grain is not None else 0,
                                           _stream()), 'gg_region_center')
     return centers
+
+
+def area_bookkeeping(x_grain, mask_grain, gj_csr, index, lxd, patch_size=40.0, mesh_size=0.08, v_scale=20.0):
+    """The QoI bookkeeping of `GNN_update` (graph_trajectory.py:1041-1051, :1100-1103) from the resident grain rows:
+    -> (area_counts [Ng] float64: pixel-equivalent area of every live grain, normalised so the live grains tile the domain, NaN for
+    dead ones; extraV [Ng] float64; vertex_area [Nj] float64: each grain's area shared equally among its joints, in um^2).
+    x_grain [Ng, >= 5] fp32 (column 3 = area, 4 = extra volume); mask_grain [Ng] or [Ng, 1] (> 0: live) or None;
+    gj_csr: EdgeCSR of ('grain','push','joint') (rows = joints); index: RegionIndex (rows = grains)."""
+    if not x_grain.is_cuda:
+        raise RuntimeError('graingraphnn_b200 runs on CUDA tensors only (no CPU fallback)')
+    n_grain, n_joint = index.n_grain, index.n_joint
+    dev = x_grain.device
+    m = None
+    if mask_grain is not None:
+        m = mask_grain.to(dev, torch.float32).reshape(mask_grain.shape[0], -1)[:, 0].contiguous()
+    s = patch_size / mesh_size + 1                                                  # :1043 (a float: no rounding here)
+    area = x_grain[:n_grain, 3].double()
+    area_sum = float(((area * m[:n_grain].double()) if m is not None else area).sum().item()) / (lxd / patch_size) ** 2
+    counts = torch.empty(n_grain, dtype=torch.float64, device=dev)
+    extra = torch.empty(n_grain, dtype=torch.float64, device=dev)
+    varea = torch.empty(n_joint, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().gg_area_bookkeeping(ptr(x_grain), x_grain.stride(0), ptr(m), 1, n_grain, float(s), area_sum, float(v_scale),
+                                             ptr(counts), ptr(extra), ptr(gj_csr.rowptr), ptr(gj_csr.col), ptr(index.rowptr), n_joint,
+                                             float(mesh_size) ** 2, ptr(varea), _stream()), 'gg_area_bookkeeping')
+    return counts, extra, varea

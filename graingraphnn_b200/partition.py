@@ -173,6 +173,15 @@ def local_features(plan, x_dict):
 
 
 # ------------------------------------------------------------------------------------------------------ transports
+def p2p_available():
+    """True when torch's symmetric memory (CUDA peer mappings over NVLink) can back the 'p2p' halo transport."""
+    try:
+        import torch.distributed._symmetric_memory as symm  # noqa: F401
+        return torch.cuda.is_available() and torch.cuda.device_count() > 1
+    except Exception:
+        return False
+
+
 def _pack_rows_cuda(src, idx, out=None):
     """out[i, :] = src[idx[i], :] with the library's pack kernel; `out` may be a raw (pointer, ld) pair on a PEER device."""
     n, w = int(idx.numel()), src.shape[1]
@@ -274,6 +283,8 @@ class PartitionedEngine(RolloutEngine):
         """x_dict / edge_index_dict: the GLOBAL graph as CPU tensors (every rank passes the same data);
         global_pos[type][:, 0] = global x fraction in [0, 1) (slab coordinate)."""
         transport = transport or os.environ.get('GG_HALO', 'nccl')
+        if transport == 'auto':
+            transport = 'p2p' if p2p_available() else 'nccl'
         owner = {t: owners_by_x(np.asarray(global_pos[t])[:, 0], world) for t in x_dict}
         n_nodes = {t: int(v.shape[0]) for t, v in x_dict.items()}
         key = None if os.environ.get('GG_SLAB_ORDER', 'morton') != 'morton' else {t: morton_key(np.asarray(global_pos[t])) for t in x_dict}
@@ -343,12 +354,19 @@ class PartitionedEngine(RolloutEngine):
         assert rows == self.plan.n_local[node_type]
         return self.halo.alloc(node_type, width)
 
-    @torch.no_grad()
-    def step(self, span=6):
-        with torch.cuda.device(self.device):
-            for items in self._step_gen(span):
-                self.halo.exchange(items)
+    def _step_impl(self, span):
+        """The step with its halo exchanges.  With the 'p2p' transport everything here is a kernel launch on the current stream
+        (pack kernels that store into the peers' halo rows + the symmetric-memory barrier), so `capture()` records the whole
+        partitioned step — exchanges included — into one CUDA graph per rank; the 'nccl' transport runs eagerly."""
+        for items in self._step_gen(span):
+            self.halo.exchange(items)
         return self.pred
+
+    @torch.no_grad()
+    def capture(self, span=6, warmup=2):
+        if self.halo is not None and self.halo.transport != 'p2p':
+            raise RuntimeError("capture() of a partitioned step needs the 'p2p' halo transport (GG_HALO=p2p): the NCCL path waits on the host")
+        return super().capture(span, warmup)
 
     def counts(self):
         c = super().counts()

@@ -65,10 +65,10 @@ class RolloutDriver:
     geometry: {'domain_factor', 'domain_offset' [Nj, 2] or 0} (test.py:310-312).  global_pos: see RolloutEngine.set_graph.
     truth (optional): {'grain_events': list over frames of sets of 1-based grain ids (traj.grain_events),
                        'alpha_pde': callable frame -> [s, s] int array (traj.alpha_pde_frames[:, :, frame].T), 'imagesize': s}
-    raster (optional): callable (polygons, s) -> alpha_field [s, s] (graph_datastruct.py:553-610)."""
+    raster: 'device' (gg_raster_polygons, row f4) or a callable (polygons, s) -> alpha_field [s, s] (graph_datastruct.py:553-610)."""
 
     def __init__(self, engine, x_dict, edge_index_dict, edge_attr_dict, mask, span=6, geometry=None, global_pos=None,
-                 truth=None, raster=None, edge_threshold=0.6, area_threshold=1e-4, frames=121, ini_height=2.0, delta_z=0.4,
+                 truth=None, raster='device', edge_threshold=0.6, area_threshold=1e-4, frames=121, ini_height=2.0, delta_z=0.4,
                  nucleation_density=0.0, lxd=None):
         self.eng, self.span, self.frames = engine, span, frames
         self.edge_threshold, self.area_threshold = edge_threshold, area_threshold
@@ -168,10 +168,18 @@ class RolloutDriver:
         return region_polygons(xj.numpy(), self.edge_index[ET_GJ].numpy())[0]
 
     def layer_error(self, truth_frame):
+        """plot_polygons + compute_error_layer (graph_datastruct.py:553-610, :346-348): on the device (raster.py) unless the
+        caller supplied its own raster callable."""
         s = self.truth['imagesize']
-        alpha = self.raster(self.polygons(), s)
         pde = self.truth['alpha_pde'](truth_frame)
-        return float(np.sum(pde != alpha) / pde.size)                                           # graph_datastruct.py:346-348
+        if self.raster == 'device':
+            from . import raster
+            alpha = raster.plot_polygons(self.polygons(), s, self.eng.device)
+            self.alpha_field = alpha
+            return raster.error_layer(torch.as_tensor(np.ascontiguousarray(pde)), alpha)
+        alpha = self.raster(self.polygons(), s)
+        self.alpha_field = alpha
+        return float(np.sum(pde != alpha) / pde.size)
 
     def qoi(self):
         out = {'frames': self.frame, 'predicted_grain_events': len(self.grain_event_list), 'switches': self.switch_count,

@@ -37,19 +37,26 @@ def state_dict_shapes(kind='regressor', C=96, f_grain=11, f_joint=8, edge_types=
     return shapes
 
 
-def synth_state_dict(kind='regressor', seed=0, gain=1.0, dtype=torch.float32, **kw):
+def synth_state_dict(kind='regressor', seed=0, gain=1.0, dtype=torch.float32, head_gain=1.0, **kw):
+    """head_gain scales the regressor's output heads (`linear.{grain,joint}`): untrained heads move every joint by ~0.1 patch per
+    step in one direction (tanh(.) / 5, models.py:503-516), which tears the tiling apart within five steps (every grain-joint edge
+    then crosses a patch boundary); a trained model moves joints by O(1e-3).  Benchmarks use head_gain = 0.02 so that the
+    geometry stays a valid tiling over the timed steps; parity tests keep 1.0 (the oracle's stand-ins)."""
     gen = torch.Generator().manual_seed(seed)
     sd = {}
     for k, shp in state_dict_shapes(kind, **kw).items():
         bound = gain if k.endswith('lin_edge.weight') else gain / math.sqrt(max(shp[-1], 1))
         sd[k] = ((torch.rand(shp, generator=gen, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+        if k.startswith('linear.'):
+            sd[k] = sd[k] * head_gain
     return sd
 
 
-def load_weights(regressor_pt=None, classifier_pt=None, seeds=(1, 2)):
+def load_weights(regressor_pt=None, classifier_pt=None, seeds=(1, 2), head_gain=1.0):
     """(sd_regressor, sd_classifier, description): the reference's files when given (test.py:178, :183), else seeded stand-ins."""
     if regressor_pt and classifier_pt:
         return (torch.load(regressor_pt, map_location='cpu'), torch.load(classifier_pt, map_location='cpu'),
                 f'{regressor_pt} / {classifier_pt}')
-    return (synth_state_dict('regressor', seeds[0]), synth_state_dict('classifier', seeds[1]),
-            'seeded stand-ins with the reference state_dict layout (regressor0.pt/classifier1.pt absent)')
+    return (synth_state_dict('regressor', seeds[0], head_gain=head_gain), synth_state_dict('classifier', seeds[1]),
+            'seeded stand-ins with the reference state_dict layout (regressor0.pt/classifier1.pt absent)'
+            + (f'; regressor heads scaled by {head_gain} (per-step joint displacement of the order a trained model produces)' if head_gain != 1.0 else ''))

@@ -320,6 +320,31 @@ int gg_region_center(const float* x_joint, int32_t ld_j, const float* joint_offs
                      const int32_t* rowptr, const int32_t* col, const int32_t* key /* nullable */, int32_t n_grain,
                      double* centers /* nullable */, float* x_grain /* nullable */, int32_t ld_g, void* stream);
 
+/* QoI bookkeeping of GNN_update (graph_trajectory.py:1041-1051 `area_counts`, `extraV_traj`; :1100-1103 `vertex_area`) from the
+ * resident grain rows (column 3 = area, 4 = extra volume):
+ *   area_counts[g] = area_g s^2 / area_sum for live grains (mask > 0; NaN otherwise), area_sum = sum(area mask) / (lxd / 40)^2 (given);
+ *   extra_v[g] = mask_g extraV_g / v_scale s^3 (v_scale = targets_scaling['grain'] = 20);
+ *   vertex_area[j] = mesh2 * sum over the grains g of joint j of area_counts[g] / #joints(g)   (rowptr_j / col_g: grain->joint CSR by
+ *   joint, rowptr_g: the same edges by grain; vertex_area may be NULL). */
+int gg_area_bookkeeping(const float* x_grain, int32_t ld_g, const float* mask_grain /* nullable */, int32_t ld_m, int32_t n_grain,
+                        double s, double area_sum, double v_scale, double* area_counts, double* extra_v,
+                        const int32_t* rowptr_j, const int32_t* col_g, const int32_t* rowptr_g, int32_t n_joint,
+                        double mesh2, double* vertex_area /* nullable */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (f4) polygon raster + layer error.  Replaces graph.plot_polygons (graph_datastruct.py:553-610, periodic branch: PIL
+ *      ImageDraw.polygon per grain into a 2s x 2s image in `region_coors` order, grain id as colour, the four quadrants folded with
+ *      max) and graph.compute_error_layer (:346-348).
+ *  gg_raster_polygons: polygon p has the integer vertices verts[2 * poly_ptr[p] .. 2 * poly_ptr[p + 1]) (x, y pairs, `int(coor * s)`
+ *      as the reference truncates them, :585) and the grain id ids[p]; polygons are given in DRAW order (a pixel keeps the last
+ *      polygon that covers it).  scratch: int32 [2s x 2s]; alpha: int32 [s x s] (Image convention [ny, nx]), 0 = never drawn.
+ *      Polygons with <= 1 or > 32 vertices are skipped (:588).
+ *  gg_count_mismatch: count[0] = number of i with a[i] != b[i] (error_layer = count / n).
+ * ---------------------------------------------------------------------------------------------- */
+int gg_raster_polygons(const int32_t* poly_ptr, const int32_t* verts, const int32_t* ids, int32_t n_poly, int32_t s,
+                       int32_t* scratch, int32_t* alpha, void* stream);
+int gg_count_mismatch(const int32_t* a, const int32_t* b, int64_t n, unsigned long long* count, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (f1, first stage) event candidates.  Replaces the host scans of the full prediction arrays,
  *      L1 = ((sigmoid(edge_event) > threshold) & (src < dst)).nonzero()            models.py:627-629

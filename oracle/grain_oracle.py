@@ -255,6 +255,34 @@ def region_center(x_joint, gj_edge_index, n_grain, joint_offset=None, domain_fac
     return centers
 
 
+def area_bookkeeping(x_grain, mask_grain, gj_edge_index, lxd, patch_size=40, mesh_size=0.08, v_scale=20):
+    """graph_trajectory.py:1041-1051 (`area_counts`, `extraV_traj`) and :1100-1103 (`vertex_area`), in the reference's numpy
+    arithmetic.  -> (area_counts {grain id (1-based): value}, extraV [Ng], vertex_area {joint: value})."""
+    import numpy as np
+    from collections import defaultdict
+    X_g = x_grain[:, 3:5].detach().numpy()
+    mask_g = mask_grain.detach().numpy().reshape(mask_grain.shape[0], -1)[:, 0]
+    s = (patch_size / mesh_size) + 1
+    area_counts = {}
+    area_sum = np.sum(X_g[:, 0] * mask_g) / (lxd / patch_size) ** 2
+    for idx, area in enumerate(X_g[:, 0]):
+        if mask_g[idx] > 0:
+            area_counts[idx + 1] = area * s ** 2 / area_sum
+    extra = mask_g * X_g[:, 1] / v_scale * s ** 3
+    gj = gj_edge_index.numpy()
+    regions = defaultdict(list)
+    seen = set()
+    for g, j in gj.T:
+        if (int(g), int(j)) not in seen:
+            seen.add((int(g), int(j)))
+            regions[int(g) + 1].append(int(j))
+    vertex_area = defaultdict(float)
+    for region, verts in regions.items():
+        for v in verts:
+            vertex_area[v] += area_counts[region] / len(verts) * mesh_size ** 2
+    return area_counts, extra, vertex_area
+
+
 def grain_xy_writeback(x_grain, centers, domain_factor=1):
     """test.py:556-559: grain (x, y) <- fp32(region centre), `(.. * domain_factor) % 1` on scaled patches.  In place."""
     for g in range(centers.shape[0]):

@@ -52,6 +52,12 @@ def test_region_polygons_equal_the_reference_update_and_layer_error_kat():
     np.testing.assert_array_equal(alpha, traj.alpha_field)
     err = ro.error_layer(traj.alpha_pde, alpha)
     assert abs(err - traj.error_layer) < 1e-12 and abs(err - 0.0240) < 5e-4
+    # the QoI bookkeeping of the same call (graph_trajectory.py:1041-1051, :1100-1103) against the oracle's restatement
+    ac, extra, va = orc.area_bookkeeping(x['grain'], mask['grain'], ei[ET[0]], traj.lxd)
+    assert ac == traj.area_traj[-1]
+    np.testing.assert_array_equal(extra, traj.extraV_traj[-1])
+    assert sorted(va) == sorted(int(k) for k in traj.vertex_area)              # three terms per joint, summed in another grain order:
+    np.testing.assert_allclose([va[k] for k in sorted(va)], [traj.vertex_area[k] for k in sorted(traj.vertex_area)], rtol=1e-14)   # an ulp
 
 
 def _oracle_loop(sd_r, sd_c, x, ei, ea, mask, steps, span, edge_thr, area_thr):
@@ -112,7 +118,34 @@ def test_rollout_driver_matches_the_reference_order_loop(rows):
     # the truth-dependent QoIs: event accounting as test.py:480-491 counts it, layer error through a raster
     truth = {'grain_events': [set()] + [{g + 1 for g in ev_ref[:2]}] * 200, 'imagesize': 501,
              'alpha_pde': lambda frame: ro.plot_polygons(drv.polygons(), 501)}
-    drv.truth, drv.raster = truth, ro.plot_polygons
+    drv.truth = truth                                                                # raster: the device kernel (row f4) against PIL's field
     drv.step()
     q = drv.qoi()
     assert q['grain_events_hit_rate'].endswith('/2') and q['last_layer_error'] == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,lxd', [('c1', 40), ('c2', 120)])
+def test_area_bookkeeping_matches_the_oracle(name, lxd):
+    """graph_trajectory.py:1041-1051, :1100-1103 on the device (row f2, the QoI part) — float64, to rounding of the sums."""
+    from graingraphnn_b200.geometry import RegionIndex, area_bookkeeping
+    from graingraphnn_b200.graph import build_csr
+    x, ei, _ = load_graph(name)
+    d = torch.device('cuda:0')
+    ng, nj = x['grain'].shape[0], x['joint'].shape[0]
+    mask = torch.ones(ng, 1)
+    mask[::17] = 0                                                  # a few eliminated grains
+    x['grain'][:, 4] = torch.rand(ng)
+    gj_host = ei[ET[0]][:, mask[ei[ET[0]][0], 0] > 0]                # an eliminated grain has lost its edges (models.py:864-896)
+    gj = gj_host.to(d)
+    counts, extra, varea = area_bookkeeping(x['grain'].to(d), mask.to(d), build_csr(gj, ng, nj), RegionIndex(gj, ng, nj), lxd)
+    ac, ex, va = orc.area_bookkeeping(x['grain'], mask, gj_host, lxd)
+    ref = np.full(ng, np.nan)
+    for g, v in ac.items():
+        ref[g - 1] = v
+    np.testing.assert_allclose(counts.cpu().numpy(), ref, rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(extra.cpu().numpy(), ex, rtol=1e-12)
+    refv = np.zeros(nj)
+    for j, v in va.items():
+        refv[j] = v
+    np.testing.assert_allclose(varea.cpu().numpy(), refv, rtol=1e-12)
