@@ -445,15 +445,15 @@ pgat_gather_tiled_kernel(const __grid_constant__ TiledParams P) {
                 for (int r = 0; r < NV; ++r) {                // vp = Wv3 p_i:  V_j + Wv3 (w_e - p_i) > 0  <=>  V_j + Wv3 w_e > vp
                     vp[r].lo = ffma2(wvz[r].lo, pz, ffma2(wvy[r].lo, py, fmul2(wvx[r].lo, px)));
                     vp[r].hi = ffma2(wvz[r].hi, pz, ffma2(wvy[r].hi, py, fmul2(wvx[r].hi, px)));
-                    acc[r].lo = acc[r].hi = 0ull;
                 }
-                m_run = -CUDART_INF_F; l_run = 0.f; ea_acc = 0.f;
             }
             // One chunk of <= CH consecutive in-edges of the target.  FAST = the chunk is full and none of its edges crosses a patch
             // boundary (decided warp-uniformly from the staged edge words): straight-line code, no clamped slots, no per-edge
             // predicates, no wrap corrections — the compiler schedules the loads of all three edges ahead of the arithmetic.
-            auto chunk = [&](auto fast_tag, const int (&ai)[CH], const int (&ww)[CH], const int n_e) {
-                constexpr bool FAST = decltype(fast_tag)::value;
+            // WHOLE = the chunk is the target's whole row (it starts and ends in this tile with exactly CH edges — every joint): the
+            // running state is written, never read (no reset, no rescale, the first edge multiplies instead of accumulating).
+            auto chunk = [&](auto fast_tag, auto whole_tag, const int (&ai)[CH], const int (&ww)[CH], const int n_e) {
+                constexpr bool FAST = decltype(fast_tag)::value, WHOLE = decltype(whole_tag)::value;
                 float ae[CH], sc[CH];
                 int wc[CH];
                 uint32_t ro[CH];                              // shared-memory address of the edge's source row (shared by duplicates)
@@ -520,8 +520,9 @@ pgat_gather_tiled_kernel(const __grid_constant__ TiledParams P) {
                     if (n_e < 2) sc[1] = -CUDART_INF_F;
                     if (n_e < 3) sc[2] = -CUDART_INF_F;
                 }
-                const float m_new = fmaxf(fmaxf(m_run, sc[0]), fmaxf(sc[1], sc[2]));
-                if (m_new > m_run) {                          // online softmax: rescale what earlier chunks accumulated
+                if (WHOLE) { m_run = fmaxf(sc[0], fmaxf(sc[1], sc[2])); l_run = 0.f; ea_acc = 0.f; }
+                const float m_new = WHOLE ? m_run : fmaxf(fmaxf(m_run, sc[0]), fmaxf(sc[1], sc[2]));
+                if (!WHOLE && m_new > m_run) {                // online softmax: rescale what earlier chunks accumulated
                     if (m_run != -CUDART_INF_F) {
                         const float scale = ex2_approx(m_run - m_new);
                         const u64 s2 = pack2(scale, scale);
@@ -554,26 +555,44 @@ pgat_gather_tiled_kernel(const __grid_constant__ TiledParams P) {
                         }
 #pragma unroll
                         for (int r = 0; r < NV; ++r) {
-                            acc[r].lo = ffma2(pe2, fmax2(v[r].lo, vp[r].lo), acc[r].lo);
-                            acc[r].hi = ffma2(pe2, fmax2(v[r].hi, vp[r].hi), acc[r].hi);
+                            if (WHOLE && e == 0) {
+                                acc[r].lo = fmul2(pe2, fmax2(v[r].lo, vp[r].lo));
+                                acc[r].hi = fmul2(pe2, fmax2(v[r].hi, vp[r].hi));
+                            } else {
+                                acc[r].lo = ffma2(pe2, fmax2(v[r].lo, vp[r].lo), acc[r].lo);
+                                acc[r].hi = ffma2(pe2, fmax2(v[r].hi, vp[r].hi), acc[r].hi);
+                            }
                         }
                     }
                 }
             };
-            for (int s0 = lo; s0 < hi; s0 += CH) {
+            bool whole = false;
+            if ((td & 0x30000) == 0x30000 && hi - lo == CH) { // the whole row in one full chunk
+                int ai[CH], ww[CH];
+                const uint32_t em = base + K::EM + 8u * lo;
+#pragma unroll
+                for (int e = 0; e < CH; ++e) lds2(em + 8u * e, ai[e], ww[e]);
+                if (((ww[0] | ww[1] | ww[2]) & 0xff) == 0) { chunk(FastTag{}, FastTag{}, ai, ww, CH); whole = true; }
+            }
+            if (!whole && (td & 0x10000)) {                   // fresh softmax state of a row that is walked chunk by chunk
+#pragma unroll
+                for (int r = 0; r < NV; ++r) acc[r].lo = acc[r].hi = 0ull;
+                m_run = -CUDART_INF_F; l_run = 0.f; ea_acc = 0.f;
+            }
+            for (int s0 = whole ? hi : lo; s0 < hi; s0 += CH) {
                 const int n_e = hi - s0;                      // >= 1, warp-uniform
                 int ai[CH], ww[CH];
                 const uint32_t em = base + K::EM + 8u * s0;
                 if (n_e >= CH) {
 #pragma unroll
                     for (int e = 0; e < CH; ++e) lds2(em + 8u * e, ai[e], ww[e]);
-                    if (((ww[0] | ww[1] | ww[2]) & 0xff) == 0) { chunk(FastTag{}, ai, ww, CH); continue; }
+                    if (((ww[0] | ww[1] | ww[2]) & 0xff) == 0) { chunk(FastTag{}, SlowTag{}, ai, ww, CH); continue; }
                 } else {                                      // slots beyond the row are clamped to its last edge
                     lds2(em, ai[0], ww[0]);
                     lds2(em + (n_e > 1 ? 8u : 0u), ai[1], ww[1]);
                     ai[2] = ai[1]; ww[2] = ww[1];
                 }
-                chunk(SlowTag{}, ai, ww, n_e);
+                chunk(SlowTag{}, SlowTag{}, ai, ww, n_e);
             }
             if (td & 0x20000) {
                 // ---- the target ends here: normalise and store (PyG softmax: exp(s - max) / (sum + 1e-16))

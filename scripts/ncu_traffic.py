@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""profiles/gather_traffic.json from an `ncu --set full` capture of the 12 gather launches of one bench step:
+"""profiles/gather_traffic.json from an `ncu --set full` capture of the gather launches of one bench step (4 since round 2: one per cell):
     ncu -i gpurun_out/prof_gather_step.ncu-rep --page raw --csv > /tmp/raw.csv
     python scripts/ncu_traffic.py /tmp/raw.csv N_GRAINS > profiles/gather_traffic.json"""
 import csv
