@@ -64,6 +64,11 @@ _PROTOS = {
     'gg_region_sort': (_I, [_P, _P, _P, _I, _P, _P]),
     'gg_region_center': (_I, [_P, _I, _P, _F, _P, _P, _P, _I, _P, _P, _I, _P]),
     'gg_area_bookkeeping': (_I, [_P, _I, _P, _I, _I, c_double, c_double, c_double, _P, _P, _P, _P, _P, _I, c_double, _P, _P]),
+    'gg_topology_caps': (_I, [_P, _P]),
+    'gg_topology_work_ints': (_L, [_L, _L, _L]),
+    'gg_topology_lists': (_I, [_P, _L, _L, _P, _P, _I, _L, _P, _P, _I, _L, _P, _P]),
+    'gg_topology_update': (_I, [_P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I,
+                                _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'gg_raster_polygons': (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     'gg_count_mismatch': (_I, [_P, _P, _L, _P, _P]),
     'gg_gather_rows': (_I, [_P, _I, _P, _I, _I, _P, _I, _P]),
@@ -111,7 +116,7 @@ def exported_symbols():
 # kernels launched by one successful call of each entry point (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {'gg_csr_build': 6, 'gg_csr_items': 5, 'gg_csr_compact': 5, 'gg_csr_tiles': 5, 'gg_pgat_gather_tiled': 1, 'gg_pgat_gather_tiled_multi': 1, 'gg_edge_wrap': 1, 'gg_edge_refresh': 1, 'gg_permute_f32': 1, 'gg_edge_length': 2, 'gg_node_proj': 1, 'gg_pgat_gather': 1,
                     'gg_gate_update': 1, 'gg_node_head': 1, 'gg_edge_head': 1, 'gg_feature_update': 3, 'gg_feature_update_batched': 1,
-                    'gg_gather_rows': 1, 'gg_scatter_rows': 1, 'gg_select_events': 1, 'gg_joint_rank': 2, 'gg_region_key': 1, 'gg_region_sort': 1, 'gg_region_center': 1, 'gg_area_bookkeeping': 2, 'gg_raster_polygons': 2, 'gg_count_mismatch': 1, 'gg_segment_mean': 1, 'gg_node_proj_tc': 1, 'gg_node_proj_fused': 1, 'gg_split_tf32': 1, 'gg_gate_update_tc': 1}
+                    'gg_gather_rows': 1, 'gg_scatter_rows': 1, 'gg_select_events': 1, 'gg_joint_rank': 2, 'gg_region_key': 1, 'gg_region_sort': 1, 'gg_region_center': 1, 'gg_area_bookkeeping': 2, 'gg_topology_lists': 6, 'gg_topology_update': 3, 'gg_raster_polygons': 2, 'gg_count_mismatch': 1, 'gg_segment_mean': 1, 'gg_node_proj_tc': 1, 'gg_node_proj_fused': 1, 'gg_split_tf32': 1, 'gg_gate_update_tc': 1}
 LAUNCHES = [0]
 
 

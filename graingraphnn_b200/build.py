@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIBNAME = 'libgraingnn_b200.so'
-SOURCES = ['api.cu', 'csr.cu', 'edge.cu', 'gather.cu', 'gather_tiled.cu', 'geometry.cu', 'raster.cu', 'events.cu', 'gemm_simt.cu', 'gemm_tc.cu']
+SOURCES = ['api.cu', 'csr.cu', 'edge.cu', 'gather.cu', 'gather_tiled.cu', 'geometry.cu', 'raster.cu', 'topology.cu', 'events.cu', 'gemm_simt.cu', 'gemm_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall']
 

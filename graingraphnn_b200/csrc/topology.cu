@@ -1,0 +1,146 @@
+// topology.cu — row f1: the topology update of a rollout step on the device (GrainNN_classifier.update, models.py:614-845 without
+// nucleation; switching_edge_index :899-1053; delete_grain_index :864-896; the two-sided sweep :716-727 / :745-755).
+//
+//   gg_topology_lists   data-parallel: the ascending position lists per joint / grain of the two edge arrays (what every
+//                       `(E == p).nonzero()` scan of the reference returns), fixed capacity per node
+//   gg_topology_update  ONE thread walks the events in the reference's order (topology_core.h — the same routine the CPU suite
+//                       checks against the reference's own outputs): eliminations by area, switches by probability, in-place edits,
+//                       appended edges, -1 for deleted columns; candidates come straight from gg_select_events' device buffers
+//   (cleanup, models.py:846-862, is a stable compaction of the columns that are not -1: the caller's stream compaction)
+// The events of a step are few (tens to hundreds at 10^5 grains) and each touches a handful of table entries, so a sequential walk
+// costs tens of microseconds per event; what it removes is the host round trip of the full prediction arrays and edge lists
+// (20 + 36 MB at 1.2 10^5 grains) and the host's O(E) indexing and compaction per step.
+#include "common.cuh"
+#include "topology_core.h"
+
+namespace {
+
+__global__ void topo_fill_lists(const int64_t* __restrict__ a, int64_t cap, int64_t n, int32_t* __restrict__ l0, int32_t* __restrict__ c0, int cap0,
+                                int64_t n0, int32_t* __restrict__ l1, int32_t* __restrict__ c1, int cap1, int64_t n1, int* __restrict__ status) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int64_t u = a[e], v = a[cap + e];
+    if (u >= 0) {
+        if (u >= n0) { atomicExch(status, GG_TOPO_CAPACITY); return; }
+        const int k = atomicAdd(&c0[u], 1);
+        if (k < cap0) l0[u * cap0 + k] = (int32_t)e; else atomicExch(status, GG_TOPO_LIST_OVERFLOW);
+    }
+    if (v >= 0) {
+        if (v >= n1) { atomicExch(status, GG_TOPO_CAPACITY); return; }
+        const int k = atomicAdd(&c1[v], 1);
+        if (k < cap1) l1[v * cap1 + k] = (int32_t)e; else atomicExch(status, GG_TOPO_LIST_OVERFLOW);
+    }
+}
+__global__ void topo_sort_lists(int32_t* __restrict__ l, int32_t* __restrict__ c, int cap, int64_t n_nodes) {
+    const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    const int n = min(c[v], cap);
+    c[v] = n;
+    int32_t* p = l + v * cap;
+    for (int a = 1; a < n; ++a) {
+        const int32_t x = p[a];
+        int b = a - 1;
+        while (b >= 0 && p[b] > x) { p[b + 1] = p[b]; --b; }
+        p[b + 1] = x;
+    }
+}
+__global__ void topo_active(const float* __restrict__ y, int ld, int n, uint8_t* __restrict__ act) {    // models.py:502-503: y[:, 0] > -10
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) act[i] = y[(size_t)i * ld] > -10.0f ? 1 : 0;
+}
+
+struct TopoArgs {
+    GGTopo t;
+    const int32_t* ge_count; const int32_t* ge_ids; const float* ge_vals; int ge_cap;       // gg_select_events buffers: grains (id, area)
+    const int32_t* l1_count; const int32_t* l1_ids; const float* l1_vals; int l1_cap;       // edges (column, logit)
+    int32_t* ge_sorted; int32_t* l1_work; float* l1_logit_work;
+    int64_t* switching_list; int32_t* grain_event_out; int32_t* work;
+    int64_t* result;                                                                         // {n_pp, n_pq, n_switch, n_grain_event, err, n_ge_in, n_l1_in}
+};
+
+__global__ void topo_update_kernel(TopoArgs A) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    GGTopo& t = A.t;
+    const int n_ge = min(*A.ge_count, A.ge_cap), n_l1 = min(*A.l1_count, A.l1_cap);
+    A.result[5] = *A.ge_count; A.result[6] = *A.l1_count;
+    // test.py:414-416: candidates sorted by predicted area ascending (equal areas: by grain id)
+    for (int i = 0; i < n_ge; ++i) A.ge_sorted[i] = i;
+    for (int a = 1; a < n_ge; ++a) {
+        const int32_t o = A.ge_sorted[a];
+        const float v = A.ge_vals[o]; const int32_t id = A.ge_ids[o];
+        int b = a - 1;
+        while (b >= 0 && (A.ge_vals[A.ge_sorted[b]] > v || (A.ge_vals[A.ge_sorted[b]] == v && A.ge_ids[A.ge_sorted[b]] > id))) { A.ge_sorted[b + 1] = A.ge_sorted[b]; --b; }
+        A.ge_sorted[b + 1] = o;
+    }
+    for (int i = 0; i < n_ge; ++i) A.ge_sorted[i] = A.ge_ids[A.ge_sorted[i]];
+    // NOTE: ge_sorted now holds grain ids; the in-place rewrite above is safe because slot i is read (as an index) before it is written
+    for (int i = 0; i < n_l1; ++i) { A.l1_work[i] = A.l1_ids[i]; A.l1_logit_work[i] = A.l1_vals[i]; }
+    GGTopoResult r = gg_topo_update(t, A.ge_sorted, n_ge, A.l1_work, A.l1_logit_work, n_l1, A.switching_list, A.grain_event_out, A.work);
+    A.result[0] = t.pp.n; A.result[1] = t.pq.n; A.result[2] = r.n_switch; A.result[3] = r.n_grain_event; A.result[4] = r.err;
+}
+
+}  // namespace
+
+extern "C" int gg_topology_lists(const int64_t* edges, int64_t cap, int64_t n, int32_t* list0, int32_t* cnt0, int32_t cap0, int64_t n0,
+                                 int32_t* list1, int32_t* cnt1, int32_t cap1, int64_t n1, int32_t* status, void* stream) {
+    if (cap < n || n < 0 || n0 < 0 || n1 < 0 || cap0 < 1 || cap1 < 1 || !cnt0 || !cnt1 || !list0 || !list1 || !status || (n > 0 && !edges)) return GG_EINVAL;
+    cudaStream_t st = GG_STREAM(stream);
+    cudaError_t err;
+    if ((err = cudaMemsetAsync(cnt0, 0, sizeof(int32_t) * (size_t)n0, st)) != cudaSuccess) return (int)err;
+    if ((err = cudaMemsetAsync(cnt1, 0, sizeof(int32_t) * (size_t)n1, st)) != cudaSuccess) return (int)err;
+    if ((err = cudaMemsetAsync(status, 0, sizeof(int32_t), st)) != cudaSuccess) return (int)err;
+    if (n > 0) { topo_fill_lists<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(edges, cap, n, list0, cnt0, cap0, n0, list1, cnt1, cap1, n1, status); GG_LAUNCH_OK(); }
+    if (n0 > 0) { topo_sort_lists<<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(list0, cnt0, cap0, n0); GG_LAUNCH_OK(); }
+    if (n1 > 0) { topo_sort_lists<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(list1, cnt1, cap1, n1); GG_LAUNCH_OK(); }
+    return 0;
+}
+
+extern "C" int gg_topology_caps(int32_t* cap_joint, int32_t* cap_grain) {
+    if (cap_joint) *cap_joint = GG_TOPO_CAP_J;
+    if (cap_grain) *cap_grain = GG_TOPO_CAP_G;
+    return 0;
+}
+
+extern "C" int64_t gg_topology_work_ints(int64_t n_l1, int64_t n_ge, int64_t n_grain) { return gg_topo_work_ints(n_l1, n_ge, n_grain); }
+
+extern "C" int gg_topology_update(int64_t* pp, int64_t cap_pp, int64_t n_pp, int64_t* pq, int64_t cap_pq, int64_t n_pq,
+                                  int32_t* pp_list0, int32_t* pp_cnt0, int32_t* pp_list1, int32_t* pp_cnt1,
+                                  int32_t* pq_list0, int32_t* pq_cnt0, int32_t* pq_list1, int32_t* pq_cnt1,
+                                  int32_t* ahead_cnt, uint8_t* ahead_flag,
+                                  float* x_joint, int32_t ld_xj, const int32_t* joint_row, int32_t col_dxy,
+                                  float* y_joint, const float* y_grain, int32_t ld_yg,
+                                  float* mask_grain, float* mask_joint, uint8_t* act_grain, uint8_t* act_joint,
+                                  int32_t n_joint, int32_t n_grain,
+                                  const int32_t* ge_count, const int32_t* ge_ids, const float* ge_vals, int32_t ge_cap,
+                                  const int32_t* l1_count, const int32_t* l1_ids, const float* l1_vals, int32_t l1_cap,
+                                  uint8_t* dirty_flag, int32_t* dirty_list, int32_t* scratch,
+                                  int32_t* ge_sorted, int32_t* l1_work, float* l1_logit_work,
+                                  int64_t* switching_list, int32_t* grain_event_out, int32_t* work, int64_t* result, void* stream) {
+    if (!pp || !pq || !x_joint || !y_joint || !y_grain || !mask_grain || !mask_joint || !act_grain || !act_joint || !result) return GG_EINVAL;
+    if (!ge_count || !l1_count || !switching_list || !grain_event_out || !work || !scratch || !dirty_flag || !dirty_list) return GG_EINVAL;
+    if (n_pp > cap_pp || n_pq > cap_pq || n_joint < 0 || n_grain < 0 || ld_xj < col_dxy + 2) return GG_EINVAL;
+    cudaStream_t st = GG_STREAM(stream);
+    topo_active<<<(n_grain + 255) / 256, 256, 0, st>>>(y_grain, ld_yg, n_grain, act_grain); GG_LAUNCH_OK();
+    topo_active<<<(n_joint + 255) / 256, 256, 0, st>>>(y_joint, 2, n_joint, act_joint); GG_LAUNCH_OK();
+    TopoArgs A;
+    memset(&A, 0, sizeof(A));
+    A.t.pp.a = pp; A.t.pp.cap = cap_pp; A.t.pp.n = n_pp;
+    A.t.pp.list[0] = pp_list0; A.t.pp.cnt[0] = pp_cnt0; A.t.pp.lcap[0] = GG_TOPO_CAP_J;
+    A.t.pp.list[1] = pp_list1; A.t.pp.cnt[1] = pp_cnt1; A.t.pp.lcap[1] = GG_TOPO_CAP_J;
+    A.t.pp.ahead_cnt = ahead_cnt; A.t.pp.ahead_flag = ahead_flag;
+    A.t.pq.a = pq; A.t.pq.cap = cap_pq; A.t.pq.n = n_pq;
+    A.t.pq.list[0] = pq_list0; A.t.pq.cnt[0] = pq_cnt0; A.t.pq.lcap[0] = GG_TOPO_CAP_J;
+    A.t.pq.list[1] = pq_list1; A.t.pq.cnt[1] = pq_cnt1; A.t.pq.lcap[1] = GG_TOPO_CAP_G;
+    A.t.xj = x_joint; A.t.ld_xj = ld_xj; A.t.jrow = joint_row; A.t.col_dxy = col_dxy;
+    A.t.yj = y_joint; A.t.yg = y_grain; A.t.ld_yg = ld_yg;
+    A.t.mask_g = mask_grain; A.t.ld_mg = 1; A.t.mask_j = mask_joint; A.t.ld_mj = 1;
+    A.t.act_g = act_grain; A.t.act_j = act_joint; A.t.n_joint = n_joint; A.t.n_grain = n_grain;
+    A.t.dirty_flag = dirty_flag; A.t.dirty_list = dirty_list; A.t.scratch = scratch;
+    A.ge_count = ge_count; A.ge_ids = ge_ids; A.ge_vals = ge_vals; A.ge_cap = ge_cap;
+    A.l1_count = l1_count; A.l1_ids = l1_ids; A.l1_vals = l1_vals; A.l1_cap = l1_cap;
+    A.ge_sorted = ge_sorted; A.l1_work = l1_work; A.l1_logit_work = l1_logit_work;
+    A.switching_list = switching_list; A.grain_event_out = grain_event_out; A.work = work; A.result = result;
+    topo_update_kernel<<<1, 32, 0, st>>>(A);
+    GG_LAUNCH_OK();
+    return 0;
+}

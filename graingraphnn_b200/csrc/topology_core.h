@@ -253,7 +253,6 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
     for (int k = 0; k < n_edges && !t.err; ++k) {
         const int32_t e = edges[k];
         const int64_t p1 = pp.get(0, e), p2 = pp.get(1, e);
-        bool done = false;
         if (p1 >= 0 && p2 >= 0 && t.act_j[p1] && t.act_j[p2]) {
             int c1, c2;
             int32_t at_q1[GG_TOPO_CAP_J], at_q2[GG_TOPO_CAP_J], at_n1[GG_TOPO_CAP_J], at_n2[GG_TOPO_CAP_J];
@@ -327,10 +326,8 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
                 for (int i = 0; i < c; ++i) pp.set(1, tmp[i], p1);
                 c = gg_topo_pp_between(t, b1, p1, true, tmp);
                 for (int i = 0; i < c; ++i) pp.set(1, tmp[i], p2);
-                done = true;
             }
         }
-        (void)done;
         // this event is no longer "to come"
         pp.ahead_flag[e] = 0;
         { const int64_t u = pp.get(0, e), v = pp.get(1, e); if (u >= 0) --pp.ahead_cnt[u]; if (v >= 0) --pp.ahead_cnt[v]; }

@@ -69,7 +69,7 @@ class RolloutDriver:
 
     def __init__(self, engine, x_dict, edge_index_dict, edge_attr_dict, mask, span=6, geometry=None, global_pos=None,
                  truth=None, raster='device', edge_threshold=0.6, area_threshold=1e-4, frames=121, ini_height=2.0, delta_z=0.4,
-                 nucleation_density=0.0, lxd=None):
+                 nucleation_density=0.0, lxd=None, topology='host'):
         self.eng, self.span, self.frames = engine, span, frames
         self.edge_threshold, self.area_threshold = edge_threshold, area_threshold
         self.geometry = geometry or {'domain_factor': 1, 'domain_offset': 0}
@@ -90,6 +90,15 @@ class RolloutDriver:
         self.grain_event_list, self.grain_acc_list, self.layer_err_list = [], [(ini_height, 0, 0, 0)], []
         self.switch_count, self.topo_steps, self.d2h_bytes, self.h2d_bytes = 0, 0, 0, 0
         self.frame = 0
+        self.topology = topology
+        self._dtopo = None
+        if topology == 'device':                                                                # row f1 without the host round trip
+            if nucleation_density:
+                raise NotImplementedError('nucleation is part of the host topology update only')
+            from .topology_device import DeviceTopology
+            self._dtopo = DeviceTopology(engine, self.edge_index, self.mask)
+        elif topology != 'host':
+            raise ValueError(topology)
 
     # ------------------------------------------------------------------------------------------------ order helpers
     def _to_caller(self, t, rows):
@@ -107,6 +116,8 @@ class RolloutDriver:
         self.frame += span
         frame = self.frame
         pred = eng.step(span)                                                                   # <1>, <2>
+        if self._dtopo is not None:
+            return self._step_device(pred, frame)
         ev = eng.fetch_events()                                                                 # <3> candidates only
         self.d2h_bytes += 16 + 8 * int(ev['L1'].numel() + ev['grain_event'].numel())
         grain_event, L1 = ev['grain_event'], ev['L1']
@@ -141,6 +152,25 @@ class RolloutDriver:
         self.switch_count += len(pairs)
         eng.region_feedback()                                                                   # <4> centres, <5> grain (x, y)
         eng.rebuild_edge_attr()                                                                 # <5> edge lengths (test.py:562-575)
+        self._account(frame)
+        return pred
+
+    def _step_device(self, pred, frame):
+        """<3> on the device (gg_topology_update): the host reads seven integers, plus the event ids for the accounting."""
+        eng = self.eng
+        out = self._dtopo.update(pred)
+        self.d2h_bytes += 56 + 8 * int(out['grain_event'].numel())
+        if out['changed']:
+            self.topo_steps += 1
+            self.edge_index = None                                                              # lives on the device: self._dtopo.edge_index()
+        self.grain_event_list.extend(int(g) for g in out['grain_event'].cpu())
+        self.switch_count += int(out['switching_list'].shape[0])
+        eng.region_feedback()
+        eng.rebuild_edge_attr()
+        self._account(frame)
+        return pred
+
+    def _account(self, frame):
         height = self.ini_height + frame * self.delta_z
         if self.truth is not None:                                                              # test.py:480-491
             tr = self.truth['grain_events']
@@ -152,7 +182,17 @@ class RolloutDriver:
             self.grain_acc_list.append((height, len(truth_set), len(self.grain_event_list), right))
             if self.raster is not None and 'alpha_pde' in self.truth:                           # test.py:523-533
                 self.layer_err_list.append((height, self.layer_error(frame // ratio)))
-        return pred
+
+    def current_edge_index(self):
+        """The caller-numbered edge lists of the current topology (CPU tensors)."""
+        if self._dtopo is not None:
+            return {e: v.cpu() for e, v in self._dtopo.edge_index().items()}
+        return self.edge_index
+
+    def current_mask(self):
+        if self._dtopo is not None:
+            return {'grain': self._dtopo.mask_g.cpu().view(-1, 1), 'joint': self._dtopo.mask_j.cpu().view(-1, 1)}
+        return self.mask
 
     def run(self, frames=None):
         for _ in range(self.span, frames or self.frames, self.span):
@@ -165,7 +205,7 @@ class RolloutDriver:
         xj = self._to_caller('joint', self.eng.x['joint'])[:, :2].cpu()
         if self.factor > 1:
             xj = (xj + self.offset) / self.factor                                               # test.py:472-474
-        return region_polygons(xj.numpy(), self.edge_index[ET_GJ].numpy())[0]
+        return region_polygons(xj.numpy(), self.current_edge_index()[ET_GJ].numpy())[0]
 
     def layer_error(self, truth_frame):
         """plot_polygons + compute_error_layer (graph_datastruct.py:553-610, :346-348): on the device (raster.py) unless the

@@ -332,6 +332,46 @@ int gg_area_bookkeeping(const float* x_grain, int32_t ld_g, const float* mask_gr
                         double mesh2, double* vertex_area /* nullable */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (f1) topology update on the device.  Replaces GrainNN_classifier.update (models.py:614-768: grain elimination in area order,
+ *      neighbour switching in probability order, the two-sided sweep; without the optional nucleation branch :771-835),
+ *      switching_edge_index (:899-1053) and delete_grain_index (:864-896); `cleanup` (:846-862) is the caller's stable compaction of
+ *      the columns whose first row is not -1.
+ *  Edge arrays: int64 [2, cap] row-major (row r at edges + r * cap), n used columns; pp = joint->joint, pq = joint->grain.  The
+ *      update edits them in place (overwrites, appended columns, -1 = deleted) exactly as the reference does, so the compacted
+ *      result equals the reference's position for position.
+ *  gg_topology_lists: ascending position lists per (row, value): list_r[v * cap_r + k], cnt_r[v]; caps from gg_topology_caps
+ *      (joint rows: cap_joint, the grain row of pq: cap_grain); status[0] != 0 on overflow / out-of-range ids.
+ *  gg_topology_update: one sequential walk over the events.  Candidates are the device buffers of gg_select_events: grains
+ *      (ge_ids, ge_vals = predicted area; sorted here by area) and joint-joint columns with src < dst (l1_ids, l1_vals = logit;
+ *      sorted here by logit descending = probability descending, models.py:730-731), each with its count (clamped to *_cap).
+ *      x_joint rows hold (x, y) in columns 0..1 and the predicted (dx, dy) in columns col_dxy, col_dxy + 1; joint_row (nullable)
+ *      maps a joint id to its row of x_joint.  y_joint [Nj, 2] and mask_grain / mask_joint (fp32 [N], 1 = live) are updated in
+ *      place; act_* are scratch (uint8 [N]).  ahead_cnt int32 [Nj] and ahead_flag uint8 [cap_pp] must be zero on entry (they are
+ *      zero again on exit); dirty_flag uint8 [Ng] zero on entry; dirty_list int32 [Ng]; scratch int32 [Ng + 2 (l1_cap + ge_cap) + 128];
+ *      ge_sorted int32 [ge_cap], l1_work int32 [l1_cap], l1_logit_work fp32 [l1_cap]; work int32 [gg_topology_work_ints(...)].
+ *      result int64 [8]: {n_pp, n_pq, switches, grain events out, error (GGTopoError, topology_core.h), ge_count, l1_count};
+ *      switching_list int64 [l1_cap, 2] (models.py:741); grain_event_out int32 [ge_cap + Ng]: the candidates followed by the forced and
+ *      two-sided eliminations (models.py:757-759).
+ * ---------------------------------------------------------------------------------------------- */
+int gg_topology_caps(int32_t* cap_joint, int32_t* cap_grain);
+int64_t gg_topology_work_ints(int64_t n_l1, int64_t n_ge, int64_t n_grain);
+int gg_topology_lists(const int64_t* edges, int64_t cap, int64_t n, int32_t* list0, int32_t* cnt0, int32_t cap0, int64_t n0,
+                      int32_t* list1, int32_t* cnt1, int32_t cap1, int64_t n1, int32_t* status, void* stream);
+int gg_topology_update(int64_t* pp, int64_t cap_pp, int64_t n_pp, int64_t* pq, int64_t cap_pq, int64_t n_pq,
+                       int32_t* pp_list0, int32_t* pp_cnt0, int32_t* pp_list1, int32_t* pp_cnt1,
+                       int32_t* pq_list0, int32_t* pq_cnt0, int32_t* pq_list1, int32_t* pq_cnt1,
+                       int32_t* ahead_cnt, uint8_t* ahead_flag,
+                       float* x_joint, int32_t ld_xj, const int32_t* joint_row /* nullable */, int32_t col_dxy,
+                       float* y_joint, const float* y_grain, int32_t ld_yg,
+                       float* mask_grain, float* mask_joint, uint8_t* act_grain, uint8_t* act_joint,
+                       int32_t n_joint, int32_t n_grain,
+                       const int32_t* ge_count, const int32_t* ge_ids, const float* ge_vals, int32_t ge_cap,
+                       const int32_t* l1_count, const int32_t* l1_ids, const float* l1_vals, int32_t l1_cap,
+                       uint8_t* dirty_flag, int32_t* dirty_list, int32_t* scratch,
+                       int32_t* ge_sorted, int32_t* l1_work, float* l1_logit_work,
+                       int64_t* switching_list, int32_t* grain_event_out, int32_t* work, int64_t* result, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (f4) polygon raster + layer error.  Replaces graph.plot_polygons (graph_datastruct.py:553-610, periodic branch: PIL
  *      ImageDraw.polygon per grain into a 2s x 2s image in `region_coors` order, grain id as colour, the four quadrants folded with
  *      max) and graph.compute_error_layer (:346-348).
