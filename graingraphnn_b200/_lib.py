@@ -116,7 +116,7 @@ def exported_symbols():
 # kernels launched by one successful call of each entry point (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {'gg_csr_build': 6, 'gg_csr_items': 5, 'gg_csr_compact': 5, 'gg_csr_tiles': 5, 'gg_pgat_gather_tiled': 1, 'gg_pgat_gather_tiled_multi': 1, 'gg_edge_wrap': 1, 'gg_edge_refresh': 1, 'gg_permute_f32': 1, 'gg_edge_length': 2, 'gg_node_proj': 1, 'gg_pgat_gather': 1,
                     'gg_gate_update': 1, 'gg_node_head': 1, 'gg_edge_head': 1, 'gg_feature_update': 3, 'gg_feature_update_batched': 1,
-                    'gg_gather_rows': 1, 'gg_scatter_rows': 1, 'gg_select_events': 1, 'gg_joint_rank': 2, 'gg_region_key': 1, 'gg_region_sort': 1, 'gg_region_center': 1, 'gg_area_bookkeeping': 2, 'gg_topology_lists': 6, 'gg_topology_update': 3, 'gg_raster_polygons': 2, 'gg_count_mismatch': 1, 'gg_segment_mean': 1, 'gg_node_proj_tc': 1, 'gg_node_proj_fused': 1, 'gg_split_tf32': 1, 'gg_gate_update_tc': 1}
+                    'gg_gather_rows': 1, 'gg_scatter_rows': 1, 'gg_select_events': 1, 'gg_joint_rank': 2, 'gg_region_key': 1, 'gg_region_sort': 1, 'gg_region_center': 1, 'gg_area_bookkeeping': 2, 'gg_topology_lists': 6, 'gg_topology_update': 5, 'gg_raster_polygons': 2, 'gg_count_mismatch': 1, 'gg_segment_mean': 1, 'gg_node_proj_tc': 1, 'gg_node_proj_fused': 1, 'gg_split_tf32': 1, 'gg_gate_update_tc': 1}
 LAUNCHES = [0]
 
 

@@ -49,6 +49,13 @@ __global__ void topo_active(const float* __restrict__ y, int ld, int n, uint8_t*
     if (i < n) act[i] = y[(size_t)i * ld] > -10.0f ? 1 : 0;
 }
 
+__global__ void topo_seed_two_sided(const int32_t* __restrict__ cnt, int n_grain, uint8_t* __restrict__ flag, int32_t* __restrict__ list, int32_t* __restrict__ n) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_grain) return;
+    const int c = cnt[g];
+    if (c > 0 && c <= 2) { flag[g] = 1; list[atomicAdd(n, 1)] = g; }
+}
+
 struct TopoArgs {
     GGTopo t;
     const int32_t* ge_count; const int32_t* ge_ids; const float* ge_vals; int ge_cap;       // gg_select_events buffers: grains (id, area)
@@ -56,11 +63,13 @@ struct TopoArgs {
     int32_t* ge_sorted; int32_t* l1_work; float* l1_logit_work;
     int64_t* switching_list; int32_t* grain_event_out; int32_t* work;
     int64_t* result;                                                                         // {n_pp, n_pq, n_switch, n_grain_event, err, n_ge_in, n_l1_in}
+    const int32_t* n_seed;                                                                   // grains with one or two joints on entry (topo_seed_two_sided)
 };
 
 __global__ void topo_update_kernel(TopoArgs A) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     GGTopo& t = A.t;
+    t.preseeded = true; t.n_dirty = *A.n_seed;
     const int n_ge = min(*A.ge_count, A.ge_cap), n_l1 = min(*A.l1_count, A.l1_cap);
     A.result[5] = *A.ge_count; A.result[6] = *A.l1_count;
     // test.py:414-416: candidates sorted by predicted area ascending (equal areas: by grain id)
@@ -140,6 +149,12 @@ extern "C" int gg_topology_update(int64_t* pp, int64_t cap_pp, int64_t n_pp, int
     A.l1_count = l1_count; A.l1_ids = l1_ids; A.l1_vals = l1_vals; A.l1_cap = l1_cap;
     A.ge_sorted = ge_sorted; A.l1_work = l1_work; A.l1_logit_work = l1_logit_work;
     A.switching_list = switching_list; A.grain_event_out = grain_event_out; A.work = work; A.result = result;
+    // the first two-sided sweep looks at the grains that have one or two joints NOW plus those the events touch, not at every grain
+    int32_t* n_seed = scratch + n_grain + 2 * (l1_cap + ge_cap) + 120;          // (the tail of scratch: 128 spare ints)
+    cudaError_t err = cudaMemsetAsync(n_seed, 0, sizeof(int32_t), st);
+    if (err != cudaSuccess) return (int)err;
+    topo_seed_two_sided<<<(n_grain + 255) / 256, 256, 0, st>>>(pq_cnt1, n_grain, dirty_flag, dirty_list, n_seed); GG_LAUNCH_OK();
+    A.n_seed = n_seed;
     topo_update_kernel<<<1, 32, 0, st>>>(A);
     GG_LAUNCH_OK();
     return 0;

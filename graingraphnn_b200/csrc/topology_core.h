@@ -126,6 +126,8 @@ struct GGTopo {
     const uint8_t* act_g; const uint8_t* act_j;
     int32_t n_joint, n_grain;
     uint8_t* dirty_flag; int32_t* dirty_list; int32_t n_dirty; bool dirty_all;   // grains whose joint count changed since the last two-side check
+    bool preseeded;                // dirty_list already holds the grains that have one or two joints on entry (a data-parallel pre-pass):
+                                   // the first sweep then looks at them and at the grains the events touched instead of at every grain
     int32_t* scratch;              // >= 2 * max events + n_grain ints
     int err;
 };
@@ -188,12 +190,37 @@ GG_TD void gg_topo_delete_grain(GGTopo& t, int64_t grain) {
     if (t.pq.err) t.err = t.pq.err;
 }
 
-GG_TD void gg_topo_sort_i32(int32_t* v, int n) {                 // insertion sort (candidate lists are short)
-    for (int a = 1; a < n; ++a) {
-        const int32_t x = v[a];
-        int b = a - 1;
-        while (b >= 0 && v[b] > x) { v[b + 1] = v[b]; --b; }
-        v[b + 1] = x;
+GG_TD void gg_topo_sort_i32(int32_t* v, int n) {                 // ascending; heapsort: the lists live in global memory and one thread sorts them
+    for (int start = n / 2 - 1; start >= 0; --start) {
+        int root = start; const int32_t x = v[root];
+        for (;;) { int c = 2 * root + 1; if (c >= n) break; if (c + 1 < n && v[c + 1] > v[c]) ++c; if (v[c] <= x) break; v[root] = v[c]; root = c; }
+        v[root] = x;
+    }
+    for (int end = n - 1; end > 0; --end) {
+        const int32_t x = v[end]; v[end] = v[0];
+        int root = 0;
+        for (;;) { int c = 2 * root + 1; if (c >= end) break; if (c + 1 < end && v[c + 1] > v[c]) ++c; if (v[c] <= x) break; v[root] = v[c]; root = c; }
+        v[root] = x;
+    }
+}
+// (id, value) pairs: by_value = false: id ascending; true: value descending, equal values by id ascending (a total order: heapsort)
+GG_TD bool gg_topo_pair_after(int32_t ia, float va, int32_t ib, float vb, bool by_value) {      // does a come after b?
+    if (!by_value) return ia > ib;
+    return va < vb || (va == vb && ia > ib);
+}
+GG_TD void gg_topo_sort_pairs(int32_t* id, float* val, int n, bool by_value) {
+    for (int start = n / 2 - 1; start >= 0; --start) {
+        int root = start; const int32_t xi = id[root]; const float xv = val[root];
+        for (;;) { int c = 2 * root + 1; if (c >= n) break; if (c + 1 < n && gg_topo_pair_after(id[c + 1], val[c + 1], id[c], val[c], by_value)) ++c;
+                   if (!gg_topo_pair_after(id[c], val[c], xi, xv, by_value)) break; id[root] = id[c]; val[root] = val[c]; root = c; }
+        id[root] = xi; val[root] = xv;
+    }
+    for (int end = n - 1; end > 0; --end) {
+        const int32_t xi = id[end]; const float xv = val[end]; id[end] = id[0]; val[end] = val[0];
+        int root = 0;
+        for (;;) { int c = 2 * root + 1; if (c >= end) break; if (c + 1 < end && gg_topo_pair_after(id[c + 1], val[c + 1], id[c], val[c], by_value)) ++c;
+                   if (!gg_topo_pair_after(id[c], val[c], xi, xv, by_value)) break; id[root] = id[c]; val[root] = val[c]; root = c; }
+        id[root] = xi; val[root] = xv;
     }
 }
 
@@ -371,14 +398,10 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
     int32_t* ord = sides + GG_TOPO_CAP_G;
     int32_t* removed = ord + GG_TOPO_CAP_G;                       // two-sided sweep output, <= n_grain
     int64_t around[GG_TOPO_CAP_G], across[GG_TOPO_CAP_G];
-    t.dirty_all = true; t.n_dirty = 0;
+    if (t.preseeded) t.dirty_all = false;
+    else { t.dirty_all = true; t.n_dirty = 0; }
     // L1 ascending by column first (the reference's nonzero order), so that ties of the later sort are by column
-    for (int a = 1; a < n_l1; ++a) {
-        const int32_t e = L1[a]; const float v = L1_logit[a];
-        int b = a - 1;
-        while (b >= 0 && L1[b] > e) { L1[b + 1] = L1[b]; L1_logit[b + 1] = L1_logit[b]; --b; }
-        L1[b + 1] = e; L1_logit[b + 1] = v;
-    }
+    gg_topo_sort_pairs(L1, L1_logit, n_l1, false);
     int n_unexpected = 0;
     int32_t* unexpected = work + n_l1 + n_ge + 8;                 // forced + swept grains, in the reference's order
     for (int gi = 0; gi < n_ge && !t.err; ++gi) {                  // models.py:638-727
@@ -443,12 +466,7 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
     }
     if (!t.err && n_l1 > 0) {                                      // models.py:730-740
         // probability descending = logit descending; equal logits keep ascending column order
-        for (int a = 1; a < n_l1; ++a) {
-            const int32_t e = L1[a]; const float v = L1_logit[a];
-            int b = a - 1;
-            while (b >= 0 && L1_logit[b] < v) { L1[b + 1] = L1[b]; L1_logit[b + 1] = L1_logit[b]; --b; }
-            L1[b + 1] = e; L1_logit[b + 1] = v;
-        }
+        gg_topo_sort_pairs(L1, L1_logit, n_l1, true);
         int w = 0;
         for (int i = 0; i < n_l1; ++i) if (t.pp.get(0, L1[i]) != -1) { L1[w] = L1[i]; L1_logit[w] = L1_logit[i]; ++w; }
         n_l1 = w;

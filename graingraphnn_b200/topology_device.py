@@ -53,6 +53,8 @@ class DeviceTopology:
         self.mask_j = mask['joint'].to(dev, torch.float32).reshape(-1).contiguous().clone()
         self.jrow = None if engine._node_rank is None else engine._node_rank['joint'].to(torch.int32).contiguous()
         self._bufs = None
+        self.profile = False          # True: update() leaves per-phase device times in self.last_ms
+        self.last_ms = None
 
     def edge_index(self):
         """The caller-numbered edge lists as the reference's cleanup leaves them (models.py:838-841)."""
@@ -91,12 +93,17 @@ class DeviceTopology:
         yj = pred['joint'] if pred['joint'].is_contiguous() else pred['joint'].contiguous()
         yg = pred['grain']
         xj = eng.xbuf['joint']
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.profile else None
+        if ev:
+            ev[0].record()
         with torch.cuda.device(self.dev):
             for name, arr, n, n0, n1, c1 in (('pp', self.pp, self.n_pp, self.nj, self.nj, self.cap_j), ('pq', self.pq, self.n_pq, self.nj, self.ng, self.cap_g)):
                 l0, c0 = self.lists[name + '0']
                 l1_, c1_ = self.lists[name + '1']
                 check(L.gg_topology_lists(ptr(arr), arr.shape[1], n, ptr(l0), ptr(c0), self.cap_j, n0, ptr(l1_), ptr(c1_), c1, n1, ptr(self.status), st),
                       'gg_topology_lists')
+            if ev:
+                ev[1].record()
             check(L.gg_topology_update(ptr(self.pp), self.pp.shape[1], self.n_pp, ptr(self.pq), self.pq.shape[1], self.n_pq,
                                        ptr(self.lists['pp0'][0]), ptr(self.lists['pp0'][1]), ptr(self.lists['pp1'][0]), ptr(self.lists['pp1'][1]),
                                        ptr(self.lists['pq0'][0]), ptr(self.lists['pq0'][1]), ptr(self.lists['pq1'][0]), ptr(self.lists['pq1'][1]),
@@ -105,6 +112,8 @@ class DeviceTopology:
                                        self.nj, self.ng, ptr(ge_count), ptr(ge_ids), ptr(ge_vals), ge_cap, ptr(l1_count), ptr(l1_ids), ptr(l1_vals), l1_cap,
                                        ptr(self.dirty_flag), ptr(self.dirty_list), ptr(w['scratch']), ptr(w['ge_sorted']), ptr(w['l1_work']), ptr(w['l1_logit']),
                                        ptr(w['switching']), ptr(w['ge_out']), ptr(w['work']), ptr(self.result), st), 'gg_topology_update')
+        if ev:
+            ev[2].record()
         res = self.result.cpu().tolist()                                     # the only host read of the step: 7 integers
         n_pp, n_pq, n_sw, n_ge_out, err, n_ge_in, n_l1_in = res[:7]
         if int(self.status.item()):
@@ -125,6 +134,13 @@ class DeviceTopology:
             self.pp[:, :self.n_pp] = pp_new
             self.pp[:, self.n_pp:n_pp] = -1
             self.pq = pq_new.contiguous()
+            if ev:
+                ev[3].record()
             eng.set_topology({ET_JJ: pp_new, ET_JG: self.pq, ET_GJ: torch.flip(self.pq, dims=[0]).contiguous()})
             eng.set_event_mask(self.mask_g)
+        if ev and changed:
+            ev[4].record()
+            torch.cuda.synchronize()
+            self.last_ms = {'lists': ev[0].elapsed_time(ev[1]), 'update_kernel': ev[1].elapsed_time(ev[2]), 'compaction': ev[2].elapsed_time(ev[3]),
+                            'set_topology': ev[3].elapsed_time(ev[4])}
         return {'switching_list': w['switching'][:n_sw].clone(), 'grain_event': w['ge_out'][:n_ge_out].long(), 'changed': changed}

@@ -33,7 +33,7 @@ def host_lib(tmp_path_factory):
     return ctypes.CDLL(out)
 
 
-def core_update(lib):
+def core_update(lib, preseed=1):
     """fn(x, ei, y, mask, active_grains, active_joints) -> (x, ei_out, pairs) with the calling convention of topology.topology_update,
     on the host build of the device routine."""
     def fn(x, ei, y, mask, active_grains, active_joints, threshold=0.6):
@@ -61,7 +61,7 @@ def core_update(lib):
         L1c, L1l = L1.copy(), L1_logit.copy()
         rc = lib.topology_update_host(P(pp), ctypes.c_int64(pp.shape[1]), ctypes.c_int64(ei[ET[2]].shape[1]), P(pq), ctypes.c_int64(pq.shape[1]),
                                       ctypes.c_int64(pq.shape[1]), P(xj), xj.shape[1], 6, P(yj), P(yg), yg.shape[1], P(mg), P(mj), P(ag), P(aj), nj, ng,
-                                      P(ge), len(ge), P(L1c), P(L1l), len(L1), P(sw), P(geo), P(n_out))
+                                      P(ge), len(ge), P(L1c), P(L1l), len(L1), P(sw), P(geo), P(n_out), preseed)
         if rc:
             raise RuntimeError(f'gg_topo_update error {rc}')
         x['joint'].copy_(torch.from_numpy(xj)); y['joint'].copy_(torch.from_numpy(yj))
@@ -74,10 +74,11 @@ def core_update(lib):
     return fn
 
 
+@pytest.mark.parametrize('preseed', [1, 0])
 @pytest.mark.parametrize('name,i', CASES)
-def test_device_routine_on_the_host_equals_the_reference_update(gold, host_lib, name, i):
+def test_device_routine_on_the_host_equals_the_reference_update(gold, host_lib, name, i, preseed):
     c = case(gold, name, i)
-    xo, eio, pairs, y, mask = _run(core_update(host_lib), name, c)
+    xo, eio, pairs, y, mask = _run(core_update(host_lib, preseed), name, c)
     for et, short in ((ET[2], 'jj'), (ET[1], 'jg'), (ET[0], 'gj')):
         assert np.array_equal(eio[et].numpy(), c[f'ei_{short}_out']), short
     assert np.array_equal(pairs.numpy(), c['switching_list'])

@@ -24,7 +24,7 @@ extern "C" int topology_update_host(int64_t* pp, int64_t cap_pp, int64_t n_pp, i
                                     float* mask_g, float* mask_j, const uint8_t* act_g, const uint8_t* act_j,
                                     int n_joint, int n_grain, const int32_t* grain_event, int n_ge,
                                     int32_t* L1, float* L1_logit, int n_l1, int64_t* switching_list, int32_t* grain_event_out,
-                                    int64_t* n_out) {
+                                    int64_t* n_out, int preseed) {
     GGTopo t;
     memset(&t, 0, sizeof(t));
     t.pp.a = pp; t.pp.cap = cap_pp; t.pp.n = n_pp;
@@ -41,6 +41,10 @@ extern "C" int topology_update_host(int64_t* pp, int64_t cap_pp, int64_t n_pp, i
     t.mask_g = mask_g; t.ld_mg = 1; t.mask_j = mask_j; t.ld_mj = 1; t.act_g = act_g; t.act_j = act_j;
     t.n_joint = n_joint; t.n_grain = n_grain;
     t.dirty_flag = dirty_flag.data(); t.dirty_list = dirty_list.data(); t.scratch = scratch.data();
+    if (preseed) {                                           // what topo_seed_two_sided does on the device
+        t.preseeded = true;
+        for (int g = 0; g < n_grain; ++g) { const int c = t.pq.cnt[1][g]; if (c > 0 && c <= 2) { dirty_flag[g] = 1; dirty_list[t.n_dirty++] = g; } }
+    }
     GGTopoResult r = gg_topo_update(t, grain_event, n_ge, L1, L1_logit, n_l1, switching_list, grain_event_out, work.data());
     n_out[0] = t.pp.n; n_out[1] = t.pq.n; n_out[2] = r.n_switch; n_out[3] = r.n_grain_event;
     return r.err;
