@@ -34,7 +34,7 @@ def build_variant(name, defines=(), replace=None, verbose=False):
         subprocess.run(cmd, check=True, stderr=None if verbose else subprocess.DEVNULL)
         objs.append(o)
     out = os.path.join(LIBDIR, 'variants', name + '.so')
-    subprocess.run([nvcc, '-shared', '-o', out] + objs + ['-lcuda'], check=True)
+    subprocess.run([nvcc, '-Wno-deprecated-gpu-targets', '-shared', '-o', out] + objs + ['-lcuda'], check=True)
     shutil.rmtree(vdir, ignore_errors=True)
     return out
 
@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
         objs.append(o)
     out = lib_path()
     if force or _stale(out, objs):
-        cmd = [nvcc, '-shared', '-o', out] + objs + ['-lcuda']
+        cmd = [nvcc, '-Wno-deprecated-gpu-targets', '-shared', '-o', out] + objs + ['-lcuda']
         if verbose:
             print(' '.join(cmd))
         subprocess.run(cmd, check=True)
