@@ -180,8 +180,9 @@ def ncu_traffic(n_grains, launches):
     return None
 
 
-def kernel_breakdown(eng, halo_times=None):
-    """Per-family device time of ONE eager step, CUDA events on the launching stream (torch's current stream)."""
+def kernel_breakdown(eng, halo_times=None, reps=5):
+    """Per-family device time of an eager step, CUDA events on the launching stream (torch's current stream) around every launch:
+    `reps` steps enqueued back to back, per launch the MEDIAN over the steps (one step alone scatters by +-5 % from run to run)."""
     from graingraphnn_b200 import _lib
     times = {}
 
@@ -222,8 +223,9 @@ def kernel_breakdown(eng, halo_times=None):
     try:
         saved = eng._graph
         eng._graph = None
-        torch.cuda._sleep(40_000_000)       # ~20 ms of device idle: the whole step is enqueued behind it, so the events bracket
-        eng.step(SPAN)                      # back-to-back kernels and not the host's launch cadence
+        torch.cuda._sleep(40_000_000)       # ~20 ms of device idle: the steps are enqueued behind it, so the events bracket
+        for _ in range(reps):               # back-to-back kernels and not the host's launch cadence
+            eng.step(SPAN)
         torch.cuda.synchronize()
         eng._graph = saved
     finally:
@@ -231,8 +233,17 @@ def kernel_breakdown(eng, halo_times=None):
         _engine._TWO_STREAMS = two
         if real_exchange is not None:
             eng.halo.exchange = real_exchange
-    return {k: {'calls': len(v), 'ms_total': sum(a.elapsed_time(b) for a, b in v), 'ms_each': [round(a.elapsed_time(b), 4) for a, b in v]}
-            for k, v in times.items()}
+    import numpy as np
+    out = {}
+    for k, v in times.items():
+        per = len(v) // reps                                  # launches of this entry point per step (the same every step)
+        ms = np.array([a.elapsed_time(b) for a, b in v[:per * reps]], dtype=np.float64).reshape(reps, per)
+        each = np.median(ms, axis=0)
+        out[k] = {'calls': per, 'ms_total': float(each.sum()), 'ms_each': [round(float(x), 4) for x in each]}
+    if halo_times is not None and halo_times:
+        per = len(halo_times) // reps
+        del halo_times[:-per]                                 # the exchanges of the last of the steps
+    return out
 
 
 def build_engine(x, ei, ea, glob, dev, rank, world, lxd=None):

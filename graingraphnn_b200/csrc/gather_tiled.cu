@@ -127,18 +127,6 @@ __device__ __forceinline__ float4 lds4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
     return r;
 }
-__device__ __forceinline__ int lds1i(uint32_t addr) {
-    int r;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ float lds1f(uint32_t addr) {
-    float r;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ void sts1i(uint32_t addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts1f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -216,7 +204,7 @@ constexpr int cfg_pick(int G, int C, int raw, int what) {
 __host__ __device__ constexpr int mode_rawk(int mode, int C) { return mode == 0 ? 0 : (mode == 1 ? 16 : 32 + C); }
 template <int NV, int G_, int MODE>
 struct TCfg {
-    static constexpr int C = 32 * NV, G = G_, GC = G * C, RAW = mode_rawk(MODE, 32 * NV);
+    static constexpr int C = 32 * NV, G = G_, RAW = mode_rawk(MODE, 32 * NV);
     static constexpr int ECAP = cfg_pick(G, C, RAW, 0), NS = cfg_pick(G, C, RAW, 1), HCAP = cfg_hcap(ECAP);
     static constexpr uint32_t ES = cfg_es(G, C, RAW), ESS = cfg_ess(G, C, RAW), QB = cfg_qb(G, C, RAW), HB = cfg_hb(G, C, RAW);
     static constexpr uint32_t POS = RAW == 0 ? QB : (RAW == 16 ? 48u : 112u);   // byte offset of x, y, z inside the target block

@@ -60,6 +60,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// One lane of a converged warp.  The MMA / TMA issuing warps run their loops with all 32 lanes (warp-uniform control flow), so the
+// compiler keeps TMEM addresses, shared-memory descriptors and barrier addresses in uniform registers; issued from inside
+// `if (lane == 0)` every operand sits in a vector register and ptxas wraps each tcgen05.mma in an ELECT / R2UR.BROADCAST x3 /
+// BRA.U.ANY loop (~60 clk per MMA: at N = 96, 48 tensor clk per MMA, the issuing thread and not the tensor pipe set the pace).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -278,19 +287,30 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 // node) is gone.
 constexpr int kFusedThreads = 384;       // warps 0-3 TMA / MMA / TMEM / idle, 4-7 epilogue, 8-11 converters
 constexpr int kFRingA = 2;               // A slots of [fp32 chunk | lo chunk] (2 x 16 KB)
-constexpr int kFRingB = 4;               // W tiles (32 KB): W_hi and W_lo of two chunks
-constexpr int FUSED_SMEM_BYTES = kFRingA * 2 * A_BYTES + kFRingB * B_BYTES + kOutBufs * OUT_BYTES + 1024 + 256;
+#ifndef GG_PROJ_RING_B
+#define GG_PROJ_RING_B 4
+#endif
+#ifndef GG_PROJ_OUT_BUFS
+#define GG_PROJ_OUT_BUFS 2
+#endif
+#ifndef GG_PROJ_DIRECT_STORE
+#define GG_PROJ_DIRECT_STORE 0
+#endif
+constexpr int kFRingB = GG_PROJ_RING_B;  // W tiles (32 KB): W_hi and W_lo of two chunks
+constexpr int kFOutBufs = GG_PROJ_OUT_BUFS;      // store staging buffers (16 KB each)
+constexpr int FUSED_SMEM_BYTES = kFRingA * 2 * A_BYTES + kFRingB * B_BYTES + kFOutBufs * OUT_BYTES + 1024 + 256;
 static_assert(FUSED_SMEM_BYTES <= 227 * 1024, "fused projection shared memory");
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
 node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                        const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, int M, int N, int chunks, int k_first_steps) {
+                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ out, int ldo,
+                       int M, int N, int chunks, int k_first_steps) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ringA = smem_base, ringB = smem_base + kFRingA * 2 * A_BYTES;
     const uint32_t out_base = ringB + kFRingB * B_BYTES;
-    const uint32_t bar_base = out_base + kOutBufs * OUT_BYTES;
+    const uint32_t bar_base = out_base + kFOutBufs * OUT_BYTES;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
     auto convA = [&](int s) { return bar_base + 8u * (kFRingA + s); };
     auto emptyA = [&](int s) { return bar_base + 8u * (2 * kFRingA + s); };
@@ -326,22 +346,26 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        // ===== TMA producer: per chunk the fp32 A tile, then W_hi, then W_lo =====
-        if (lane == 0) {
+        // ===== TMA producer: per chunk the fp32 A tile, then W_hi, then W_lo (warp-uniform loops, one lane issues) =====
+        {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             auto load_b = [&](const CUtensorMap* map, int k0, int n0) {
                 mbar_wait(emptyB(sb), pb ^ 1u);
-                mbar_expect_tx(fullB(sb), B_BYTES);
-                tma_load_2d(ringB + sb * B_BYTES, map, fullB(sb), k0, n0);
+                if (elect_one()) {
+                    mbar_expect_tx(fullB(sb), B_BYTES);
+                    tma_load_2d(ringB + sb * B_BYTES, map, fullB(sb), k0, n0);
+                }
                 if (++sb == kFRingB) { sb = 0; pb ^= 1u; }
             };
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int m0 = (t / n_blocks) * BM, n0 = (t % n_blocks) * BN;
                 for (int c = 0; c < chunks; ++c) {
                     mbar_wait(emptyA(sa), pa ^ 1u);
-                    mbar_expect_tx(fullA(sa), A_BYTES);
-                    if (c == 0) tma_load_2d(ringA + sa * 2 * A_BYTES, &tmX, fullA(sa), 0, m0);
-                    else tma_load_2d(ringA + sa * 2 * A_BYTES, &tmH, fullA(sa), (c - 1) * BK, m0);
+                    if (elect_one()) {
+                        mbar_expect_tx(fullA(sa), A_BYTES);
+                        if (c == 0) tma_load_2d(ringA + sa * 2 * A_BYTES, &tmX, fullA(sa), 0, m0);
+                        else tma_load_2d(ringA + sa * 2 * A_BYTES, &tmH, fullA(sa), (c - 1) * BK, m0);
+                    }
                     if (++sa == kFRingA) { sa = 0; pa ^= 1u; }
                     load_b(&tmW_hi, c * BK, n0);
                     load_b(&tmW_lo, c * BK, n0);
@@ -349,8 +373,8 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (single thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer: warp-uniform loops, one elected lane issues (see elect_one) =====
+        {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -364,9 +388,11 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const int ks = c == 0 ? k_first_steps : BK / 8;      // MMAs of the zero padding behind the features are not issued
                     auto group = [&](uint32_t a_addr, uint32_t b_addr, bool first) {
                         const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(b_addr);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k)
-                            if (k < ks) umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                            for (int k = 0; k < BK / 8; ++k)
+                                if (k < ks) umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                        }
                     };
                     const int a_s = sa; const uint32_t a_par = pa;
                     if (++sa == kFRingA) { sa = 0; pa ^= 1u; }
@@ -380,15 +406,14 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const int b_lo = sb; mbar_wait(fullB(sb), pb); if (++sb == kFRingB) { sb = 0; pb ^= 1u; }
                     tc_fence_after();
                     group(a_hi, ringB + b_lo * B_BYTES, false);
-                    umma_commit(emptyB(b_lo));
+                    if (elect_one()) umma_commit(emptyB(b_lo));
                     // (A_lo, W_hi): the converters have written the lo half by now
                     mbar_wait(convA(a_s), a_par);
                     tc_fence_after();
                     group(a_lo, ringB + b_hi * B_BYTES, false);
-                    umma_commit(emptyA(a_s));
-                    umma_commit(emptyB(b_hi));
+                    if (elect_one()) { umma_commit(emptyA(a_s)); umma_commit(emptyB(b_hi)); }
                 }
-                umma_commit(tfull_bar(acc));
+                if (elect_one()) umma_commit(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -420,6 +445,49 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             }
         }
     } else if (warp >= 4) {
+#if GG_PROJ_DIRECT_STORE
+        // ===== epilogue: TMEM -> registers -> (+bias) -> global.  tcgen05.ld in the 16x256b shape hands four lanes 32 contiguous
+        // bytes of one accumulator row (lane i: row i / 4 and row i / 4 + 8, columns 2 (i % 4), + 1, and the same every 8 columns),
+        // so a warp-wide 8-byte store writes eight whole 32-byte sectors: no shared-memory staging, no TMA store, no CTA barriers
+        // in the epilogue.  (The 32x32b shape, one row per lane, scatters 32 x 16 B per store: measured 1.5 TB/s chip-wide.) =====
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int m0 = (t / n_blocks) * BM, n0 = (t % n_blocks) * BN;
+            int ncols = N - n0; ncols = ncols > BN ? BN : ncols;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[16];
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32 + 16 * half) << 16) + (uint32_t)(acc * BN + c0);
+                    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                 : "r"(ta));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int row0 = m0 + q * 32 + 16 * half + (lane >> 2), row1 = row0 + 8;
+                    const int col = n0 + c0 + 2 * (lane & 3);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int cc = col + 8 * k;
+                        if (cc < N) {
+                            float2 b = make_float2(0.f, 0.f);
+                            if (bias) b = __ldg(reinterpret_cast<const float2*>(bias + cc));
+                            if (row0 < M) *reinterpret_cast<float2*>(out + (size_t)row0 * ldo + cc) = make_float2(__uint_as_float(v[4 * k]) + b.x, __uint_as_float(v[4 * k + 1]) + b.y);
+                            if (row1 < M) *reinterpret_cast<float2*>(out + (size_t)row1 * ldo + cc) = make_float2(__uint_as_float(v[4 * k + 2]) + b.x, __uint_as_float(v[4 * k + 3]) + b.y);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+#else
         // ===== epilogue: TMEM -> registers -> (+bias) -> swizzled smem staging -> TMA store (as in node_proj_tc_kernel) =====
         const int q = warp & 3;
         const int r = q * 32 + lane;
@@ -433,7 +501,7 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             for (int c0 = 0; c0 < ncols; c0 += OUT_CHUNK) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kOutBufs - 1) : "memory");
+                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kFOutBufs - 1) : "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const uint32_t srow = out_base + obuf * OUT_BYTES + (uint32_t)r * 128u;
 #pragma unroll
@@ -454,7 +522,7 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                                  ::"l"(&tmOut), "r"(out_base + obuf * OUT_BYTES), "r"(n0 + c0), "r"(m0) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if (++obuf == kOutBufs) obuf = 0;
+                if (++obuf == kFOutBufs) obuf = 0;
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
@@ -462,6 +530,7 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
         if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -592,8 +661,8 @@ gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
 
     if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
-        // ===== TMA producer: one fp32 A chunk + the matching W_hi / W_lo tiles per stage =====
-        if (lane == 0) {
+        // ===== TMA producer: one fp32 A chunk + the matching W_hi / W_lo tiles per stage (warp-uniform loops, one lane issues) =====
+        {
             int stage = 0; uint32_t phase = 0;
             auto a_chunk = [&](int g, int ck, const CUtensorMap*& am, int& acol) {
                 if (ck < n_in * CC) { am = &maps.agg[ck / CC]; acol = g * C + (ck % CC) * BK; }
@@ -611,10 +680,12 @@ gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
                             a_chunk(g, ck, am, acol);
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             const uint32_t sa = smem_base + stage * slot_bytes;
-                            mbar_expect_tx(full_bar(stage), stage_tx);
-                            tma_load_2d(sa, am, full_bar(stage), acol, m0);
-                            tma_load_2d(sa + G_A_BYTES, &maps.w_hi, full_bar(stage), ck * BK, g * C);
-                            tma_load_2d(sa + G_A_BYTES + w_bytes, &maps.w_lo, full_bar(stage), ck * BK, g * C);
+                            if (elect_one()) {
+                                mbar_expect_tx(full_bar(stage), stage_tx);
+                                tma_load_2d(sa, am, full_bar(stage), acol, m0);
+                                tma_load_2d(sa + G_A_BYTES, &maps.w_hi, full_bar(stage), ck * BK, g * C);
+                                tma_load_2d(sa + G_A_BYTES + w_bytes, &maps.w_lo, full_bar(stage), ck * BK, g * C);
+                            }
                             if (++stage == S) { stage = 0; phase ^= 1u; }
                         }
                     }
@@ -622,8 +693,8 @@ gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: warp-uniform loops, one elected lane issues (see elect_one) =====
+        {
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t bphase = 0;                           // bit b = phase of TMEM buffer b
             const uint32_t idesc = make_idesc(BM, C);
@@ -640,17 +711,19 @@ gate_update_tc_kernel(const __grid_constant__ GateMaps maps, const GateEpi ep) {
                             const uint32_t sa = smem_base + stage * slot_bytes;
                             const uint32_t ah = tmem_base + a_col0 + (uint32_t)(stage * 64), al = ah + 32u;
                             const uint64_t whdesc = make_desc(sa + G_A_BYTES), wldesc = make_desc(sa + G_A_BYTES + w_bytes);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, al + 8u * k, whdesc + 2u * k, idesc, (ck | k) ? 1u : 0u);
+                                for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, al + 8u * k, whdesc + 2u * k, idesc, (ck | k) ? 1u : 0u);
 #pragma unroll
-                            for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, ah + 8u * k, wldesc + 2u * k, idesc, 1u);
+                                for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, ah + 8u * k, wldesc + 2u * k, idesc, 1u);
 #pragma unroll
-                            for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, ah + 8u * k, whdesc + 2u * k, idesc, 1u);
-                            umma_commit(empty_bar(stage));      // frees the smem slot AND the TMEM ring slot
+                                for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(tmem_d, ah + 8u * k, whdesc + 2u * k, idesc, 1u);
+                                umma_commit(empty_bar(stage));      // frees the smem slot AND the TMEM ring slot
+                            }
                             if (++stage == S) { stage = 0; phase ^= 1u; }
                         }
                     }
-                    umma_commit(tfull_bar(buf));
+                    if (elect_one()) umma_commit(tfull_bar(buf));
                     bphase ^= 1u << buf;
                     buf ^= 1;
                 }
@@ -975,7 +1048,7 @@ extern "C" int gg_node_proj_fused(const float* X, int32_t ldx, int32_t K1, const
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < n_sms ? tiles : n_sms;
-    node_proj_fused_kernel<<<grid, kFusedThreads, FUSED_SMEM_BYTES, GG_STREAM(stream)>>>(mX, mH, mW_hi, mW_lo, mOut, bias, M, N, Kp / BK, (K1 + 7) / 8);
+    node_proj_fused_kernel<<<grid, kFusedThreads, FUSED_SMEM_BYTES, GG_STREAM(stream)>>>(mX, mH, mW_hi, mW_lo, mOut, bias, out, ldo, M, N, Kp / BK, (K1 + 7) / 8);
     GG_LAUNCH_OK();
     return 0;
 }

@@ -11,6 +11,50 @@
 // costs tens of microseconds per event; what it removes is the host round trip of the full prediction arrays and edge lists
 // (20 + 36 MB at 1.2 10^5 grains) and the host's O(E) indexing and compaction per step.
 #include "common.cuh"
+#ifdef GG_TOPO_PROFILE
+#include <stdio.h>
+#endif
+
+// ---- look-ahead of the walking thread (hooks of topology_core.h).  The walk is a chain of dependent look-ups, each an L2 round
+// trip (~0.3 us): ~100 per event.  A second warp of the same CTA reads the table entries of the next few events ahead of the
+// walker, so that the walker finds them in the SM's L1.  It only loads (every index bounds-checked, since it may read a list while
+// the walker edits it) and never stores to global memory; the walker's results do not depend on it.
+#define GG_HINT_SMALL 32
+struct TopoHint {
+    int32_t small_list[GG_HINT_SMALL];     // copy of a short event list (the caller's array may live in the walker's local memory)
+    const int32_t* edges;                  // a long event list, in global memory
+    int n, k, epoch, done;
+};
+extern __shared__ __align__(16) unsigned char gg_topo_smem[];
+static __host__ __device__ __forceinline__ void topo_hint_begin(const int32_t* edges, int n) {
+#ifdef __CUDA_ARCH__
+    volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
+    if (n <= GG_HINT_SMALL) { for (int i = 0; i < n; ++i) h->small_list[i] = edges[i]; h->edges = nullptr; }
+    else h->edges = edges;
+    h->n = n; h->k = 0;
+    __threadfence();                       // the list (written by this thread) is visible before the epoch moves
+    h->epoch = h->epoch + 1;
+#endif
+}
+static __host__ __device__ __forceinline__ void topo_hint_at(int k) {
+#ifdef __CUDA_ARCH__
+    reinterpret_cast<volatile TopoHint*>(gg_topo_smem)->k = k;
+#endif
+}
+#ifdef GG_TOPO_PROFILE
+__device__ long long g_topo_clk[8];
+__device__ long long g_topo_last;
+static __host__ __device__ __forceinline__ void topo_mark(int b) {
+#ifdef __CUDA_ARCH__
+    const long long now = clock64();
+    g_topo_clk[b] += now - g_topo_last;
+    g_topo_last = now;
+#endif
+}
+#define GG_TOPO_MARK(b) topo_mark(b)
+#endif
+#define GG_TOPO_HINT_BEGIN(edges, n) topo_hint_begin(edges, n)
+#define GG_TOPO_HINT_AT(k) topo_hint_at(k)
 #include "topology_core.h"
 
 namespace {
@@ -64,10 +108,94 @@ struct TopoArgs {
     int64_t* switching_list; int32_t* grain_event_out; int32_t* work;
     int64_t* result;                                                                         // {n_pp, n_pq, n_switch, n_grain_event, err, n_ge_in, n_l1_in}
     const int32_t* n_seed;                                                                   // grains with one or two joints on entry (topo_seed_two_sided)
+    int prefetch;
 };
 
+// What the switch of edge column e will look at, read by 8 lanes: lanes 0-3 its first end point, 4-7 the second; of each four, lane 0
+// walks the joint's own entries and its three grains, lanes 1-3 one joint neighbour each with that neighbour's lists.
+__device__ void topo_prefetch_event(const GGTopo& t, int32_t e, int role, unsigned& sink) {
+    const GGRows& pp = t.pp;
+    const GGRows& pq = t.pq;
+    if (e < 0 || e >= pp.cap) return;
+    const int side = role >> 2, j = role & 3;
+    const int64_t p = pp.a[side * pp.cap + e];
+    if (role == 0) sink += pp.ahead_flag[e];
+    if (p < 0 || p >= t.n_joint) return;
+    auto joint_row = [&](int64_t v) {
+        const int64_t jr = t.jrow ? t.jrow[v] : v;
+        if (jr >= 0 && jr < t.n_joint) sink += __float_as_uint(t.xj[jr * t.ld_xj]) + __float_as_uint(t.xj[jr * t.ld_xj + t.col_dxy]);
+    };
+    if (j == 0) {
+        sink += t.act_j[p] + pp.ahead_cnt[p] + __float_as_uint(t.yj[2 * p]) + pp.cnt[1][p] + pp.list[1][p * GG_TOPO_CAP_J];
+        joint_row(p);
+        const int c = min(pq.cnt[0][p], GG_TOPO_CAP_J);
+        for (int i = 0; i < c; ++i) {
+            const int32_t pos = pq.list[0][p * GG_TOPO_CAP_J + i];
+            if (pos < 0 || pos >= pq.cap) continue;
+            sink += (unsigned)pq.a[pos];
+            const int64_t q = pq.a[pq.cap + pos];
+            if (q >= 0 && q < t.n_grain) sink += pq.cnt[1][q] + pq.list[1][q * GG_TOPO_CAP_G] + t.dirty_flag[q];
+        }
+    } else {
+        const int c = min(pp.cnt[0][p], GG_TOPO_CAP_J);
+        if (j - 1 >= c) return;
+        const int32_t pos = pp.list[0][p * GG_TOPO_CAP_J + j - 1];
+        if (pos < 0 || pos >= pp.cap) return;
+        sink += (unsigned)pp.a[pos] + pp.ahead_flag[pos];
+        const int64_t n = pp.a[pp.cap + pos];
+        if (n < 0 || n >= t.n_joint) return;
+        sink += pp.ahead_cnt[n] + pp.cnt[1][n] + pp.list[1][n * GG_TOPO_CAP_J];
+        joint_row(n);
+        const int cq = min(pq.cnt[0][n], GG_TOPO_CAP_J);
+        for (int i = 0; i < cq; ++i) {
+            const int32_t p2 = pq.list[0][n * GG_TOPO_CAP_J + i];
+            if (p2 >= 0 && p2 < pq.cap) sink += (unsigned)pq.a[pq.cap + p2];
+        }
+        const int cp = min(pp.cnt[0][n], GG_TOPO_CAP_J);
+        for (int i = 0; i < cp; ++i) {
+            const int32_t p3 = pp.list[0][n * GG_TOPO_CAP_J + i];
+            if (p3 >= 0 && p3 < pp.cap) sink += (unsigned)pp.a[pp.cap + p3] + (unsigned)pp.a[p3] + pp.ahead_flag[p3];
+        }
+    }
+}
+
+constexpr int kTopoLookAhead = 6;          // events: ~150 lines of 128 B per event, the L1 holds ~1800
+
+__device__ void topo_prefetch_warp(const GGTopo& t) {
+    volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
+    const int lane = threadIdx.x & 31;
+    int seen = 0;
+    unsigned sink = 0;
+    for (;;) {
+        if (h->done) break;
+        const int ep = h->epoch;
+        if (ep == seen) { __nanosleep(200); continue; }
+        seen = ep;
+        const int n = h->n;
+        const int32_t* edges = const_cast<const int32_t*>(h->edges);
+        for (int base = 0; base < n; base += 4) {
+            while (h->k + kTopoLookAhead < base && h->epoch == ep && !h->done) __nanosleep(100);
+            if (h->epoch != ep || h->done) break;
+            const int idx = base + (lane >> 3);
+            if (idx < n) topo_prefetch_event(t, edges ? __ldcg(edges + idx) : h->small_list[idx], lane & 7, sink);
+            __syncwarp();
+        }
+    }
+    if (sink == 0x9E3779B9u) h->small_list[0] = (int32_t)sink;      // keeps the loads
+}
+
 __global__ void topo_update_kernel(TopoArgs A) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    {
+        volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
+        if (threadIdx.x == 0) { h->n = 0; h->k = 0; h->epoch = 0; h->done = 0; h->edges = nullptr; }
+        __syncthreads();
+        if (threadIdx.x >= 32) { topo_prefetch_warp(A.t); return; }
+    }
+    if (threadIdx.x != 0) return;
+#ifdef GG_TOPO_PROFILE
+    for (int i = 0; i < 8; ++i) g_topo_clk[i] = 0;
+    g_topo_last = clock64();
+#endif
     GGTopo& t = A.t;
     t.preseeded = true; t.n_dirty = *A.n_seed;
     const int n_ge = min(*A.ge_count, A.ge_cap), n_l1 = min(*A.l1_count, A.l1_cap);
@@ -86,6 +214,11 @@ __global__ void topo_update_kernel(TopoArgs A) {
     for (int i = 0; i < n_l1; ++i) { A.l1_work[i] = A.l1_ids[i]; A.l1_logit_work[i] = A.l1_vals[i]; }
     GGTopoResult r = gg_topo_update(t, A.ge_sorted, n_ge, A.l1_work, A.l1_logit_work, n_l1, A.switching_list, A.grain_event_out, A.work);
     A.result[0] = t.pp.n; A.result[1] = t.pq.n; A.result[2] = r.n_switch; A.result[3] = r.n_grain_event; A.result[4] = r.err;
+    reinterpret_cast<volatile TopoHint*>(gg_topo_smem)->done = 1;
+#ifdef GG_TOPO_PROFILE
+    printf("topo clk: sort %lld | eliminations %lld | sweeps %lld | L1 sort %lld | switch pre %lld main %lld post %lld | last sweep %lld\n",
+           g_topo_clk[0], g_topo_clk[1], g_topo_clk[2], g_topo_clk[3], g_topo_clk[4], g_topo_clk[5], g_topo_clk[6], g_topo_clk[7]);
+#endif
 }
 
 }  // namespace
@@ -155,7 +288,8 @@ extern "C" int gg_topology_update(int64_t* pp, int64_t cap_pp, int64_t n_pp, int
     if (err != cudaSuccess) return (int)err;
     topo_seed_two_sided<<<(n_grain + 255) / 256, 256, 0, st>>>(pq_cnt1, n_grain, dirty_flag, dirty_list, n_seed); GG_LAUNCH_OK();
     A.n_seed = n_seed;
-    topo_update_kernel<<<1, 32, 0, st>>>(A);
+    { const char* e = getenv("GG_TOPO_PREFETCH"); A.prefetch = !(e && e[0] == '0'); }
+    topo_update_kernel<<<1, A.prefetch ? 64 : 32, sizeof(TopoHint), st>>>(A);
     GG_LAUNCH_OK();
     return 0;
 }

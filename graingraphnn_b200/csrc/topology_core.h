@@ -22,6 +22,17 @@
 #define GG_TD __host__ __device__ __forceinline__
 #endif
 
+// Hooks of the device build (topology.cu defines them before including this header): the walking thread announces the list of
+// switching events it is about to process and its position in it, so that a second warp can pull the table entries of the events
+// to come into the SM's L1 (results are unaffected; the host build compiles them away).
+#ifndef GG_TOPO_HINT_BEGIN
+#define GG_TOPO_HINT_BEGIN(edges, n) ((void)0)
+#define GG_TOPO_HINT_AT(k) ((void)0)
+#endif
+#ifndef GG_TOPO_MARK
+#define GG_TOPO_MARK(bucket) ((void)0)     // profiling build of the device kernel: time since the last mark goes to `bucket`
+#endif
+
 #define GG_TOPO_CAP_J 8        // positions per joint and row (3 in a valid tiling, 4 transiently inside a switch)
 #define GG_TOPO_CAP_G 32       // joints per grain
 
@@ -277,7 +288,10 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
         ++pp.ahead_cnt[pp.get(0, edges[k])];
         ++pp.ahead_cnt[pp.get(1, edges[k])];
     }
+    GG_TOPO_MARK(elim_grain < 0 ? 4 : 1);
+    GG_TOPO_HINT_BEGIN(edges, n_edges);
     for (int k = 0; k < n_edges && !t.err; ++k) {
+        GG_TOPO_HINT_AT(k);
         const int32_t e = edges[k];
         const int64_t p1 = pp.get(0, e), p2 = pp.get(1, e);
         if (p1 >= 0 && p2 >= 0 && t.act_j[p1] && t.act_j[p2]) {
@@ -359,6 +373,7 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
         pp.ahead_flag[e] = 0;
         { const int64_t u = pp.get(0, e), v = pp.get(1, e); if (u >= 0) --pp.ahead_cnt[u]; if (v >= 0) --pp.ahead_cnt[v]; }
     }
+    GG_TOPO_MARK(elim_grain < 0 ? 5 : 1);
     if (t.err) {                                                  // leave the ahead tables clean
         for (int k = 0; k < n_edges; ++k) if (pp.ahead_flag[edges[k]]) {
             pp.ahead_flag[edges[k]] = 0;
@@ -377,6 +392,7 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
     }
     if (pp.err) t.err = pp.err;
     if (pq.err) t.err = pq.err;
+    GG_TOPO_MARK(elim_grain < 0 ? 6 : 1);
     return n_forced;
 }
 
@@ -402,6 +418,7 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
     else { t.dirty_all = true; t.n_dirty = 0; }
     // L1 ascending by column first (the reference's nonzero order), so that ties of the later sort are by column
     gg_topo_sort_pairs(L1, L1_logit, n_l1, false);
+    GG_TOPO_MARK(0);
     int n_unexpected = 0;
     int32_t* unexpected = work + n_l1 + n_ge + 8;                 // forced + swept grains, in the reference's order
     for (int gi = 0; gi < n_ge && !t.err; ++gi) {                  // models.py:638-727
@@ -462,7 +479,9 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
               if (!hit) { L1[w] = L1[i]; L1_logit[w] = L1_logit[i]; ++w; }
           }
           n_l1 = w; }
+        GG_TOPO_MARK(1);
         gg_topo_delete_two_sided(t, removed);                     // (its victims are not reported, models.py:716-727)
+        GG_TOPO_MARK(2);
     }
     if (!t.err && n_l1 > 0) {                                      // models.py:730-740
         // probability descending = logit descending; equal logits keep ascending column order
@@ -470,6 +489,7 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
         int w = 0;
         for (int i = 0; i < n_l1; ++i) if (t.pp.get(0, L1[i]) != -1) { L1[w] = L1[i]; L1_logit[w] = L1_logit[i]; ++w; }
         n_l1 = w;
+        GG_TOPO_MARK(3);
         gg_topo_switch(t, L1, n_l1, -1, forced, 0);
         for (int i = 0; i < n_l1; ++i) { switching_list[2 * i] = t.pp.get(0, L1[i]); switching_list[2 * i + 1] = t.pp.get(1, L1[i]); }
         res.n_switch = n_l1;
@@ -477,6 +497,7 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
     if (!t.err) {
         const int n = gg_topo_delete_two_sided(t, removed);
         for (int i = 0; i < n; ++i) unexpected[n_unexpected++] = removed[i];
+        GG_TOPO_MARK(7);
     }
     for (int i = 0; i < n_unexpected; ++i) grain_event_out[n_out++] = unexpected[i];
     res.n_grain_event = n_out;
