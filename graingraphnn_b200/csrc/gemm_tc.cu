@@ -293,9 +293,6 @@ constexpr int kFRingA = 2;               // A slots of [fp32 chunk | lo chunk] (
 #ifndef GG_PROJ_OUT_BUFS
 #define GG_PROJ_OUT_BUFS 2
 #endif
-#ifndef GG_PROJ_DIRECT_STORE
-#define GG_PROJ_DIRECT_STORE 0
-#endif
 constexpr int kFRingB = GG_PROJ_RING_B;  // W tiles (32 KB): W_hi and W_lo of two chunks
 constexpr int kFOutBufs = GG_PROJ_OUT_BUFS;      // store staging buffers (16 KB each)
 constexpr int FUSED_SMEM_BYTES = kFRingA * 2 * A_BYTES + kFRingB * B_BYTES + kFOutBufs * OUT_BYTES + 1024 + 256;
@@ -304,8 +301,7 @@ static_assert(FUSED_SMEM_BYTES <= 227 * 1024, "fused projection shared memory");
 __global__ void __launch_bounds__(kFusedThreads, 1)
 node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                        const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, float* __restrict__ out, int ldo,
-                       int M, int N, int chunks, int k_first_steps) {
+                       const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ bias, int M, int N, int chunks, int k_first_steps) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ringA = smem_base, ringB = smem_base + kFRingA * 2 * A_BYTES;
@@ -445,50 +441,11 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             }
         }
     } else if (warp >= 4) {
-#if GG_PROJ_DIRECT_STORE
-        // ===== epilogue: TMEM -> registers -> (+bias) -> global.  tcgen05.ld in the 16x256b shape hands four lanes 32 contiguous
-        // bytes of one accumulator row (lane i: row i / 4 and row i / 4 + 8, columns 2 (i % 4), + 1, and the same every 8 columns),
-        // so a warp-wide 8-byte store writes eight whole 32-byte sectors: no shared-memory staging, no TMA store, no CTA barriers
-        // in the epilogue.  (The 32x32b shape, one row per lane, scatters 32 x 16 B per store: measured 1.5 TB/s chip-wide.) =====
-        const int q = warp & 3;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int m0 = (t / n_blocks) * BM, n0 = (t % n_blocks) * BN;
-            int ncols = N - n0; ncols = ncols > BN ? BN : ncols;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[16];
-                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32 + 16 * half) << 16) + (uint32_t)(acc * BN + c0);
-                    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                                 : "r"(ta));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    const int row0 = m0 + q * 32 + 16 * half + (lane >> 2), row1 = row0 + 8;
-                    const int col = n0 + c0 + 2 * (lane & 3);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int cc = col + 8 * k;
-                        if (cc < N) {
-                            float2 b = make_float2(0.f, 0.f);
-                            if (bias) b = __ldg(reinterpret_cast<const float2*>(bias + cc));
-                            if (row0 < M) *reinterpret_cast<float2*>(out + (size_t)row0 * ldo + cc) = make_float2(__uint_as_float(v[4 * k]) + b.x, __uint_as_float(v[4 * k + 1]) + b.y);
-                            if (row1 < M) *reinterpret_cast<float2*>(out + (size_t)row1 * ldo + cc) = make_float2(__uint_as_float(v[4 * k + 2]) + b.x, __uint_as_float(v[4 * k + 3]) + b.y);
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        }
-    }
-#else
         // ===== epilogue: TMEM -> registers -> (+bias) -> swizzled smem staging -> TMA store (as in node_proj_tc_kernel) =====
+        // (Tried in round 2: tcgen05.ld.16x256b, which hands four lanes 32 contiguous bytes of a row, and 8-byte global stores
+        // straight from the registers - eight whole sectors per warp store, no staging, no barriers.  Correct, and twice as slow:
+        // 1.2 ms against 0.60 ms for the decoder projection of 2.5e5 joints.  More staging buffers (4 x 16 KB with a 3-slot W
+        // ring) changed nothing: profiles/r2_gemm_ablations.txt.)
         const int q = warp & 3;
         const int r = q * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
@@ -530,7 +487,6 @@ node_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
         if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -1048,7 +1004,7 @@ extern "C" int gg_node_proj_fused(const float* X, int32_t ldx, int32_t K1, const
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < n_sms ? tiles : n_sms;
-    node_proj_fused_kernel<<<grid, kFusedThreads, FUSED_SMEM_BYTES, GG_STREAM(stream)>>>(mX, mH, mW_hi, mW_lo, mOut, bias, out, ldo, M, N, Kp / BK, (K1 + 7) / 8);
+    node_proj_fused_kernel<<<grid, kFusedThreads, FUSED_SMEM_BYTES, GG_STREAM(stream)>>>(mX, mH, mW_hi, mW_lo, mOut, bias, M, N, Kp / BK, (K1 + 7) / 8);
     GG_LAUNCH_OK();
     return 0;
 }

@@ -55,7 +55,78 @@ static __host__ __device__ __forceinline__ void topo_mark(int b) {
 #endif
 #define GG_TOPO_HINT_BEGIN(edges, n) topo_hint_begin(edges, n)
 #define GG_TOPO_HINT_AT(k) topo_hint_at(k)
+
+// ---- helper warp.  The sorts of the walk and its loops over whole lists (the touched joints before and after the switches, the
+// candidate list, the sweep's change list) are data-parallel; the walking thread hands the long ones to a third warp of the CTA
+// through a request slot in shared memory and waits.  Same integer results by construction, the same single-rounding float
+// operations per element; short lists (and lists in the walker's local memory) stay with the walker.
+struct GGTopo;
+enum { TOPO_OP_PRE = 1, TOPO_OP_POST, TOPO_OP_SORT_PAIRS, TOPO_OP_L1_MARK, TOPO_OP_L1_COMPACT, TOPO_OP_SWEEP };
+struct TopoSvc { int req, ack, op, n, flag, ret, enabled, pad; const void* a; void* b; void* c; };
+constexpr int kTopoSortCap = 2048;         // elements the helper warp sorts in shared memory; longer lists fall back to the walker
+constexpr int kTopoSvcMin = 48;            // shorter lists are not worth the hand-over
+__device__ __forceinline__ volatile TopoSvc* topo_svc() { return reinterpret_cast<volatile TopoSvc*>(gg_topo_smem + sizeof(TopoHint)); }
+static __device__ int topo_service_call(int op, const void* a, void* b, void* c, int n, int flag) {
+    volatile TopoSvc* s = topo_svc();
+    s->op = op; s->a = a; s->b = b; s->c = c; s->n = n; s->flag = flag;
+    __threadfence_block();
+    const int seq = s->req + 1;
+    s->req = seq;
+    while (s->ack != seq) { }
+    __threadfence_block();
+    return s->ret;
+}
+static __host__ __device__ __forceinline__ int topo_switch_pre_dev(GGTopo& t, const int32_t* edges, int n, int32_t* touched);
+static __host__ __device__ __forceinline__ void topo_switch_post_dev(GGTopo& t, const int32_t* touched, int nt);
+static __host__ __device__ __forceinline__ void topo_sort_pairs_dev(int32_t* id, float* val, int n, bool by_value);
+static __host__ __device__ __forceinline__ void topo_l1_mark_dev(GGTopo& t, const int32_t* l1, int n);
+static __host__ __device__ __forceinline__ int topo_l1_compact_dev(GGTopo& t, int32_t* l1, float* logit, int n);
+static __host__ __device__ __forceinline__ int topo_sweep_collect_dev(GGTopo& t, int32_t* cand);
+#define GG_TOPO_SWITCH_PRE(t, edges, n, touched) topo_switch_pre_dev(t, edges, n, touched)
+#define GG_TOPO_SWITCH_POST(t, touched, nt) topo_switch_post_dev(t, touched, nt)
+#define GG_TOPO_SORT_PAIRS(id, val, n, by_value) topo_sort_pairs_dev(id, val, n, by_value)
+#define GG_TOPO_L1_MARK(t, l1, n) topo_l1_mark_dev(t, l1, n)
+#define GG_TOPO_L1_COMPACT(t, l1, logit, n) topo_l1_compact_dev(t, l1, logit, n)
+#define GG_TOPO_SWEEP_COLLECT(t, cand) topo_sweep_collect_dev(t, cand)
 #include "topology_core.h"
+
+// the walker's side of the hooks
+static __host__ __device__ __forceinline__ int topo_switch_pre_dev(GGTopo& t, const int32_t* edges, int n, int32_t* touched) {
+#ifdef __CUDA_ARCH__
+    if (topo_svc()->enabled && n >= kTopoSvcMin && 2 * n <= kTopoSortCap && __isGlobal(edges)) return topo_service_call(TOPO_OP_PRE, edges, touched, nullptr, n, 0);
+#endif
+    return gg_topo_switch_pre_seq(t, edges, n, touched);
+}
+static __host__ __device__ __forceinline__ void topo_switch_post_dev(GGTopo& t, const int32_t* touched, int nt) {
+#ifdef __CUDA_ARCH__
+    if (topo_svc()->enabled && nt >= kTopoSvcMin) { topo_service_call(TOPO_OP_POST, touched, nullptr, nullptr, nt, 0); return; }
+#endif
+    gg_topo_switch_post_seq(t, touched, nt);
+}
+static __host__ __device__ __forceinline__ void topo_sort_pairs_dev(int32_t* id, float* val, int n, bool by_value) {
+#ifdef __CUDA_ARCH__
+    if (topo_svc()->enabled && n >= kTopoSvcMin && n <= kTopoSortCap) { topo_service_call(TOPO_OP_SORT_PAIRS, nullptr, id, val, n, by_value ? 1 : 0); return; }
+#endif
+    gg_topo_sort_pairs(id, val, n, by_value);
+}
+static __host__ __device__ __forceinline__ void topo_l1_mark_dev(GGTopo& t, const int32_t* l1, int n) {
+#ifdef __CUDA_ARCH__
+    if (topo_svc()->enabled && n >= kTopoSvcMin) { topo_service_call(TOPO_OP_L1_MARK, l1, nullptr, nullptr, n, 0); return; }
+#endif
+    gg_topo_l1_mark_seq(t, l1, n);
+}
+static __host__ __device__ __forceinline__ int topo_l1_compact_dev(GGTopo& t, int32_t* l1, float* logit, int n) {
+#ifdef __CUDA_ARCH__
+    if (topo_svc()->enabled && n >= kTopoSvcMin) return topo_service_call(TOPO_OP_L1_COMPACT, nullptr, l1, logit, n, 0);
+#endif
+    return gg_topo_l1_compact_seq(t, l1, logit, n);
+}
+static __host__ __device__ __forceinline__ int topo_sweep_collect_dev(GGTopo& t, int32_t* cand) {
+#ifdef __CUDA_ARCH__
+    if (topo_svc()->enabled && !t.dirty_all && t.n_dirty >= kTopoSvcMin && t.n_dirty <= kTopoSortCap) return topo_service_call(TOPO_OP_SWEEP, t.dirty_list, cand, nullptr, t.n_dirty, 0);
+#endif
+    return gg_topo_sweep_collect_seq(t, cand);
+}
 
 namespace {
 
@@ -108,7 +179,7 @@ struct TopoArgs {
     int64_t* switching_list; int32_t* grain_event_out; int32_t* work;
     int64_t* result;                                                                         // {n_pp, n_pq, n_switch, n_grain_event, err, n_ge_in, n_l1_in}
     const int32_t* n_seed;                                                                   // grains with one or two joints on entry (topo_seed_two_sided)
-    int prefetch;
+    int prefetch, service;
 };
 
 // What the switch of edge column e will look at, read by 8 lanes: lanes 0-3 its first end point, 4-7 the second; of each four, lane 0
@@ -159,6 +230,136 @@ __device__ void topo_prefetch_event(const GGTopo& t, int32_t e, int role, unsign
     }
 }
 
+// ---- helper warp: bitonic sort of 64-bit keys in shared memory + the list loops
+__device__ __forceinline__ uint32_t topo_ord_i32(int32_t v) { return (uint32_t)v ^ 0x80000000u; }              // signed order -> unsigned order
+__device__ __forceinline__ uint32_t topo_ord_f32(float v) {                                                     // float order -> unsigned order (-0 = +0)
+    uint32_t u = __float_as_uint(v);
+    if (u == 0x80000000u) u = 0u;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float topo_unord_f32(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
+__device__ void topo_warp_sort(unsigned long long* key, int n, int lane) {          // ascending; key[n .. n2) are padded with ~0
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + lane; i < n2; i += 32) key[i] = ~0ull;
+    __syncwarp();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n2; i += 32) {
+                const int x = i ^ j;
+                if (x > i) {
+                    const unsigned long long a = key[i], b = key[x];
+                    if ((a > b) == ((i & k) == 0)) { key[i] = b; key[x] = a; }
+                }
+            }
+            __syncwarp();
+        }
+}
+// order-preserving compaction of the elements with keep(i): every lane calls with its own i per chunk of 32; returns the new count
+template <class Keep, class Move>
+__device__ int topo_warp_compact(int n, int lane, Keep keep, Move move) {
+    int w = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool k = i < n && keep(i);
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        move(i, k ? w + __popc(m & ((1u << lane) - 1u)) : -1);       // reads of the chunk happen before its writes (two phases inside)
+        w += __popc(m);
+    }
+    return w;
+}
+
+__device__ void topo_service_warp(const GGTopo& t) {
+    __shared__ unsigned long long key[kTopoSortCap];
+    volatile TopoSvc* s = topo_svc();
+    volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
+    const int lane = threadIdx.x & 31;
+    const GGRows& pp = t.pp;
+    int done = 0;
+    for (;;) {
+        int r = 0;
+        if (lane == 0) { while ((r = s->req) == done && !h->done) __nanosleep(40); if (r == done) r = -1; }
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r < 0) return;
+        __threadfence_block();
+        const int op = s->op, n = s->n, flag = s->flag;
+        const void* a = const_cast<const void*>(s->a);
+        void* b = const_cast<void*>(s->b);
+        void* c = const_cast<void*>(s->c);
+        int ret = 0;
+        if (op == TOPO_OP_PRE) {                                 // gg_topo_switch_pre_seq
+            const int32_t* edges = static_cast<const int32_t*>(a);
+            int32_t* touched = static_cast<int32_t*>(b);
+            for (int k = lane; k < n; k += 32) {
+                const int32_t e = edges[k];
+                const int64_t u = pp.get(0, e), v = pp.get(1, e);
+                key[2 * k] = topo_ord_i32((int32_t)u); key[2 * k + 1] = topo_ord_i32((int32_t)v);
+                pp.ahead_flag[e] |= 1;
+                atomicAdd(&pp.ahead_cnt[u], 1);
+                atomicAdd(&pp.ahead_cnt[v], 1);
+            }
+            __syncwarp();
+            topo_warp_sort(key, 2 * n, lane);
+            const int nt = topo_warp_compact(2 * n, lane, [&](int i) { return i == 0 || key[i] != key[i - 1]; },
+                                             [&](int i, int w) { if (w >= 0) touched[w] = (int32_t)((uint32_t)key[i] ^ 0x80000000u); });
+            __syncwarp();
+            for (int i = lane; i < nt; i += 32) {
+                const int64_t p = touched[i];
+                float* x = gg_topo_xrow(t, p);
+                x[0] = gg_tsub(x[0], gg_tdiv(t.yj[2 * p], 5.0f));
+                x[1] = gg_tsub(x[1], gg_tdiv(t.yj[2 * p + 1], 5.0f));
+            }
+            ret = nt;
+        } else if (op == TOPO_OP_POST) {                         // gg_topo_switch_post_seq
+            const int32_t* touched = static_cast<const int32_t*>(a);
+            for (int i = lane; i < n; i += 32) {
+                const int64_t p = touched[i];
+                float* x = gg_topo_xrow(t, p);
+                const float y0 = gg_tmul(5.0f, gg_tsub(x[0], x[0])), y1 = gg_tmul(5.0f, gg_tsub(x[1], x[1]));
+                t.yj[2 * p] = y0; t.yj[2 * p + 1] = y1;
+                x[t.col_dxy] = y0; x[t.col_dxy + 1] = y1;
+            }
+        } else if (op == TOPO_OP_SORT_PAIRS) {                   // gg_topo_sort_pairs (a total order: any correct sort gives the same array)
+            int32_t* id = static_cast<int32_t*>(b);
+            float* val = static_cast<float*>(c);
+            for (int i = lane; i < n; i += 32)
+                key[i] = flag ? ((unsigned long long)(~topo_ord_f32(val[i])) << 32) | topo_ord_i32(id[i])
+                              : ((unsigned long long)topo_ord_i32(id[i]) << 32) | __float_as_uint(val[i]);
+            __syncwarp();
+            topo_warp_sort(key, n, lane);
+            for (int i = lane; i < n; i += 32) {
+                const unsigned long long kk = key[i];
+                if (flag) { id[i] = (int32_t)((uint32_t)kk ^ 0x80000000u); val[i] = topo_unord_f32(~(uint32_t)(kk >> 32)); }
+                else { id[i] = (int32_t)((uint32_t)(kk >> 32) ^ 0x80000000u); val[i] = __uint_as_float((uint32_t)kk); }
+            }
+        } else if (op == TOPO_OP_L1_MARK) {
+            const int32_t* l1 = static_cast<const int32_t*>(a);
+            for (int i = lane; i < n; i += 32) pp.ahead_flag[l1[i]] |= 4;
+        } else if (op == TOPO_OP_L1_COMPACT) {                   // gg_topo_l1_compact_seq
+            int32_t* l1 = static_cast<int32_t*>(b);
+            float* logit = static_cast<float*>(c);
+            int32_t e = 0; float lg = 0.f;
+            ret = topo_warp_compact(n, lane,
+                                    [&](int i) { e = l1[i]; lg = logit[i]; const uint8_t f = pp.ahead_flag[e]; pp.ahead_flag[e] = f & 1; return !(f & 2); },
+                                    [&](int i, int w) { __syncwarp(); if (w >= 0) { l1[w] = e; logit[w] = lg; } __syncwarp(); });
+        } else if (op == TOPO_OP_SWEEP) {                        // gg_topo_sweep_collect_seq, the change-list branch
+            const int32_t* dirty = static_cast<const int32_t*>(a);
+            int32_t* cand = static_cast<int32_t*>(b);
+            const int nc = topo_warp_compact(n, lane, [&](int i) { const int cg = t.pq.cnt[1][dirty[i]]; return cg > 0 && cg <= 2; },
+                                             [&](int i, int w) { if (w >= 0) key[w] = topo_ord_i32(dirty[i]); });
+            __syncwarp();
+            topo_warp_sort(key, nc, lane);
+            for (int i = lane; i < nc; i += 32) cand[i] = (int32_t)((uint32_t)key[i] ^ 0x80000000u);
+            for (int i = lane; i < n; i += 32) t.dirty_flag[dirty[i]] = 0;
+            ret = nc;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) { s->ret = ret; __threadfence_block(); s->ack = r; }
+        done = r;
+    }
+}
+
 constexpr int kTopoLookAhead = 6;          // events: ~150 lines of 128 B per event, the L1 holds ~1800
 
 __device__ void topo_prefetch_warp(const GGTopo& t) {
@@ -187,9 +388,14 @@ __device__ void topo_prefetch_warp(const GGTopo& t) {
 __global__ void topo_update_kernel(TopoArgs A) {
     {
         volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
-        if (threadIdx.x == 0) { h->n = 0; h->k = 0; h->epoch = 0; h->done = 0; h->edges = nullptr; }
+        if (threadIdx.x == 0) {
+            h->n = 0; h->k = 0; h->epoch = 0; h->done = 0; h->edges = nullptr;
+            volatile TopoSvc* sv = topo_svc();
+            sv->req = 0; sv->ack = 0; sv->enabled = A.service;
+        }
         __syncthreads();
-        if (threadIdx.x >= 32) { topo_prefetch_warp(A.t); return; }
+        if (threadIdx.x >= 64) { if (A.service) topo_service_warp(A.t); return; }
+        if (threadIdx.x >= 32) { if (A.prefetch) topo_prefetch_warp(A.t); return; }
     }
     if (threadIdx.x != 0) return;
 #ifdef GG_TOPO_PROFILE
@@ -288,8 +494,14 @@ extern "C" int gg_topology_update(int64_t* pp, int64_t cap_pp, int64_t n_pp, int
     if (err != cudaSuccess) return (int)err;
     topo_seed_two_sided<<<(n_grain + 255) / 256, 256, 0, st>>>(pq_cnt1, n_grain, dirty_flag, dirty_list, n_seed); GG_LAUNCH_OK();
     A.n_seed = n_seed;
-    { const char* e = getenv("GG_TOPO_PREFETCH"); A.prefetch = !(e && e[0] == '0'); }
-    topo_update_kernel<<<1, A.prefetch ? 64 : 32, sizeof(TopoHint), st>>>(A);
+    { const char* e = getenv("GG_TOPO_PREFETCH"); A.prefetch = !(e && e[0] == '0'); }        // (measurement switches)
+    { const char* e = getenv("GG_TOPO_SERVICE"); A.service = !(e && e[0] == '0'); }
+    static bool carve_set = false;
+    if (!carve_set) {                     // the walk lives on L1 hits (look-ahead warp): keep shared memory at what the helper warp needs
+        cudaFuncSetAttribute(topo_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
+        carve_set = true;
+    }
+    topo_update_kernel<<<1, 96, sizeof(TopoHint) + sizeof(TopoSvc), st>>>(A);
     GG_LAUNCH_OK();
     return 0;
 }

@@ -29,6 +29,16 @@
 #define GG_TOPO_HINT_BEGIN(edges, n) ((void)0)
 #define GG_TOPO_HINT_AT(k) ((void)0)
 #endif
+// The data-parallel parts of the walk (the two sorts, the loops over the touched joints before and after the switches of a list,
+// the bookkeeping of the candidate list) go through these; the device build hands the long ones to a helper warp.
+#ifndef GG_TOPO_SWITCH_PRE
+#define GG_TOPO_SWITCH_PRE(t, edges, n, touched) gg_topo_switch_pre_seq(t, edges, n, touched)
+#define GG_TOPO_SWITCH_POST(t, touched, nt) gg_topo_switch_post_seq(t, touched, nt)
+#define GG_TOPO_SORT_PAIRS(id, val, n, by_value) gg_topo_sort_pairs(id, val, n, by_value)
+#define GG_TOPO_L1_MARK(t, l1, n) gg_topo_l1_mark_seq(t, l1, n)
+#define GG_TOPO_L1_COMPACT(t, l1, logit, n) gg_topo_l1_compact_seq(t, l1, logit, n)
+#define GG_TOPO_SWEEP_COLLECT(t, cand) gg_topo_sweep_collect_seq(t, cand)
+#endif
 #ifndef GG_TOPO_MARK
 #define GG_TOPO_MARK(bucket) ((void)0)     // profiling build of the device kernel: time since the last mark goes to `bucket`
 #endif
@@ -83,7 +93,8 @@ struct GGRows {
     int32_t* cnt[2];
     int32_t lcap[2];
     int32_t* ahead_cnt;    // (pp only, inside switch) occurrences of every joint among the end points of the events still to come
-    uint8_t* ahead_flag;   // (pp only) column is one of the events still to come
+    uint8_t* ahead_flag;   // (pp only) bit 0: column is one of the events still to come; bit 2: column is a switching candidate of this
+                           // step (L1), bit 1: ... that was a switched side of an eliminated grain and leaves L1 (models.py:713)
     int err;
 
     GG_TD int64_t get(int r, int64_t pos) const { return a[r * cap + pos]; }
@@ -110,7 +121,7 @@ struct GGRows {
         if (old == v) return;
         if (old >= 0) list_remove(r, old, (int32_t)pos);
         if (v >= 0) list_insert(r, v, (int32_t)pos);
-        if (ahead_flag && ahead_flag[pos]) {
+        if (ahead_flag && (ahead_flag[pos] & 1)) {
             if (old >= 0) --ahead_cnt[old];
             if (v >= 0) ++ahead_cnt[v];
         }
@@ -237,8 +248,9 @@ GG_TD void gg_topo_sort_pairs(int32_t* id, float* val, int n, bool by_value) {
 
 // The two-sided sweep (models.py:716-727 / :745-755): every grain left with one or two joints is deleted; returns how many were
 // appended to `out` (ascending grain ids).
-GG_TD int gg_topo_delete_two_sided(GGTopo& t, int32_t* out) {
-    int32_t* cand = t.scratch;
+// candidates of a sweep: the grains with one or two joints among those whose joint count changed (all grains on the first sweep of
+// a step that was not pre-seeded), ascending; the change list is emptied
+GG_TD int gg_topo_sweep_collect_seq(GGTopo& t, int32_t* cand) {
     int nc = 0;
     if (t.dirty_all) {                                            // first check of the step: every grain (torch.unique over E_pq[1])
         for (int32_t g = 0; g < t.n_grain; ++g) { const int c = t.pq.cnt[1][g]; if (c > 0 && c <= 2) cand[nc++] = g; }
@@ -247,6 +259,11 @@ GG_TD int gg_topo_delete_two_sided(GGTopo& t, int32_t* out) {
         gg_topo_sort_i32(cand, nc);
     }
     for (int i = 0; i < t.n_dirty; ++i) t.dirty_flag[t.dirty_list[i]] = 0;
+    return nc;
+}
+GG_TD int gg_topo_delete_two_sided(GGTopo& t, int32_t* out) {
+    int32_t* cand = t.scratch;
+    const int nc = GG_TOPO_SWEEP_COLLECT(t, cand);
     t.n_dirty = 0;
     t.dirty_all = false;
     // the candidate list lives in scratch, which delete_grain does not touch
@@ -265,13 +282,9 @@ GG_TD bool gg_topo_inside(const float* t_, const float* v1, const float* v2, con
     return !(neg && pos);
 }
 
-// switching_edge_index (models.py:899-1053) over the edge columns `edges[0..n_edges)`; elim_grain < 0: plain neighbour switching.
-// Forced eliminations are appended to forced[] (returns the new count).
-GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t elim_grain, int32_t* forced, int n_forced) {
+// Before the switches of a list (models.py:905-907 and the bookkeeping of "the events still to come"); returns |touched|.
+GG_TD int gg_topo_switch_pre_seq(GGTopo& t, const int32_t* edges, int n_edges, int32_t* touched) {
     GGRows& pp = t.pp;
-    GGRows& pq = t.pq;
-    // touched = sorted set of the end points; every touched joint first steps back by its predicted displacement (:905-907)
-    int32_t* touched = t.scratch + t.n_grain;                     // (scratch[0 .. n_grain) is the two-sided sweep's)
     int nt = 0;
     for (int k = 0; k < n_edges; ++k) { touched[nt++] = (int32_t)pp.get(0, edges[k]); touched[nt++] = (int32_t)pp.get(1, edges[k]); }
     gg_topo_sort_i32(touched, nt);
@@ -282,12 +295,46 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
         x[0] = gg_tsub(x[0], gg_tdiv(t.yj[2 * p], 5.0f));
         x[1] = gg_tsub(x[1], gg_tdiv(t.yj[2 * p + 1], 5.0f));
     }
-    // the end points of the events still to come, counted per joint and kept current by GGRows::set
     for (int k = 0; k < n_edges; ++k) {
-        pp.ahead_flag[edges[k]] = 1;
+        pp.ahead_flag[edges[k]] |= 1;
         ++pp.ahead_cnt[pp.get(0, edges[k])];
         ++pp.ahead_cnt[pp.get(1, edges[k])];
     }
+    return nt;
+}
+// After them: y <- 5 (x - before) with `before` a VIEW of x in the reference (it has followed every move): exactly zero (:1046-1050)
+GG_TD void gg_topo_switch_post_seq(GGTopo& t, const int32_t* touched, int nt) {
+    for (int i = 0; i < nt; ++i) {
+        const int64_t p = touched[i];
+        float* x = gg_topo_xrow(t, p);
+        const float y0 = gg_tmul(5.0f, gg_tsub(x[0], x[0])), y1 = gg_tmul(5.0f, gg_tsub(x[1], x[1]));
+        t.yj[2 * p] = y0; t.yj[2 * p + 1] = y1;
+        x[t.col_dxy] = y0; x[t.col_dxy + 1] = y1;
+    }
+}
+// `L1 = [e for e in L1 if e not in sides]` after every elimination (models.py:713) is applied once, before the switches: the
+// candidates are flagged, an elimination flags those of its switched sides that are candidates, the compaction drops them.
+GG_TD void gg_topo_l1_mark_seq(GGTopo& t, const int32_t* L1, int n) { for (int i = 0; i < n; ++i) t.pp.ahead_flag[L1[i]] |= 4; }
+GG_TD int gg_topo_l1_compact_seq(GGTopo& t, int32_t* L1, float* logit, int n) {      // keeps the order; clears the flags
+    int w = 0;
+    for (int i = 0; i < n; ++i) {
+        const int32_t e = L1[i];
+        const uint8_t f = t.pp.ahead_flag[e];
+        t.pp.ahead_flag[e] = f & 1;
+        if (!(f & 2)) { L1[w] = e; logit[w] = logit[i]; ++w; }
+    }
+    return w;
+}
+
+// switching_edge_index (models.py:899-1053) over the edge columns `edges[0..n_edges)`; elim_grain < 0: plain neighbour switching.
+// Forced eliminations are appended to forced[] (returns the new count).
+GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t elim_grain, int32_t* forced, int n_forced) {
+    GGRows& pp = t.pp;
+    GGRows& pq = t.pq;
+    // touched = sorted set of the end points; every touched joint first steps back by its predicted displacement (:905-907);
+    // the end points of the events still to come are counted per joint and kept current by GGRows::set
+    int32_t* touched = t.scratch + t.n_grain;                     // (scratch[0 .. n_grain) is the two-sided sweep's)
+    const int nt = GG_TOPO_SWITCH_PRE(t, edges, n_edges, touched);
     GG_TOPO_MARK(elim_grain < 0 ? 4 : 1);
     GG_TOPO_HINT_BEGIN(edges, n_edges);
     for (int k = 0; k < n_edges && !t.err; ++k) {
@@ -358,6 +405,7 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
                     { const int64_t s = a2; a2 = b2; b2 = s; }
                 }
                 if (ng1 != 1 || ng2 != 1 || ns1 < 2 || ns2 < 1) { t.err = GG_TOPO_GROW; break; }
+                GG_TOPO_MARK(elim_grain < 0 ? 5 : 1);
                 gg_topo_pq_set_grain(t, slots1[1], grow2);
                 gg_topo_pq_set_grain(t, slots2[0], grow1);
                 pp.set(0, at_n1[1], p2);
@@ -367,29 +415,23 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
                 for (int i = 0; i < c; ++i) pp.set(1, tmp[i], p1);
                 c = gg_topo_pp_between(t, b1, p1, true, tmp);
                 for (int i = 0; i < c; ++i) pp.set(1, tmp[i], p2);
+                GG_TOPO_MARK(elim_grain < 0 ? 6 : 1);
             }
         }
         // this event is no longer "to come"
-        pp.ahead_flag[e] = 0;
+        pp.ahead_flag[e] &= (uint8_t)~1u;
         { const int64_t u = pp.get(0, e), v = pp.get(1, e); if (u >= 0) --pp.ahead_cnt[u]; if (v >= 0) --pp.ahead_cnt[v]; }
     }
     GG_TOPO_MARK(elim_grain < 0 ? 5 : 1);
     if (t.err) {                                                  // leave the ahead tables clean
-        for (int k = 0; k < n_edges; ++k) if (pp.ahead_flag[edges[k]]) {
-            pp.ahead_flag[edges[k]] = 0;
+        for (int k = 0; k < n_edges; ++k) if (pp.ahead_flag[edges[k]] & 1) {
+            pp.ahead_flag[edges[k]] &= (uint8_t)~1u;
             const int64_t u = pp.get(0, edges[k]), v = pp.get(1, edges[k]);
             if (u >= 0) --pp.ahead_cnt[u];
             if (v >= 0) --pp.ahead_cnt[v];
         }
     }
-    // y <- 5 (x - before) with `before` a VIEW of x in the reference (it has followed every move): exactly zero (:1046-1050)
-    for (int i = 0; i < nt; ++i) {
-        const int64_t p = touched[i];
-        float* x = gg_topo_xrow(t, p);
-        const float y0 = gg_tmul(5.0f, gg_tsub(x[0], x[0])), y1 = gg_tmul(5.0f, gg_tsub(x[1], x[1]));
-        t.yj[2 * p] = y0; t.yj[2 * p + 1] = y1;
-        x[t.col_dxy] = y0; x[t.col_dxy + 1] = y1;
-    }
+    GG_TOPO_SWITCH_POST(t, touched, nt);
     if (pp.err) t.err = pp.err;
     if (pq.err) t.err = pq.err;
     GG_TOPO_MARK(elim_grain < 0 ? 6 : 1);
@@ -417,7 +459,8 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
     if (t.preseeded) t.dirty_all = false;
     else { t.dirty_all = true; t.n_dirty = 0; }
     // L1 ascending by column first (the reference's nonzero order), so that ties of the later sort are by column
-    gg_topo_sort_pairs(L1, L1_logit, n_l1, false);
+    GG_TOPO_SORT_PAIRS(L1, L1_logit, n_l1, false);
+    GG_TOPO_L1_MARK(t, L1, n_l1);
     GG_TOPO_MARK(0);
     int n_unexpected = 0;
     int32_t* unexpected = work + n_l1 + n_ge + 8;                 // forced + swept grains, in the reference's order
@@ -472,20 +515,15 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
         gg_topo_delete_grain(t, grain);
         for (int i = 0; i < nf && !t.err; ++i) gg_topo_delete_grain(t, forced[i]);
         if (t.err) break;
-        { int w = 0;                                             // L1 = [e for e in L1 if e not in sides]
-          for (int i = 0; i < n_l1; ++i) {
-              bool hit = false;
-              for (int k = 0; k < n_sw; ++k) hit = hit || sw[k] == L1[i];
-              if (!hit) { L1[w] = L1[i]; L1_logit[w] = L1_logit[i]; ++w; }
-          }
-          n_l1 = w; }
+        for (int k = 0; k < n_sw; ++k) if (t.pp.ahead_flag[sw[k]] & 4) t.pp.ahead_flag[sw[k]] |= 2;     // L1 = [e for e in L1 if e not in sides]
         GG_TOPO_MARK(1);
         gg_topo_delete_two_sided(t, removed);                     // (its victims are not reported, models.py:716-727)
         GG_TOPO_MARK(2);
     }
+    n_l1 = GG_TOPO_L1_COMPACT(t, L1, L1_logit, n_l1);             // (also on an error: the flags are left clean)
     if (!t.err && n_l1 > 0) {                                      // models.py:730-740
         // probability descending = logit descending; equal logits keep ascending column order
-        gg_topo_sort_pairs(L1, L1_logit, n_l1, true);
+        GG_TOPO_SORT_PAIRS(L1, L1_logit, n_l1, true);
         int w = 0;
         for (int i = 0; i < n_l1; ++i) if (t.pp.get(0, L1[i]) != -1) { L1[w] = L1[i]; L1_logit[w] = L1_logit[i]; ++w; }
         n_l1 = w;

@@ -152,3 +152,40 @@ def test_rollout_driver_with_the_device_update_equals_the_host_update(rows):
     ma, mb = drv['host'].current_mask(), drv['device'].current_mask()
     assert torch.equal(ma['grain'].float(), mb['grain']) and torch.equal(ma['joint'].float(), mb['joint'])
     assert drv['device'].d2h_bytes < drv['host'].d2h_bytes / 20
+
+
+@pytest.mark.parametrize('name,n_switch,n_vanish', [('c2', 150, 25), ('c2', 400, 60)])
+def test_device_update_equals_the_host_update_on_dense_event_sets(name, n_switch, n_vanish):
+    """Hundreds of events on the 1,043-grain graph (adjacent switching edges, grains of up to 8 sides, forced eliminations): long
+    candidate lists, so the helper warp's sorts / list loops and the look-ahead warp run; every array equals the host update's
+    (itself pinned by the reference's outputs), or both refuse the event set."""
+    from test_topology_golden import _craft
+    from graingraphnn_b200 import topology
+    x0, ei, _ = load_graph(name)
+    agreed = 0
+    for seed in range(4):
+        y0 = _craft(np.random.default_rng(7000 + seed), x0, ei, n_switch, n_vanish, 8)
+        res = []
+        for fn in (topology.topology_update, device_update):
+            x = {k: v.clone() for k, v in x0.items()}
+            y = {k: v.clone() for k, v in y0.items()}
+            orc.regressor_update(x, y, span=0)
+            _, y['grain_event'] = orc.event_candidates(y, ei[ET[2]])
+            mask = {'grain': torch.ones(x['grain'].shape[0], 1), 'joint': torch.ones(x['joint'].shape[0], 1)}
+            active = ((y['grain'][:, 0] > -10).nonzero().view(-1), (y['joint'][:, 0] > -10).nonzero().view(-1))
+            try:
+                _, eio, pairs = fn(x, ei, y, mask, *active)
+                res.append((x, eio, pairs, y, mask))
+            except (KeyError, AssertionError, ValueError, RuntimeError, IndexError):
+                res.append(None)
+        if res[0] is None or res[1] is None:
+            assert res[0] is None and res[1] is None, seed
+            continue
+        (xa, ea_, pa, ya, ma), (xb, eb, pb, yb, mb) = res
+        for et in ET:
+            assert torch.equal(ea_[et], eb[et]), (seed, et)
+        assert torch.equal(pa, pb) and torch.equal(ya['grain_event'], yb['grain_event'])
+        for t in ('joint', 'grain'):
+            assert torch.equal(xa[t], xb[t]) and torch.equal(ma[t], mb[t]) and torch.equal(ya[t], yb[t]), (seed, t)
+        agreed += 1
+    assert agreed >= 1
