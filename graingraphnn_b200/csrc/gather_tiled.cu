@@ -194,7 +194,12 @@ constexpr int cfg_hcap(int ecap) { return ecap / 3 + 2; }
 // The largest tile (multiple of 6 edges: joints have 3 in-edges, grains ~6) that fits 227 KB with three stages, else with two
 // (measured on the bench graph, encoder form: 54 edges x 3 stages 179 / 152 / 179 us per launch, 36 x 4: 192 / 164 / 192 us).
 // what = 0: ECAP, 1: stages
+#ifndef GG_DEC_ECAP
+#define GG_DEC_ECAP 0      // (measurement override of the decoder form's tile: edges per tile, stages)
+#define GG_DEC_NS 0
+#endif
 constexpr int cfg_pick(int G, int C, int raw, int what) {
+    if (GG_DEC_ECAP && raw > 16) return what == 0 ? GG_DEC_ECAP : GG_DEC_NS;
     for (int ns = 3; ns >= 2; --ns)
         for (int ecap = 60; ecap >= 12; ecap -= 6)
             if ((long long)ns * cfg_stage_bytes(G, C, raw, ecap, cfg_hcap(ecap)) <= 227 * 1024 - 256) return what == 0 ? ecap : ns;
