@@ -31,6 +31,7 @@ import torch  # noqa: E402
 WEAK_LXD = {1: 1320, 2: 1880, 4: 2640, 8: 3720}
 STRONG_LXD = 3720
 CPU_SAMPLE_LXD = 240
+CPU_BASELINE_LXD = 640           # `cpu_baseline` of the N = 1 line: 29,6xx grains, ~10 s of CPU work on 24 cores
 SPAN = 6
 ET = [('grain', 'push', 'joint'), ('joint', 'pull', 'grain'), ('joint', 'connect', 'joint')]
 GEOM = {}          # lxd -> (per-joint patch offsets [Nj, 2], domain_factor) of the domains made so far (test.py:310-312)
@@ -137,7 +138,7 @@ def synth_weights():
 
 def cpu_reference_run(steps, warmup, lxd=CPU_SAMPLE_LXD):
     """The reference-order CPU restatement (oracle/grain_oracle.py; PyG is not installable here) on a bounded sample of the
-    workload: the same generator, seed and physical parameters at lxd = 240 um (4,176 grains), all host threads."""
+    workload: the same generator, seed and physical parameters on a smaller (or, time permitting, the same) domain, all host threads."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import grain_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
@@ -163,6 +164,18 @@ def cpu_reference_run(steps, warmup, lxd=CPU_SAMPLE_LXD):
             'sample': f'{steps} steps of the same generate-mode workload at lxd = {lxd} um ({x["grain"].shape[0]} grains, {edges} edges), '
                       f'oracle/grain_oracle.py in reference op order (without the per-grain Python loop of the grain-centre update)', 'ms_per_step': dt / steps * 1e3,
             'steps_per_s': steps / dt}
+
+
+def reference_sample_lxd(steps, warmup, target_lxd, budget_s=180.0):
+    """The largest domain of the ladder (up to the GPU arm's own) on which `warmup + steps` CPU steps are expected to end within
+    `budget_s`: a 2-step probe at lxd = 240 gives edges/s, halved as a margin for the larger working set."""
+    probe = cpu_reference_run(2, 1, lxd=CPU_SAMPLE_LXD)
+    eps = 0.5 * probe['value']
+    edges_240 = 75168.0
+    for lxd in (1320, 920, 640, 480):
+        if lxd <= target_lxd and (steps + warmup) * edges_240 * (lxd / 240.0) ** 2 / eps <= budget_s:
+            return lxd
+    return CPU_SAMPLE_LXD
 
 
 def ncu_traffic(n_grains, launches):
@@ -345,8 +358,8 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        steps, warmup = min(args.steps, 10), min(args.warmup, 2)
-        r = cpu_reference_run(steps, warmup)
+        steps, warmup = args.steps, args.warmup
+        r = cpu_reference_run(steps, warmup, lxd=reference_sample_lxd(steps, warmup, lxd))
         print(json.dumps({'metric': 'rollout_edges_per_sec', 'value': r['value'], 'unit': 'edges/s', 'impl': 'reference',
                           'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
                           'steps_per_sec': r['steps_per_s'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -537,7 +550,7 @@ def main():
         except Exception as exc:                                   # never lose the headline line to the extra measurement
             widened = {'error': repr(exc)[:200]}
 
-    cpu = None if args.no_cpu_baseline else cpu_reference_run(5, 1)
+    cpu = None if args.no_cpu_baseline else cpu_reference_run(5, 1, lxd=CPU_BASELINE_LXD)
     steps_per_s = args.steps / (ms / 1e3)
     part = (f'; x-slab partition over {n_gpus} GPUs, {halo["transport"]} halo exchange per message-passing hop' if n_gpus > 1 else '; single B200 rollout')
     line = {
