@@ -286,7 +286,10 @@ node_proj_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 // 16 + 64 KB come through TMA instead of 32 + 64 KB, and gg_split_tf32 (one read of [X | h], two writes of 32 + C floats per
 // node) is gone.
 constexpr int kFusedThreads = 384;       // warps 0-3 TMA / MMA / TMEM / idle, 4-7 epilogue, 8-11 converters
-constexpr int kFRingA = 2;               // A slots of [fp32 chunk | lo chunk] (2 x 16 KB)
+#ifndef GG_PROJ_RING_A
+#define GG_PROJ_RING_A 2
+#endif
+constexpr int kFRingA = GG_PROJ_RING_A;  // A slots of [fp32 chunk | lo chunk] (2 x 16 KB)
 #ifndef GG_PROJ_RING_B
 #define GG_PROJ_RING_B 4
 #endif
