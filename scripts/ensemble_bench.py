@@ -3,6 +3,7 @@
 communication (replicas only — DESIGN.md §6).
 
     python scripts/ensemble_bench.py                       # 1 GPU: the 64 rollouts as 8 batches of 8, one after the other
+    GG_ENSEMBLE_BATCH=64 python scripts/ensemble_bench.py  # 1 GPU: all 64 in one block-diagonal batch
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/ensemble_bench.py    # 8 rollouts per GPU
 
 Every member is what `graph_trajectory.py --mode=generate --lxd 40 --seed s --G g --R r` builds (graingraphnn_b200/generate.py,
@@ -44,7 +45,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
-    per_batch = 8
+    per_batch = int(os.environ.get('GG_ENSEMBLE_BATCH', '8'))                     # 8 = BASELINE config 5's "8 per GPU"; 64 = the whole ensemble as one block-diagonal batch
+    assert 64 % per_batch == 0
     mine = [b for b in range(64 // per_batch) if b % world == rank]               # batches of this rank
     sd_r, sd_c, wdesc = load_weights(os.environ.get('GG_REGRESSOR_PT'), os.environ.get('GG_CLASSIFIER_PT'))
     eng = EnsembleEngine.from_state_dicts(sd_r, sd_c, device=dev)
@@ -82,7 +84,7 @@ def main():
         print(json.dumps({'metric': 'ensemble_rollouts_per_sec', 'value': 64 / (ms_total / 1e3), 'unit': 'rollouts/s', 'n_gpus': world,
                           'member_steps_per_sec': total_member_steps / (ms_total / 1e3), 'ms_total': ms_total,
                           'config': {'workload': '64 generate-mode 40x40 rollouts (seeds 1..64, (G, R) on an 8 x 8 grid, spans 6..120 by the '
-                                                 'reference\'s lookup), block-diagonal batches of 8, one batch at a time per GPU, no communication',
+                                                 'reference\'s lookup), block-diagonal batches of ' + str(per_batch) + ', one batch at a time per GPU, no communication',
                                      'batch_nodes': c, 'weights': wdesc, 'cuda_graph': True,
                                      'step': 'nn-step per member with its own span; fixed topology'}}))
     if world > 1:
