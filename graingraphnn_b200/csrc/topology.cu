@@ -360,7 +360,10 @@ __device__ void topo_service_warp(const GGTopo& t) {
     }
 }
 
-constexpr int kTopoLookAhead = 6;          // events: ~150 lines of 128 B per event, the L1 holds ~1800
+#ifndef GG_TOPO_LOOKAHEAD
+#define GG_TOPO_LOOKAHEAD 1      // events between the walker and the next wave of four (measured: 1: 5.0 ms, 3: 5.1, 6: 5.35, 12: 6.05 for 320 events)
+#endif
+constexpr int kTopoLookAhead = GG_TOPO_LOOKAHEAD;
 
 __device__ void topo_prefetch_warp(const GGTopo& t) {
     volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
