@@ -24,6 +24,7 @@ struct TopoHint {
     int32_t small_list[GG_HINT_SMALL];     // copy of a short event list (the caller's array may live in the walker's local memory)
     const int32_t* edges;                  // a long event list, in global memory
     int n, k, epoch, done;
+    int grain, gepoch;                     // the grain of the NEXT elimination (its joints' entries are read ahead too)
 };
 extern __shared__ __align__(16) unsigned char gg_topo_smem[];
 static __host__ __device__ __forceinline__ void topo_hint_begin(const int32_t* edges, int n) {
@@ -53,8 +54,16 @@ static __host__ __device__ __forceinline__ void topo_mark(int b) {
 }
 #define GG_TOPO_MARK(b) topo_mark(b)
 #endif
+static __host__ __device__ __forceinline__ void topo_hint_grain(int g) {
+#ifdef __CUDA_ARCH__
+    volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
+    h->grain = g;
+    h->gepoch = h->gepoch + 1;
+#endif
+}
 #define GG_TOPO_HINT_BEGIN(edges, n) topo_hint_begin(edges, n)
 #define GG_TOPO_HINT_AT(k) topo_hint_at(k)
+#define GG_TOPO_HINT_GRAIN(g) topo_hint_grain((int)(g))
 
 // ---- helper warp.  The sorts of the walk and its loops over whole lists (the touched joints before and after the switches, the
 // candidate list, the sweep's change list) are data-parallel; the walking thread hands the long ones to a third warp of the CTA
@@ -184,13 +193,11 @@ struct TopoArgs {
 
 // What the switch of edge column e will look at, read by 8 lanes: lanes 0-3 its first end point, 4-7 the second; of each four, lane 0
 // walks the joint's own entries and its three grains, lanes 1-3 one joint neighbour each with that neighbour's lists.
-__device__ void topo_prefetch_event(const GGTopo& t, int32_t e, int role, unsigned& sink) {
+// What an event will look at around joint p: j = 0 the joint's own entries and its three grains, j = 1..3 one joint neighbour each
+// with that neighbour's lists.
+__device__ void topo_prefetch_joint(const GGTopo& t, int64_t p, int j, unsigned& sink) {
     const GGRows& pp = t.pp;
     const GGRows& pq = t.pq;
-    if (e < 0 || e >= pp.cap) return;
-    const int side = role >> 2, j = role & 3;
-    const int64_t p = pp.a[side * pp.cap + e];
-    if (role == 0) sink += pp.ahead_flag[e];
     if (p < 0 || p >= t.n_joint) return;
     auto joint_row = [&](int64_t v) {
         const int64_t jr = t.jrow ? t.jrow[v] : v;
@@ -205,7 +212,7 @@ __device__ void topo_prefetch_event(const GGTopo& t, int32_t e, int role, unsign
             if (pos < 0 || pos >= pq.cap) continue;
             sink += (unsigned)pq.a[pos];
             const int64_t q = pq.a[pq.cap + pos];
-            if (q >= 0 && q < t.n_grain) sink += pq.cnt[1][q] + pq.list[1][q * GG_TOPO_CAP_G] + t.dirty_flag[q];
+            if (q >= 0 && q < t.n_grain) sink += pq.cnt[1][q] + pq.list[1][q * GG_TOPO_CAP_G] + t.dirty_flag[q] + __float_as_uint(t.yg[q * t.ld_yg]);
         }
     } else {
         const int c = min(pp.cnt[0][p], GG_TOPO_CAP_J);
@@ -228,6 +235,23 @@ __device__ void topo_prefetch_event(const GGTopo& t, int32_t e, int role, unsign
             if (p3 >= 0 && p3 < pp.cap) sink += (unsigned)pp.a[pp.cap + p3] + (unsigned)pp.a[p3] + pp.ahead_flag[p3];
         }
     }
+}
+// The switch of edge column e, read by 8 lanes: lanes 0-3 its first end point, 4-7 the second.
+__device__ void topo_prefetch_event(const GGTopo& t, int32_t e, int role, unsigned& sink) {
+    if (e < 0 || e >= t.pp.cap) return;
+    if (role == 0) sink += t.pp.ahead_flag[e];
+    topo_prefetch_joint(t, t.pp.a[(role >> 2) * t.pp.cap + e], role & 3, sink);
+}
+// The elimination of grain g: lane i takes the i-th joint around it, four lanes per joint as above.
+__device__ void topo_prefetch_grain(const GGTopo& t, int g, int lane, unsigned& sink) {
+    if (g < 0 || g >= t.n_grain) return;
+    sink += t.act_g[g] + t.dirty_flag[g];
+    const int c = min(t.pq.cnt[1][g], 8);
+    const int i = lane >> 2;
+    if (i >= c) return;
+    const int32_t pos = t.pq.list[1][(int64_t)g * GG_TOPO_CAP_G + i];
+    if (pos < 0 || pos >= t.pq.cap) return;
+    topo_prefetch_joint(t, t.pq.a[pos], lane & 3, sink);
 }
 
 // ---- helper warp: bitonic sort of 64-bit keys in shared memory + the list loops
@@ -368,10 +392,12 @@ constexpr int kTopoLookAhead = GG_TOPO_LOOKAHEAD;
 __device__ void topo_prefetch_warp(const GGTopo& t) {
     volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
     const int lane = threadIdx.x & 31;
-    int seen = 0;
+    int seen = 0, gseen = 0;
     unsigned sink = 0;
     for (;;) {
         if (h->done) break;
+        const int gep = h->gepoch;
+        if (gep != gseen) { gseen = gep; topo_prefetch_grain(t, h->grain, lane, sink); __syncwarp(); }
         const int ep = h->epoch;
         if (ep == seen) { __nanosleep(200); continue; }
         seen = ep;
@@ -392,7 +418,7 @@ __global__ void topo_update_kernel(TopoArgs A) {
     {
         volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
         if (threadIdx.x == 0) {
-            h->n = 0; h->k = 0; h->epoch = 0; h->done = 0; h->edges = nullptr;
+            h->n = 0; h->k = 0; h->epoch = 0; h->done = 0; h->edges = nullptr; h->grain = -1; h->gepoch = 0;
             volatile TopoSvc* sv = topo_svc();
             sv->req = 0; sv->ack = 0; sv->enabled = A.service;
         }

@@ -29,6 +29,9 @@
 #define GG_TOPO_HINT_BEGIN(edges, n) ((void)0)
 #define GG_TOPO_HINT_AT(k) ((void)0)
 #endif
+#ifndef GG_TOPO_HINT_GRAIN
+#define GG_TOPO_HINT_GRAIN(g) ((void)0)     // the grain whose elimination comes after the current one
+#endif
 // The data-parallel parts of the walk (the two sorts, the loops over the touched joints before and after the switches of a list,
 // the bookkeeping of the candidate list) go through these; the device build hands the long ones to a helper warp.
 #ifndef GG_TOPO_SWITCH_PRE
@@ -466,6 +469,7 @@ GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_g
     int32_t* unexpected = work + n_l1 + n_ge + 8;                 // forced + swept grains, in the reference's order
     for (int gi = 0; gi < n_ge && !t.err; ++gi) {                  // models.py:638-727
         const int64_t grain = grain_event[gi];
+        GG_TOPO_HINT_GRAIN(gi + 1 < n_ge ? grain_event[gi + 1] : -1);
         if (!t.act_g[grain]) continue;
         int na; const int32_t* lg = t.pq.at(1, grain, &na);
         if (na == 0 || na > GG_TOPO_CAP_G) continue;
