@@ -71,6 +71,7 @@ class RolloutDriver:
                  truth=None, raster='device', edge_threshold=0.6, area_threshold=1e-4, frames=121, ini_height=2.0, delta_z=0.4,
                  nucleation_density=0.0, lxd=None, topology='host'):
         self.eng, self.span, self.frames = engine, span, frames
+        self.time_steps, self.step_seconds = False, []
         self.edge_threshold, self.area_threshold = edge_threshold, area_threshold
         self.geometry = geometry or {'domain_factor': 1, 'domain_offset': 0}
         self.factor = float(self.geometry.get('domain_factor', 1))
@@ -112,6 +113,17 @@ class RolloutDriver:
     # ------------------------------------------------------------------------------------------------ one frame
     @torch.no_grad()
     def step(self):
+        if getattr(self, 'time_steps', False):                                                  # (scripts/rollout.py --time-steps)
+            import time
+            torch.cuda.synchronize(self.eng.device)
+            t0 = time.perf_counter()
+            out = self._step()
+            torch.cuda.synchronize(self.eng.device)
+            self.step_seconds.append(time.perf_counter() - t0)
+            return out
+        return self._step()
+
+    def _step(self):
         eng, span = self.eng, self.span
         self.frame += span
         frame = self.frame

@@ -38,6 +38,8 @@ def main():
     ap.add_argument('--head-gain', type=float, default=0.02, help='stand-in weights only: scale of the regressor heads')
     ap.add_argument('--edge-bias', type=float, default=-0.63, help='stand-in weights only: shift of the edge-event logit (untrained logits sit at ~1.0)')
     ap.add_argument('--device', default='cuda:0')
+    ap.add_argument('--time-steps', action='store_true', help='synchronise around every step and report the per-step wall times')
+    ap.add_argument('--topology', default='device', choices=['device', 'host'], help="where the topology update runs (models.py:614-845)")
     a = ap.parse_args()
     hg = G.generate_graph(lxd=a.lxd, seed=a.seed, G=a.G, R=a.R, span=a.span)
     x, ei, ea, geom = G.model_inputs(hg, a.lxd)
@@ -51,12 +53,15 @@ def main():
         truth = {'grain_events': [set(v) for v in z['grain_events']], 'imagesize': int(z['alpha_pde'].shape[1]),
                  'alpha_pde': lambda f: z['alpha_pde'][f], 'train_test_frame_ratio': int(z['ratio']) if 'ratio' in z else 1}
     eng = RolloutEngine.from_state_dicts(sd_r, sd_c, device=a.device)
-    drv = RolloutDriver(eng, x, ei, ea, mask, span=a.span, geometry=geom, global_pos=geom['global'], truth=truth, frames=a.frames, lxd=a.lxd)
+    drv = RolloutDriver(eng, x, ei, ea, mask, span=a.span, geometry=geom, global_pos=geom['global'], truth=truth, frames=a.frames, lxd=a.lxd, topology=a.topology)
+    drv.time_steps = a.time_steps
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     q = drv.run()
     torch.cuda.synchronize()
-    q.update({'seconds': time.perf_counter() - t0, 'grains': int(x['grain'].shape[0]), 'weights': wdesc})
+    q.update({'seconds': time.perf_counter() - t0, 'grains': int(x['grain'].shape[0]), 'weights': wdesc, 'topology': a.topology})
+    if a.time_steps:
+        q['step_ms'] = [round(t * 1e3, 2) for t in drv.step_seconds]
     print(json.dumps(q))
 
 
