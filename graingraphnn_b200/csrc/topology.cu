@@ -70,10 +70,14 @@ static __host__ __device__ __forceinline__ void topo_hint_grain(int g) {
 // through a request slot in shared memory and waits.  Same integer results by construction, the same single-rounding float
 // operations per element; short lists (and lists in the walker's local memory) stay with the walker.
 struct GGTopo;
-enum { TOPO_OP_PRE = 1, TOPO_OP_POST, TOPO_OP_SORT_PAIRS, TOPO_OP_L1_MARK, TOPO_OP_L1_COMPACT, TOPO_OP_SWEEP };
-struct TopoSvc { int req, ack, op, n, flag, ret, enabled, pad; const void* a; void* b; void* c; };
+enum { TOPO_OP_PRE = 1, TOPO_OP_POST, TOPO_OP_SORT_PAIRS, TOPO_OP_L1_MARK, TOPO_OP_L1_COMPACT, TOPO_OP_SWEEP, TOPO_OP_SWITCH_PAR };
+struct TopoSvc { int req, ack, op, n, flag, ret, enabled, par_enabled; const void* a; void* b; void* c;
+                 int par_seq, n_dirty, par_pending, par_err; };      // the concurrent switches: job counter of the worker warps, shared change-list counter
 constexpr int kTopoSortCap = 2048;         // elements the helper warp sorts in shared memory; longer lists fall back to the walker
 constexpr int kTopoSvcMin = 48;            // shorter lists are not worth the hand-over
+constexpr int kTopoParMin = 64;            // ... nor worth the rounds of the concurrent switches
+constexpr int kTopoThreads = 512;          // warp 0 walker | 1 look-ahead | 2 helper | 2..15 the worker group of the concurrent switches
+constexpr int kTopoWorkers = kTopoThreads - 64;
 __device__ __forceinline__ volatile TopoSvc* topo_svc() { return reinterpret_cast<volatile TopoSvc*>(gg_topo_smem + sizeof(TopoHint)); }
 static __device__ int topo_service_call(int op, const void* a, void* b, void* c, int n, int flag) {
     volatile TopoSvc* s = topo_svc();
@@ -91,12 +95,14 @@ static __host__ __device__ __forceinline__ void topo_sort_pairs_dev(int32_t* id,
 static __host__ __device__ __forceinline__ void topo_l1_mark_dev(GGTopo& t, const int32_t* l1, int n);
 static __host__ __device__ __forceinline__ int topo_l1_compact_dev(GGTopo& t, int32_t* l1, float* logit, int n);
 static __host__ __device__ __forceinline__ int topo_sweep_collect_dev(GGTopo& t, int32_t* cand);
+static __host__ __device__ __forceinline__ bool topo_switch_parallel_dev(GGTopo& t, const int32_t* edges, int n);
 #define GG_TOPO_SWITCH_PRE(t, edges, n, touched) topo_switch_pre_dev(t, edges, n, touched)
 #define GG_TOPO_SWITCH_POST(t, touched, nt) topo_switch_post_dev(t, touched, nt)
 #define GG_TOPO_SORT_PAIRS(id, val, n, by_value) topo_sort_pairs_dev(id, val, n, by_value)
 #define GG_TOPO_L1_MARK(t, l1, n) topo_l1_mark_dev(t, l1, n)
 #define GG_TOPO_L1_COMPACT(t, l1, logit, n) topo_l1_compact_dev(t, l1, logit, n)
 #define GG_TOPO_SWEEP_COLLECT(t, cand) topo_sweep_collect_dev(t, cand)
+#define GG_TOPO_SWITCH_PARALLEL(t, edges, n) topo_switch_parallel_dev(t, edges, n)
 #include "topology_core.h"
 
 // the walker's side of the hooks
@@ -129,6 +135,19 @@ static __host__ __device__ __forceinline__ int topo_l1_compact_dev(GGTopo& t, in
     if (topo_svc()->enabled && n >= kTopoSvcMin) return topo_service_call(TOPO_OP_L1_COMPACT, nullptr, l1, logit, n, 0);
 #endif
     return gg_topo_l1_compact_seq(t, l1, logit, n);
+}
+static __host__ __device__ __forceinline__ bool topo_switch_parallel_dev(GGTopo& t, const int32_t* edges, int n) {
+#ifdef __CUDA_ARCH__
+    volatile TopoSvc* s = topo_svc();
+    if (!s->par_enabled || n < kTopoParMin || n > GG_TOPO_PAR_MAX || !t.par_work || !__isGlobal(edges)) return false;
+    s->n_dirty = t.n_dirty;
+    const int err = topo_service_call(TOPO_OP_SWITCH_PAR, edges, t.par_work, nullptr, n, 0);
+    t.n_dirty = s->n_dirty;
+    if (err) t.err = err;
+    return true;
+#else
+    return false;
+#endif
 }
 static __host__ __device__ __forceinline__ int topo_sweep_collect_dev(GGTopo& t, int32_t* cand) {
 #ifdef __CUDA_ARCH__
@@ -188,7 +207,7 @@ struct TopoArgs {
     int64_t* switching_list; int32_t* grain_event_out; int32_t* work;
     int64_t* result;                                                                         // {n_pp, n_pq, n_switch, n_grain_event, err, n_ge_in, n_l1_in}
     const int32_t* n_seed;                                                                   // grains with one or two joints on entry (topo_seed_two_sided)
-    int prefetch, service;
+    int prefetch, service, parallel;
 };
 
 // What the switch of edge column e will look at, read by 8 lanes: lanes 0-3 its first end point, 4-7 the second; of each four, lane 0
@@ -293,6 +312,118 @@ __device__ int topo_warp_compact(int n, int lane, Keep keep, Move move) {
     return w;
 }
 
+// ---- the plain switches of a list in conflict-free rounds (worker group: warps 2..15, named barrier 1).
+// A switch writes the lists, counters and coordinates of its two end points and the joint lists of the (<= 4) grains around them; it
+// reads, besides, the entries of the end points' joint neighbours.  Every round each pending event records that footprint on the
+// CURRENT tables and marks it with its rank (atomicMin into hashed mark tables: a collision only adds a false conflict); an event
+// runs when no event of lower rank that is still pending writes what it reads, reads what it writes, or shares a grain with it.
+// The lowest pending rank always runs, so the rounds end; what an event sees is what it would see in the sequential order, because
+// a pending lower-rank event can only grow into joints that lower-rank footprints already hold (a switch permutes adjacency
+// among its own six joints).  The per-event code is the sequential one (gg_topo_switch_one).
+__device__ __forceinline__ void topo_par_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTopoWorkers) : "memory"); }
+__device__ void topo_parallel_switch(const GGTopo& t0, const int32_t* edges, int n, int32_t* work, int tid) {
+    volatile TopoSvc* sv = topo_svc();
+    GGTopo t = t0;                                               // private copy: error fields, the shared change-list counter
+    t.n_dirty_shared = const_cast<int32_t*>(&sv->n_dirty);
+    t.dirty_all = false;
+    const int64_t M = gg_topo_par_marks(n);
+    const uint32_t mask = (uint32_t)(M - 1);
+    int32_t* done = work;
+    int32_t* fp = work + n;
+    int32_t* mark_r = fp + (int64_t)n * GG_TOPO_PAR_FP;
+    int32_t* mark_w = mark_r + M;
+    int32_t* mark_g = mark_w + M;
+    for (int64_t i = tid; i < 3 * M; i += kTopoWorkers) mark_r[i] = 0x7FFFFFFF;
+    for (int i = tid; i < n; i += kTopoWorkers) done[i] = 0;
+    if (tid == 0) { sv->par_err = 0; sv->par_pending = 0; }
+    topo_par_bar();
+    for (;;) {
+        // (a) footprints of the pending events on the current tables, marked with their ranks
+        for (int i = tid; i < n; i += kTopoWorkers) {
+            if (done[i]) continue;
+            int32_t* f = fp + (int64_t)i * GG_TOPO_PAR_FP;
+            const int32_t e = edges[i];
+            int nw = 0, nj = 0, ng = 0;
+            int32_t* J = f + 3;
+            int32_t* G = f + 3 + 18;
+            const int64_t pe[2] = {t.pp.get(0, e), t.pp.get(1, e)};
+            for (int k = 0; k < 2; ++k) if (pe[k] >= 0 && (k == 0 || pe[1] != pe[0])) J[nj++] = (int32_t)pe[k];
+            nw = nj;
+            for (int k = 0; k < nw; ++k) {
+                const int64_t p = J[k];
+                int c; const int32_t* l = t.pp.at(0, p, &c);
+                for (int q = 0; q < c && q < GG_TOPO_CAP_J; ++q) {
+                    const int32_t v = (int32_t)t.pp.get(1, l[q]);
+                    bool seen = v < 0;
+                    for (int z = 0; z < nj; ++z) seen = seen || J[z] == v;
+                    if (!seen && nj < 18) J[nj++] = v;
+                }
+                l = t.pq.at(0, p, &c);
+                for (int q = 0; q < c && q < GG_TOPO_CAP_J; ++q) {
+                    const int32_t g = (int32_t)t.pq.get(1, l[q]);
+                    bool seen = g < 0;
+                    for (int z = 0; z < ng; ++z) seen = seen || G[z] == g;
+                    if (!seen && ng < 6) G[ng++] = g;
+                }
+            }
+            f[0] = nw; f[1] = nj; f[2] = ng;
+            for (int z = 0; z < nj; ++z) atomicMin(&mark_r[(uint32_t)J[z] & mask], i);
+            for (int z = 0; z < nw; ++z) atomicMin(&mark_w[(uint32_t)J[z] & mask], i);
+            for (int z = 0; z < ng; ++z) atomicMin(&mark_g[(uint32_t)G[z] & mask], i);
+        }
+        topo_par_bar();
+        // (b) the events no pending lower rank interferes with run now
+        for (int i = tid; i < n; i += kTopoWorkers) {
+            if (done[i]) continue;
+            const int32_t* f = fp + (int64_t)i * GG_TOPO_PAR_FP;
+            const int nw = f[0], nj = f[1], ng = f[2];
+            const int32_t* J = f + 3;
+            const int32_t* G = f + 3 + 18;
+            bool ok = true;
+            for (int z = 0; z < nj; ++z) ok = ok && mark_w[(uint32_t)J[z] & mask] >= i;
+            for (int z = 0; z < nw; ++z) ok = ok && mark_r[(uint32_t)J[z] & mask] >= i;
+            for (int z = 0; z < ng; ++z) ok = ok && mark_g[(uint32_t)G[z] & mask] >= i;
+            if (!ok) continue;
+            gg_topo_switch_one(t, edges[i], -1, nullptr, 0);
+            const int err = t.err ? t.err : (t.pp.err ? t.pp.err : t.pq.err);
+            if (err) atomicCAS(const_cast<int*>(&sv->par_err), 0, err);
+            done[i] = 2;
+        }
+        topo_par_bar();
+        // (c) clear the marks of this round, count what is left
+        for (int i = tid; i < n; i += kTopoWorkers) {
+            if (done[i] == 1) continue;
+            const int32_t* f = fp + (int64_t)i * GG_TOPO_PAR_FP;
+            for (int z = 0; z < f[1]; ++z) { mark_r[(uint32_t)f[3 + z] & mask] = 0x7FFFFFFF; mark_w[(uint32_t)f[3 + z] & mask] = 0x7FFFFFFF; }
+            for (int z = 0; z < f[2]; ++z) mark_g[(uint32_t)f[3 + 18 + z] & mask] = 0x7FFFFFFF;
+            if (done[i] == 2) done[i] = 1;
+            else atomicAdd(const_cast<int*>(&sv->par_pending), 1);
+        }
+        topo_par_bar();
+        const int left = sv->par_pending, err = sv->par_err;
+        topo_par_bar();
+        if (tid == 0) sv->par_pending = 0;
+        if (left == 0 || err) break;
+    }
+    topo_par_bar();
+}
+// warps 3..15: wait for a job of the concurrent switches, take part, wait again
+__device__ void topo_worker_warp(const GGTopo& t) {
+    volatile TopoSvc* s = topo_svc();
+    volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
+    const int lane = threadIdx.x & 31;
+    int seen = 0;
+    for (;;) {
+        int j = 0;
+        if (lane == 0) { while ((j = s->par_seq) == seen && !h->done) __nanosleep(500); if (j == seen) j = -1; }
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j < 0) return;
+        seen = j;
+        __threadfence_block();
+        topo_parallel_switch(t, static_cast<const int32_t*>(const_cast<const void*>(s->a)), s->n, static_cast<int32_t*>(const_cast<void*>(s->b)), (int)threadIdx.x - 64);
+    }
+}
+
 __device__ void topo_service_warp(const GGTopo& t) {
     __shared__ unsigned long long key[kTopoSortCap];
     volatile TopoSvc* s = topo_svc();
@@ -366,6 +497,11 @@ __device__ void topo_service_warp(const GGTopo& t) {
             ret = topo_warp_compact(n, lane,
                                     [&](int i) { e = l1[i]; lg = logit[i]; const uint8_t f = pp.ahead_flag[e]; pp.ahead_flag[e] = f & 1; return !(f & 2); },
                                     [&](int i, int w) { __syncwarp(); if (w >= 0) { l1[w] = e; logit[w] = lg; } __syncwarp(); });
+        } else if (op == TOPO_OP_SWITCH_PAR) {                   // release the worker warps and take part (threads 0..31 of the group)
+            if (lane == 0) { __threadfence_block(); s->par_seq = s->par_seq + 1; }
+            __syncwarp();
+            topo_parallel_switch(t, static_cast<const int32_t*>(a), n, static_cast<int32_t*>(b), lane);
+            ret = s->par_err;
         } else if (op == TOPO_OP_SWEEP) {                        // gg_topo_sweep_collect_seq, the change-list branch
             const int32_t* dirty = static_cast<const int32_t*>(a);
             int32_t* cand = static_cast<int32_t*>(b);
@@ -414,15 +550,16 @@ __device__ void topo_prefetch_warp(const GGTopo& t) {
     if (sink == 0x9E3779B9u) h->small_list[0] = (int32_t)sink;      // keeps the loads
 }
 
-__global__ void topo_update_kernel(TopoArgs A) {
+__global__ void __launch_bounds__(kTopoThreads, 1) topo_update_kernel(TopoArgs A) {
     {
         volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
         if (threadIdx.x == 0) {
             h->n = 0; h->k = 0; h->epoch = 0; h->done = 0; h->edges = nullptr; h->grain = -1; h->gepoch = 0;
             volatile TopoSvc* sv = topo_svc();
-            sv->req = 0; sv->ack = 0; sv->enabled = A.service;
+            sv->req = 0; sv->ack = 0; sv->enabled = A.service; sv->par_enabled = A.service && A.parallel; sv->par_seq = 0;
         }
         __syncthreads();
+        if (threadIdx.x >= 96) { if (A.service && A.parallel) topo_worker_warp(A.t); return; }
         if (threadIdx.x >= 64) { if (A.service) topo_service_warp(A.t); return; }
         if (threadIdx.x >= 32) { if (A.prefetch) topo_prefetch_warp(A.t); return; }
     }
@@ -525,12 +662,14 @@ extern "C" int gg_topology_update(int64_t* pp, int64_t cap_pp, int64_t n_pp, int
     A.n_seed = n_seed;
     { const char* e = getenv("GG_TOPO_PREFETCH"); A.prefetch = !(e && e[0] == '0'); }        // (measurement switches)
     { const char* e = getenv("GG_TOPO_SERVICE"); A.service = !(e && e[0] == '0'); }
+    { const char* e = getenv("GG_TOPO_PARALLEL"); A.parallel = !(e && e[0] == '0'); }
+    A.t.par_work = work + gg_topo_seq_ints(l1_cap, ge_cap, n_grain);
     static bool carve_set = false;
     if (!carve_set) {                     // the walk lives on L1 hits (look-ahead warp): keep shared memory at what the helper warp needs
         cudaFuncSetAttribute(topo_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
         carve_set = true;
     }
-    topo_update_kernel<<<1, 96, sizeof(TopoHint) + sizeof(TopoSvc), st>>>(A);
+    topo_update_kernel<<<1, kTopoThreads, sizeof(TopoHint) + sizeof(TopoSvc), st>>>(A);
     GG_LAUNCH_OK();
     return 0;
 }

@@ -11,8 +11,9 @@
 // scan of the reference is answered from an ascending position list kept per joint / grain (fixed capacity: a joint has three
 // joint and three grain neighbours, a grain at most GG_TOPO_CAP_G joints).  Float arithmetic is IEEE single, one rounding per
 // operation like torch's (no contraction: -ffp-contract=off on the host, __f*_rn on the device).
-// Orders: eliminations by predicted area ascending (test.py:416), switches by logit descending (= probability descending,
-// models.py:730-731; ties, which torch.sort leaves unspecified, by edge position).
+// Orders: eliminations by predicted area ascending (test.py:416), switches by probability descending (models.py:730-731) with
+// equal probabilities — logits that saturate or collide in fp32 included — in ascending edge position, as the reference's sort
+// leaves them: the caller hands over sigmoid(logit) as torch computes it, not the logit.
 #pragma once
 #include <stdint.h>
 #ifndef __CUDACC__
@@ -41,6 +42,9 @@
 #define GG_TOPO_L1_MARK(t, l1, n) gg_topo_l1_mark_seq(t, l1, n)
 #define GG_TOPO_L1_COMPACT(t, l1, logit, n) gg_topo_l1_compact_seq(t, l1, logit, n)
 #define GG_TOPO_SWEEP_COLLECT(t, cand) gg_topo_sweep_collect_seq(t, cand)
+#endif
+#ifndef GG_TOPO_SWITCH_PARALLEL
+#define GG_TOPO_SWITCH_PARALLEL(t, edges, n) false      // device build: the plain switches of a list run in conflict-free rounds
 #endif
 #ifndef GG_TOPO_MARK
 #define GG_TOPO_MARK(bucket) ((void)0)     // profiling build of the device kernel: time since the last mark goes to `bucket`
@@ -151,6 +155,8 @@ struct GGTopo {
     const uint8_t* act_g; const uint8_t* act_j;
     int32_t n_joint, n_grain;
     uint8_t* dirty_flag; int32_t* dirty_list; int32_t n_dirty; bool dirty_all;   // grains whose joint count changed since the last two-side check
+    int32_t* n_dirty_shared;       // device, events running concurrently: the list is appended through this counter (else NULL)
+    int32_t* par_work;             // device: work area of the concurrent switches (gg_topo_par_ints ints behind the sequential work area)
     bool preseeded;                // dirty_list already holds the grains that have one or two joints on entry (a data-parallel pre-pass):
                                    // the first sweep then looks at them and at the grains the events touched instead of at every grain
     int32_t* scratch;              // >= 2 * max events + n_grain ints
@@ -161,6 +167,14 @@ GG_TD float* gg_topo_xrow(const GGTopo& t, int64_t p) { return t.xj + (int64_t)(
 
 GG_TD void gg_topo_dirty_add(GGTopo& t, int64_t g) {
     if (t.dirty_all || g < 0) return;
+#ifdef __CUDA_ARCH__
+    if (t.n_dirty_shared) {                                        // test-and-set of the grain's flag byte, then an atomic append
+        unsigned* w = reinterpret_cast<unsigned*>(t.dirty_flag + (g & ~(int64_t)3));
+        const unsigned bit = 1u << (8 * (unsigned)(g & 3));
+        if (!(atomicOr(w, bit) & (0xFFu << (8 * (unsigned)(g & 3))))) t.dirty_list[atomicAdd(t.n_dirty_shared, 1)] = (int32_t)g;
+        return;
+    }
+#endif
     if (!t.dirty_flag[g]) { t.dirty_flag[g] = 1; t.dirty_list[t.n_dirty++] = (int32_t)g; }
 }
 GG_TD void gg_topo_pq_set_grain(GGTopo& t, int64_t pos, int64_t g) {
@@ -329,6 +343,95 @@ GG_TD int gg_topo_l1_compact_seq(GGTopo& t, int32_t* L1, float* logit, int n) { 
     return w;
 }
 
+// One switching event: edge column e of pp (the loop body of switching_edge_index, models.py:909-1040).
+GG_TD int gg_topo_switch_one(GGTopo& t, int32_t e, int64_t elim_grain, int32_t* forced, int n_forced) {
+    GGRows& pp = t.pp;
+    GGRows& pq = t.pq;
+    const int64_t p1 = pp.get(0, e), p2 = pp.get(1, e);
+    if (p1 >= 0 && p2 >= 0 && t.act_j[p1] && t.act_j[p2]) {
+        int c1, c2;
+        int32_t at_q1[GG_TOPO_CAP_J], at_q2[GG_TOPO_CAP_J], at_n1[GG_TOPO_CAP_J], at_n2[GG_TOPO_CAP_J];
+        int64_t q1[GG_TOPO_CAP_J], q2[GG_TOPO_CAP_J];
+        { const int32_t* l = pq.at(0, p1, &c1); for (int i = 0; i < c1; ++i) { at_q1[i] = l[i]; q1[i] = pq.get(1, l[i]); } }
+        { const int32_t* l = pq.at(0, p2, &c2); for (int i = 0; i < c2; ++i) { at_q2[i] = l[i]; q2[i] = pq.get(1, l[i]); } }
+        const int nn1 = gg_topo_pp_between(t, p1, p2, false, at_n1), nn2 = gg_topo_pp_between(t, p2, p1, false, at_n2);
+        if (c1 != 3 || c2 != 3 || nn1 < 2 || nn2 < 2) { t.err = GG_TOPO_BAD_VALENCE; return n_forced; }
+        int64_t n1[2] = {pp.get(1, at_n1[0]), pp.get(1, at_n1[1])}, n2[2] = {pp.get(1, at_n2[0]), pp.get(1, at_n2[1])};
+        // grains: the two shared ones shrink, the unshared one of each joint grows across (:925-945)
+        int64_t grow1 = -1, grow2 = -1, shrink[2];
+        int ng1 = 0, ng2 = 0, ns = 0;
+        for (int i = 0; i < 3; ++i) {
+            int m = 0; for (int j = 0; j < 3; ++j) m += q2[j] == q1[i];
+            if (m != 1) { grow1 = q1[i]; ++ng1; }
+            if (m != 0) { if (ns < 2) shrink[ns] = q1[i]; ++ns; }
+        }
+        for (int i = 0; i < 3; ++i) {
+            int m = 0; for (int j = 0; j < 3; ++j) m += q1[j] == q2[i];
+            if (m != 1) { grow2 = q2[i]; ++ng2; }
+        }
+        if (ns != 2) { t.err = GG_TOPO_NO_COMMON_GRAIN; return n_forced; }
+        const int64_t shrink_a = shrink[0], shrink_b = shrink[1];
+        int32_t slots1[2 * GG_TOPO_CAP_J], slots2[2 * GG_TOPO_CAP_J];
+        int ns1 = 0, ns2 = 0;
+        for (int i = 0; i < 3; ++i) if (q1[i] == shrink_a) slots1[ns1++] = at_q1[i];
+        for (int i = 0; i < 3; ++i) if (q1[i] == shrink_b) slots1[ns1++] = at_q1[i];
+        for (int i = 0; i < 3; ++i) if (q2[i] == shrink_a) slots2[ns2++] = at_q2[i];
+        for (int i = 0; i < 3; ++i) if (q2[i] == shrink_b) slots2[ns2++] = at_q2[i];
+        // order the outer neighbours: the one that touches shrink_a first (:947-975)
+        for (int side = 0; side < 2; ++side) {
+            int64_t* nn = side == 0 ? n1 : n2;
+            int32_t* at = side == 0 ? at_n1 : at_n2;
+            int c; const int32_t* l = pq.at(0, nn[0], &c);
+            bool touches = false;
+            for (int i = 0; i < c; ++i) touches = touches || pq.get(1, l[i]) == shrink_a;
+            if (!touches) { const int64_t tn = nn[0]; nn[0] = nn[1]; nn[1] = tn; const int32_t ta = at[0]; at[0] = at[1]; at[1] = ta; }
+        }
+        int64_t a1 = n1[0], b1 = n1[1], a2 = n2[0], b2 = n2[1];
+        if (!(elim_grain < 0 && (a1 == a2 || b1 == b2))) {
+            if (a1 == a2 && shrink_a != elim_grain) forced[n_forced++] = (int32_t)shrink_a;
+            if (b1 == b2 && shrink_b != elim_grain) forced[n_forced++] = (int32_t)shrink_b;
+            // both ends collapse onto the midpoint (:989-996)
+            float* x1 = gg_topo_xrow(t, p1);
+            float* x2 = gg_topo_xrow(t, p2);
+            const float m0 = gg_tmul(0.5f, gg_tadd(x1[0], gg_wrap_to(x2[0], x1[0])));
+            const float m1 = gg_tmul(0.5f, gg_tadd(x1[1], gg_wrap_to(x2[1], x1[1])));
+            const float w0 = gg_wrap_to(m0, x2[0]), w1 = gg_wrap_to(m1, x2[1]);
+            x1[0] = m0; x1[1] = m1; x2[0] = w0; x2[1] = w1;
+            bool swap = gg_topo_inside(x2, x1, gg_topo_xrow(t, a1), gg_topo_xrow(t, a2));
+            const int32_t* ah = pp.ahead_cnt;
+            if (ah[a2] > 0 && !(ah[b2] > 0)) swap = false;
+            if (ah[b2] > 0 && !(ah[a2] > 0)) swap = true;
+            if (ah[a1] > 0 && !(ah[b1] > 0)) swap = true;
+            if (ah[b1] > 0 && !(ah[a1] > 0)) swap = false;
+            if (swap) {
+                for (int i = 0; i < ns1 / 2; ++i) { const int32_t s = slots1[i]; slots1[i] = slots1[ns1 - 1 - i]; slots1[ns1 - 1 - i] = s; }
+                for (int i = 0; i < ns2 / 2; ++i) { const int32_t s = slots2[i]; slots2[i] = slots2[ns2 - 1 - i]; slots2[ns2 - 1 - i] = s; }
+                { const int32_t s = at_n1[0]; at_n1[0] = at_n1[1]; at_n1[1] = s; }
+                { const int32_t s = at_n2[0]; at_n2[0] = at_n2[1]; at_n2[1] = s; }
+                { const int64_t s = a1; a1 = b1; b1 = s; }
+                { const int64_t s = a2; a2 = b2; b2 = s; }
+            }
+            if (ng1 != 1 || ng2 != 1 || ns1 < 2 || ns2 < 1) { t.err = GG_TOPO_GROW; return n_forced; }
+            GG_TOPO_MARK(elim_grain < 0 ? 5 : 1);
+            gg_topo_pq_set_grain(t, slots1[1], grow2);
+            gg_topo_pq_set_grain(t, slots2[0], grow1);
+            pp.set(0, at_n1[1], p2);
+            pp.set(0, at_n2[0], p1);
+            int32_t tmp[GG_TOPO_CAP_J];
+            int c = gg_topo_pp_between(t, a2, p2, true, tmp);
+            for (int i = 0; i < c; ++i) pp.set(1, tmp[i], p1);
+            c = gg_topo_pp_between(t, b1, p1, true, tmp);
+            for (int i = 0; i < c; ++i) pp.set(1, tmp[i], p2);
+            GG_TOPO_MARK(elim_grain < 0 ? 6 : 1);
+        }
+    }
+    // this event is no longer "to come"
+    pp.ahead_flag[e] &= (uint8_t)~1u;
+    { const int64_t u = pp.get(0, e), v = pp.get(1, e); if (u >= 0) --pp.ahead_cnt[u]; if (v >= 0) --pp.ahead_cnt[v]; }
+
+    return n_forced;
+}
+
 // switching_edge_index (models.py:899-1053) over the edge columns `edges[0..n_edges)`; elim_grain < 0: plain neighbour switching.
 // Forced eliminations are appended to forced[] (returns the new count).
 GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t elim_grain, int32_t* forced, int n_forced) {
@@ -339,91 +442,12 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
     int32_t* touched = t.scratch + t.n_grain;                     // (scratch[0 .. n_grain) is the two-sided sweep's)
     const int nt = GG_TOPO_SWITCH_PRE(t, edges, n_edges, touched);
     GG_TOPO_MARK(elim_grain < 0 ? 4 : 1);
-    GG_TOPO_HINT_BEGIN(edges, n_edges);
-    for (int k = 0; k < n_edges && !t.err; ++k) {
-        GG_TOPO_HINT_AT(k);
-        const int32_t e = edges[k];
-        const int64_t p1 = pp.get(0, e), p2 = pp.get(1, e);
-        if (p1 >= 0 && p2 >= 0 && t.act_j[p1] && t.act_j[p2]) {
-            int c1, c2;
-            int32_t at_q1[GG_TOPO_CAP_J], at_q2[GG_TOPO_CAP_J], at_n1[GG_TOPO_CAP_J], at_n2[GG_TOPO_CAP_J];
-            int64_t q1[GG_TOPO_CAP_J], q2[GG_TOPO_CAP_J];
-            { const int32_t* l = pq.at(0, p1, &c1); for (int i = 0; i < c1; ++i) { at_q1[i] = l[i]; q1[i] = pq.get(1, l[i]); } }
-            { const int32_t* l = pq.at(0, p2, &c2); for (int i = 0; i < c2; ++i) { at_q2[i] = l[i]; q2[i] = pq.get(1, l[i]); } }
-            const int nn1 = gg_topo_pp_between(t, p1, p2, false, at_n1), nn2 = gg_topo_pp_between(t, p2, p1, false, at_n2);
-            if (c1 != 3 || c2 != 3 || nn1 < 2 || nn2 < 2) { t.err = GG_TOPO_BAD_VALENCE; break; }
-            int64_t n1[2] = {pp.get(1, at_n1[0]), pp.get(1, at_n1[1])}, n2[2] = {pp.get(1, at_n2[0]), pp.get(1, at_n2[1])};
-            // grains: the two shared ones shrink, the unshared one of each joint grows across (:925-945)
-            int64_t grow1 = -1, grow2 = -1, shrink[2];
-            int ng1 = 0, ng2 = 0, ns = 0;
-            for (int i = 0; i < 3; ++i) {
-                int m = 0; for (int j = 0; j < 3; ++j) m += q2[j] == q1[i];
-                if (m != 1) { grow1 = q1[i]; ++ng1; }
-                if (m != 0) { if (ns < 2) shrink[ns] = q1[i]; ++ns; }
-            }
-            for (int i = 0; i < 3; ++i) {
-                int m = 0; for (int j = 0; j < 3; ++j) m += q1[j] == q2[i];
-                if (m != 1) { grow2 = q2[i]; ++ng2; }
-            }
-            if (ns != 2) { t.err = GG_TOPO_NO_COMMON_GRAIN; break; }
-            const int64_t shrink_a = shrink[0], shrink_b = shrink[1];
-            int32_t slots1[2 * GG_TOPO_CAP_J], slots2[2 * GG_TOPO_CAP_J];
-            int ns1 = 0, ns2 = 0;
-            for (int i = 0; i < 3; ++i) if (q1[i] == shrink_a) slots1[ns1++] = at_q1[i];
-            for (int i = 0; i < 3; ++i) if (q1[i] == shrink_b) slots1[ns1++] = at_q1[i];
-            for (int i = 0; i < 3; ++i) if (q2[i] == shrink_a) slots2[ns2++] = at_q2[i];
-            for (int i = 0; i < 3; ++i) if (q2[i] == shrink_b) slots2[ns2++] = at_q2[i];
-            // order the outer neighbours: the one that touches shrink_a first (:947-975)
-            for (int side = 0; side < 2; ++side) {
-                int64_t* nn = side == 0 ? n1 : n2;
-                int32_t* at = side == 0 ? at_n1 : at_n2;
-                int c; const int32_t* l = pq.at(0, nn[0], &c);
-                bool touches = false;
-                for (int i = 0; i < c; ++i) touches = touches || pq.get(1, l[i]) == shrink_a;
-                if (!touches) { const int64_t tn = nn[0]; nn[0] = nn[1]; nn[1] = tn; const int32_t ta = at[0]; at[0] = at[1]; at[1] = ta; }
-            }
-            int64_t a1 = n1[0], b1 = n1[1], a2 = n2[0], b2 = n2[1];
-            if (!(elim_grain < 0 && (a1 == a2 || b1 == b2))) {
-                if (a1 == a2 && shrink_a != elim_grain) forced[n_forced++] = (int32_t)shrink_a;
-                if (b1 == b2 && shrink_b != elim_grain) forced[n_forced++] = (int32_t)shrink_b;
-                // both ends collapse onto the midpoint (:989-996)
-                float* x1 = gg_topo_xrow(t, p1);
-                float* x2 = gg_topo_xrow(t, p2);
-                const float m0 = gg_tmul(0.5f, gg_tadd(x1[0], gg_wrap_to(x2[0], x1[0])));
-                const float m1 = gg_tmul(0.5f, gg_tadd(x1[1], gg_wrap_to(x2[1], x1[1])));
-                const float w0 = gg_wrap_to(m0, x2[0]), w1 = gg_wrap_to(m1, x2[1]);
-                x1[0] = m0; x1[1] = m1; x2[0] = w0; x2[1] = w1;
-                bool swap = gg_topo_inside(x2, x1, gg_topo_xrow(t, a1), gg_topo_xrow(t, a2));
-                const int32_t* ah = pp.ahead_cnt;
-                if (ah[a2] > 0 && !(ah[b2] > 0)) swap = false;
-                if (ah[b2] > 0 && !(ah[a2] > 0)) swap = true;
-                if (ah[a1] > 0 && !(ah[b1] > 0)) swap = true;
-                if (ah[b1] > 0 && !(ah[a1] > 0)) swap = false;
-                if (swap) {
-                    for (int i = 0; i < ns1 / 2; ++i) { const int32_t s = slots1[i]; slots1[i] = slots1[ns1 - 1 - i]; slots1[ns1 - 1 - i] = s; }
-                    for (int i = 0; i < ns2 / 2; ++i) { const int32_t s = slots2[i]; slots2[i] = slots2[ns2 - 1 - i]; slots2[ns2 - 1 - i] = s; }
-                    { const int32_t s = at_n1[0]; at_n1[0] = at_n1[1]; at_n1[1] = s; }
-                    { const int32_t s = at_n2[0]; at_n2[0] = at_n2[1]; at_n2[1] = s; }
-                    { const int64_t s = a1; a1 = b1; b1 = s; }
-                    { const int64_t s = a2; a2 = b2; b2 = s; }
-                }
-                if (ng1 != 1 || ng2 != 1 || ns1 < 2 || ns2 < 1) { t.err = GG_TOPO_GROW; break; }
-                GG_TOPO_MARK(elim_grain < 0 ? 5 : 1);
-                gg_topo_pq_set_grain(t, slots1[1], grow2);
-                gg_topo_pq_set_grain(t, slots2[0], grow1);
-                pp.set(0, at_n1[1], p2);
-                pp.set(0, at_n2[0], p1);
-                int32_t tmp[GG_TOPO_CAP_J];
-                int c = gg_topo_pp_between(t, a2, p2, true, tmp);
-                for (int i = 0; i < c; ++i) pp.set(1, tmp[i], p1);
-                c = gg_topo_pp_between(t, b1, p1, true, tmp);
-                for (int i = 0; i < c; ++i) pp.set(1, tmp[i], p2);
-                GG_TOPO_MARK(elim_grain < 0 ? 6 : 1);
-            }
+    if (!(elim_grain < 0 && GG_TOPO_SWITCH_PARALLEL(t, edges, n_edges))) {
+        GG_TOPO_HINT_BEGIN(edges, n_edges);
+        for (int k = 0; k < n_edges && !t.err; ++k) {
+            GG_TOPO_HINT_AT(k);
+            n_forced = gg_topo_switch_one(t, edges[k], elim_grain, forced, n_forced);
         }
-        // this event is no longer "to come"
-        pp.ahead_flag[e] &= (uint8_t)~1u;
-        { const int64_t u = pp.get(0, e), v = pp.get(1, e); if (u >= 0) --pp.ahead_cnt[u]; if (v >= 0) --pp.ahead_cnt[v]; }
     }
     GG_TOPO_MARK(elim_grain < 0 ? 5 : 1);
     if (t.err) {                                                  // leave the ahead tables clean
@@ -442,12 +466,20 @@ GG_TD int gg_topo_switch(GGTopo& t, const int32_t* edges, int n_edges, int64_t e
 }
 
 // GrainNN_classifier.update (models.py:614-768).  grain_event[0..n_ge): candidate grains sorted by predicted area ascending;
-// L1[0..n_l1): candidate edge columns with their logits, ANY order (sorted here: logit descending, then column ascending).
+// L1[0..n_l1): candidate edge columns with their probabilities, ANY order (sorted here: probability descending, then column ascending).
 // Outputs: switching_list [<= n_l1][2], grain_event_out (the input followed by the forced / two-sided eliminations).
 // work: int32 [3 * (n_l1 + n_ge) + 64 + ...] see gg_topo_work_ints.
 struct GGTopoResult { int32_t n_switch, n_grain_event, err; };
 
-GG_TD int64_t gg_topo_work_ints(int64_t n_l1, int64_t n_ge, int64_t n_grain) { return 4 * n_l1 + 2 * n_grain + 2 * n_ge + 4 * GG_TOPO_CAP_G + 64; }
+#define GG_TOPO_PAR_MAX 16384      // the concurrent-switch path of the device build takes lists up to this long
+#define GG_TOPO_PAR_FP 28          // ints of an event's footprint record: {writes, joints, grains, joints[18], grains[6], pad}
+GG_TD int64_t gg_topo_par_marks(int64_t n) { int64_t m = 4096; while (m < 64 * n) m <<= 1; return m; }      // slots of one mark table
+GG_TD int64_t gg_topo_seq_ints(int64_t n_l1, int64_t n_ge, int64_t n_grain) { return 4 * n_l1 + 2 * n_grain + 2 * n_ge + 4 * GG_TOPO_CAP_G + 64; }
+GG_TD int64_t gg_topo_par_ints(int64_t n_l1) {
+    const int64_t n = n_l1 < GG_TOPO_PAR_MAX ? n_l1 : GG_TOPO_PAR_MAX;
+    return n * (1 + GG_TOPO_PAR_FP) + 3 * gg_topo_par_marks(n);
+}
+GG_TD int64_t gg_topo_work_ints(int64_t n_l1, int64_t n_ge, int64_t n_grain) { return gg_topo_seq_ints(n_l1, n_ge, n_grain) + gg_topo_par_ints(n_l1); }
 
 GG_TD GGTopoResult gg_topo_update(GGTopo& t, const int32_t* grain_event, int n_ge, int32_t* L1, float* L1_logit, int n_l1,
                                   int64_t* switching_list, int32_t* grain_event_out, int32_t* work) {

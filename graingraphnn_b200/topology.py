@@ -340,7 +340,9 @@ def topology_update(x_dict, edge_index_dict, y_dict, mask, active_grains, active
         L1 = [e for e in L1 if e not in sides]
         s.delete_two_sided()
     if L1:
-        _, order = torch.sort(prob[torch.tensor(L1)], dim=0, descending=True)                 # models.py:730-731
+        # models.py:730-731.  Equal probabilities (logits that saturate or collide in fp32): the reference's torch.sort is not a stable
+        # one beyond 16 elements and leaves their order to the implementation; here, and in the device update, they keep edge order
+        _, order = torch.sort(prob[torch.tensor(L1)], dim=0, descending=True, stable=True)
         L1 = [L1[int(i)] for i in order]
     L1 = [e for e in L1 if s.pp.get(0, e) != -1]
     s.switch(L1, elim_grain=None)

@@ -72,6 +72,8 @@ class DeviceTopology:
                                 'ge_out': i32(ge_cap + self.ng), 'work': i32(L.gg_topology_work_ints(l1_cap, ge_cap, self.ng))})
         return self._bufs[1]
 
+    edge_prob_fn = staticmethod(torch.sigmoid)     # (a test may put the CPU's sigmoid here to compare with a host run bit for bit)
+
     @torch.no_grad()
     def update(self, pred):
         """Run the update for the step whose predictions are `pred` (the dict RolloutEngine.step returned: caller numbering).
@@ -83,6 +85,9 @@ class DeviceTopology:
             raise RuntimeError('enable_event_selection() first')
         (l1_count, l1_ids, l1_vals, l1_cap, _), (ge_count, ge_ids, ge_vals, ge_cap, _) = sel._buf['edge'], sel._buf['grain']
         w = self._work(l1_cap, ge_cap)
+        # the switches run in the order of their PROBABILITIES (models.py:730-731 sorts sigmoid(edge_event)); logits that saturate or
+        # collide in fp32 are ties there and keep their column order, so the kernel is handed torch's own sigmoid of the candidates
+        l1_vals = self.edge_prob_fn(l1_vals)
         if self.pp.shape[1] - self.n_pp < 2 * (ge_cap + 2):                  # head room for the appended edges of this step
             grown = torch.full((2, self.n_pp + max(4096, 4 * (ge_cap + 2))), -1, dtype=torch.int64, device=self.dev)
             grown[:, :self.n_pp] = self.pp[:, :self.n_pp]

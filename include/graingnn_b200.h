@@ -342,8 +342,9 @@ int gg_area_bookkeeping(const float* x_grain, int32_t ld_g, const float* mask_gr
  *  gg_topology_lists: ascending position lists per (row, value): list_r[v * cap_r + k], cnt_r[v]; caps from gg_topology_caps
  *      (joint rows: cap_joint, the grain row of pq: cap_grain); status[0] != 0 on overflow / out-of-range ids.
  *  gg_topology_update: one sequential walk over the events.  Candidates are the device buffers of gg_select_events: grains
- *      (ge_ids, ge_vals = predicted area; sorted here by area) and joint-joint columns with src < dst (l1_ids, l1_vals = logit;
- *      sorted here by logit descending = probability descending, models.py:730-731), each with its count (clamped to *_cap).
+ *      (ge_ids, ge_vals = predicted area; sorted here by area) and joint-joint columns with src < dst (l1_ids, l1_vals = the
+ *      candidate's PROBABILITY, i.e. sigmoid of its logit as torch computes it; sorted here by probability descending, equal
+ *      probabilities - saturated or colliding in fp32 - in ascending column order like the reference's sort, models.py:730-731), each with its count (clamped to *_cap).
  *      x_joint rows hold (x, y) in columns 0..1 and the predicted (dx, dy) in columns col_dxy, col_dxy + 1; joint_row (nullable)
  *      maps a joint id to its row of x_joint.  y_joint [Nj, 2] and mask_grain / mask_joint (fp32 [N], 1 = live) are updated in
  *      place; act_* are scratch (uint8 [N]).  ahead_cnt int32 [Nj] and ahead_flag uint8 [cap_pp] must be zero on entry (they are

@@ -189,7 +189,7 @@ def topology_update(x_dict, edge_index_dict, y_dict, mask, active_grains, active
             if e in L1:
                 L1 = L1[L1 != e]
         t.delete_two_sided()
-    _, order = torch.sort(prob[L1], dim=0, descending=True)                                  # :730-731
+    _, order = torch.sort(prob[L1], dim=0, descending=True, stable=True)                     # :730-731 (ties: unspecified in the reference; edge order here)
     L1 = L1[order]
     for e in L1:
         if t.pp[0, e] == -1:

@@ -65,6 +65,7 @@ def main():
         sel.select_grain_events(area.index_select(0, eng.node_order['grain']), eng._event_mask)      # engine rows, as the step selects them
         dt = DeviceTopology(eng, ei, mask)
         dt.profile = True
+        dt.edge_prob_fn = lambda v: torch.sigmoid(v.cpu()).to(v.device)          # the host run's own sigmoid: equal probabilities (ties) are the same in both
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()

@@ -35,7 +35,7 @@ def device_update(x, ei, y, mask, active_grains, active_joints, threshold=0.6):
     g = torch.Generator().manual_seed(0)
     shuffle = torch.randperm(L1.numel(), generator=g)                   # the selection kernel leaves its candidates in any order
     l1_ids = L1[shuffle].to(torch.int32).to(d)
-    l1_vals = y['edge_event'][L1[shuffle]].to(d)
+    l1_vals = prob[L1[shuffle]].to(d)                                   # the candidates' probabilities: the order of the switches (models.py:730-731)
     gshuf = torch.randperm(ge.numel(), generator=g)
     ge_ids, ge_vals = ge[gshuf].to(torch.int32).to(d), y['grain_area'][ge[gshuf]].to(d)
     l1_cap, ge_cap = max(L1.numel(), 1), max(ge.numel(), 1)

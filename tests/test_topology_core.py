@@ -42,7 +42,7 @@ def core_update(lib, preseed=1):
         prob = torch.sigmoid(y['edge_event'])
         pp0 = ei[ET[2]]
         L1 = ((prob > threshold) & (pp0[0] < pp0[1])).nonzero().view(-1).numpy().astype(np.int32)      # models.py:627-629
-        L1_logit = logit[L1].astype(np.float32)
+        L1_logit = prob.numpy()[L1].astype(np.float32)                  # the order of the switches is by probability (models.py:730-731)
         ge = y['grain_event'].numpy().astype(np.int32)
         extra = 2 * (len(ge) + 8) + 2 * ng // 8 + 64                   # appended jj edges: two per deleted grain
         def grow(e, cap_extra):
