@@ -72,13 +72,19 @@ static __host__ __device__ __forceinline__ void topo_hint_grain(int g) {
 struct GGTopo;
 enum { TOPO_OP_PRE = 1, TOPO_OP_POST, TOPO_OP_SORT_PAIRS, TOPO_OP_L1_MARK, TOPO_OP_L1_COMPACT, TOPO_OP_SWEEP, TOPO_OP_SWITCH_PAR };
 struct TopoSvc { int req, ack, op, n, flag, ret, enabled, par_enabled; const void* a; void* b; void* c;
-                 int par_seq, n_dirty, par_pending, par_err; };      // the concurrent switches: job counter of the worker warps, shared change-list counter
+                 int par_seq, n_dirty, par_pending, par_err;
+                 int gcap; unsigned long long* gkey; };                 // sort keys of lists too long for shared memory: the work area of the concurrent switches      // the concurrent switches: job counter of the worker warps, shared change-list counter
 constexpr int kTopoSortCap = 2048;         // elements the helper warp sorts in shared memory; longer lists fall back to the walker
 constexpr int kTopoSvcMin = 48;            // shorter lists are not worth the hand-over
 constexpr int kTopoParMin = 64;            // ... nor worth the rounds of the concurrent switches
 constexpr int kTopoThreads = 512;          // warp 0 walker | 1 look-ahead | 2 helper | 2..15 the worker group of the concurrent switches
 constexpr int kTopoWorkers = kTopoThreads - 64;
 __device__ __forceinline__ volatile TopoSvc* topo_svc() { return reinterpret_cast<volatile TopoSvc*>(gg_topo_smem + sizeof(TopoHint)); }
+__device__ __forceinline__ bool topo_sort_fits(int n) {        // keys of the helper warp's sort: shared memory, else the global area
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    return n2 <= kTopoSortCap || n2 <= topo_svc()->gcap;
+}
 static __device__ int topo_service_call(int op, const void* a, void* b, void* c, int n, int flag) {
     volatile TopoSvc* s = topo_svc();
     s->op = op; s->a = a; s->b = b; s->c = c; s->n = n; s->flag = flag;
@@ -108,7 +114,7 @@ static __host__ __device__ __forceinline__ bool topo_switch_parallel_dev(GGTopo&
 // the walker's side of the hooks
 static __host__ __device__ __forceinline__ int topo_switch_pre_dev(GGTopo& t, const int32_t* edges, int n, int32_t* touched) {
 #ifdef __CUDA_ARCH__
-    if (topo_svc()->enabled && n >= kTopoSvcMin && 2 * n <= kTopoSortCap && __isGlobal(edges)) return topo_service_call(TOPO_OP_PRE, edges, touched, nullptr, n, 0);
+    if (topo_svc()->enabled && n >= kTopoSvcMin && topo_sort_fits(2 * n) && __isGlobal(edges)) return topo_service_call(TOPO_OP_PRE, edges, touched, nullptr, n, 0);
 #endif
     return gg_topo_switch_pre_seq(t, edges, n, touched);
 }
@@ -120,7 +126,7 @@ static __host__ __device__ __forceinline__ void topo_switch_post_dev(GGTopo& t, 
 }
 static __host__ __device__ __forceinline__ void topo_sort_pairs_dev(int32_t* id, float* val, int n, bool by_value) {
 #ifdef __CUDA_ARCH__
-    if (topo_svc()->enabled && n >= kTopoSvcMin && n <= kTopoSortCap) { topo_service_call(TOPO_OP_SORT_PAIRS, nullptr, id, val, n, by_value ? 1 : 0); return; }
+    if (topo_svc()->enabled && n >= kTopoSvcMin && topo_sort_fits(n)) { topo_service_call(TOPO_OP_SORT_PAIRS, nullptr, id, val, n, by_value ? 1 : 0); return; }
 #endif
     gg_topo_sort_pairs(id, val, n, by_value);
 }
@@ -151,7 +157,7 @@ static __host__ __device__ __forceinline__ bool topo_switch_parallel_dev(GGTopo&
 }
 static __host__ __device__ __forceinline__ int topo_sweep_collect_dev(GGTopo& t, int32_t* cand) {
 #ifdef __CUDA_ARCH__
-    if (topo_svc()->enabled && !t.dirty_all && t.n_dirty >= kTopoSvcMin && t.n_dirty <= kTopoSortCap) return topo_service_call(TOPO_OP_SWEEP, t.dirty_list, cand, nullptr, t.n_dirty, 0);
+    if (topo_svc()->enabled && !t.dirty_all && t.n_dirty >= kTopoSvcMin && topo_sort_fits(t.n_dirty)) return topo_service_call(TOPO_OP_SWEEP, t.dirty_list, cand, nullptr, t.n_dirty, 0);
 #endif
     return gg_topo_sweep_collect_seq(t, cand);
 }
@@ -207,7 +213,7 @@ struct TopoArgs {
     int64_t* switching_list; int32_t* grain_event_out; int32_t* work;
     int64_t* result;                                                                         // {n_pp, n_pq, n_switch, n_grain_event, err, n_ge_in, n_l1_in}
     const int32_t* n_seed;                                                                   // grains with one or two joints on entry (topo_seed_two_sided)
-    int prefetch, service, parallel;
+    int prefetch, service, parallel, gcap;
 };
 
 // What the switch of edge column e will look at, read by 8 lanes: lanes 0-3 its first end point, 4-7 the second; of each four, lane 0
@@ -425,7 +431,7 @@ __device__ void topo_worker_warp(const GGTopo& t) {
 }
 
 __device__ void topo_service_warp(const GGTopo& t) {
-    __shared__ unsigned long long key[kTopoSortCap];
+    __shared__ unsigned long long key_smem[kTopoSortCap];
     volatile TopoSvc* s = topo_svc();
     volatile TopoHint* h = reinterpret_cast<volatile TopoHint*>(gg_topo_smem);
     const int lane = threadIdx.x & 31;
@@ -442,6 +448,10 @@ __device__ void topo_service_warp(const GGTopo& t) {
         void* b = const_cast<void*>(s->b);
         void* c = const_cast<void*>(s->c);
         int ret = 0;
+        const int need = op == TOPO_OP_PRE ? 2 * n : n;          // keys this request sorts: shared memory when they fit, else the global area
+        int need2 = 1;
+        while (need2 < need) need2 <<= 1;
+        unsigned long long* key = need2 <= kTopoSortCap ? key_smem : const_cast<unsigned long long*>(s->gkey);
         if (op == TOPO_OP_PRE) {                                 // gg_topo_switch_pre_seq
             const int32_t* edges = static_cast<const int32_t*>(a);
             int32_t* touched = static_cast<int32_t*>(b);
@@ -557,6 +567,7 @@ __global__ void __launch_bounds__(kTopoThreads, 1) topo_update_kernel(TopoArgs A
             h->n = 0; h->k = 0; h->epoch = 0; h->done = 0; h->edges = nullptr; h->grain = -1; h->gepoch = 0;
             volatile TopoSvc* sv = topo_svc();
             sv->req = 0; sv->ack = 0; sv->enabled = A.service; sv->par_enabled = A.service && A.parallel; sv->par_seq = 0;
+            sv->gkey = reinterpret_cast<unsigned long long*>(A.t.par_work); sv->gcap = A.gcap;
         }
         __syncthreads();
         if (threadIdx.x >= 96) { if (A.service && A.parallel) topo_worker_warp(A.t); return; }
@@ -664,6 +675,7 @@ extern "C" int gg_topology_update(int64_t* pp, int64_t cap_pp, int64_t n_pp, int
     { const char* e = getenv("GG_TOPO_SERVICE"); A.service = !(e && e[0] == '0'); }
     { const char* e = getenv("GG_TOPO_PARALLEL"); A.parallel = !(e && e[0] == '0'); }
     A.t.par_work = work + gg_topo_seq_ints(l1_cap, ge_cap, n_grain);
+    { int64_t g = 1; while (2 * g <= gg_topo_par_ints(l1_cap) / 2) g <<= 1; A.gcap = (int)(g > (1 << 20) ? (1 << 20) : g); }
     static bool carve_set = false;
     if (!carve_set) {                     // the walk lives on L1 hits (look-ahead warp): keep shared memory at what the helper warp needs
         cudaFuncSetAttribute(topo_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
