@@ -3,13 +3,14 @@
 //
 //   gg_topology_lists   data-parallel: the ascending position lists per joint / grain of the two edge arrays (what every
 //                       `(E == p).nonzero()` scan of the reference returns), fixed capacity per node
-//   gg_topology_update  ONE thread walks the events in the reference's order (topology_core.h — the same routine the CPU suite
-//                       checks against the reference's own outputs): eliminations by area, switches by probability, in-place edits,
-//                       appended edges, -1 for deleted columns; candidates come straight from gg_select_events' device buffers
+//   gg_topology_update  one CTA: a walking thread takes the eliminations in the reference's order (topology_core.h — the same routine the
+//                       CPU suite checks against the reference's own outputs: in-place edits, appended edges, -1 for deleted columns),
+//                       the plain switches of the step run concurrently in conflict-free rounds on fourteen worker warps, a helper
+//                       warp sorts and loops over whole lists, a look-ahead warp pulls the walker's table entries into L1;
+//                       candidates come straight from gg_select_events' device buffers
 //   (cleanup, models.py:846-862, is a stable compaction of the columns that are not -1: the caller's stream compaction)
-// The events of a step are few (tens to hundreds at 10^5 grains) and each touches a handful of table entries, so a sequential walk
-// costs tens of microseconds per event; what it removes is the host round trip of the full prediction arrays and edge lists
-// (20 + 36 MB at 1.2 10^5 grains) and the host's O(E) indexing and compaction per step.
+// What it removes is the host round trip of the full prediction arrays and edge lists (20 + 36 MB at 1.2 10^5 grains) and the host's
+// O(E) indexing and compaction per step; an elimination costs the walker ~85 us, a switch a fraction of a microsecond amortised.
 #include "common.cuh"
 #ifdef GG_TOPO_PROFILE
 #include <stdio.h>

@@ -341,7 +341,8 @@ int gg_area_bookkeeping(const float* x_grain, int32_t ld_g, const float* mask_gr
  *      result equals the reference's position for position.
  *  gg_topology_lists: ascending position lists per (row, value): list_r[v * cap_r + k], cnt_r[v]; caps from gg_topology_caps
  *      (joint rows: cap_joint, the grain row of pq: cap_grain); status[0] != 0 on overflow / out-of-range ids.
- *  gg_topology_update: one sequential walk over the events.  Candidates are the device buffers of gg_select_events: grains
+ *  gg_topology_update: the update of one step in one CTA (eliminations one after the other, the plain switches concurrently in
+ *      conflict-free rounds; results are those of the reference's sequential order).  Candidates are the device buffers of gg_select_events: grains
  *      (ge_ids, ge_vals = predicted area; sorted here by area) and joint-joint columns with src < dst (l1_ids, l1_vals = the
  *      candidate's PROBABILITY, i.e. sigmoid of its logit as torch computes it; sorted here by probability descending, equal
  *      probabilities - saturated or colliding in fp32 - in ascending column order like the reference's sort, models.py:730-731), each with its count (clamped to *_cap).
