@@ -28,6 +28,7 @@ def main():
     ap.add_argument('--lxd', type=int, default=1320)
     ap.add_argument('--switches', type=int, default=300)
     ap.add_argument('--vanish', type=int, default=20)
+    ap.add_argument('--cases', type=int, default=3)
     ap.add_argument('--out', default=os.path.join(ROOT, 'profiles', 'r2_topology_device_bench.json'))
     a = ap.parse_args()
     dev = torch.device('cuda:0')
@@ -35,7 +36,7 @@ def main():
     sd_r, sd_c, _ = bench.synth_weights()
     ng, nj = x['grain'].shape[0], x['joint'].shape[0]
     res = {'domain': desc, 'cases': []}
-    for seed in range(12):
+    for seed in range(4 * a.cases):
         y = _craft(np.random.default_rng(9000 + seed), x, ei, a.switches, a.vanish, 6)
         mask = {'grain': torch.ones(ng, 1), 'joint': torch.ones(nj, 1)}
         # ---- host path on CPU copies (what RolloutDriver(topology='host') does on a step with candidates)
@@ -82,7 +83,7 @@ def main():
                              'device_update_wall_s': t_dev_wall, 'device_phases_ms': dt.last_ms,
                              'note': 'device time = lists + sequential kernel + compaction + set_topology (CSR, tile index rebuilt) on the stream; '
                                      'host time = the position-list update alone, without the D2H / H2D of its inputs and outputs'})
-        if len(res['cases']) >= 3:
+        if len(res['cases']) >= a.cases:
             break
     with open(a.out, 'w') as f:
         json.dump(res, f, indent=1)
